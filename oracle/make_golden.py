@@ -1,0 +1,130 @@
+"""ORACLE tooling: regenerate tests/golden/*.npz in the AUTHORING container.
+
+Golden vectors come from the real pieces, not from the restatement:
+  * LM arithmetic: the installed HF `LlamaModel` (transformers, third-party
+    dependency of the reference) driven through the reference's loop shape
+    (plangen_base.py:567-607) with the reference's mask / no-position_ids call
+    pattern (:571-576);
+  * VQ decode: the reference's own `three_party/Janus/janus/models/vq_model.py`
+    imported by file path from /root/reference (read-only), both the real
+    `VQ_models['VQ-16']()` class on a 4x4 token grid and a tiny-channel Decoder.
+
+Run:  python oracle/make_golden.py          (needs /root/reference; CPU only)
+The GPU box never runs this; it only reads the committed .npz files.
+"""
+from __future__ import annotations
+
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import janus_oracle as O            # noqa: E402
+from oracle.philox import PhiloxSampler         # noqa: E402
+
+REF_VQ = "/root/reference/three_party/Janus/janus/models/vq_model.py"
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def load_ref_vq():
+    spec = importlib.util.spec_from_file_location("ref_vq_model", REF_VQ)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_vq_model"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def hf_llama(d: O.JanusDims, sd):
+    from transformers import LlamaConfig, LlamaModel
+    cfg = LlamaConfig(hidden_size=d.D, intermediate_size=d.F, num_hidden_layers=d.L,
+                      num_attention_heads=d.H, num_key_value_heads=d.H, head_dim=d.head_dim,
+                      vocab_size=d.vocab, rms_norm_eps=d.rms_eps, rope_theta=d.rope_theta,
+                      max_position_embeddings=4096, attn_implementation="eager")
+    m = LlamaModel(cfg).eval()
+    pre = "language_model.model."
+    missing, unexpected = m.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)},
+                                            strict=True)
+    assert not missing and not unexpected
+    return m
+
+
+def versions():
+    import transformers
+    return np.array([torch.__version__, transformers.__version__])
+
+
+def golden_lm(name: str, d: O.JanusDims, batch: int, steps: int, lo: int, hi: int, neg_len: int):
+    sd = O.init_state_dict(d, seed=0, with_vq=False)
+    hf = hf_llama(d, sd)
+    cond, neg = O.synthetic_prompts(d, batch, seed=1234, lo=lo, hi=hi, neg_len=neg_len)
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, d.pad_id, d.n_img_tokens)
+    trace: dict = {}
+    with torch.inference_mode():
+        emb = O.embed_tokens(sd, ids)
+        toks = O.sample_image(sd, d, emb, batch, steps, mask, 5.0, 1.0, PhiloxSampler(0, 148),
+                              mode="fp32", trace=trace,
+                              lm_forward=lambda **kw: hf(**kw))
+    np.savez_compressed(
+        os.path.join(OUT, name), dims=np.array(d.name), ids=ids.numpy(), mask=mask.numpy(),
+        hidden=torch.stack(trace["hidden"]).numpy(), logits=torch.stack(trace["logits"]).numpy(),
+        tokens=toks.numpy(), cfg_weight=5.0, temperature=1.0, seed=0, num_sms=148,
+        versions=versions())
+    print(name, "tokens", toks.tolist())
+
+
+def golden_vq_ref_class(name: str):
+    """The reference's real VQ-16 (ch=128, 71.9M params) on a 4x4 token grid."""
+    ref = load_ref_vq()
+    d = O.JANUS_1P3B
+    sd = O.init_state_dict(d, seed=0, only="gen_vision_model.")
+    m = ref.VQ_models["VQ-16"]().eval()
+    pre = "gen_vision_model."
+    res = m.load_state_dict({k[len(pre):]: v for k, v in sd.items()}, strict=False)
+    assert not res.unexpected_keys
+    assert all(k.startswith(("encoder.", "quant_conv.", "quantize.codebook_used")) for k in res.missing_keys), res.missing_keys
+    g = torch.Generator().manual_seed(7)
+    codes = torch.randint(0, d.img_vocab, (1, 16), generator=g, dtype=torch.int32)
+    with torch.inference_mode():
+        out = m.decode_code(codes, shape=[1, 8, 4, 4])
+    np.savez_compressed(os.path.join(OUT, name), codes=codes.numpy(), out=out.numpy(), versions=versions())
+    print(name, tuple(out.shape), float(out.abs().mean()))
+
+
+def golden_vq_tiny(name: str, d: O.JanusDims, batch: int):
+    """Reference Decoder / VectorQuantizer classes at test-sized channel counts."""
+    ref = load_ref_vq()
+    sd = O.init_state_dict(d, seed=0, only="gen_vision_model.")
+    dec = ref.Decoder(z_channels=d.vq_z, ch=d.vq_ch, ch_mult=d.vq_ch_mult,
+                      num_res_blocks=d.vq_res_blocks).eval()
+    quant = ref.VectorQuantizer(d.img_vocab, d.code_dim, 0.25, 0.0, True, False).eval()
+    pqc = torch.nn.Conv2d(d.code_dim, d.vq_z, 1)
+    pre = "gen_vision_model."
+    dec.load_state_dict({k[len(pre + "decoder."):]: v for k, v in sd.items() if k.startswith(pre + "decoder.")})
+    quant.load_state_dict({"embedding.weight": sd[pre + "quantize.embedding.weight"]})
+    pqc.load_state_dict({"weight": sd[pre + "post_quant_conv.weight"], "bias": sd[pre + "post_quant_conv.bias"]})
+    g = torch.Generator().manual_seed(11)
+    codes = torch.randint(0, d.img_vocab, (batch, d.n_img_tokens), generator=g, dtype=torch.int32)
+    with torch.inference_mode():
+        zq = quant.get_codebook_entry(codes, [batch, d.code_dim, d.grid, d.grid], True)
+        out = dec(pqc(zq))
+    np.savez_compressed(os.path.join(OUT, name), dims=np.array(d.name), codes=codes.numpy(),
+                        out=out.numpy(), versions=versions())
+    print(name, tuple(out.shape), float(out.abs().mean()))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    golden_lm("lm_tiny_fp32.npz", O.TINY, batch=2, steps=8, lo=5, hi=12, neg_len=7)
+    golden_lm("lm_small_fp32.npz", O.SMALL, batch=3, steps=6, lo=9, hi=40, neg_len=13)
+    golden_vq_tiny("vq_tiny.npz", O.TINY, batch=2)
+    golden_vq_tiny("vq_small.npz", O.SMALL, batch=1)
+    golden_vq_ref_class("vq16_grid4.npz")
+
+
+if __name__ == "__main__":
+    main()
