@@ -1,0 +1,123 @@
+/* plangen_b200 C-ABI — the drop-in boundary for PlanGen's CFG image-token decode path.
+ *
+ * The reference (360CVGroup/PlanGen) is pure Python: the seam is duck-typed attribute
+ * access on `self.vl_gpt` from `System.t2i` / `System.sample_image`
+ * (project/plangen/plangen_base.py:525-607).  Each entry point below names the
+ * reference call it replaces.  All pointers are DEVICE pointers unless a name ends in
+ * `_host`; sizes are explicit; `stream` is a `cudaStream_t` passed as `void*`.
+ * Every function returns 0 on success and a non-zero status otherwise (never throws);
+ * `pg_last_error()` gives the message.  The caller owns all memory; weights are
+ * borrowed read-only for the engine's lifetime.  One host thread per engine.
+ */
+#ifndef PLANGEN_B200_H
+#define PLANGEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_ABI_VERSION 1
+
+/* arithmetic regimes */
+#define PG_MODE_BF16 0 /* the reference's regime: fp32 master weights under autocast(bf16), plangen_base.py:360 */
+#define PG_MODE_FP32 1 /* fp32 check mode (BASELINE config 1; north_star "fp32 check mode") */
+
+typedef struct pg_engine pg_engine;
+
+typedef struct pg_dims {
+  int32_t D, L, H, head_dim, F;      /* LlamaConfig: hidden, layers, heads, head_dim, intermediate */
+  int32_t vocab, img_vocab, code_dim, img_embed, grid;
+  float rms_eps, rope_theta;
+  int32_t vq_ch, vq_nres, vq_ch_mult[8], vq_z, vq_res_blocks;
+  int32_t mode;                      /* PG_MODE_* */
+  int32_t max_rows;                  /* R = 2 * B * parallel_size upper bound */
+  int32_t max_prompt;                /* padded prompt length P upper bound */
+  int32_t max_steps;                 /* image tokens per image (576) upper bound */
+} pg_dims;
+
+const char* pg_last_error(void);
+int pg_abi_version(void);
+
+/* Engine lifetime.  replaces: MultiModalityCausalLM.__init__ / from_pretrained
+ * (three_party/Janus/janus/models/modeling_vlm.py:190-219; plangen_base.py:95-97). */
+int pg_engine_create(const pg_dims* dims, int device, pg_engine** out);
+int pg_engine_destroy(pg_engine* e);
+
+/* Bytes of KV cache / scratch workspace the caller must allocate and bind. */
+int pg_engine_query_bytes(const pg_engine* e, size_t* kv_bytes, size_t* ws_bytes);
+int pg_engine_bind_buffers(pg_engine* e, void* kv, size_t kv_bytes, void* ws, size_t ws_bytes);
+
+/* Register one weight tensor by its (packed) name; see plangen_b200/weights.py for the
+ * packing of the reference state_dict names into these slots. */
+int pg_engine_set_tensor(pg_engine* e, const char* name, const void* dev_ptr, size_t nbytes);
+
+/* Build derived tables (gen_aligner(gen_embed(.)) table, L2-normalised codebook,
+ * TMA descriptors).  Must be called once after all tensors are set. */
+int pg_engine_finalize(pg_engine* e, void* stream);
+
+/* replaces: language_model.get_input_embeddings()(ids)   plangen_base.py:548
+ * ids int32 [R*P] -> x fp32 [R*P, D] */
+int pg_embed_tokens(pg_engine* e, const int32_t* ids, int n_tokens, float* x_out, void* stream);
+
+/* replaces: language_model.model(inputs_embeds=(R,P,D), attention_mask, use_cache=True,
+ *           past_key_values=None)                           plangen_base.py:571-576 (i == 0)
+ * x fp32 [R,P,D] is consumed in place (residual stream).  kv_start[r] = number of LEFT pad
+ * columns of row r (lossless encoding of the 0/1 mask).
+ * hidden_out: final-norm'ed last_hidden_state; all_positions=1 -> [R,P,D], 0 -> [R,D] (last). */
+int pg_prefill(pg_engine* e, float* x, const int32_t* kv_start, int R, int P,
+               float* hidden_out, int all_positions, void* stream);
+
+/* replaces: language_model.model(inputs_embeds=(R,1,D), past_key_values=prev)  (i >= 1)
+ * x fp32 [R,D]; pos = absolute column index of this token (P + i - 1). */
+int pg_decode_step(pg_engine* e, const float* x, const int32_t* kv_start, int R, int pos,
+                   float* hidden_out, void* stream);
+
+/* replaces: vl_gpt.gen_head(h)          modeling_vlm.py:36-51 / plangen_base.py:579
+ * hidden fp32 [R,D] -> logits fp32 [R,img_vocab] (bf16-rounded values in PG_MODE_BF16). */
+int pg_gen_head(pg_engine* e, const float* hidden, int R, float* logits_out, void* stream);
+
+/* replaces: plangen_base.py:580-604 — CFG combine, /temperature, softmax,
+ * torch.multinomial(1) (Philox4x32-10, bit-compatible with torch's CUDA generator at
+ * (seed, philox_offset)), teacher-forcing override (:593-598), token duplication and
+ * prepare_gen_img_embeds.  logits fp32 [2B, V] (rows interleaved cond/uncond).
+ * edit_region / gt_labels: int32 [B, n_steps] or NULL.  greedy != 0 -> argmax.
+ * tokens_out int32 [B, n_steps] (column `step` written); x_next fp32 [2B, D]. */
+int pg_cfg_sample_embed(pg_engine* e, const float* logits, int B, float cfg_weight,
+                        float temperature, uint64_t seed, uint64_t philox_offset, int greedy,
+                        const int32_t* edit_region, const int32_t* gt_labels, int step,
+                        int n_steps, int32_t* tokens_out, float* x_next, void* stream);
+
+/* replaces: vl_gpt.prepare_gen_img_embeds(ids)     modeling_vlm.py:270-271
+ * ids int32 [n] -> fp32 [n, D] */
+int pg_prepare_gen_img_embeds(pg_engine* e, const int32_t* ids, int n, float* out, void* stream);
+
+/* replaces: System.sample_image (plangen_base.py:567-607), whole loop on the device:
+ * prefill + n_steps x (gen_head, CFG, sample, embed, decode step) with no host sync.
+ * x_prompt fp32 [R,P,D] (consumed).  tokens_out int32 [R/2, n_steps]. */
+int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_start, int R, int P,
+                    int n_steps, float cfg_weight, float temperature, uint64_t seed, int greedy,
+                    const int32_t* edit_region, const int32_t* gt_labels,
+                    int32_t* tokens_out, void* stream);
+
+/* replaces: gen_vision_model.decode_code(code_b, shape=[B,8,g,g], channel_first=True)
+ *           three_party/Janus/janus/models/vq_model.py:505-508
+ * codes int32 [B, gh*gw] -> image fp32 NCHW [B,3,16*gh,16*gw] (unclamped). */
+int pg_vq_decode_code(pg_engine* e, const int32_t* codes, int B, int gh, int gw,
+                      float* image_out, void* stream);
+
+/* Bench / profiling helpers */
+int pg_engine_set_option(pg_engine* e, const char* key, int64_t value);
+int pg_engine_get_counter(const pg_engine* e, const char* key, int64_t* value);
+
+/* Plain GEMM exposed for unit tests:  C[m,n] = sum_k X[m,k] * W[n,k]
+ * impl 0 = SIMT (fp32 or bf16 inputs), 1 = tcgen05 (bf16 inputs).  C fp32 [splits][M][N]. */
+int pg_test_gemm(pg_engine* e, int impl, int is_bf16, const void* X, const void* W, int M, int N,
+                 int K, int splits, float* C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLANGEN_B200_H */

@@ -1,0 +1,932 @@
+// plangen_b200 engine: host-side orchestration of the sm_100a kernels behind the C-ABI declared in
+// include/plangen_b200.h.  No torch, no CPU fallback: every entry point launches CUDA kernels or fails.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/plangen_b200.h"
+#include "common.cuh"
+#include "gemm.cuh"
+#include "lm_kernels.cuh"
+#include "sample.cuh"
+#include "vq_kernels.cuh"
+
+using namespace pg;
+
+// ------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t _e = (call);                                                                       \
+    if (_e != cudaSuccess) return fail("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e)); \
+  } while (0)
+#define TRY(call)                 \
+  do {                            \
+    int _r = (call);              \
+    if (_r) return _r;            \
+  } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------ engine
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct Carve {
+  uint8_t* base = nullptr;
+  size_t off = 0;
+  void* take(size_t bytes) {
+    off = align_up(off, 1024);
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    return p;
+  }
+};
+
+struct pg_engine {
+  pg_dims d;
+  int device = 0, num_sms = 0, max_threads_per_sm = 2048;
+  bool bf16 = true;
+  size_t esz = 2;                 // bytes per activation / weight element
+  int Tmax = 0, HD = 0;
+  std::unordered_map<std::string, std::pair<const void*, size_t>> tensors;
+  EncodeTiledFn encode = nullptr;
+  // options
+  int use_tc = 1, use_pdl = 1, use_graph = 1, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
+  float* dbg_logits = nullptr;
+  int64_t launches = 0;
+  bool finalized = false;
+  // bound buffers
+  void* kv = nullptr; size_t kv_bytes = 0;
+  void* ws = nullptr; size_t ws_bytes = 0;
+  // workspace carve-outs
+  void *xn = nullptr, *qbuf = nullptr, *attn_out = nullptr, *hbuf = nullptr, *hidden_t = nullptr, *head_h = nullptr;
+  float *part = nullptr, *x_dec = nullptr, *hidden_f = nullptr, *attn_ws = nullptr;
+  size_t part_bytes = 0;
+  int *attn_cnt = nullptr, *step_ctr = nullptr;
+  void *embed_table = nullptr, *align_tmp = nullptr;
+  void *vq_act[3] = {nullptr, nullptr, nullptr};
+  void* vq_col = nullptr; float* vq_part = nullptr; float *gn_partial = nullptr, *gn_stats = nullptr;
+  size_t vq_act_elems = 0, vq_col_elems = 0, vq_part_elems = 0;
+  int gn_chunks_max = 0;
+  // graph cache
+  cudaGraphExec_t graph_exec = nullptr;
+  std::string graph_key;
+  int64_t graph_launches = 0;     // kernels per replay, counted while capturing
+};
+
+static const void* T_(pg_engine* e, const std::string& name, size_t* nbytes = nullptr) {
+  auto it = e->tensors.find(name);
+  if (it == e->tensors.end()) return nullptr;
+  if (nbytes) *nbytes = it->second.second;
+  return it->second.first;
+}
+#define NEED(var, type, name)                                        \
+  const type* var = (const type*)T_(e, (name));                      \
+  if (!var) return fail("tensor '%s' was not registered", std::string(name).c_str());
+
+// ------------------------------------------------------------------------------ launch helper
+template <typename... KArgs, typename... Args>
+static int launch(pg_engine* e, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                  Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = e->use_pdl ? 1 : 0;
+  e->launches++;
+  CK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ GEMM dispatch
+static int make_map_2d(pg_engine* e, CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t K, uint32_t box_rows) {
+  cuuint64_t gdim[2] = {K, rows};
+  cuuint64_t gstr[1] = {K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = e->encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu K=%llu ptr=%p", (int)r,
+                                     (unsigned long long)rows, (unsigned long long)K, ptr);
+  return 0;
+}
+
+template <int NT>
+static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx, float* C, int M, int N, int K,
+                     int splits, int kb_per_split, cudaStream_t st) {
+  using Cfg = TcCfg<NT>;
+  int stages = e->tc_stages > 0 ? e->tc_stages : (200 * 1024) / Cfg::STAGE_BYTES;
+  stages = std::max(2, std::min(stages, 12));
+  stages = std::min(stages, std::max(2, kb_per_split));
+  const size_t smem = Cfg::smem_bytes(stages);
+  dim3 grid((N + TC_BM - 1) / TC_BM, (M + NT - 1) / NT, splits);
+  return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
+                e->use_pdl);
+}
+
+// C[splits][M][N] fp32 = X[M][K] * W[N][K]^T.  Returns the number of splits used through *splits_out.
+static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, int K, float* C, size_t c_bytes,
+                    int* splits_out, cudaStream_t st, int force_impl = -1, int force_splits = 0) {
+  const bool tc = e->bf16 && ((force_impl == 1) || (force_impl < 0 && e->use_tc)) && (K % 8 == 0) &&
+                  (((uintptr_t)X & 15) == 0) && (((uintptr_t)W & 15) == 0);
+  if (force_impl == 1 && !tc) return fail("tcgen05 GEMM needs bf16 operands, K %% 8 == 0 and 16-byte aligned pointers");
+  int splits = 1;
+  if (tc) {
+    const int NT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+    const int tiles = ((N + TC_BM - 1) / TC_BM) * ((M + NT - 1) / NT);
+    const int num_kb = (K + TC_BK - 1) / TC_BK;
+    int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : std::max(1, e->num_sms / tiles));
+    want = std::min(std::min(want, 16), num_kb);
+    while (want > 1 && (size_t)want * M * N * 4 > c_bytes) --want;
+    const int kb_per_split = (num_kb + want - 1) / want;
+    splits = (num_kb + kb_per_split - 1) / kb_per_split;
+    if ((size_t)splits * M * N * 4 > c_bytes) return fail("GEMM partial buffer too small (%d x %d x %d)", splits, M, N);
+    CUtensorMap mw, mx;
+    TRY(make_map_2d(e, &mw, W, (uint64_t)N, (uint64_t)K, TC_BM));
+    TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
+    switch (NT) {
+      case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
+      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
+      case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
+      case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
+      default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
+    }
+  } else {
+    if (K % 4 != 0) return fail("SIMT GEMM needs K %% 4 == 0 (K=%d)", K);
+    const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
+    int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : std::max(1, (2 * e->num_sms) / tiles));
+    want = std::min(std::min(want, 16), (K + 15) / 16);
+    while (want > 1 && (size_t)want * M * N * 4 > c_bytes) --want;
+    int k_per_split = ((K + want - 1) / want + 15) / 16 * 16;
+    splits = (K + k_per_split - 1) / k_per_split;
+    if ((size_t)splits * M * N * 4 > c_bytes) return fail("GEMM partial buffer too small (%d x %d x %d)", splits, M, N);
+    dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+    if (e->bf16)
+      TRY(launch(e, gemm_simt_kernel<bf16>, grid, dim3(256), 0, st, (const bf16*)X, (const bf16*)W, C, M, N, K, k_per_split));
+    else
+      TRY(launch(e, gemm_simt_kernel<float>, grid, dim3(256), 0, st, (const float*)X, (const float*)W, C, M, N, K, k_per_split));
+  }
+  *splits_out = splits;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ sizes
+static int vq_chunk_of(const pg_engine* e) { return e->vq_chunk > 0 ? e->vq_chunk : (e->bf16 ? 4 : 1); }
+
+static void layout_workspace(pg_engine* e, Carve& c) {
+  const pg_dims& d = e->d;
+  const size_t es = e->esz;
+  const size_t max_tok = (size_t)d.max_rows * std::max(d.max_prompt, 1);
+  const size_t R = d.max_rows;
+  const size_t wide = std::max<size_t>(std::max(3 * e->HD, 2 * d.F), std::max(d.D, d.img_embed));
+  e->xn = c.take(max_tok * d.D * es);
+  e->qbuf = c.take(max_tok * e->HD * es);
+  e->attn_out = c.take(max_tok * e->HD * es);
+  e->hbuf = c.take(max_tok * d.F * es);
+  size_t pb = max_tok * wide * 4;                                         // prefill, 1 split
+  pb = std::max(pb, (size_t)16 * R * std::max<size_t>(wide, d.img_vocab) * 4);   // decode, <= 16 splits
+  pb = std::max(pb, (size_t)d.img_vocab * d.D * 4);                       // gen_aligner table build
+  e->part_bytes = pb;
+  e->part = (float*)c.take(pb);
+  e->x_dec = (float*)c.take(R * d.D * 4);
+  e->hidden_f = (float*)c.take(R * d.D * 4);
+  e->hidden_t = c.take(R * d.D * es);
+  e->head_h = c.take(R * d.img_embed * es);
+  e->attn_ws = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 4);
+  e->attn_cnt = (int*)c.take(R * d.H * 4);
+  e->step_ctr = (int*)c.take(256);
+  e->embed_table = c.take((size_t)d.img_vocab * d.D * es);
+  e->align_tmp = c.take((size_t)d.img_vocab * d.D * es);
+  // VQ decoder scratch, per chunk of images
+  const int Bc = vq_chunk_of(e);
+  size_t act = 0, col = 0, part = 0;
+  {
+    int res = d.grid;
+    const int nres = d.vq_nres;
+    int ch = d.vq_ch * d.vq_ch_mult[nres - 1];
+    act = std::max(act, (size_t)res * res * std::max(ch, d.vq_z));
+    col = std::max(col, (size_t)res * res * 9 * std::max(ch, d.vq_z));
+    col = std::max(col, (size_t)res * res * ch * 6 + (size_t)res * res * res * res);   // attention scratch
+    part = std::max(part, (size_t)res * res * std::max<size_t>(ch, (size_t)res * res));
+    for (int idx = 0; idx < nres; ++idx) {
+      const int i_level = nres - 1 - idx;
+      const int cout = d.vq_ch * d.vq_ch_mult[i_level];
+      act = std::max(act, (size_t)res * res * std::max(ch, cout));
+      col = std::max(col, (size_t)res * res * 9 * std::max(ch, cout));
+      part = std::max(part, (size_t)res * res * std::max(ch, cout));
+      ch = cout;
+      if (idx != nres - 1) {
+        res *= 2;
+        act = std::max(act, (size_t)res * res * ch);
+        col = std::max(col, (size_t)res * res * 9 * ch);
+        part = std::max(part, (size_t)res * res * ch);
+      }
+    }
+  }
+  e->vq_act_elems = act * Bc; e->vq_col_elems = col * Bc; e->vq_part_elems = part * Bc;
+  for (int i = 0; i < 3; ++i) e->vq_act[i] = c.take(e->vq_act_elems * es);
+  e->vq_col = c.take(e->vq_col_elems * es);
+  e->vq_part = (float*)c.take(e->vq_part_elems * 4);
+  e->gn_chunks_max = 1024;
+  e->gn_partial = (float*)c.take((size_t)Bc * e->gn_chunks_max * 32 * 2 * 4);
+  e->gn_stats = (float*)c.take((size_t)Bc * 32 * 2 * 4);
+}
+
+// ------------------------------------------------------------------------------ C-ABI: lifetime
+extern "C" const char* pg_last_error(void) { return g_err; }
+extern "C" int pg_abi_version(void) { return PG_ABI_VERSION; }
+
+extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out) {
+  if (!dims || !out) return fail("null argument");
+  if (dims->head_dim != HEAD_DIM) return fail("head_dim must be %d", HEAD_DIM);
+  if (dims->D % 8 || dims->F % 8 || dims->img_embed % 8) return fail("D, F, img_embed must be multiples of 8");
+  if (dims->vq_nres < 1 || dims->vq_nres > 8) return fail("bad vq_nres");
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("no CUDA device %d (have %d): plangen_b200 has no CPU path", device, ndev);
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail("plangen_b200 kernels are built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+  pg_engine* e = new pg_engine();
+  e->d = *dims;
+  e->device = device;
+  e->num_sms = prop.multiProcessorCount;
+  e->max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
+  e->bf16 = dims->mode == PG_MODE_BF16;
+  e->esz = e->bf16 ? 2 : 4;
+  e->HD = dims->H * dims->head_dim;
+  e->Tmax = (int)align_up((size_t)dims->max_prompt + dims->max_steps, 64);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) { delete e; return fail("cuTensorMapEncodeTiled not available"); }
+  e->encode = (EncodeTiledFn)fn;
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(attn_prefill_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
+  CK(cudaFuncSetAttribute(attn_prefill_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
+  CK(cudaFuncSetAttribute(cfg_sample_embed_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dims->img_vocab * 4));
+  CK(cudaFuncSetAttribute(cfg_sample_embed_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, dims->img_vocab * 4));
+  *out = e;
+  return 0;
+}
+
+extern "C" int pg_engine_destroy(pg_engine* e) {
+  if (!e) return 0;
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  delete e;
+  return 0;
+}
+
+extern "C" int pg_engine_query_bytes(const pg_engine* e_, size_t* kv_bytes, size_t* ws_bytes) {
+  if (!e_) return fail("null engine");
+  pg_engine tmp = *e_;
+  Carve c;
+  layout_workspace(&tmp, c);
+  if (kv_bytes) *kv_bytes = (size_t)tmp.d.L * 2 * tmp.d.max_rows * tmp.d.H * tmp.Tmax * HEAD_DIM * tmp.esz;
+  if (ws_bytes) *ws_bytes = align_up(c.off, 1024) + 1024;
+  tmp.graph_exec = nullptr;
+  return 0;
+}
+
+extern "C" int pg_engine_bind_buffers(pg_engine* e, void* kv, size_t kv_bytes, void* ws, size_t ws_bytes) {
+  if (!e) return fail("null engine");
+  size_t need_kv, need_ws;
+  TRY(pg_engine_query_bytes(e, &need_kv, &need_ws));
+  if (kv_bytes < need_kv) return fail("kv buffer too small: %zu < %zu", kv_bytes, need_kv);
+  if (ws_bytes < need_ws) return fail("workspace too small: %zu < %zu", ws_bytes, need_ws);
+  if (((uintptr_t)kv & 255) || ((uintptr_t)ws & 255)) return fail("buffers must be 256-byte aligned");
+  e->kv = kv; e->kv_bytes = kv_bytes; e->ws = ws; e->ws_bytes = ws_bytes;
+  Carve c;
+  c.base = (uint8_t*)align_up((uintptr_t)ws, 1024);
+  layout_workspace(e, c);
+  return 0;
+}
+
+extern "C" int pg_engine_set_tensor(pg_engine* e, const char* name, const void* dev_ptr, size_t nbytes) {
+  if (!e || !name || !dev_ptr) return fail("null argument");
+  if ((uintptr_t)dev_ptr & 15) return fail("tensor '%s' is not 16-byte aligned", name);
+  e->tensors[name] = {dev_ptr, nbytes};
+  return 0;
+}
+
+extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value) {
+  if (!e || !key) return fail("null argument");
+  const std::string k(key);
+  if (k == "use_tc") e->use_tc = (int)value;
+  else if (k == "use_pdl") e->use_pdl = (int)value;
+  else if (k == "use_graph") e->use_graph = (int)value;
+  else if (k == "tc_stages") e->tc_stages = (int)value;
+  else if (k == "vq_chunk") e->vq_chunk = (int)value;
+  else if (k == "attn_splits") e->attn_splits = (int)value;
+  else if (k == "gemm_splits") e->gemm_splits = (int)value;
+  else if (k == "dbg_logits_ptr") e->dbg_logits = (float*)(uintptr_t)value;
+  else if (k == "reset_launches") e->launches = 0;
+  else return fail("unknown option '%s'", key);
+  if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+  return 0;
+}
+
+extern "C" int pg_engine_get_counter(const pg_engine* e, const char* key, int64_t* value) {
+  if (!e || !key || !value) return fail("null argument");
+  const std::string k(key);
+  if (k == "launches") *value = e->launches;
+  else if (k == "num_sms") *value = e->num_sms;
+  else if (k == "max_threads_per_sm") *value = e->max_threads_per_sm;
+  else if (k == "tmax") *value = e->Tmax;
+  else if (k == "philox_offset_per_step") *value = 0;
+  else return fail("unknown counter '%s'", key);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ typed dispatch helpers
+#define DISPATCH_T(e, expr_bf16, expr_f32) \
+  do {                                     \
+    if ((e)->bf16) { TRY(expr_bf16); }     \
+    else { TRY(expr_f32); }                \
+  } while (0)
+
+static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t sstride, const float* w, void* xn,
+                        float* y, int rows, int in_stride, int in_off, int flags, cudaStream_t st) {
+  const int D = e->d.D;
+  DISPATCH_T(e,
+             launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(256), 0, st, x, part, S, sstride, w, (bf16*)xn, y, D,
+                    e->d.rms_eps, in_stride, in_off, flags, e->step_ctr),
+             launch(e, resid_rmsnorm_kernel<float>, dim3(rows), dim3(256), 0, st, x, part, S, sstride, w, (float*)xn, y,
+                    D, e->d.rms_eps, in_stride, in_off, flags, e->step_ctr));
+  return 0;
+}
+
+static void* kv_ptr(pg_engine* e, int layer, int which, int R) {
+  // [L][2][R][H][Tmax][128]; R here is the row count of the CURRENT batch (cache is re-laid per batch)
+  const size_t per = (size_t)R * e->d.H * e->Tmax * HEAD_DIM * e->esz;
+  return (uint8_t*)e->kv + ((size_t)layer * 2 + which) * per;
+}
+
+static int check_ready(pg_engine* e) {
+  if (!e) return fail("null engine");
+  if (!e->ws || !e->kv) return fail("buffers not bound (pg_engine_bind_buffers)");
+  if (!e->finalized) return fail("engine not finalized (pg_engine_finalize)");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ finalize
+extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
+  if (!e) return fail("null engine");
+  if (!e->ws) return fail("bind buffers before finalize");
+  cudaStream_t st = (cudaStream_t)stream;
+  const pg_dims& d = e->d;
+  // gen_aligner(gen_embed(v)) for every v: the next-input embedding is a pure function of the id
+  NEED(gen_embed, float, "gen_embed");
+  NEED(w0, void, "align.w0");
+  NEED(b0, float, "align.b0");
+  NEED(w1, void, "align.w1");
+  NEED(b1, float, "align.b1");
+  const size_t total = (size_t)d.img_vocab * d.D;
+  void* htmp = e->align_tmp;   // scratch: V x D activations
+  const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+  const int saved_pdl = e->use_pdl;
+  e->use_pdl = 0;
+  int rc = 0;
+  do {
+    if (e->bf16) rc = launch(e, aligner_l0_kernel<bf16>, dim3(blocks), dim3(256), 0, st, gen_embed, (const bf16*)w0, b0, (bf16*)htmp, d.code_dim, d.D, total);
+    else rc = launch(e, aligner_l0_kernel<float>, dim3(blocks), dim3(256), 0, st, gen_embed, (const float*)w0, b0, (float*)htmp, d.code_dim, d.D, total);
+    if (rc) break;
+    int S = 1;
+    rc = run_gemm(e, htmp, w1, d.img_vocab, d.D, d.D, e->part, e->part_bytes, &S, st, -1, 1);
+    if (rc) break;
+    if (e->bf16) rc = launch(e, bias_act_kernel<bf16>, dim3(blocks), dim3(256), 0, st, e->part, S, total, b1, (bf16*)e->embed_table, (float*)nullptr, d.D, total, 0);
+    else rc = launch(e, bias_act_kernel<float>, dim3(blocks), dim3(256), 0, st, e->part, S, total, b1, (float*)e->embed_table, (float*)nullptr, d.D, total, 0);
+  } while (0);
+  e->use_pdl = saved_pdl;
+  if (rc) return rc;
+  CK(cudaMemsetAsync(e->attn_cnt, 0, (size_t)d.max_rows * d.H * 4, st));
+  CK(cudaMemsetAsync(e->step_ctr, 0, 256, st));
+  CK(cudaStreamSynchronize(st));
+  e->finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ a9
+extern "C" int pg_embed_tokens(pg_engine* e, const int32_t* ids, int n_tokens, float* x_out, void* stream) {
+  TRY(check_ready(e));
+  NEED(table, float, "embed_tokens");
+  return launch(e, embed_gather_kernel, dim3(n_tokens), dim3(256), 0, (cudaStream_t)stream, ids, table, x_out, e->d.D,
+                e->d.vocab);
+}
+
+// ------------------------------------------------------------------------------ LM layers
+struct LayerW { const float *ln1, *ln2; const void *wqkv, *wo, *wgu, *wd; };
+static int layer_weights(pg_engine* e, int l, LayerW* w) {
+  const std::string p = "l" + std::to_string(l) + ".";
+  w->ln1 = (const float*)T_(e, p + "ln1"); w->ln2 = (const float*)T_(e, p + "ln2");
+  w->wqkv = T_(e, p + "wqkv"); w->wo = T_(e, p + "wo"); w->wgu = T_(e, p + "wgu"); w->wd = T_(e, p + "wd");
+  if (!w->ln1 || !w->ln2 || !w->wqkv || !w->wo || !w->wgu || !w->wd) return fail("layer %d weights missing", l);
+  return 0;
+}
+
+static int elementwise_blocks(pg_engine* e, size_t total) {
+  return (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)e->num_sms * 16));
+}
+
+// a3: prompt prefill.  x fp32 [R*P, D] in place.
+extern "C" int pg_prefill(pg_engine* e, float* x, const int32_t* kv_start, int R, int P, float* hidden_out,
+                          int all_positions, void* stream) {
+  TRY(check_ready(e));
+  const pg_dims& d = e->d;
+  if (R < 1 || R > d.max_rows || P < 1 || P > d.max_prompt) return fail("prefill shape R=%d P=%d exceeds engine limits", R, P);
+  cudaStream_t st = (cudaStream_t)stream;
+  NEED(cosT, float, "rope_cos");
+  NEED(sinT, float, "rope_sin");
+  NEED(normw, float, "norm");
+  const int tok = R * P, D = d.D, HD = e->HD, F = d.F;
+  const float scale = 1.0f / sqrtf((float)HEAD_DIM);
+  int S = 1;
+  for (int l = 0; l < d.L; ++l) {
+    LayerW w;
+    TRY(layer_weights(e, l, &w));
+    if (l == 0) TRY(k_resid_norm(e, x, nullptr, 0, 0, w.ln1, e->xn, nullptr, tok, 1, 0, 0, st));
+    TRY(run_gemm(e, e->xn, w.wqkv, tok, 3 * HD, D, e->part, e->part_bytes, &S, st));
+    DISPATCH_T(e,
+               launch(e, qkv_rope_store_kernel<bf16>, dim3(tok), dim3(256), 0, st, e->part, S, (size_t)tok * 3 * HD, cosT, sinT,
+                      (bf16*)e->qbuf, (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax),
+               launch(e, qkv_rope_store_kernel<float>, dim3(tok), dim3(256), 0, st, e->part, S, (size_t)tok * 3 * HD, cosT, sinT,
+                      (float*)e->qbuf, (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax));
+    DISPATCH_T(e,
+               launch(e, attn_prefill_kernel<bf16>, dim3((P + 63) / 64, d.H, R), dim3(256), ATTN_PREFILL_SMEM, st,
+                      (const bf16*)e->qbuf, (const bf16*)kv_ptr(e, l, 0, R), (const bf16*)kv_ptr(e, l, 1, R), kv_start,
+                      (bf16*)e->attn_out, P, d.H, e->Tmax, scale),
+               launch(e, attn_prefill_kernel<float>, dim3((P + 63) / 64, d.H, R), dim3(256), ATTN_PREFILL_SMEM, st,
+                      (const float*)e->qbuf, (const float*)kv_ptr(e, l, 0, R), (const float*)kv_ptr(e, l, 1, R), kv_start,
+                      (float*)e->attn_out, P, d.H, e->Tmax, scale));
+    TRY(run_gemm(e, e->attn_out, w.wo, tok, D, HD, e->part, e->part_bytes, &S, st));
+    TRY(k_resid_norm(e, x, e->part, S, (size_t)tok * D, w.ln2, e->xn, nullptr, tok, 1, 0, 0, st));
+    TRY(run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st));
+    {
+      const size_t total = (size_t)tok * F;
+      DISPATCH_T(e,
+                 launch(e, swiglu_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (bf16*)e->hbuf, F, total),
+                 launch(e, swiglu_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (float*)e->hbuf, F, total));
+    }
+    TRY(run_gemm(e, e->hbuf, w.wd, tok, D, F, e->part, e->part_bytes, &S, st));
+    if (l + 1 < d.L) {
+      LayerW wn;
+      TRY(layer_weights(e, l + 1, &wn));
+      TRY(k_resid_norm(e, x, e->part, S, (size_t)tok * D, wn.ln1, e->xn, nullptr, tok, 1, 0, 0, st));
+    }
+  }
+  // final norm: all positions -> caller's buffer; last position of every row -> hidden_t for gen_head
+  if (all_positions) {
+    TRY(k_resid_norm(e, x, e->part, S, (size_t)tok * D, normw, nullptr, hidden_out, tok, 1, 0, 0, st));
+    TRY(k_resid_norm(e, x, nullptr, 0, 0, normw, e->hidden_t, e->hidden_f, R, P, P - 1, 0, st));
+  } else {
+    TRY(k_resid_norm(e, x, e->part, S, (size_t)tok * D, normw, e->hidden_t, e->hidden_f, R, P, P - 1, 0, st));
+    if (hidden_out) CK(cudaMemcpyAsync(hidden_out, e->hidden_f, (size_t)R * D * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+static int attn_split_count(pg_engine* e, int R, int T) {
+  if (e->attn_splits > 0) return std::min(e->attn_splits, 64);
+  const int ctas = R * e->d.H;
+  int s = (4 * e->num_sms + ctas - 1) / ctas;
+  s = std::min(s, std::max(1, T / 64));
+  return std::max(1, std::min(s, 64));
+}
+
+// one decode step over e->x_dec (fp32 [R, D]); xn for layer 0 already in e->xn when first_norm_done
+static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_base, const int* step_ptr,
+                         bool first_norm_done, bool inc_step, int T_hint, cudaStream_t st) {
+  const pg_dims& d = e->d;
+  NEED(cosT, float, "rope_cos");
+  NEED(sinT, float, "rope_sin");
+  NEED(normw, float, "norm");
+  const int D = d.D, HD = e->HD, F = d.F;
+  const float scale = 1.0f / sqrtf((float)HEAD_DIM);
+  const int rflag = e->bf16 ? RN_ROUND_RESID : 0;
+  const int nsp = attn_split_count(e, R, T_hint);
+  int S = 1;
+  for (int l = 0; l < d.L; ++l) {
+    LayerW w;
+    TRY(layer_weights(e, l, &w));
+    if (l == 0 && !first_norm_done) TRY(k_resid_norm(e, e->x_dec, nullptr, 0, 0, w.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
+    TRY(run_gemm(e, e->xn, w.wqkv, R, 3 * HD, D, e->part, e->part_bytes, &S, st));
+    DISPATCH_T(e,
+               launch(e, attn_decode_kernel<bf16>, dim3(d.H, R, nsp), dim3(128), 0, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
+                      (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ws,
+                      e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, 1),
+               launch(e, attn_decode_kernel<float>, dim3(d.H, R, nsp), dim3(128), 0, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
+                      (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), kv_start, (float*)e->attn_out, e->attn_ws,
+                      e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, 0));
+    TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &S, st));
+    TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st));
+    TRY(run_gemm(e, e->xn, w.wgu, R, 2 * F, D, e->part, e->part_bytes, &S, st));
+    {
+      const size_t total = (size_t)R * F;
+      DISPATCH_T(e,
+                 launch(e, swiglu_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)R * 2 * F, (bf16*)e->hbuf, F, total),
+                 launch(e, swiglu_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)R * 2 * F, (float*)e->hbuf, F, total));
+    }
+    TRY(run_gemm(e, e->hbuf, w.wd, R, D, F, e->part, e->part_bytes, &S, st));
+    if (l + 1 < d.L) {
+      LayerW wn;
+      TRY(layer_weights(e, l + 1, &wn));
+      TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, wn.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
+    }
+  }
+  TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, normw, e->hidden_t, e->hidden_f, R, 1, 0,
+                   rflag | (inc_step ? RN_INC_STEP : 0), st));
+  return 0;
+}
+
+// a4
+extern "C" int pg_decode_step(pg_engine* e, const float* x, const int32_t* kv_start, int R, int pos, float* hidden_out,
+                              void* stream) {
+  TRY(check_ready(e));
+  if (R < 1 || R > e->d.max_rows || pos < 0 || pos >= e->Tmax) return fail("decode shape R=%d pos=%d exceeds engine limits", R, pos);
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(e->x_dec, x, (size_t)R * e->d.D * 4, cudaMemcpyDeviceToDevice, st));
+  TRY(decode_layers(e, kv_start, R, pos, nullptr, false, false, pos + 1, st));
+  if (hidden_out) CK(cudaMemcpyAsync(hidden_out, e->hidden_f, (size_t)R * e->d.D * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// gen_head GEMMs: hidden_t -> head_h -> logits partials in e->part.  Returns split count / stride.
+static int head_gemms(pg_engine* e, int R, int* S_out, cudaStream_t st) {
+  const pg_dims& d = e->d;
+  NEED(w0, void, "head.w0");
+  NEED(b0, float, "head.b0");
+  NEED(w1, void, "head.w1");
+  int S = 1;
+  TRY(run_gemm(e, e->hidden_t, w0, R, d.img_embed, d.D, e->part, e->part_bytes, &S, st));
+  const size_t total = (size_t)R * d.img_embed;
+  DISPATCH_T(e,
+             launch(e, bias_act_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, total, b0, (bf16*)e->head_h, (float*)nullptr, d.img_embed, total, 1),
+             launch(e, bias_act_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, total, b0, (float*)e->head_h, (float*)nullptr, d.img_embed, total, 1));
+  TRY(run_gemm(e, e->head_h, w1, R, d.img_vocab, d.img_embed, e->part, e->part_bytes, &S, st));
+  *S_out = S;
+  return 0;
+}
+
+// a5
+extern "C" int pg_gen_head(pg_engine* e, const float* hidden, int R, float* logits_out, void* stream) {
+  TRY(check_ready(e));
+  const pg_dims& d = e->d;
+  if (R < 1 || R > d.max_rows) return fail("gen_head R=%d exceeds engine limits", R);
+  cudaStream_t st = (cudaStream_t)stream;
+  NEED(b1, float, "head.b1");
+  // cast the caller's fp32 hidden states to the activation type (autocast cast at the Linear)
+  const size_t n = (size_t)R * d.D;
+  DISPATCH_T(e,
+             launch(e, bias_act_kernel<bf16>, dim3(elementwise_blocks(e, n)), dim3(256), 0, st, hidden, 1, n, (const float*)nullptr, (bf16*)e->hidden_t, (float*)nullptr, d.D, n, 0),
+             launch(e, bias_act_kernel<float>, dim3(elementwise_blocks(e, n)), dim3(256), 0, st, hidden, 1, n, (const float*)nullptr, (float*)e->hidden_t, (float*)nullptr, d.D, n, 0));
+  int S = 1;
+  TRY(head_gemms(e, R, &S, st));
+  const size_t total = (size_t)R * d.img_vocab;
+  DISPATCH_T(e,
+             launch(e, bias_act_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, total, b1, (bf16*)nullptr, logits_out, d.img_vocab, total, 0),
+             launch(e, bias_act_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, total, b1, (float*)nullptr, logits_out, d.img_vocab, total, 0));
+  return 0;
+}
+
+static void philox_policy(pg_engine* e, size_t numel, uint64_t* counter_offset, uint64_t* stride) {
+  // torch calc_execution_policy (ATen/native/cuda/DistributionTemplates.h:50-62), unroll 4, block 256
+  const uint64_t block = 256;
+  uint64_t grid = (numel + block - 1) / block;
+  const uint64_t cap = (uint64_t)e->num_sms * (e->max_threads_per_sm / block);
+  grid = std::min(grid, cap);
+  *counter_offset = ((numel - 1) / (block * grid * 4) + 1) * 4;
+  *stride = grid * block;
+}
+
+static int k_sample(pg_engine* e, const float* part, int S, size_t sstride, const float* bias, int B, float cfg_weight,
+                    float temperature, uint64_t seed, uint64_t offset_base, int greedy, const int32_t* edit_region,
+                    const int32_t* gt_labels, int step_base, const int* step_ptr, int n_steps, int32_t* tokens_out,
+                    float* x_next, const float* next_norm_w, void* xn_next, cudaStream_t st) {
+  const pg_dims& d = e->d;
+  uint64_t per_step, stride;
+  philox_policy(e, (size_t)B * d.img_vocab, &per_step, &stride);
+  const size_t smem = (size_t)d.img_vocab * 4;
+  DISPATCH_T(e,
+             launch(e, cfg_sample_embed_kernel<bf16>, dim3(B), dim3(SAMPLE_THREADS), smem, st, part, S, sstride, bias, B, d.img_vocab,
+                    cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, edit_region, gt_labels, step_base,
+                    step_ptr, n_steps, tokens_out, (const bf16*)e->embed_table, d.D, x_next, next_norm_w, (bf16*)xn_next,
+                    d.rms_eps, 1, e->dbg_logits),
+             launch(e, cfg_sample_embed_kernel<float>, dim3(B), dim3(SAMPLE_THREADS), smem, st, part, S, sstride, bias, B, d.img_vocab,
+                    cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, edit_region, gt_labels, step_base,
+                    step_ptr, n_steps, tokens_out, (const float*)e->embed_table, d.D, x_next, next_norm_w, (float*)xn_next,
+                    d.rms_eps, 0, e->dbg_logits));
+  return 0;
+}
+
+// a6-a8
+extern "C" int pg_cfg_sample_embed(pg_engine* e, const float* logits, int B, float cfg_weight, float temperature,
+                                   uint64_t seed, uint64_t philox_offset, int greedy, const int32_t* edit_region,
+                                   const int32_t* gt_labels, int step, int n_steps, int32_t* tokens_out, float* x_next,
+                                   void* stream) {
+  TRY(check_ready(e));
+  if (B < 1 || 2 * B > e->d.max_rows) return fail("sample B=%d exceeds engine limits", B);
+  if (step < 0 || step >= n_steps) return fail("step %d out of range", step);
+  return k_sample(e, logits, 1, 0, nullptr, B, cfg_weight, temperature, seed, philox_offset, greedy, edit_region,
+                  gt_labels, step, nullptr, n_steps, tokens_out, x_next, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int pg_prepare_gen_img_embeds(pg_engine* e, const int32_t* ids, int n, float* out, void* stream) {
+  TRY(check_ready(e));
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(e,
+             launch(e, gen_embed_gather_kernel<bf16>, dim3(n), dim3(256), 0, st, ids, (const bf16*)e->embed_table, out, e->d.D, e->d.img_vocab),
+             launch(e, gen_embed_gather_kernel<float>, dim3(n), dim3(256), 0, st, ids, (const float*)e->embed_table, out, e->d.D, e->d.img_vocab));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ a2: the whole loop
+static int one_step(pg_engine* e, const int32_t* kv_start, int R, int P, int n_steps, float cfg_weight, float temperature,
+                    uint64_t seed, int greedy, const int32_t* edit_region, const int32_t* gt_labels, int32_t* tokens_out,
+                    bool with_lm, cudaStream_t st) {
+  NEED(b1, float, "head.b1");
+  LayerW w0;
+  TRY(layer_weights(e, 0, &w0));
+  int S = 1;
+  TRY(head_gemms(e, R, &S, st));
+  TRY(k_sample(e, e->part, S, (size_t)R * e->d.img_vocab, b1, R / 2, cfg_weight, temperature, seed, 0, greedy, edit_region,
+               gt_labels, 0, e->step_ctr, n_steps, tokens_out, with_lm ? e->x_dec : nullptr, w0.ln1, with_lm ? e->xn : nullptr, st));
+  if (with_lm) TRY(decode_layers(e, kv_start, R, P, e->step_ctr, true, true, P + n_steps / 2, st));
+  return 0;
+}
+
+extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_start, int R, int P, int n_steps,
+                               float cfg_weight, float temperature, uint64_t seed, int greedy,
+                               const int32_t* edit_region, const int32_t* gt_labels, int32_t* tokens_out, void* stream) {
+  TRY(check_ready(e));
+  if (R % 2) return fail("R must be even (interleaved cond/uncond rows)");
+  if (n_steps < 1 || n_steps > e->d.max_steps) return fail("n_steps %d exceeds engine limit %d", n_steps, e->d.max_steps);
+  cudaStream_t st = (cudaStream_t)stream;
+  TRY(pg_prefill(e, x_prompt, kv_start, R, P, nullptr, 0, stream));
+  CK(cudaMemsetAsync(e->step_ctr, 0, 4, st));
+  if (n_steps > 1) {
+    if (e->use_graph) {
+      char key[512];
+      snprintf(key, sizeof(key), "%d/%d/%d/%a/%a/%llu/%d/%p/%p/%p/%p/%d/%d/%d", R, P, n_steps, cfg_weight, temperature,
+               (unsigned long long)seed, greedy, (const void*)kv_start, (const void*)edit_region, (const void*)gt_labels,
+               (void*)tokens_out, e->use_pdl, e->use_tc, e->bf16 ? 1 : 0);
+      if (!e->graph_exec || e->graph_key != key) {
+        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int64_t before = e->launches;
+        int rc = one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels,
+                          tokens_out, true, st);
+        cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        e->graph_launches = e->launches - before;
+        e->launches = before;
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail("stream capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) { e->graph_exec = nullptr; return fail("graph instantiate failed: %s", cudaGetErrorString(ce)); }
+        e->graph_key = key;
+      }
+      for (int i = 0; i < n_steps - 1; ++i) CK(cudaGraphLaunch(e->graph_exec, st));
+      e->launches += e->graph_launches * (n_steps - 1);
+    } else {
+      for (int i = 0; i < n_steps - 1; ++i)
+        TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, true, st));
+    }
+  }
+  // last token: head + sample only (the reference computes and drops one more embed)
+  TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, false, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ a10: VQ decode
+struct VqCtx {
+  pg_engine* e; cudaStream_t st; int Bc;
+};
+
+static int vq_gn_stats(VqCtx& c, const void* x, int HW, int C) {
+  pg_engine* e = c.e;
+  int chunk_pix = std::max(64, (HW + e->gn_chunks_max - 1) / e->gn_chunks_max);
+  chunk_pix = std::max(chunk_pix, (HW + 255) / 256);
+  const int nchunks = (HW + chunk_pix - 1) / chunk_pix;
+  if (nchunks > e->gn_chunks_max) return fail("internal: gn chunks");
+  if (C % 32) return fail("GroupNorm(32) needs C %% 32 == 0 (C=%d)", C);
+  DISPATCH_T(e,
+             launch(e, gn_partial_kernel<bf16>, dim3(nchunks, c.Bc), dim3(256), 0, c.st, (const bf16*)x, e->gn_partial, HW, C, chunk_pix),
+             launch(e, gn_partial_kernel<float>, dim3(nchunks, c.Bc), dim3(256), 0, c.st, (const float*)x, e->gn_partial, HW, C, chunk_pix));
+  TRY(launch(e, gn_finalize_kernel, dim3(c.Bc), dim3(32), 0, c.st, (const float*)e->gn_partial, e->gn_stats, nchunks,
+             1.0 / ((double)HW * (C / 32)), 1e-6f));
+  return 0;
+}
+
+static int vq_im2col(VqCtx& c, const void* in, void* col, int Hi, int Wi, int C, int ks, int up, bool gn,
+                     const std::string& gn_name, bool swish) {
+  pg_engine* e = c.e;
+  const float *gamma = nullptr, *beta = nullptr;
+  if (gn) {
+    gamma = (const float*)T_(e, "vq." + gn_name + ".weight");
+    beta = (const float*)T_(e, "vq." + gn_name + ".bias");
+    if (!gamma || !beta) return fail("missing GroupNorm tensors for %s", gn_name.c_str());
+  }
+  if (C % 4) return fail("im2col needs C %% 4 == 0");
+  const size_t total = (size_t)c.Bc * Hi * up * Wi * up * ks * ks * (C / 4);
+  if (total * 4 > e->vq_col_elems) return fail("internal: im2col scratch too small");
+  const float* stats = gn ? e->gn_stats : nullptr;
+  DISPATCH_T(e,
+             launch(e, im2col_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, c.st, (const bf16*)in, (bf16*)col, stats, gamma, beta, Hi, Wi, C, ks, up, swish ? 1 : 0, total),
+             launch(e, im2col_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, c.st, (const float*)in, (float*)col, stats, gamma, beta, Hi, Wi, C, ks, up, swish ? 1 : 0, total));
+  return 0;
+}
+
+static int vq_epilogue(VqCtx& c, const float* part, const float* bias, const void* residual, void* out, float* out_nchw,
+                       int Cout, int HW, size_t pixels, int bias_per_row) {
+  pg_engine* e = c.e;
+  const size_t total = pixels * Cout;
+  DISPATCH_T(e,
+             launch(e, conv_epilogue_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, c.st, part, bias, (const bf16*)residual, (bf16*)out, out_nchw, Cout, HW, total, bias_per_row),
+             launch(e, conv_epilogue_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, c.st, part, bias, (const float*)residual, (float*)out, out_nchw, Cout, HW, total, bias_per_row));
+  return 0;
+}
+
+// conv2d(ks x ks, pad ks/2) over NHWC `in` [Bc, Hi, Wi, Cin] (optionally GroupNorm+swish'ed and x2 upsampled first)
+static int vq_conv(VqCtx& c, const void* in, int Hi, int Wi, int Cin, const std::string& name, int Cout, int ks, int up,
+                   const char* gn_name, bool swish, const void* residual, void* out, float* out_nchw) {
+  pg_engine* e = c.e;
+  const void* W = T_(e, "vq." + name + ".weight");
+  const float* bias = (const float*)T_(e, "vq." + name + ".bias");
+  if (!W || !bias) return fail("missing conv tensors for %s", name.c_str());
+  const int Ho = Hi * up, Wo = Wi * up;
+  const size_t pixels = (size_t)c.Bc * Ho * Wo;
+  const void* X = in;
+  if (gn_name) TRY(vq_gn_stats(c, in, Hi * Wi, Cin));
+  if (ks != 1 || gn_name || up != 1) {
+    TRY(vq_im2col(c, in, e->vq_col, Hi, Wi, Cin, ks, up, gn_name != nullptr, gn_name ? gn_name : "", swish));
+    X = e->vq_col;
+  }
+  if (pixels * Cout > e->vq_part_elems) return fail("internal: vq partial buffer too small");
+  int S = 1;
+  TRY(run_gemm(e, X, W, (int)pixels, Cout, ks * ks * Cin, e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1));
+  TRY(vq_epilogue(c, e->vq_part, bias, residual, out, out_nchw, Cout, Ho * Wo, pixels, 0));
+  return 0;
+}
+
+// ResnetBlock (vq_model.py:337-352).  bufs: x (input), t (scratch), y (output)
+static int vq_resblock(VqCtx& c, const std::string& name, const void* x, void* t, void* y, int H, int W, int Cin, int Cout) {
+  const std::string n1 = name + ".norm1", n2 = name + ".norm2";
+  TRY(vq_conv(c, x, H, W, Cin, name + ".conv1", Cout, 3, 1, n1.c_str(), true, nullptr, t, nullptr));
+  const void* res = x;
+  if (Cin != Cout) {
+    TRY(vq_conv(c, x, H, W, Cin, name + ".nin_shortcut", Cout, 1, 1, nullptr, false, nullptr, y, nullptr));
+    res = y;   // in-place residual: epilogue reads y[i] then writes y[i]
+  }
+  TRY(vq_conv(c, t, H, W, Cout, name + ".conv2", Cout, 3, 1, n2.c_str(), true, res, y, nullptr));
+  return 0;
+}
+
+// AttnBlock (vq_model.py:366-390): single head over H*W tokens, head dim C
+static int vq_attnblock(VqCtx& c, const std::string& name, const void* x, void* y, int H, int W, int C) {
+  pg_engine* e = c.e;
+  const size_t es = e->esz;
+  const int HW = H * W;
+  const size_t pix = (size_t)c.Bc * HW;
+  uint8_t* scratch = (uint8_t*)e->vq_col;
+  void* hn = scratch;                                   // [Bc*HW, C]
+  void* qb = scratch + pix * C * es;                    // [Bc*HW, C]
+  void* kb = scratch + 2 * pix * C * es;
+  void* vT = scratch + 3 * pix * C * es;                // [Bc][C, HW]
+  void* ha = scratch + 4 * pix * C * es;                // [Bc*HW, C]
+  void* Pm = scratch + 5 * pix * C * es;                // [HW, HW] (one image at a time)
+  if ((5 * pix * C + (size_t)HW * HW) > e->vq_col_elems) return fail("internal: attention scratch too small");
+  const std::string nn = name + ".norm";
+  TRY(vq_gn_stats(c, x, HW, C));
+  TRY(vq_im2col(c, x, hn, H, W, C, 1, 1, true, nn, false));
+  const char* names[2] = {".q", ".k"};
+  void* outs[2] = {qb, kb};
+  int S = 1;
+  for (int i = 0; i < 2; ++i) {
+    const void* Wt = T_(e, "vq." + name + names[i] + ".weight");
+    const float* bias = (const float*)T_(e, "vq." + name + names[i] + ".bias");
+    if (!Wt || !bias) return fail("missing attn tensors for %s", name.c_str());
+    TRY(run_gemm(e, hn, Wt, (int)pix, C, C, e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1));
+    TRY(vq_epilogue(c, e->vq_part, bias, nullptr, outs[i], nullptr, C, HW, pix, 0));
+  }
+  const void* Wv = T_(e, "vq." + name + ".v.weight");
+  const float* bv = (const float*)T_(e, "vq." + name + ".v.bias");
+  if (!Wv || !bv) return fail("missing attn v tensors for %s", name.c_str());
+  const float scale = 1.0f / sqrtf((float)C);
+  for (int b = 0; b < c.Bc; ++b) {
+    const uint8_t* hn_b = (const uint8_t*)hn + (size_t)b * HW * C * es;
+    uint8_t* vT_b = (uint8_t*)vT + (size_t)b * HW * C * es;
+    // v^T[c][pix] = sum_k Wv[c][k] hn[pix][k] + bv[c]
+    TRY(run_gemm(e, Wv, hn_b, C, HW, C, e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1));
+    VqCtx one = c; one.Bc = 1;
+    TRY(vq_epilogue(one, e->vq_part, bv, nullptr, vT_b, nullptr, HW, HW, (size_t)C, 1));
+    // scores[i][j] = q_i . k_j
+    TRY(run_gemm(e, (const uint8_t*)qb + (size_t)b * HW * C * es, (const uint8_t*)kb + (size_t)b * HW * C * es, HW, HW, C,
+                 e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1));
+    DISPATCH_T(e,
+               launch(e, softmax_rows_kernel<bf16>, dim3(HW), dim3(256), 0, c.st, (const float*)e->vq_part, (bf16*)Pm, HW, scale),
+               launch(e, softmax_rows_kernel<float>, dim3(HW), dim3(256), 0, c.st, (const float*)e->vq_part, (float*)Pm, HW, scale));
+    // h[i][c] = sum_j P[i][j] v^T[c][j]
+    TRY(run_gemm(e, Pm, vT_b, HW, C, HW, e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1));
+    TRY(vq_epilogue(one, e->vq_part, nullptr, nullptr, (uint8_t*)ha + (size_t)b * HW * C * es, nullptr, C, HW, (size_t)HW, 0));
+  }
+  TRY(vq_conv(c, ha, H, W, C, name + ".proj_out", C, 1, 1, nullptr, false, x, y, nullptr));
+  return 0;
+}
+
+extern "C" int pg_vq_decode_code(pg_engine* e, const int32_t* codes, int B, int gh, int gw, float* image_out, void* stream) {
+  TRY(check_ready(e));
+  const pg_dims& d = e->d;
+  if (gh < 1 || gw < 1 || gh > d.grid || gw > d.grid) return fail("token grid %dx%d exceeds engine limit %d", gh, gw, d.grid);
+  cudaStream_t st = (cudaStream_t)stream;
+  NEED(codebook, float, "vq.codebook");
+  NEED(pqc_w, void, "vq.pqc.w");
+  NEED(pqc_b, float, "vq.pqc.b");
+  const int nres = d.vq_nres;
+  const int scale_up = 1 << (nres - 1);
+  const int chunk = vq_chunk_of(e);
+  const int saved_pdl = e->use_pdl;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    VqCtx c{e, st, std::min(chunk, B - b0)};
+    void *A = e->vq_act[0], *Bf = e->vq_act[1], *Cf = e->vq_act[2];
+    const size_t n_pix = (size_t)c.Bc * gh * gw;
+    const int32_t* cb = codes + (size_t)b0 * gh * gw;
+    DISPATCH_T(e,
+               launch(e, vq_codebook_pqc_kernel<bf16>, dim3((unsigned)n_pix), dim3(128), 0, st, cb, codebook, (const bf16*)pqc_w, pqc_b, (bf16*)A, d.code_dim, d.vq_z, d.img_vocab, n_pix),
+               launch(e, vq_codebook_pqc_kernel<float>, dim3((unsigned)n_pix), dim3(128), 0, st, cb, codebook, (const float*)pqc_w, pqc_b, (float*)A, d.code_dim, d.vq_z, d.img_vocab, n_pix));
+    int H = gh, W = gw;
+    int ch = d.vq_ch * d.vq_ch_mult[nres - 1];
+    TRY(vq_conv(c, A, H, W, d.vq_z, "decoder.conv_in", ch, 3, 1, nullptr, false, nullptr, Bf, nullptr));
+    // cur = Bf
+    void *cur = Bf, *t1 = A, *t2 = Cf;
+    auto rot = [&](void* newcur) {   // newcur becomes cur; old cur becomes scratch
+      void* old = cur;
+      if (newcur == t1) t1 = old; else t2 = old;
+      cur = newcur;
+    };
+    TRY(vq_resblock(c, "decoder.mid.0", cur, t1, t2, H, W, ch, ch)); rot(t2);
+    TRY(vq_attnblock(c, "decoder.mid.1", cur, t1, H, W, ch)); rot(t1);
+    TRY(vq_resblock(c, "decoder.mid.2", cur, t1, t2, H, W, ch, ch)); rot(t2);
+    for (int idx = 0; idx < nres; ++idx) {
+      const int i_level = nres - 1 - idx;
+      const int cout = d.vq_ch * d.vq_ch_mult[i_level];
+      for (int j = 0; j < d.vq_res_blocks + 1; ++j) {
+        const std::string rn = "decoder.conv_blocks." + std::to_string(idx) + ".res." + std::to_string(j);
+        TRY(vq_resblock(c, rn, cur, t1, t2, H, W, ch, cout)); rot(t2);
+        ch = cout;
+        if (idx == 0) {
+          const std::string an = "decoder.conv_blocks." + std::to_string(idx) + ".attn." + std::to_string(j);
+          TRY(vq_attnblock(c, an, cur, t1, H, W, ch)); rot(t1);
+        }
+      }
+      if (idx != nres - 1) {
+        const std::string un = "decoder.conv_blocks." + std::to_string(idx) + ".upsample.conv";
+        TRY(vq_conv(c, cur, H, W, ch, un, ch, 3, 2, nullptr, false, nullptr, t1, nullptr)); rot(t1);
+        H *= 2; W *= 2;
+      }
+    }
+    float* img = image_out + (size_t)b0 * 3 * gh * scale_up * gw * scale_up;
+    TRY(vq_conv(c, cur, H, W, ch, "decoder.conv_out", 3, 3, 1, "decoder.norm_out", true, nullptr, nullptr, img));
+  }
+  e->use_pdl = saved_pdl;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ unit-test hook
+extern "C" int pg_test_gemm(pg_engine* e, int impl, int is_bf16, const void* X, const void* W, int M, int N, int K,
+                            int splits, float* C, void* stream) {
+  if (!e) return fail("null engine");
+  if ((is_bf16 != 0) != e->bf16) return fail("operand type does not match the engine mode");
+  int S = 0;
+  TRY(run_gemm(e, X, W, M, N, K, C, (size_t)std::max(splits, 1) * M * N * 4, &S, (cudaStream_t)stream, impl, std::max(splits, 1)));
+  if (S != std::max(splits, 1)) {
+    // fewer splits were possible: zero the remainder so the caller can always sum `splits` slabs
+    CK(cudaMemsetAsync(C + (size_t)S * M * N, 0, (size_t)(std::max(splits, 1) - S) * M * N * 4, (cudaStream_t)stream));
+  }
+  return 0;
+}

@@ -1,0 +1,463 @@
+// Row-wise kernels around the LM contractions: embedding gather, residual + RMSNorm, RoPE +
+// KV-cache append, SwiGLU, bias + GELU, prefill attention and KV-cache decode attention.
+// All of them consume the fp32 split-K partials written by gemm.cuh, reduce the splits in a fixed
+// order, and reproduce the rounding points of the reference's regime (fp32 master weights under
+// torch.autocast(bf16), plangen_base.py:360) when T = bf16; T = float is the fp32 check mode.
+//
+// Every kernel calls pdl_wait() before touching data produced by the previous kernel and
+// pdl_launch_dependents() at its top, so a chain of them can be launched with programmatic
+// dependent launch (the next GEMM prefetches its weight tiles while these run).
+#pragma once
+#include "common.cuh"
+
+namespace pg {
+
+constexpr int HEAD_DIM = 128;
+
+// flags for resid_rmsnorm_kernel
+constexpr int RN_ROUND_RESID = 1;   // keep the residual stream bf16-rounded (decode steps in the autocast regime:
+                                    // inputs_embeds there is the bf16 output of gen_aligner, so HF's residual adds are bf16)
+constexpr int RN_INC_STEP = 2;      // block 0 increments *step_ptr at the end (last kernel of a decode-step graph)
+
+PG_DEVINL float reduce_splits(const float* __restrict__ part, int S, size_t split_stride, size_t idx) {
+  float a = part[idx];
+  for (int s = 1; s < S; ++s) a += part[(size_t)s * split_stride + idx];
+  return a;
+}
+
+// ------------------------------------------------------------------- a9: embed_tokens
+// replaces language_model.get_input_embeddings()(ids)  (plangen_base.py:548)
+__global__ void embed_gather_kernel(const int32_t* __restrict__ ids, const float* __restrict__ table,
+                                    float* __restrict__ x, int D, int vocab) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tok = blockIdx.x;
+  int id = ids[tok];
+  id = min(max(id, 0), vocab - 1);
+  const float4* src = reinterpret_cast<const float4*>(table + (size_t)id * D);
+  float4* dst = reinterpret_cast<float4*>(x + (size_t)tok * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = src[i];
+}
+
+// ------------------------------------------------- a4.1: residual add + LlamaRMSNorm
+// x[tok] += rnd(sum_s part[s][tok]);  xn = w * (x * rsqrt(mean(x^2) + eps))   (HF modeling_llama.py:60-65)
+// One CTA per output row.  Input row index = blockIdx.x * in_stride + in_off (lets the final norm of
+// a prefill pick only the last position of every prompt row).
+template <typename T>
+__global__ void __launch_bounds__(256)
+resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int S, size_t split_stride,
+                     const float* __restrict__ w, T* __restrict__ xn_out, float* __restrict__ y_out, int D,
+                     float eps, int in_stride, int in_off, int flags, int* step_ptr) {
+  __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t row_in = (size_t)blockIdx.x * in_stride + in_off;
+  const size_t row_out = blockIdx.x;
+  float* xr = x + row_in * D;
+  float ss = 0.f;
+  // pass 1: residual update + sum of squares (values are re-read from x in pass 2; row stays in L1/L2)
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float v = xr[d];
+    if (part != nullptr) {
+      const float a = Act<T>::rnd(reduce_splits(part, S, split_stride, row_in * D + d));
+      v = v + a;
+      if (flags & RN_ROUND_RESID) v = Act<T>::rnd(v);
+      xr[d] = v;
+    }
+    ss += v * v;
+  }
+  ss = block_sum(ss, red);
+  const float r = rsqrtf(ss / (float)D + eps);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float hn = xr[d] * r;
+    if (flags & RN_ROUND_RESID) hn = Act<T>::rnd(hn);      // `.to(input_dtype)` with a bf16 residual stream
+    const float y = w[d] * hn;
+    if (xn_out) Act<T>::st(xn_out + row_out * D + d, y);   // autocast cast at the next Linear
+    if (y_out) y_out[row_out * D + d] = y;
+  }
+  if ((flags & RN_INC_STEP) && blockIdx.x == 0 && threadIdx.x == 0) *step_ptr += 1;
+}
+
+// plain RMSNorm of externally supplied rows (used for the first layer of a decode step when the
+// caller hands in inputs_embeds through the drop-in API)
+// -> same kernel with part == nullptr.
+
+// ------------------------------------------------------ a4.2: RoPE (HF :138-168)
+// q_embed = q * cos + rotate_half(q) * sin, rotate_half = [-x2, x1] over the two halves of head_dim.
+// bf16_trig: decode steps in the autocast regime get cos/sin cast to bf16 and bf16 arithmetic
+// (cos.to(x.dtype) with x = bf16 hidden states); prefill keeps fp32 trig (x = fp32 embeddings).
+template <typename T>
+PG_DEVINL void rope_pair(float x1, float x2, float c, float s, bool bf16_trig, float& o1, float& o2) {
+  if (bf16_trig) {
+    c = Act<T>::rnd(c); s = Act<T>::rnd(s);
+    o1 = Act<T>::rnd(Act<T>::rnd(__fmul_rn(x1, c)) + Act<T>::rnd(__fmul_rn(-x2, s)));
+    o2 = Act<T>::rnd(Act<T>::rnd(__fmul_rn(x2, c)) + Act<T>::rnd(__fmul_rn(x1, s)));
+  } else {
+    o1 = Act<T>::rnd(__fadd_rn(__fmul_rn(x1, c), __fmul_rn(-x2, s)));
+    o2 = Act<T>::rnd(__fadd_rn(__fmul_rn(x2, c), __fmul_rn(x1, s)));
+  }
+}
+
+// Prefill: reduce QKV partials, RoPE, write q [tok][H*128] and K/V into the cache
+// cache layout per layer: [2 (k,v)][R][H][Tmax][128]
+template <typename T>
+__global__ void __launch_bounds__(256)
+qkv_rope_store_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ cosT,
+                      const float* __restrict__ sinT, T* __restrict__ q_out, T* __restrict__ kcache,
+                      T* __restrict__ vcache, int P, int H, int Tmax) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tok = blockIdx.x;
+  const int r = tok / P, p = tok % P;
+  const int HD = H * HEAD_DIM;
+  const float* row = part + (size_t)tok * 3 * HD;
+  for (int i = threadIdx.x; i < H * 64; i += blockDim.x) {
+    const int h = i >> 6, j = i & 63;
+    const float c = cosT[p * 64 + j], s = sinT[p * 64 + j];
+    const size_t o1 = (size_t)h * HEAD_DIM + j, o2 = o1 + 64;
+    float q1 = Act<T>::rnd(reduce_splits(row, S, split_stride, o1));
+    float q2 = Act<T>::rnd(reduce_splits(row, S, split_stride, o2));
+    float k1 = Act<T>::rnd(reduce_splits(row, S, split_stride, HD + o1));
+    float k2 = Act<T>::rnd(reduce_splits(row, S, split_stride, HD + o2));
+    const float v1 = reduce_splits(row, S, split_stride, 2 * HD + o1);
+    const float v2 = reduce_splits(row, S, split_stride, 2 * HD + o2);
+    float a, b;
+    rope_pair<T>(q1, q2, c, s, false, a, b);
+    Act<T>::st(q_out + (size_t)tok * HD + o1, a);
+    Act<T>::st(q_out + (size_t)tok * HD + o2, b);
+    rope_pair<T>(k1, k2, c, s, false, a, b);
+    const size_t cidx = (((size_t)r * H + h) * Tmax + p) * HEAD_DIM + j;
+    Act<T>::st(kcache + cidx, a);
+    Act<T>::st(kcache + cidx + 64, b);
+    Act<T>::st(vcache + cidx, v1);
+    Act<T>::st(vcache + cidx + 64, v2);
+  }
+}
+
+// ---------------------------------------------------------------- a4.3: SwiGLU
+// h = silu(gate) * up   (HF LlamaMLP :182-184); partial layout [S][tok][2F] = [gate | up]
+template <typename T>
+__global__ void __launch_bounds__(256)
+swiglu_kernel(const float* __restrict__ part, int S, size_t split_stride, T* __restrict__ h, int F, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t tok = i / F, f = i % F;
+    const float g = Act<T>::rnd(reduce_splits(part, S, split_stride, tok * 2 * F + f));
+    const float u = Act<T>::rnd(reduce_splits(part, S, split_stride, tok * 2 * F + F + f));
+    const float sg = Act<T>::rnd(g / (1.0f + expf(-g)));
+    Act<T>::st(h + i, sg * u);
+  }
+}
+
+// ------------------------------------------------------- bias (+ exact GELU) epilogue
+// out = act(rnd(sum_s part + bias)); GELU is the erf form (nn.GELU() default, modeling_vlm.py:43)
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_act_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ bias,
+                T* __restrict__ out_t, float* __restrict__ out_f, int N, size_t total, int gelu) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float v = reduce_splits(part, S, split_stride, i);
+    if (bias) v += bias[i % N];
+    v = Act<T>::rnd(v);
+    if (gelu) v = Act<T>::rnd(v * 0.5f * (1.0f + erff(v * 0.70710678118654752440f)));
+    if (out_t) Act<T>::st(out_t + i, v);
+    if (out_f) out_f[i] = v;
+  }
+}
+
+// --------------------------------------------------------- a3: prefill attention
+// Causal attention with LEFT padding: key j is visible to the query at column p iff
+// kv_start[r] <= j <= p (the reference's (R, P+576) 0/1 mask + HF create_causal_mask).
+// CUDA-core flash-style kernel: CTA = 64 queries x one head x one row, 256 threads;
+// S = Q K^T in 4x4 register tiles, online softmax in fp32, O += P V in 4x8 register tiles.
+template <typename T>
+__global__ void __launch_bounds__(256)
+attn_prefill_kernel(const T* __restrict__ q, const T* __restrict__ kcache, const T* __restrict__ vcache,
+                    const int32_t* __restrict__ kv_start, T* __restrict__ out, int P, int H, int Tmax, float scale) {
+  extern __shared__ float sm[];
+  constexpr int LDQ = HEAD_DIM + 1;
+  float* Qs = sm;                       // [64][129]
+  float* Ks = Qs + 64 * LDQ;            // [64][129]
+  float* Vs = Ks + 64 * LDQ;            // [64][128]
+  float* Ss = Vs + 64 * HEAD_DIM;       // [64][65]
+  float* row_m = Ss + 64 * 65;          // [64]
+  float* row_l = row_m + 64;            // [64]
+  float* row_c = row_l + 64;            // [64] correction factor of the current tile
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const int q0 = blockIdx.x * 64, h = blockIdx.y, r = blockIdx.z;
+  const int HD = H * HEAD_DIM;
+  const int start = kv_start[r];
+  const T* kbase = kcache + ((size_t)r * H + h) * Tmax * HEAD_DIM;
+  const T* vbase = vcache + ((size_t)r * H + h) * Tmax * HEAD_DIM;
+  for (int i = tid; i < 64 * HEAD_DIM; i += 256) {
+    const int qi = i >> 7, d = i & 127;
+    const int p = q0 + qi;
+    Qs[qi * LDQ + d] = (p < P) ? Act<T>::ld(q + ((size_t)r * P + p) * HD + h * HEAD_DIM + d) * scale : 0.f;
+  }
+  if (tid < 64) { row_m[tid] = -INFINITY; row_l[tid] = 0.f; }
+  const int ty = tid >> 4, tx = tid & 15;
+  float o[4][8] = {};
+  const int q_hi = min(q0 + 63, P - 1);
+  const int j_begin = (start / 64) * 64;
+  for (int j0 = j_begin; j0 <= q_hi; j0 += 64) {
+    __syncthreads();
+    for (int i = tid; i < 64 * HEAD_DIM; i += 256) {
+      const int kj = i >> 7, d = i & 127;
+      const int j = j0 + kj;
+      const bool ok = j < P;
+      Ks[kj * LDQ + d] = ok ? Act<T>::ld(kbase + (size_t)j * HEAD_DIM + d) : 0.f;
+      Vs[kj * HEAD_DIM + d] = ok ? Act<T>::ld(vbase + (size_t)j * HEAD_DIM + d) : 0.f;
+    }
+    __syncthreads();
+    float s[4][4] = {};
+    for (int d = 0; d < HEAD_DIM; ++d) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = Qs[(ty * 4 + i) * LDQ + d]; b[i] = Ks[(tx * 4 + i) * LDQ + d]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[i][j] = fmaf(a[i], b[j], s[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = q0 + ty * 4 + i, kj = j0 + tx * 4 + j;
+        const bool vis = (kj >= start) && (kj <= p) && (p < P);
+        Ss[(ty * 4 + i) * 65 + tx * 4 + j] = vis ? s[i][j] : -INFINITY;
+      }
+    __syncthreads();
+    {   // online softmax: 4 threads per query row, 16 columns each
+      const int row = tid >> 2, part4 = tid & 3;
+      float mx = -INFINITY;
+      for (int c = part4 * 16; c < part4 * 16 + 16; ++c) mx = fmaxf(mx, Ss[row * 65 + c]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float m_old = row_m[row];
+      const float m_new = fmaxf(m_old, mx);
+      float sum = 0.f;
+      for (int c = part4 * 16; c < part4 * 16 + 16; ++c) {
+        const float sv = Ss[row * 65 + c];
+        const float pv = (sv == -INFINITY) ? 0.f : expf(sv - m_new);
+        Ss[row * 65 + c] = pv;
+        sum += pv;
+      }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      if (part4 == 0) {
+        const float corr = (m_new == -INFINITY) ? 1.f : expf(m_old - m_new);   // expf(-inf) = 0 on the first tile
+        row_c[row] = corr;
+        row_l[row] = row_l[row] * corr + sum;
+        row_m[row] = m_new;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float c = row_c[ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[i][j] *= c;
+    }
+    for (int kj = 0; kj < 64; ++kj) {
+      float pv[4], vv[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pv[i] = Ss[(ty * 4 + i) * 65 + kj];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) vv[j] = Vs[kj * HEAD_DIM + tx * 8 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[i][j] = fmaf(pv[i], vv[j], o[i][j]);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int p = q0 + ty * 4 + i;
+    if (p >= P) continue;
+    const float l = row_l[ty * 4 + i];
+    const float inv = l > 0.f ? 1.f / l : 0.f;      // pad queries (nothing visible) produce zeros
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      Act<T>::st(out + ((size_t)r * P + p) * HD + h * HEAD_DIM + tx * 8 + j, o[i][j] * inv);
+  }
+}
+constexpr int ATTN_PREFILL_SMEM = (64 * 129 * 2 + 64 * 128 + 64 * 65 + 3 * 64) * 4;
+
+// ------------------------------------------------- a4: KV-cache decode attention (paired CFG batch)
+// One launch covers every (row, head) of the interleaved cond/uncond batch.  grid = (H, R, n_split);
+// each CTA: reduces its head's q (and, for the last split, k/v) from the QKV partials, applies RoPE at
+// column `pos`, the last split appends k/v to the cache, then every CTA streams its slice of the cached
+// keys/values [kv_start[r], pos) with coalesced 256/512-byte row loads, 4 rows in flight per warp,
+// online softmax in fp32.  Split results are merged by the last CTA to finish (threadfence + counter).
+template <typename T> struct Row4;
+template <> struct Row4<float> {
+  static PG_DEVINL void ld(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <> struct Row4<bf16> {
+  static PG_DEVINL void ld(const bf16* p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = bf16lo(t.x); v[1] = bf16hi(t.x); v[2] = bf16lo(t.y); v[3] = bf16hi(t.y);
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+attn_decode_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ cosT,
+                   const float* __restrict__ sinT, T* __restrict__ kcache, T* __restrict__ vcache,
+                   const int32_t* __restrict__ kv_start, T* __restrict__ out, float* __restrict__ ws_part,
+                   int* __restrict__ ws_count, int H, int Tmax, int pos_base, const int* __restrict__ step_ptr,
+                   float scale, int bf16_trig) {
+  __shared__ float q_s[HEAD_DIM], k_s[HEAD_DIM], v_s[HEAD_DIM];
+  __shared__ float m_s[4], l_s[4], o_s[4][HEAD_DIM];
+  __shared__ int is_last;
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = blockIdx.x, r = blockIdx.y, sp = blockIdx.z, nsp = gridDim.z;
+  const int HD = H * HEAD_DIM;
+  pdl_wait();
+  const int pos = pos_base + (step_ptr ? *step_ptr : 0);
+  const int start = kv_start[r];
+  // ---- q (all CTAs) and k, v (last split) of the current token
+  {
+    const float* row = part + (size_t)r * 3 * HD;
+    const int j = tid & 63;
+    const float c = cosT[pos * 64 + j], s = sinT[pos * 64 + j];
+    if (tid < 64) {
+      const float x1 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)h * HEAD_DIM + j));
+      const float x2 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)h * HEAD_DIM + j + 64));
+      float a, b;
+      rope_pair<T>(x1, x2, c, s, bf16_trig != 0, a, b);
+      q_s[j] = a * scale; q_s[j + 64] = b * scale;
+    } else if (sp == nsp - 1) {
+      const float x1 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)HD + h * HEAD_DIM + j));
+      const float x2 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)HD + h * HEAD_DIM + j + 64));
+      float a, b;
+      rope_pair<T>(x1, x2, c, s, bf16_trig != 0, a, b);
+      const float v1 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)2 * HD + h * HEAD_DIM + j));
+      const float v2 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)2 * HD + h * HEAD_DIM + j + 64));
+      k_s[j] = a; k_s[j + 64] = b; v_s[j] = v1; v_s[j + 64] = v2;
+      const size_t cidx = (((size_t)r * H + h) * Tmax + pos) * HEAD_DIM + j;
+      Act<T>::st(kcache + cidx, a); Act<T>::st(kcache + cidx + 64, b);
+      Act<T>::st(vcache + cidx, v1); Act<T>::st(vcache + cidx + 64, v2);
+    }
+  }
+  __syncthreads();
+  // ---- this CTA's slice of the cached tokens [start, pos)
+  const int n_old = max(pos - start, 0);
+  const int per = (n_old + nsp - 1) / nsp;
+  const int t_lo = start + sp * per;
+  const int t_hi = min(start + (sp + 1) * per, pos);
+  const T* kb = kcache + ((size_t)r * H + h) * Tmax * HEAD_DIM + lane * 4;
+  const T* vb = vcache + ((size_t)r * H + h) * Tmax * HEAD_DIM + lane * 4;
+  float qv[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) qv[i] = q_s[lane * 4 + i];
+  float m = -INFINITY, l = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int t0 = t_lo + warp * 4; t0 < t_hi; t0 += 16) {
+    float kv[4][4], vv[4][4], sc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = min(t0 + u, t_hi - 1);                  // clamp: duplicates are masked below
+      Row4<T>::ld(kb + (size_t)t * HEAD_DIM, kv[u]);
+      Row4<T>::ld(vb + (size_t)t * HEAD_DIM, vv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float d = kv[u][0] * qv[0];
+      d = fmaf(kv[u][1], qv[1], d); d = fmaf(kv[u][2], qv[2], d); d = fmaf(kv[u][3], qv[3], d);
+      sc[u] = d;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], off);
+    }
+    float mx = m;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t0 + u >= t_hi) sc[u] = -INFINITY;
+      mx = fmaxf(mx, sc[u]);
+    }
+    const float corr = (mx == -INFINITY) ? 1.f : expf(m - mx);
+    l *= corr;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] *= corr;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float p = (sc[u] == -INFINITY) ? 0.f : expf(sc[u] - mx);
+      l += p;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[i] = fmaf(p, vv[u][i], o[i]);
+    }
+    m = mx;
+  }
+  // ---- the current token itself (last split, warp 0), from shared memory
+  if (sp == nsp - 1 && warp == 0) {
+    float d = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d = fmaf(k_s[lane * 4 + i], qv[i], d);
+    d = warp_sum(d);
+    const float mx = fmaxf(m, d);
+    const float corr = (m == -INFINITY) ? 0.f : expf(m - mx);
+    const float p = expf(d - mx);
+    l = l * corr + p;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = fmaf(p, v_s[lane * 4 + i], o[i] * corr);
+    m = mx;
+  }
+  // ---- merge the 4 warps
+  if (lane == 0) { m_s[warp] = m; l_s[warp] = l; }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o_s[warp][lane * 4 + i] = o[i];
+  __syncthreads();
+  float M = fmaxf(fmaxf(m_s[0], m_s[1]), fmaxf(m_s[2], m_s[3]));
+  float Ltot = 0.f, acc = 0.f;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const float f = (m_s[w] == -INFINITY) ? 0.f : expf(m_s[w] - M);
+    Ltot += l_s[w] * f;
+    acc += o_s[w][tid] * f;
+  }
+  const size_t oidx = (size_t)r * HD + h * HEAD_DIM + tid;
+  if (nsp == 1) {
+    Act<T>::st(out + oidx, acc / Ltot);
+    return;
+  }
+  // ---- split-T merge: last CTA of this (row, head) to arrive reduces all partials
+  float* wp = ws_part + (((size_t)r * H + h) * nsp + sp) * (HEAD_DIM + 2);
+  wp[tid] = acc;
+  if (tid == 0) { wp[HEAD_DIM] = M; wp[HEAD_DIM + 1] = Ltot; }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(ws_count + r * H + h, 1);
+    is_last = (prev == nsp - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const float* wb = ws_part + ((size_t)r * H + h) * nsp * (HEAD_DIM + 2);
+  float Mg = -INFINITY;
+  for (int s2 = 0; s2 < nsp; ++s2) Mg = fmaxf(Mg, __ldcg(wb + (size_t)s2 * (HEAD_DIM + 2) + HEAD_DIM));
+  float Lg = 0.f, og = 0.f;
+  for (int s2 = 0; s2 < nsp; ++s2) {
+    const float ms = __ldcg(wb + (size_t)s2 * (HEAD_DIM + 2) + HEAD_DIM);
+    const float f = (ms == -INFINITY) ? 0.f : expf(ms - Mg);
+    Lg += __ldcg(wb + (size_t)s2 * (HEAD_DIM + 2) + HEAD_DIM + 1) * f;
+    og += __ldcg(wb + (size_t)s2 * (HEAD_DIM + 2) + tid) * f;
+  }
+  Act<T>::st(out + oidx, og / Lg);
+  if (tid == 0) ws_count[r * H + h] = 0;        // re-arm for the next launch / graph replay
+}
+
+}  // namespace pg

@@ -1,0 +1,180 @@
+// Fused CFG combine -> /temperature -> softmax -> torch.multinomial(1)-compatible Philox sampling
+// -> teacher-forcing override -> token duplication -> prepare_gen_img_embeds (table gather).
+// Replaces plangen_base.py:580-604.  One CTA per image (cond row 2b, uncond row 2b+1).
+//
+// Bit-compatibility with torch.multinomial on a CUDA generator (see oracle/philox.py for the
+// restated algorithm and its sources): next = argmax_v( p[v] / q[v] ),  q = -log(u),
+// u = curand_uniform4(Philox4x32-10(seed, subsequence = thread idx, offset)) where element
+// li = b*V + v of the (B,V) tensor is produced by thread idx = li % (grid*256), component
+// (li / (grid*256)) % 4, loop iteration li / (4*grid*256), grid = min(SMs * (maxThreadsPerSM/256),
+// ceil(B*V/256)) — i.e. the mapping depends on the SM count of the device, as in torch.
+#pragma once
+#include "common.cuh"
+
+namespace pg {
+
+struct PhiloxOut { uint32_t v[4]; };
+
+PG_DEVINL PhiloxOut philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  PhiloxOut o; o.v[0] = c0; o.v[1] = c1; o.v[2] = c2; o.v[3] = c3;
+  return o;
+}
+
+// q for element li, exactly as torch's exponential_ kernel computes it
+PG_DEVINL float torch_exponential_at(uint64_t li, uint64_t stride, uint64_t seed, uint64_t offset) {
+  const uint64_t idx = li % stride, slot = li / stride;
+  const uint32_t comp = (uint32_t)(slot & 3);
+  const uint64_t ctr = offset / 4 + (slot >> 2);
+  const PhiloxOut r = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)idx, (uint32_t)(idx >> 32),
+                                    (uint32_t)seed, (uint32_t)(seed >> 32));
+  const uint32_t x = comp == 0 ? r.v[0] : comp == 1 ? r.v[1] : comp == 2 ? r.v[2] : r.v[3];
+  const float u = fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f);   // curand_uniform: (0, 1]
+  // transformation::exponential (CUDA branch): u >= 1 - eps/2 -> eps/2, else -log(u)
+  const float lg = (u >= 1.0f - 5.9604644775390625e-08f) ? -5.9604644775390625e-08f : logf(u);
+  return -lg;
+}
+
+constexpr int SAMPLE_THREADS = 1024;
+
+// logits: fp32 split partials [S][2B][V] of gen_head's second Linear (+ bias added here), or, when
+// bias == nullptr and S == 1, final logits handed in through the drop-in API.
+template <typename T>
+__global__ void __launch_bounds__(SAMPLE_THREADS)
+cfg_sample_embed_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ bias,
+                        int B, int V, float cfg_weight, float temperature, uint64_t seed, uint64_t offset_base,
+                        uint64_t offset_per_step, uint64_t philox_stride, int greedy,
+                        const int32_t* __restrict__ edit_region, const int32_t* __restrict__ gt_labels,
+                        int step_base, const int* __restrict__ step_ptr, int n_steps,
+                        int32_t* __restrict__ tokens_out, const T* __restrict__ embed_table, int D,
+                        float* __restrict__ x_next, const float* __restrict__ next_norm_w, T* __restrict__ xn_next,
+                        float eps, int round_resid, float* __restrict__ dbg_logits) {
+  extern __shared__ float sh[];      // [V] CFG logits -> probabilities
+  __shared__ float red[32];
+  __shared__ float bestv[32];
+  __shared__ int besti[32];
+  __shared__ int tok_s;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int step = step_base + (step_ptr ? *step_ptr : 0);
+  const uint64_t offset = offset_base + offset_per_step * (uint64_t)(step - step_base);
+  const size_t rc = (size_t)(2 * b) * V, ru = (size_t)(2 * b + 1) * V;
+  float mx = -INFINITY;
+  for (int v = tid; v < V; v += SAMPLE_THREADS) {
+    float c = reduce_splits(part, S, split_stride, rc + v);
+    float u = reduce_splits(part, S, split_stride, ru + v);
+    if (bias) { c += bias[v]; u += bias[v]; }
+    c = Act<T>::rnd(c); u = Act<T>::rnd(u);
+    // logits = uncond + w * (cond - uncond); / temperature     (plangen_base.py:587-588); each op
+    // is a separate rounded elementwise kernel in the reference (bf16 under autocast)
+    float t = Act<T>::rnd(__fsub_rn(c, u));
+    t = Act<T>::rnd(__fmul_rn(cfg_weight, t));
+    t = Act<T>::rnd(__fadd_rn(u, t));
+    t = Act<T>::rnd(__fdiv_rn(t, temperature));
+    sh[v] = t;
+    if (dbg_logits) dbg_logits[((size_t)step * B + b) * V + v] = t;
+    mx = fmaxf(mx, t);
+  }
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int v = tid; v < V; v += SAMPLE_THREADS) {
+    const float e = expf(sh[v] - mx);
+    sh[v] = e;
+    sum += e;
+  }
+  sum = block_sum(sum, red);
+  // argmax over p/q (first index wins ties, like torch.argmax)
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = tid; v < V; v += SAMPLE_THREADS) {
+    const float p = __fdiv_rn(sh[v], sum);
+    float score = p;
+    if (!greedy) {
+      const float q = torch_exponential_at((uint64_t)b * V + v, philox_stride, seed, offset);
+      score = __fdiv_rn(p, q);
+    }
+    if (score > bv || (score == bv && v < bi)) { bv = score; bi = v; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((tid & 31) == 0) { bestv[tid >> 5] = bv; besti[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid < 32) {
+    bv = bestv[tid]; bi = besti[tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (tid == 0) {
+      int tok = bi;
+      // teacher forcing (plangen_base.py:593-598): outside the edit region keep the ground truth
+      if (edit_region != nullptr && edit_region[(size_t)b * n_steps + step] == 0) tok = gt_labels[(size_t)b * n_steps + step];
+      tok = min(max(tok, 0), V - 1);
+      tok_s = tok;
+      tokens_out[(size_t)b * n_steps + step] = tok;
+    }
+  }
+  __syncthreads();
+  if (x_next == nullptr) return;
+  // next input = gen_aligner(gen_embed(tok)) duplicated to the cond and uncond rows (:602-604),
+  // plus (optionally) the first decoder layer's input RMSNorm of those rows
+  const T* erow = embed_table + (size_t)tok_s * D;
+  float ss = 0.f;
+  for (int d = tid; d < D; d += SAMPLE_THREADS) {
+    const float v = Act<T>::ld(erow + d);
+    x_next[(size_t)(2 * b) * D + d] = v;
+    x_next[(size_t)(2 * b + 1) * D + d] = v;
+    ss += v * v;
+  }
+  if (xn_next == nullptr) return;
+  ss = block_sum(ss, red);
+  const float r = rsqrtf(ss / (float)D + eps);
+  for (int d = tid; d < D; d += SAMPLE_THREADS) {
+    float hn = Act<T>::ld(erow + d) * r;
+    if (round_resid) hn = Act<T>::rnd(hn);
+    const float y = next_norm_w[d] * hn;
+    Act<T>::st(xn_next + (size_t)(2 * b) * D + d, y);
+    Act<T>::st(xn_next + (size_t)(2 * b + 1) * D + d, y);
+  }
+}
+
+// prepare_gen_img_embeds through the precomputed table (modeling_vlm.py:270-271)
+template <typename T>
+__global__ void gen_embed_gather_kernel(const int32_t* __restrict__ ids, const T* __restrict__ table,
+                                        float* __restrict__ out, int D, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int i = blockIdx.x;
+  const int id = min(max(ids[i], 0), V - 1);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) out[(size_t)i * D + d] = Act<T>::ld(table + (size_t)id * D + d);
+}
+
+// first Linear of gen_aligner on the 8-wide codes: h[v][n] = gelu(rnd(sum_k rnd(E[v][k]) * W0[n][k] + b0[n]))
+template <typename T>
+__global__ void aligner_l0_kernel(const float* __restrict__ gen_embed, const T* __restrict__ w0,
+                                  const float* __restrict__ b0, T* __restrict__ h, int code_dim, int D, size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t v = i / D, n = i % D;
+    float acc = 0.f;
+    for (int k = 0; k < code_dim; ++k)
+      acc = fmaf(Act<T>::rnd(gen_embed[v * code_dim + k]), Act<T>::ld(w0 + n * code_dim + k), acc);
+    acc = Act<T>::rnd(acc + b0[n]);
+    Act<T>::st(h + i, acc * 0.5f * (1.0f + erff(acc * 0.70710678118654752440f)));
+  }
+}
+
+}  // namespace pg

@@ -1,0 +1,185 @@
+// VQ-16 decode side (three_party/Janus/janus/models/vq_model.py:505-508 -> :284-299, :500-503,
+// :193-214): codebook gather with L2 normalisation, post_quant_conv, and the conv decoder.
+// Activations are kept channels-last (NHWC, [B*H*W, C]) so every convolution is the TN contraction
+// of gemm.cuh: C[pixel][cout] = sum_k col[pixel][k] * Wc[cout][k], k = (ky, kx, cin).  The im2col
+// producer fuses GroupNorm(32, eps 1e-6) + swish (x * sigmoid(x)) and the nearest x2 upsample of
+// `Upsample.forward` (:417-427); zero padding is applied after the activation, as conv2d does.
+#pragma once
+#include "common.cuh"
+
+namespace pg {
+
+// ---------------------------------------------------------------- codebook + post_quant_conv
+// z_q = F.normalize(codebook)[code] (vq_model.py:286-290, every call), then 1x1 conv 8 -> Z.
+template <typename T>
+__global__ void vq_codebook_pqc_kernel(const int32_t* __restrict__ codes, const float* __restrict__ codebook,
+                                       const T* __restrict__ w, const float* __restrict__ bias, T* __restrict__ out,
+                                       int code_dim, int Z, int V, size_t n_pix) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t pix = blockIdx.x;
+  if (pix >= n_pix) return;
+  __shared__ float e[32];
+  const int code = min(max(codes[pix], 0), V - 1);
+  if (threadIdx.x == 0) {
+    float ss = 0.f;
+    for (int k = 0; k < code_dim; ++k) { const float v = codebook[(size_t)code * code_dim + k]; ss += v * v; }
+    const float denom = fmaxf(sqrtf(ss), 1e-12f);
+    for (int k = 0; k < code_dim; ++k) e[k] = Act<T>::rnd(codebook[(size_t)code * code_dim + k] / denom);
+  }
+  __syncthreads();
+  for (int z = threadIdx.x; z < Z; z += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < code_dim; ++k) acc = fmaf(e[k], Act<T>::ld(w + (size_t)z * code_dim + k), acc);
+    Act<T>::st(out + pix * Z + z, acc + bias[z]);
+  }
+}
+
+// ------------------------------------------------------------------------- GroupNorm statistics
+// stage 1: per (image, pixel chunk) partial sum / sum of squares for all 32 groups.
+template <typename T>
+__global__ void __launch_bounds__(256)
+gn_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW, int C, int chunk_pix) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float s_sum[32], s_sq[32];
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  const int cpg = C / 32;
+  const int p0 = chunk * chunk_pix, p1 = min(HW, p0 + chunk_pix);
+  // thread -> fixed channel (so its group is fixed), strided over pixels
+  const int c = threadIdx.x % C;
+  const int prow = threadIdx.x / C, pstride = max(1, (int)blockDim.x / C);
+  if (C <= (int)blockDim.x) {
+    float a = 0.f, q = 0.f;
+    if (prow < pstride)
+      for (int p = p0 + prow; p < p1; p += pstride) {
+        const float v = Act<T>::ld(x + ((size_t)b * HW + p) * C + c);
+        a += v; q += v * v;
+      }
+    atomicAdd(&s_sum[c / cpg], a);
+    atomicAdd(&s_sq[c / cpg], q);
+  } else {
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+      float a = 0.f, q = 0.f;
+      for (int p = p0; p < p1; ++p) {
+        const float v = Act<T>::ld(x + ((size_t)b * HW + p) * C + cc);
+        a += v; q += v * v;
+      }
+      atomicAdd(&s_sum[cc / cpg], a);
+      atomicAdd(&s_sq[cc / cpg], q);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float* o = partial + (((size_t)b * nchunks + chunk) * 32 + threadIdx.x) * 2;
+    o[0] = s_sum[threadIdx.x]; o[1] = s_sq[threadIdx.x];
+  }
+}
+// stage 2: combine chunks in double -> (mean, rstd) per (image, group)
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nchunks,
+                                   double inv_count, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, g = threadIdx.x;
+  if (g >= 32) return;
+  double a = 0.0, q = 0.0;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* o = partial + (((size_t)b * nchunks + c) * 32 + g) * 2;
+    a += (double)o[0]; q += (double)o[1];
+  }
+  const double mean = a * inv_count;
+  double var = q * inv_count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  stats[((size_t)b * 32 + g) * 2 + 0] = (float)mean;
+  stats[((size_t)b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+// ----------------------------------------------------- im2col (+ GroupNorm + swish + upsample x2)
+// in:  [B][Hi][Wi][C] (T), out col: [B*Ho*Wo][ks*ks*C] (T), Ho = Hi * up, pad = ks / 2.
+// stats == nullptr -> no normalisation; swish only applies together with stats.
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const T* __restrict__ in, T* __restrict__ col, const float* __restrict__ stats,
+              const float* __restrict__ gamma, const float* __restrict__ beta, int Hi, int Wi, int C, int ks, int up,
+              int swish, size_t total /* B*Ho*Wo*ks*ks*(C/4) */) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int Ho = Hi * up, Wo = Wi * up, C4 = C / 4, pad = ks / 2, cpg = C / 32;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i % C4);
+    size_t t = i / C4;
+    const int tap = (int)(t % (ks * ks));
+    t /= (ks * ks);
+    const int ox = (int)(t % Wo);
+    t /= Wo;
+    const int oy = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    const int iy = oy + tap / ks - pad, ix = ox + tap % ks - pad;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (iy >= 0 && iy < Ho && ix >= 0 && ix < Wo) {
+      const T* src = in + (((size_t)b * Hi + iy / up) * Wi + ix / up) * C + c4 * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = Act<T>::ld(src + j);
+      if (stats) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = c4 * 4 + j;
+          const float mean = stats[((size_t)b * 32 + c / cpg) * 2], rstd = stats[((size_t)b * 32 + c / cpg) * 2 + 1];
+          float y = (v[j] - mean) * rstd * gamma[c] + beta[c];      // group_norm runs in fp32 under autocast
+          if (swish) y = y / (1.0f + expf(-y));                     // x * sigmoid(x)
+          v[j] = y;
+        }
+      }
+    }
+    T* dst = col + i * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) Act<T>::st(dst + j, v[j]);
+  }
+}
+
+// -------------------------------------------------------- conv epilogue: + bias (+ residual)
+// out[pix][co] = rnd(rnd(part + bias) + residual)   NHWC; or NCHW fp32 for the final conv_out.
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_epilogue_kernel(const float* __restrict__ part, const float* __restrict__ bias, const T* __restrict__ residual,
+                     T* __restrict__ out, float* __restrict__ out_nchw, int Cout, int HW, size_t total,
+                     int bias_per_row) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t pix = i / Cout;
+    const int co = (int)(i % Cout);
+    float v = part[i];
+    if (bias) v += bias_per_row ? bias[pix] : bias[co];
+    v = Act<T>::rnd(v);
+    if (residual) v = Act<T>::rnd(v + Act<T>::ld(residual + i));
+    if (out) Act<T>::st(out + i, v);
+    if (out_nchw) {
+      const size_t b = pix / HW, p = pix % HW;
+      out_nchw[(b * Cout + co) * HW + p] = v;
+    }
+  }
+}
+
+// --------------------------------------------- AttnBlock softmax: P = softmax(scores * C^-0.5, dim=-1)
+template <typename T>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ scores, T* __restrict__ P, int n, float scale) {
+  __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t row = blockIdx.x;
+  const float* s = scores + row * n;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) mx = fmaxf(mx, Act<T>::rnd(Act<T>::rnd(s[j]) * scale));
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) sum += expf(Act<T>::rnd(Act<T>::rnd(s[j]) * scale) - mx);
+  sum = block_sum(sum, red);
+  for (int j = threadIdx.x; j < n; j += blockDim.x)
+    Act<T>::st(P + row * n + j, expf(Act<T>::rnd(Act<T>::rnd(s[j]) * scale) - mx) / sum);
+}
+
+}  // namespace pg

@@ -1,0 +1,331 @@
+"""Host-side mirror of the reference interface for the CFG image-token decode path.
+
+`FastJanus` exposes the attribute surface PlanGen's `System` touches on `self.vl_gpt`
+(project/plangen/plangen_base.py:525-607):
+
+    vl_gpt.language_model.get_input_embeddings()(ids)
+    vl_gpt.language_model.model(inputs_embeds=, attention_mask=, use_cache=True, past_key_values=)
+    vl_gpt.gen_head(h)
+    vl_gpt.prepare_gen_img_embeds(ids)
+    vl_gpt.gen_vision_model.decode_code(code_b, shape=[B, 8, h, w], channel_first=True)
+
+plus the fused fast path with the reference's own signatures, `sample_image(...)` / `t2i(...)`,
+which runs the whole 576-step loop on the device (CUDA graph, no host sync, no logits round trip).
+PyTorch is used only for device memory, streams and host<->device copies; all arithmetic happens in
+the sm_100a kernels behind the C-ABI (include/plangen_b200.h).  There is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib
+from .config import Dims
+from .weights import pack_state_dict
+
+MODE_IDS = {"bf16": 0, "fp32": 1}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def kv_start_from_mask(mask: torch.Tensor, P: int) -> torch.Tensor:
+    """Lossless encoding of the reference's 0/1 mask (LEFT padding only, image part all ones;
+    plangen_base.py:708-712,668,686): number of leading pad columns per row.  Any other mask shape is
+    rejected - the reference never produces one on this path."""
+    m = (mask[:, :P] != 0)
+    if mask.shape[1] > P and not bool((mask[:, P:] != 0).all()):
+        raise ValueError("attention_mask must be all ones on the image-token part")
+    first = torch.where(m.any(1), m.int().argmax(1), torch.full((m.shape[0],), P, device=m.device))
+    ar = torch.arange(P, device=m.device)[None, :]
+    if not bool((m == (ar >= first[:, None])).all()):
+        raise ValueError("attention_mask must be LEFT padded (zeros then ones)")
+    return first.to(torch.int32).contiguous()
+
+
+@dataclass
+class ModelOutput:
+    """BaseModelOutputWithPast stand-in (`.last_hidden_state`, `.past_key_values`)."""
+    last_hidden_state: torch.Tensor
+    past_key_values: "KVHandle"
+
+
+class KVHandle:
+    """Opaque `past_key_values` the caller threads back (the cache itself lives in the engine)."""
+
+    def __init__(self, rows: int, length: int, kv_start: torch.Tensor, serial: int):
+        self.rows, self.length, self.kv_start, self.serial = rows, length, kv_start, serial
+
+    def get_seq_length(self) -> int:
+        return self.length
+
+
+class _Embedding:
+    def __init__(self, eng: "FastJanus"):
+        self._e = eng
+
+    def __call__(self, ids: torch.Tensor) -> torch.Tensor:
+        e = self._e
+        ids32 = ids.to(device=e.device, dtype=torch.int32).contiguous()
+        out = torch.empty(*ids32.shape, e.dims.D, device=e.device, dtype=torch.float32)
+        _lib.check(e._lib.pg_embed_tokens(e._h, _ptr(ids32), ids32.numel(), _ptr(out), _stream_ptr(e.device)))
+        return out
+
+
+class _LlamaModel:
+    def __init__(self, eng: "FastJanus"):
+        self._e = eng
+
+    def __call__(self, inputs_embeds=None, attention_mask=None, use_cache=True, past_key_values=None, **kw):
+        e = self._e
+        if inputs_embeds is None:
+            raise ValueError("inputs_embeds is required (the reference never passes input_ids here)")
+        R, q, D = inputs_embeds.shape
+        st = _stream_ptr(e.device)
+        if past_key_values is None:
+            P = q
+            if attention_mask is None:
+                kv_start = torch.zeros(R, dtype=torch.int32, device=e.device)
+            else:
+                kv_start = kv_start_from_mask(attention_mask.to(e.device), P)
+            x = inputs_embeds.to(device=e.device, dtype=torch.float32).contiguous().clone()
+            hidden = torch.empty(R, P, D, device=e.device, dtype=torch.float32)
+            _lib.check(e._lib.pg_prefill(e._h, _ptr(x), _ptr(kv_start), R, P, _ptr(hidden), 1, st))
+            e._serial += 1
+            return ModelOutput(hidden, KVHandle(R, P, kv_start, e._serial))
+        h = past_key_values
+        if not isinstance(h, KVHandle) or h.serial != e._serial or h.rows != R or q != 1:
+            raise ValueError("past_key_values does not belong to the engine's live cache")
+        x = inputs_embeds.to(device=e.device, dtype=torch.float32).contiguous().view(R, D)
+        hidden = torch.empty(R, 1, D, device=e.device, dtype=torch.float32)
+        _lib.check(e._lib.pg_decode_step(e._h, _ptr(x), _ptr(h.kv_start), R, h.length, _ptr(hidden), st))
+        h.length += 1
+        return ModelOutput(hidden, h)
+
+
+class _LanguageModel:
+    def __init__(self, eng: "FastJanus"):
+        self.model = _LlamaModel(eng)
+        self._emb = _Embedding(eng)
+
+    def get_input_embeddings(self):
+        return self._emb
+
+
+class _GenVisionModel:
+    def __init__(self, eng: "FastJanus"):
+        self._e = eng
+
+    def decode_code(self, code_b: torch.Tensor, shape: Optional[Sequence[int]] = None, channel_first: bool = True):
+        e = self._e
+        if not channel_first:
+            raise NotImplementedError("the reference only calls decode_code(channel_first=True)")
+        codes = code_b.to(device=e.device, dtype=torch.int32).contiguous()
+        if shape is None:
+            B, g = codes.shape[0], int(round(codes.shape[1] ** 0.5))
+            gh = gw = g
+        else:
+            B, _, gh, gw = [int(s) for s in shape]
+        codes = codes.reshape(B, gh * gw)
+        up = 2 ** (len(e.dims.vq_ch_mult) - 1)
+        out = torch.empty(B, 3, gh * up, gw * up, device=e.device, dtype=torch.float32)
+        _lib.check(e._lib.pg_vq_decode_code(e._h, _ptr(codes), B, gh, gw, _ptr(out), _stream_ptr(e.device)))
+        return out.to(e.out_dtype)
+
+
+class FastJanus:
+    """B200 engine behind the `MultiModalityCausalLM` attribute surface."""
+
+    def __init__(self, state_dict: Dict[str, torch.Tensor], dims: Dims, mode: str = "bf16",
+                 max_batch: int = 16, max_prompt: int = 512, max_steps: Optional[int] = None,
+                 device: str = "cuda:0", seed: int = 0, with_vq: bool = True, options: Optional[dict] = None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("plangen_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if mode not in MODE_IDS:
+            raise ValueError(mode)
+        self.dims, self.mode, self.seed = dims, mode, seed
+        self.device = torch.device(device)
+        self.out_dtype = torch.bfloat16 if mode == "bf16" else torch.float32
+        self.max_rows = 2 * max_batch
+        self.max_prompt = max_prompt
+        self.max_steps = max_steps or dims.n_img_tokens
+        self._lib = _lib.load()
+        self._serial = 0
+        pd = _lib.PgDims()
+        for k in ("D", "L", "H", "head_dim", "F", "vocab", "img_vocab", "code_dim", "img_embed", "grid", "vq_ch",
+                  "vq_z", "vq_res_blocks"):
+            setattr(pd, k, getattr(dims, k))
+        pd.rms_eps, pd.rope_theta = dims.rms_eps, dims.rope_theta
+        pd.vq_nres = len(dims.vq_ch_mult)
+        for i, m in enumerate(dims.vq_ch_mult):
+            pd.vq_ch_mult[i] = m
+        pd.mode, pd.max_rows, pd.max_prompt, pd.max_steps = MODE_IDS[mode], self.max_rows, max_prompt, self.max_steps
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pg_engine_create(C.byref(pd), self.device.index or 0, C.byref(h)))
+            self._h = h
+            for k, v in (options or {}).items():
+                self.set_option(k, v)
+            kvb, wsb = C.c_size_t(), C.c_size_t()
+            _lib.check(self._lib.pg_engine_query_bytes(h, C.byref(kvb), C.byref(wsb)))
+            self._kv = torch.empty(kvb.value, dtype=torch.uint8, device=self.device)
+            self._ws = torch.empty(wsb.value, dtype=torch.uint8, device=self.device)
+            _lib.check(self._lib.pg_engine_bind_buffers(h, _ptr(self._kv), kvb.value, _ptr(self._ws), wsb.value))
+            tmax = self.counter("tmax")
+            self._weights = pack_state_dict(state_dict, dims, mode, self.device, tmax, with_vq=with_vq)
+            for name, t in self._weights.items():
+                _lib.check(self._lib.pg_engine_set_tensor(h, name.encode(), _ptr(t), t.numel() * t.element_size()))
+            _lib.check(self._lib.pg_engine_finalize(h, _stream_ptr(self.device)))
+        self.language_model = _LanguageModel(self)
+        self.gen_vision_model = _GenVisionModel(self)
+        self.weight_bytes_per_step = self._weight_bytes_per_step()
+
+    # ------------------------------------------------------------------ plumbing
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.pg_engine_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        _lib.check(self._lib.pg_engine_set_option(self._h, key.encode(), int(value)))
+
+    def counter(self, key: str) -> int:
+        v = C.c_int64()
+        _lib.check(self._lib.pg_engine_get_counter(self._h, key.encode(), C.byref(v)))
+        return v.value
+
+    def eval(self):
+        return self
+
+    def train(self, mode: bool = True):
+        if mode:
+            raise NotImplementedError("plangen_b200 is an inference engine")
+        return self
+
+    def parameters(self):
+        return iter(self._weights.values())
+
+    def _weight_bytes_per_step(self) -> int:
+        """Algorithmic weight bytes one decode step must stream (the gen_aligner
+        MLP is replaced by a table gather so its weights are not counted)."""
+        d = self.dims
+        es = 2 if self.mode == "bf16" else 4
+        HD = d.H * d.head_dim
+        per_layer = (3 * HD * d.D + d.D * HD + 2 * d.F * d.D + d.D * d.F) * es + 2 * d.D * 4
+        head = (d.img_embed * d.D + d.img_vocab * d.img_embed) * es + (d.img_embed + d.img_vocab) * 4
+        return d.L * per_layer + d.D * 4 + head
+
+    # ------------------------------------------------------------------ duck-typed pieces
+    def gen_head(self, h: torch.Tensor) -> torch.Tensor:
+        R = h.shape[0]
+        x = h.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty(R, self.dims.img_vocab, device=self.device, dtype=torch.float32)
+        _lib.check(self._lib.pg_gen_head(self._h, _ptr(x), R, _ptr(out), _stream_ptr(self.device)))
+        return out.to(self.out_dtype)
+
+    def prepare_gen_img_embeds(self, image_ids: torch.Tensor) -> torch.Tensor:
+        ids = image_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        out = torch.empty(*ids.shape, self.dims.D, device=self.device, dtype=torch.float32)
+        _lib.check(self._lib.pg_prepare_gen_img_embeds(self._h, _ptr(ids), ids.numel(), _ptr(out), _stream_ptr(self.device)))
+        return out.to(self.out_dtype)
+
+    def cfg_sample_embed(self, logits: torch.Tensor, cfg_weight: float, temperature: float, seed: int, offset: int,
+                         step: int, n_steps: int, tokens_out: torch.Tensor, greedy: bool = False,
+                         edit_region: Optional[torch.Tensor] = None, gt_labels: Optional[torch.Tensor] = None):
+        """plangen_base.py:580-604 in one launch; returns the next inputs_embeds (2B, D) fp32."""
+        B = logits.shape[0] // 2
+        lg = logits.to(device=self.device, dtype=torch.float32).contiguous()
+        x_next = torch.empty(2 * B, self.dims.D, device=self.device, dtype=torch.float32)
+        _lib.check(self._lib.pg_cfg_sample_embed(self._h, _ptr(lg), B, cfg_weight, temperature, seed, offset, int(greedy),
+                                                 _ptr(edit_region), _ptr(gt_labels), step, n_steps, _ptr(tokens_out),
+                                                 _ptr(x_next), _stream_ptr(self.device)))
+        return x_next
+
+    def philox_offset_per_step(self, B: int) -> int:
+        numel = B * self.dims.img_vocab
+        grid = min((numel + 255) // 256, self.counter("num_sms") * (self.counter("max_threads_per_sm") // 256))
+        return ((numel - 1) // (256 * grid * 4) + 1) * 4
+
+    # ------------------------------------------------------------------ fused fast path
+    @torch.inference_mode()
+    def sample_image(self, inputs_embeds, num_gen, image_token_num_per_image, mask, cfg_weight, temperature,
+                     generator=None, batch=None, gt_labels=None, greedy: bool = False):
+        """System.sample_image (plangen_base.py:567-607).  `generator`: torch CUDA generator (its seed and
+        philox offset are honoured and advanced) or an int seed.  Teacher forcing when `batch` carries
+        'edit_region' and gt_labels is given (:593-598)."""
+        R, P, D = inputs_embeds.shape
+        if R != 2 * num_gen:
+            raise ValueError("inputs_embeds rows must be 2 * num_gen (interleaved cond/uncond)")
+        n = int(image_token_num_per_image)
+        if isinstance(generator, torch.Generator):
+            seed, off = generator.initial_seed(), generator.get_offset()
+        else:
+            seed, off = int(self.seed if generator is None else generator), 0
+        if off != 0:
+            raise ValueError("generator must be freshly seeded (the reference reseeds per t2i call, :526)")
+        kv_start = (kv_start_from_mask(mask.to(self.device), P) if mask is not None
+                    else torch.zeros(R, dtype=torch.int32, device=self.device))
+        x = inputs_embeds.to(device=self.device, dtype=torch.float32).contiguous().clone()
+        tokens = torch.zeros(num_gen, n, dtype=torch.int32, device=self.device)
+        er = gl = None
+        if gt_labels is not None and batch is not None and batch.get("edit_region") is not None:
+            er = batch["edit_region"].to(device=self.device, dtype=torch.int32).reshape(num_gen, -1)[:, :n].contiguous()
+            gl = gt_labels.to(device=self.device, dtype=torch.int32).reshape(num_gen, -1)[:, :n].contiguous()
+        self._keep = (kv_start, x, er, gl)        # keep alive until the stream has consumed them
+        _lib.check(self._lib.pg_sample_image(self._h, _ptr(x), _ptr(kv_start), R, P, n, float(cfg_weight),
+                                             float(temperature), seed, int(greedy), _ptr(er), _ptr(gl), _ptr(tokens),
+                                             _stream_ptr(self.device)))
+        self._serial += 1
+        if isinstance(generator, torch.Generator):
+            generator.set_offset(off + n * self.philox_offset_per_step(num_gen))
+        return tokens
+
+    @torch.inference_mode()
+    def t2i(self, inputs_ids=None, parallel_size=1, image_token_num_per_image=None, cfg_weight=5.0, temperature=1.0,
+            img_size=None, patch_size=16, gt_image=None, batch=None, mask=None, tokens=None, emb=None,
+            gt_labels=None, greedy: bool = False):
+        """System.t2i (plangen_base.py:525-565), `tokens`/`emb` branches.  Returns (dec, mask_image);
+        gt_labels replaces the VQ-encoder call of the editing path (encoder is out of scope here)."""
+        n = image_token_num_per_image or self.dims.n_img_tokens
+        img_size = img_size or self.dims.img_size
+        if tokens is None and emb is None:
+            raise NotImplementedError("pass `tokens` (2B, P) or `emb`; the un-batched branch is unused by PlanGen")
+        if tokens is not None:
+            tokens = torch.cat([tokens.to(self.device)] * parallel_size)
+            inputs_embeds = self.language_model.get_input_embeddings()(tokens)
+        else:
+            inputs_embeds = emb
+        mask = torch.cat([mask.to(self.device)] * parallel_size)
+        num_gen = inputs_embeds.shape[0] // 2
+        gen = self.sample_image(inputs_embeds, num_gen, n, mask, cfg_weight, temperature, None, batch, gt_labels, greedy)
+        g = img_size // patch_size
+        dec = self.gen_vision_model.decode_code(gen.to(dtype=torch.int), shape=[num_gen, self.dims.code_dim, g, g])
+        self.last_tokens = gen
+        return dec, None
+
+    # ------------------------------------------------------------------ host-buffer entry (end to end)
+    @torch.inference_mode()
+    def generate_from_host(self, ids_host: torch.Tensor, mask_host: torch.Tensor, cfg_weight=5.0, temperature=1.0,
+                           out_host: Optional[torch.Tensor] = None):
+        """ids/mask in (pinned) host memory -> uint8 images in host memory; H2D / D2H inside."""
+        ids = ids_host.to(self.device, non_blocking=True)
+        mask = mask_host.to(self.device, non_blocking=True)
+        dec, _ = self.t2i(tokens=ids, mask=mask, cfg_weight=cfg_weight, temperature=temperature)
+        # denorm_pt (src/utils/funcs.py:511-512) then `(x*255).astype(np.uint8)` (funcs.py:508): truncation
+        img = (((dec.float().clamp(-1, 1) + 1) / 2) * 255).to(torch.uint8)
+        if out_host is None:
+            out_host = torch.empty(img.shape, dtype=torch.uint8, pin_memory=True)
+        out_host.copy_(img, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return out_host

@@ -1,0 +1,78 @@
+"""Packing of the reference state_dict (names in SURVEY.md §8b) into the device tensors the engine
+registers through `pg_engine_set_tensor`.
+
+  language_model.model.layers.{i}.self_attn.{q,k,v}_proj.weight -> l{i}.wqkv  [3*H*128, D]  (rows q | k | v)
+  ...mlp.{gate,up}_proj.weight                                   -> l{i}.wgu   [2*F, D]      (rows gate | up)
+  conv weights [Cout, Cin, kh, kw]                               -> [Cout, kh*kw*Cin]        (channels-last taps)
+
+Weights are stored in the engine's operand type: bf16 (round-to-nearest-even of the fp32 master
+weights - exactly the cast torch.autocast performs at every Linear/conv call, plangen_base.py:360)
+or fp32 (check mode).  Norm scales, biases, the text embedding table, gen_embed and the VQ codebook
+stay fp32 as they do in the reference."""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from .config import Dims
+
+
+def rope_tables(dims: Dims, tmax: int):
+    """cos/sin of LlamaRotaryEmbedding (HF modeling_llama.py:124-136) for positions 0..tmax-1, fp32
+    [tmax, head_dim/2] (the two halves of HF's `emb = cat(freqs, freqs)` are identical)."""
+    inv_freq = 1.0 / (dims.rope_theta ** (torch.arange(0, dims.head_dim, 2, dtype=torch.int64).to(torch.float) / dims.head_dim))
+    pos = torch.arange(tmax, dtype=torch.float)
+    freqs = pos[:, None] * inv_freq[None, :]
+    return freqs.cos().contiguous(), freqs.sin().contiguous()
+
+
+def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, mode: str, device, tmax: int,
+                    with_vq: bool = True) -> Dict[str, torch.Tensor]:
+    wt = torch.bfloat16 if mode == "bf16" else torch.float32
+    out: Dict[str, torch.Tensor] = {}
+
+    def w(t):   # operand-typed weight
+        return t.detach().to(device=device, dtype=torch.float32).to(wt).contiguous()
+
+    def f(t):   # stays fp32
+        return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+    lm = "language_model.model."
+    out["embed_tokens"] = f(sd[lm + "embed_tokens.weight"])
+    for i in range(dims.L):
+        p = lm + f"layers.{i}."
+        out[f"l{i}.ln1"] = f(sd[p + "input_layernorm.weight"])
+        out[f"l{i}.ln2"] = f(sd[p + "post_attention_layernorm.weight"])
+        out[f"l{i}.wqkv"] = w(torch.cat([sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"],
+                                         sd[p + "self_attn.v_proj.weight"]], dim=0))
+        out[f"l{i}.wo"] = w(sd[p + "self_attn.o_proj.weight"])
+        out[f"l{i}.wgu"] = w(torch.cat([sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]], dim=0))
+        out[f"l{i}.wd"] = w(sd[p + "mlp.down_proj.weight"])
+    out["norm"] = f(sd[lm + "norm.weight"])
+    out["head.w0"] = w(sd["gen_head.output_mlp_projector.weight"])
+    out["head.b0"] = f(sd["gen_head.output_mlp_projector.bias"])
+    out["head.w1"] = w(sd["gen_head.vision_head.weight"])
+    out["head.b1"] = f(sd["gen_head.vision_head.bias"])
+    out["gen_embed"] = f(sd["gen_embed.weight"])
+    out["align.w0"] = w(sd["gen_aligner.layers.0.weight"])
+    out["align.b0"] = f(sd["gen_aligner.layers.0.bias"])
+    out["align.w1"] = w(sd["gen_aligner.layers.2.weight"])
+    out["align.b1"] = f(sd["gen_aligner.layers.2.bias"])
+    cos, sin = rope_tables(dims, tmax)
+    out["rope_cos"] = cos.to(device)
+    out["rope_sin"] = sin.to(device)
+    if with_vq:
+        g = "gen_vision_model."
+        out["vq.codebook"] = f(sd[g + "quantize.embedding.weight"])
+        out["vq.pqc.w"] = w(sd[g + "post_quant_conv.weight"].reshape(dims.vq_z, dims.code_dim))
+        out["vq.pqc.b"] = f(sd[g + "post_quant_conv.bias"])
+        for k, v in sd.items():
+            if not k.startswith(g + "decoder."):
+                continue
+            name = "vq." + k[len(g):]
+            if v.dim() == 4:       # conv weight -> [Cout, kh*kw*Cin]
+                out[name] = w(v.permute(0, 2, 3, 1).reshape(v.shape[0], -1))
+            else:                  # conv bias / GroupNorm scale+shift
+                out[name] = f(v)
+    return out

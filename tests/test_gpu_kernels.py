@@ -1,0 +1,100 @@
+"""-m gpu: unit parity of the individual CUDA kernels through the C-ABI."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import janus_oracle as O
+from oracle import philox as PX
+from tests.gpu_util import get_engine, assert_close, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(eng, impl, X, W, splits):
+    from plangen_b200 import _lib
+    M, K = X.shape
+    N = W.shape[0]
+    out = torch.empty(splits, M, N, device=X.device, dtype=torch.float32)
+    _lib.check(eng._lib.pg_test_gemm(eng._h, impl, int(X.dtype == torch.bfloat16), C.c_void_p(X.data_ptr()),
+                                     C.c_void_p(W.data_ptr()), M, N, K, splits, C.c_void_p(out.data_ptr()),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    return out.sum(0)
+
+
+@pytest.mark.parametrize("M,N,K,splits", [
+    (2, 128, 64, 1), (2, 256, 256, 1), (16, 256, 512, 2), (32, 384, 2048, 3), (5, 130, 72, 1),
+    (64, 1024, 1408, 4), (128, 512, 512, 1), (200, 256, 320, 1), (576, 576, 512, 1), (1000, 3, 1152, 1),
+    (32, 6144, 2048, 3), (32, 2048, 5632, 9),
+])
+def test_gemm_tcgen05_matches_torch(M, N, K, splits):
+    eng = get_engine(O.TINY, "bf16")
+    g = torch.Generator(device="cuda").manual_seed(M * 7919 + N * 31 + K)
+    X = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    got = _gemm(eng, 1, X, W, splits)
+    want = X.double() @ W.double().T            # bf16 products are exact; only the fp32 summation order differs
+    assert_close(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-4, atol_frac=2e-6, what=f"tc gemm {M}x{N}x{K}/{splits}")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+@pytest.mark.parametrize("M,N,K,splits", [(2, 64, 16, 1), (3, 70, 8, 1), (33, 200, 1024, 4), (130, 96, 72, 2)])
+def test_gemm_simt_matches_torch(mode, M, N, K, splits):
+    eng = get_engine(O.TINY, mode)
+    dt = torch.float32 if mode == "fp32" else torch.bfloat16
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    X = torch.randn(M, K, device="cuda", generator=g).to(dt)
+    W = torch.randn(N, K, device="cuda", generator=g).to(dt)
+    got = _gemm(eng, 0, X, W, splits)
+    want = X.double() @ W.double().T
+    assert_close(got.cpu().numpy(), want.cpu().numpy(), rtol=1e-5, atol_frac=2e-6, what=f"simt gemm {mode}")
+
+
+@pytest.mark.parametrize("B,V", [(1, 2048), (3, 16384), (16, 16384), (20, 16384)])
+def test_sampler_is_bit_exact_with_torch_multinomial(B, V):
+    """Index work: the fused sampler must pick exactly the tokens torch.multinomial picks on this GPU
+    for the same (seed, offset) and the same probabilities, over several consecutive calls."""
+    d = O.JanusDims(**{**O.TINY.__dict__, "name": f"tiny-v{V}", "img_vocab": V})
+    eng = get_engine(d, "fp32", max_batch=max(B, 4), with_vq=False)
+    props = torch.cuda.get_device_properties(0)
+    gen = torch.Generator(device="cuda").manual_seed(1234)
+    tg = torch.Generator(device="cuda").manual_seed(99)
+    n_steps = 5
+    toks = torch.zeros(B, n_steps, dtype=torch.int32, device="cuda")
+    off = 0
+    for step in range(n_steps):
+        logits = torch.randn(2 * B, V, device="cuda", generator=tg) * 2.0
+        cfg = logits[1::2] + 5.0 * (logits[0::2] - logits[1::2])
+        probs = torch.softmax(cfg / 1.0, dim=-1)
+        assert gen.get_offset() == off
+        want = torch.multinomial(probs, 1, generator=gen).squeeze(-1)
+        # oracle's CPU port of the CUDA algorithm
+        port, off2 = PX.cuda_multinomial1(probs.cpu().numpy(), 1234, off, props.multi_processor_count,
+                                          props.max_threads_per_multi_processor)
+        eng.cfg_sample_embed(logits, 5.0, 1.0, 1234, off, step, n_steps, toks)
+        torch.cuda.synchronize()
+        assert toks[:, step].tolist() == want.tolist(), f"step {step}"
+        assert port.tolist() == want.tolist(), f"oracle port, step {step}"
+        off = gen.get_offset()
+        assert off2 == off and eng.philox_offset_per_step(B) == off2 // (step + 1)
+
+
+def test_sampler_teacher_forcing_and_greedy():
+    eng = get_engine(O.TINY, "fp32")
+    B, V, n = 2, O.TINY.img_vocab, 3
+    logits = torch.randn(2 * B, V, device="cuda")
+    toks = torch.zeros(B, n, dtype=torch.int32, device="cuda")
+    er = torch.tensor([[1, 0, 1], [0, 0, 1]], dtype=torch.int32, device="cuda")
+    gt = torch.tensor([[7, 8, 9], [17, 18, 19]], dtype=torch.int32, device="cuda")
+    x = eng.cfg_sample_embed(logits, 5.0, 1.0, 0, 0, 1, n, toks, greedy=True, edit_region=er, gt_labels=gt)
+    assert toks[:, 1].tolist() == [8, 18]
+    x2 = eng.cfg_sample_embed(logits, 5.0, 1.0, 0, 0, 2, n, toks, greedy=True, edit_region=er, gt_labels=gt)
+    cfg = logits[1::2] + 5.0 * (logits[0::2] - logits[1::2])
+    assert toks[:, 2].tolist() == cfg.argmax(-1).tolist()
+    # next inputs are gen_aligner(gen_embed(tok)) duplicated to the cond/uncond rows
+    sd = {k: v.cuda() for k, v in O.init_state_dict(O.TINY, seed=0, with_vq=False).items() if k.startswith("gen_")}
+    want = O.prepare_gen_img_embeds(sd, toks[:, 2].long())
+    assert_close(x2[0::2].cpu().numpy(), want.cpu().numpy(), 1e-4, 1e-5, "embed cond rows")
+    assert torch.equal(x2[0::2], x2[1::2])

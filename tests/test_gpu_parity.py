@@ -1,0 +1,169 @@
+"""-m gpu: parity of the CUDA path (through the C-ABI) against the oracle and the golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import janus_oracle as O
+from oracle import philox as PX
+from tests.gpu_util import get_engine, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _num_sms():
+    p = torch.cuda.get_device_properties(0)
+    return p.multi_processor_count, p.max_threads_per_multi_processor
+
+
+# ------------------------------------------------------------------------------- fp32 check mode
+@pytest.mark.parametrize("name,dims,steps", [("lm_tiny_fp32.npz", O.TINY, 8), ("lm_small_fp32.npz", O.SMALL, 6)])
+def test_fp32_dropin_api_matches_golden(golden_dir, name, dims, steps):
+    """Drive the engine exactly the way System.sample_image drives vl_gpt (plangen_base.py:567-607),
+    teacher-forced on the golden tokens, and compare hidden states / CFG logits (rtol 1e-4)."""
+    g = np.load(os.path.join(golden_dir, name))
+    eng = get_engine(dims, "fp32", with_vq=False)
+    ids = torch.from_numpy(g["ids"]).cuda()
+    mask = torch.from_numpy(g["mask"]).cuda()
+    emb = eng.language_model.get_input_embeddings()(ids)
+    sd_emb = O.init_state_dict(dims, seed=0, with_vq=False)["language_model.model.embed_tokens.weight"]
+    assert torch.equal(emb.cpu(), sd_emb[ids.cpu().long()])
+    outputs = None
+    for i in range(steps):
+        outputs = eng.language_model.model(inputs_embeds=emb, attention_mask=mask, use_cache=True,
+                                           past_key_values=outputs.past_key_values if i != 0 else None)
+        h = outputs.last_hidden_state[:, -1, :]
+        assert_close(h.cpu().numpy(), g["hidden"][i], 1e-4, 1e-5, f"hidden step {i}")
+        logits = eng.gen_head(h)
+        cfg = logits[1::2] + 5.0 * (logits[0::2] - logits[1::2])
+        assert_close(cfg.cpu().numpy(), g["logits"][i], 1e-4, 2e-5, f"cfg logits step {i}")
+        tok = torch.from_numpy(g["tokens"][:, i]).cuda().long()
+        nxt = torch.stack([tok, tok], 1).view(-1)
+        emb = eng.prepare_gen_img_embeds(nxt).unsqueeze(1)
+
+
+@pytest.mark.parametrize("name,dims,steps", [("lm_tiny_fp32.npz", O.TINY, 8), ("lm_small_fp32.npz", O.SMALL, 6)])
+@pytest.mark.parametrize("graph", [0, 1])
+def test_fp32_fused_loop_reproduces_golden_tokens(golden_dir, name, dims, steps, graph):
+    """The fused device loop with the torch-compatible Philox sampler must emit the golden token ids
+    when the box has the SM count the golden was made for; otherwise compare with the oracle re-run."""
+    g = np.load(os.path.join(golden_dir, name))
+    eng = get_engine(dims, "fp32", with_vq=False)
+    eng.set_option("use_graph", graph)
+    ids = torch.from_numpy(g["ids"]).cuda()
+    mask = torch.from_numpy(g["mask"]).cuda()
+    emb = eng.language_model.get_input_embeddings()(ids)
+    dbg = torch.zeros(steps, ids.shape[0] // 2, dims.img_vocab, device="cuda")
+    eng.set_option("dbg_logits_ptr", dbg.data_ptr())
+    try:
+        toks = eng.sample_image(emb, ids.shape[0] // 2, steps, mask, 5.0, 1.0, generator=0)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("dbg_logits_ptr", 0)
+        eng.set_option("use_graph", 1)
+    sms, mt = _num_sms()
+    if sms == int(g["num_sms"]):
+        want = g["tokens"]
+    else:
+        sd = O.init_state_dict(dims, seed=0, with_vq=False)
+        want, _ = O.t2i(sd, dims, ids.cpu(), mask.cpu(), sampler=PX.PhiloxSampler(0, sms, mt),
+                        image_token_num_per_image=steps, decode=False)
+        want = want.numpy()
+    assert toks.cpu().numpy().tolist() == want.tolist()
+    if sms == int(g["num_sms"]):
+        assert_close(dbg.cpu().numpy(), g["logits"], 1e-4, 2e-5, "fused-loop CFG logits")
+
+
+def test_fp32_greedy_sequence_identical_and_ragged_batch():
+    """fp32 greedy tokens identical to the oracle on a ragged batch (rows with 0..many pad columns)."""
+    d = O.SMALL
+    sd = O.init_state_dict(d, seed=0, with_vq=False)
+    eng = get_engine(d, "fp32", with_vq=False)
+    cond = [[5, 6, 7], list(range(10, 45)), [9] * 17, [3]]
+    neg = [[1, 2]] * 4
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, d.pad_id, d.n_img_tokens)
+    steps = 12
+    want, _ = O.t2i(sd, d, ids, mask, sampler=O.greedy_sampler, image_token_num_per_image=steps, decode=False)
+    emb = eng.language_model.get_input_embeddings()(ids.cuda())
+    got = eng.sample_image(emb, 4, steps, mask.cuda(), 5.0, 1.0, generator=0, greedy=True)
+    assert got.cpu().tolist() == want.tolist()
+
+
+# --------------------------------------------------------------------------- bf16 (autocast) regime
+@pytest.mark.parametrize("dims,steps", [(O.TINY, 6), (O.SMALL, 6)])
+@pytest.mark.parametrize("use_tc", [1, 0])
+def test_bf16_logits_match_autocast_reference(dims, steps, use_tc):
+    """Reference regime: fp32 master weights under torch.autocast(bf16) on the SAME GPU (the reference
+    PyTorch path).  Teacher-forced on the reference's tokens; CFG logits within rtol 2e-2 (north_star)."""
+    sd = O.init_state_dict(dims, seed=0, with_vq=False)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    cond, neg = O.synthetic_prompts(dims, 3, seed=77, lo=9, hi=40, neg_len=13)
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
+    trace = {}
+    ref_tok, _ = O.t2i(sdc, dims, ids.cuda(), mask.cuda(), sampler=O.greedy_sampler, mode="autocast",
+                       image_token_num_per_image=steps, decode=False, trace=trace)
+    ref_logits = torch.stack(trace["logits"]).numpy()
+    eng = get_engine(dims, "bf16", with_vq=False)
+    eng.set_option("use_tc", use_tc)
+    dbg = torch.zeros(steps, 3, dims.img_vocab, device="cuda")
+    eng.set_option("dbg_logits_ptr", dbg.data_ptr())
+    try:
+        emb = eng.language_model.get_input_embeddings()(ids.cuda())
+        forced = {"edit_region": torch.zeros(3, steps, dtype=torch.int32)}
+        got = eng.sample_image(emb, 3, steps, mask.cuda(), 5.0, 1.0, generator=0, batch=forced,
+                               gt_labels=ref_tok, greedy=True)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("dbg_logits_ptr", 0)
+        eng.set_option("use_tc", 1)
+    assert got.cpu().tolist() == ref_tok.cpu().tolist()            # forced
+    assert_close(dbg.cpu().numpy(), ref_logits, 2e-2, 2e-2, f"bf16 CFG logits (tc={use_tc})")
+
+
+# ----------------------------------------------------------------------------------------- VQ decode
+@pytest.mark.parametrize("name,dims", [("vq_tiny.npz", O.TINY), ("vq_small.npz", O.SMALL)])
+def test_vq_fp32_matches_reference_golden(golden_dir, name, dims):
+    g = np.load(os.path.join(golden_dir, name))
+    eng = get_engine(dims, "fp32", with_vq=True)
+    codes = torch.from_numpy(g["codes"]).cuda()
+    out = eng.gen_vision_model.decode_code(codes, shape=[codes.shape[0], dims.code_dim, dims.grid, dims.grid])
+    assert_close(out.cpu().numpy(), g["out"], 1e-4, 2e-5, "vq fp32")
+
+
+def test_vq16_fp32_matches_reference_class_golden(golden_dir):
+    """The real VQ-16 architecture (ch 128, 5 levels) on a 4x4 token grid vs the reference class output."""
+    g = np.load(os.path.join(golden_dir, "vq16_grid4.npz"))
+    d = O.JanusDims(**{**O.TINY.__dict__, "name": "tiny-vq16", "img_vocab": 16384, "vq_ch": 128,
+                       "vq_ch_mult": (1, 1, 2, 2, 4), "vq_z": 256})
+    sd = O.init_state_dict(d, seed=0, with_vq=False)
+    sd.update(O.init_state_dict(O.JANUS_1P3B, seed=0, only="gen_vision_model."))
+    eng = get_engine(d, "fp32", sd=sd, cache=False)
+    out = eng.gen_vision_model.decode_code(torch.from_numpy(g["codes"]).cuda(), shape=[1, 8, 4, 4])
+    assert_close(out.cpu().numpy(), g["out"], 1e-4, 5e-5, "vq16 fp32")
+
+
+@pytest.mark.parametrize("dims", [O.TINY, O.SMALL])
+def test_vq_bf16_matches_autocast_reference(dims):
+    sd = O.init_state_dict(dims, seed=0, only="gen_vision_model.")
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(5)
+    codes = torch.randint(0, dims.img_vocab, (3, dims.n_img_tokens), generator=g, dtype=torch.int32)
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        want = O.decode_code(sdc, dims, codes.cuda(), [3, dims.code_dim, dims.grid, dims.grid]).float()
+    eng = get_engine(dims, "bf16", with_vq=True)
+    out = eng.gen_vision_model.decode_code(codes.cuda(), shape=[3, dims.code_dim, dims.grid, dims.grid]).float()
+    assert_close(out.cpu().numpy(), want.cpu().numpy(), 2e-2, 3e-2, "vq bf16")
+
+
+def test_t2i_end_to_end_small():
+    """System.t2i shape/dtype contract + host-buffer entry."""
+    d = O.SMALL
+    eng = get_engine(d, "bf16", with_vq=True)
+    cond, neg = O.synthetic_prompts(d, 2, seed=3, lo=9, hi=30, neg_len=11)
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, d.pad_id, d.n_img_tokens)
+    dec, _ = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), cfg_weight=5.0, temperature=1.0)
+    assert dec.shape == (2, 3, d.img_size, d.img_size) and dec.dtype == torch.bfloat16
+    assert torch.isfinite(dec.float()).all()
+    img = eng.generate_from_host(ids.pin_memory(), mask.pin_memory())
+    assert img.dtype == torch.uint8 and img.shape == (2, 3, d.img_size, d.img_size) and not img.is_cuda
