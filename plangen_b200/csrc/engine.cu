@@ -89,6 +89,10 @@ struct pg_engine {
   cudaGraphExec_t graph_exec = nullptr;
   std::string graph_key;
   int64_t graph_launches = 0;     // kernels per replay, counted while capturing
+  // the decode loop runs on the engine's own stream (the caller's may be the legacy default stream,
+  // which cannot be captured); ordered against the caller's stream with events
+  cudaStream_t own_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 static const void* T_(pg_engine* e, const std::string& name, size_t* nbytes = nullptr) {
@@ -133,7 +137,7 @@ static int make_map_2d(pg_engine* e, CUtensorMap* m, const void* ptr, uint64_t r
 
 template <int NT>
 static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx, float* C, int M, int N, int K,
-                     int splits, int kb_per_split, cudaStream_t st) {
+                     int splits, int kb_per_split, bool w_const, cudaStream_t st) {
   using Cfg = TcCfg<NT>;
   int stages = e->tc_stages > 0 ? e->tc_stages : (200 * 1024) / Cfg::STAGE_BYTES;
   stages = std::max(2, std::min(stages, 12));
@@ -141,12 +145,12 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   const size_t smem = Cfg::smem_bytes(stages);
   dim3 grid((N + TC_BM - 1) / TC_BM, (M + NT - 1) / NT, splits);
   return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
-                e->use_pdl);
+                e->use_pdl ? (w_const ? 3 : 1) : 0);
 }
 
 // C[splits][M][N] fp32 = X[M][K] * W[N][K]^T.  Returns the number of splits used through *splits_out.
 static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, int K, float* C, size_t c_bytes,
-                    int* splits_out, cudaStream_t st, int force_impl = -1, int force_splits = 0) {
+                    int* splits_out, cudaStream_t st, int force_impl = -1, int force_splits = 0, bool w_const = true) {
   const bool tc = e->bf16 && ((force_impl == 1) || (force_impl < 0 && e->use_tc)) && (K % 8 == 0) &&
                   (((uintptr_t)X & 15) == 0) && (((uintptr_t)W & 15) == 0);
   if (force_impl == 1 && !tc) return fail("tcgen05 GEMM needs bf16 operands, K %% 8 == 0 and 16-byte aligned pointers");
@@ -165,11 +169,11 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     TRY(make_map_2d(e, &mw, W, (uint64_t)N, (uint64_t)K, TC_BM));
     TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
     switch (NT) {
-      case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
-      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
-      case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
-      case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
-      default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, st)); break;
+      case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
+      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
+      case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
+      case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
+      default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
     }
   } else {
     if (K % 4 != 0) return fail("SIMT GEMM needs K %% 4 == 0 (K=%d)", K);
@@ -282,6 +286,9 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) { delete e; return fail("cuTensorMapEncodeTiled not available"); }
   e->encode = (EncodeTiledFn)fn;
+  CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -298,6 +305,9 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
 extern "C" int pg_engine_destroy(pg_engine* e) {
   if (!e) return 0;
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
   delete e;
   return 0;
 }
@@ -685,8 +695,11 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
   TRY(check_ready(e));
   if (R % 2) return fail("R must be even (interleaved cond/uncond rows)");
   if (n_steps < 1 || n_steps > e->d.max_steps) return fail("n_steps %d exceeds engine limit %d", n_steps, e->d.max_steps);
-  cudaStream_t st = (cudaStream_t)stream;
-  TRY(pg_prefill(e, x_prompt, kv_start, R, P, nullptr, 0, stream));
+  cudaStream_t user = (cudaStream_t)stream;
+  cudaStream_t st = e->own_stream;
+  CK(cudaEventRecord(e->ev_in, user));
+  CK(cudaStreamWaitEvent(st, e->ev_in, 0));
+  TRY(pg_prefill(e, x_prompt, kv_start, R, P, nullptr, 0, (void*)st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 4, st));
   if (n_steps > 1) {
     if (e->use_graph) {
@@ -720,6 +733,8 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
   }
   // last token: head + sample only (the reference computes and drops one more embed)
   TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, false, st));
+  CK(cudaEventRecord(e->ev_out, st));
+  CK(cudaStreamWaitEvent(user, e->ev_out, 0));
   return 0;
 }
 
@@ -842,17 +857,17 @@ static int vq_attnblock(VqCtx& c, const std::string& name, const void* x, void* 
     const uint8_t* hn_b = (const uint8_t*)hn + (size_t)b * HW * C * es;
     uint8_t* vT_b = (uint8_t*)vT + (size_t)b * HW * C * es;
     // v^T[c][pix] = sum_k Wv[c][k] hn[pix][k] + bv[c]
-    TRY(run_gemm(e, Wv, hn_b, C, HW, C, e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1));
+    TRY(run_gemm(e, Wv, hn_b, C, HW, C, e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1, false));
     VqCtx one = c; one.Bc = 1;
     TRY(vq_epilogue(one, e->vq_part, bv, nullptr, vT_b, nullptr, HW, HW, (size_t)C, 1));
     // scores[i][j] = q_i . k_j
     TRY(run_gemm(e, (const uint8_t*)qb + (size_t)b * HW * C * es, (const uint8_t*)kb + (size_t)b * HW * C * es, HW, HW, C,
-                 e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1));
+                 e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1, false));
     DISPATCH_T(e,
                launch(e, softmax_rows_kernel<bf16>, dim3(HW), dim3(256), 0, c.st, (const float*)e->vq_part, (bf16*)Pm, HW, scale),
                launch(e, softmax_rows_kernel<float>, dim3(HW), dim3(256), 0, c.st, (const float*)e->vq_part, (float*)Pm, HW, scale));
     // h[i][c] = sum_j P[i][j] v^T[c][j]
-    TRY(run_gemm(e, Pm, vT_b, HW, C, HW, e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1));
+    TRY(run_gemm(e, Pm, vT_b, HW, C, HW, e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1, false));
     TRY(vq_epilogue(one, e->vq_part, nullptr, nullptr, (uint8_t*)ha + (size_t)b * HW * C * es, nullptr, C, HW, (size_t)HW, 0));
   }
   TRY(vq_conv(c, ha, H, W, C, name + ".proj_out", C, 1, 1, nullptr, false, x, y, nullptr));
@@ -923,7 +938,7 @@ extern "C" int pg_test_gemm(pg_engine* e, int impl, int is_bf16, const void* X, 
   if (!e) return fail("null engine");
   if ((is_bf16 != 0) != e->bf16) return fail("operand type does not match the engine mode");
   int S = 0;
-  TRY(run_gemm(e, X, W, M, N, K, C, (size_t)std::max(splits, 1) * M * N * 4, &S, (cudaStream_t)stream, impl, std::max(splits, 1)));
+  TRY(run_gemm(e, X, W, M, N, K, C, (size_t)std::max(splits, 1) * M * N * 4, &S, (cudaStream_t)stream, impl, std::max(splits, 1), false));
   if (S != std::max(splits, 1)) {
     // fewer splits were possible: zero the remainder so the caller can always sum `splits` slabs
     CK(cudaMemsetAsync(C + (size_t)S * M * N, 0, (size_t)(std::max(splits, 1) - S) * M * N * 4, (cudaStream_t)stream));

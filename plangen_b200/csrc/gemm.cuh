@@ -77,11 +77,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       const uint64_t pol_w = policy_evict_first();   // weights are streamed once per step
       const uint64_t pol_x = policy_evict_last();    // activations are re-read by every CTA
       const int pre = min(nkb, num_stages);
-      for (int i = 0; i < pre; ++i) {                // weights do not depend on the previous kernel
+      // use_pdl bit 1: the W operand is a constant weight, so its tiles may be requested before the
+      // previous kernel has finished (it is an activation in the VQ attention contractions)
+      if (use_pdl == 1) pdl_wait();
+      for (int i = 0; i < pre; ++i) {
         mbar_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
         tma_load_2d(smem + i * Cfg::STAGE_BYTES, &map_w, &full_bar[i], (kb_begin + i) * TC_BK, n0, pol_w);
       }
-      if (use_pdl) pdl_wait();
+      if (use_pdl == 3) pdl_wait();
       for (int i = 0; i < pre; ++i)
         tma_load_2d(smem + i * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[i], (kb_begin + i) * TC_BK, m0, pol_x);
       for (int i = pre; i < nkb; ++i) {
@@ -168,6 +171,8 @@ gemm_simt_kernel(const T* __restrict__ X, const T* __restrict__ W, float* __rest
                  int k_per_split) {
   __shared__ float Xs[16][64 + 4];
   __shared__ float Ws[16][64 + 4];
+  pdl_launch_dependents();
+  pdl_wait();          // every kernel of a PDL chain must wait, or completion is no longer transitive
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   const int k_begin = blockIdx.z * k_per_split;

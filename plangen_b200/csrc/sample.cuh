@@ -167,6 +167,8 @@ __global__ void gen_embed_gather_kernel(const int32_t* __restrict__ ids, const T
 template <typename T>
 __global__ void aligner_l0_kernel(const float* __restrict__ gen_embed, const T* __restrict__ w0,
                                   const float* __restrict__ b0, T* __restrict__ h, int code_dim, int D, size_t total) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t v = i / D, n = i % D;
     float acc = 0.f;

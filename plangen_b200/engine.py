@@ -293,12 +293,13 @@ class FastJanus:
 
     @torch.inference_mode()
     def t2i(self, inputs_ids=None, parallel_size=1, image_token_num_per_image=None, cfg_weight=5.0, temperature=1.0,
-            img_size=None, patch_size=16, gt_image=None, batch=None, mask=None, tokens=None, emb=None,
+            img_size=None, patch_size=None, gt_image=None, batch=None, mask=None, tokens=None, emb=None,
             gt_labels=None, greedy: bool = False):
         """System.t2i (plangen_base.py:525-565), `tokens`/`emb` branches.  Returns (dec, mask_image);
         gt_labels replaces the VQ-encoder call of the editing path (encoder is out of scope here)."""
         n = image_token_num_per_image or self.dims.n_img_tokens
         img_size = img_size or self.dims.img_size
+        patch_size = patch_size or 2 ** (len(self.dims.vq_ch_mult) - 1)      # 16 for VQ-16
         if tokens is None and emb is None:
             raise NotImplementedError("pass `tokens` (2B, P) or `emb`; the un-batched branch is unused by PlanGen")
         if tokens is not None:

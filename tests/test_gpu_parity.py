@@ -153,7 +153,13 @@ def test_vq_bf16_matches_autocast_reference(dims):
         want = O.decode_code(sdc, dims, codes.cuda(), [3, dims.code_dim, dims.grid, dims.grid]).float()
     eng = get_engine(dims, "bf16", with_vq=True)
     out = eng.gen_vision_model.decode_code(codes.cuda(), shape=[3, dims.code_dim, dims.grid, dims.grid]).float()
-    assert_close(out.cpu().numpy(), want.cpu().numpy(), 2e-2, 3e-2, "vq bf16")
+    # Two bf16 evaluations of this ~30-conv GroupNorm decoder differ by accumulated rounding noise: the
+    # reference under autocast vs the reference in fp32 differ by max 6.5e-2 / mean 8e-3 on SMALL
+    # (measured with the oracle on CPU), max|out| ~ 1.9.  Tolerance: rtol 2e-2 plus 5% of max|ref|
+    # per element, and a mean error below 1% of max|ref|.
+    a, b = out.cpu().numpy(), want.cpu().numpy()
+    assert_close(a, b, 2e-2, 5e-2, "vq bf16")
+    assert np.abs(a - b).mean() < 1e-2 * np.abs(b).max()
 
 
 def test_t2i_end_to_end_small():
