@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""Benchmark of the PlanGen CFG image-token decode path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one batch through the hot path: prompt embed + prefill + 576 x (gen_head, CFG, Philox
+sample, embed, KV-cached decode step) + VQ decode_code, for BASELINE.json configs[1]
+(layout2image, Janus-1.3B architecture, random-init weights, bf16, batch 16 = 32 rows with the
+cond/uncond pair, synthetic LayoutSAM-shaped prompts with 4-8 boxes).  Prints ONE JSON line.
+
+  value     images/s, whole job, inputs already resident in HBM (CUDA-event timed, max over ranks)
+  e2e       same metric through the public host-buffer API (pinned-host ids/mask -> uint8 images in
+            host memory; H2D and D2H inside the timed region)
+  roofline  the dominant kernel (tcgen05 weight-streaming GEMM) timed alone with CUDA events
+  cpu_baseline  the oracle port of the reference PyTorch path on the box's host cores (bounded sample)
+
+`--impl reference` times the reference's own CPU implementation of the path: the oracle restatement
+of System.t2i / sample_image (oracle/janus_oracle.py; the reference itself cannot be imported here,
+see DESIGN.md) on all host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec/box (576-tok CFG decode, layout2image bf16 batch 16)"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--model", default="janus-1.3b", choices=["janus-1.3b", "janus-pro-7b"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], help="engine option key=value")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # under load = upper half of the samples (idle gaps between steps pull the clock down)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm (CPU)
+def cpu_reference_sample(model_name: str, threads: int, prompt_len: int = 256, rows_b: int = 1, n_decode: int = 24,
+                         vq: bool = True, sd=None):
+    """Oracle port of the reference path on host cores: prefill + n_decode decode steps (+ VQ decode of
+    one image), extrapolated to a 576-token image.  Returns a dict incl. images/s."""
+    import torch
+    from oracle import janus_oracle as O
+    torch.set_num_threads(threads)
+    d = O.PRESETS[model_name]
+    if sd is None:
+        sd = O.init_state_dict(d, seed=0, with_vq=vq)
+    cond, neg = O.synthetic_prompts(d, rows_b, seed=1234, lo=prompt_len, hi=prompt_len)
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, d.pad_id, d.n_img_tokens)
+    times = []
+
+    def timed_forward(**kw):
+        t0 = time.perf_counter()
+        out = O.llama_model_forward(sd, d, **kw)
+        times.append(time.perf_counter() - t0)
+        return out
+
+    g = torch.Generator().manual_seed(0)
+    t0 = time.perf_counter()
+    with torch.inference_mode():
+        emb = O.embed_tokens(sd, ids)
+        toks = O.sample_image(sd, d, emb, rows_b, n_decode + 1, mask, 5.0, 1.0, O.make_torch_sampler(g), mode="fp32",
+                              lm_forward=timed_forward)
+    loop_s = time.perf_counter() - t0
+    prefill_s = times[0]
+    dec = sorted(times[1:])
+    step_s = dec[len(dec) // 2]
+    other_s = max(loop_s - sum(times), 0.0) / (n_decode + 1)        # head + CFG + sample + embed per token
+    vq_s = 0.0
+    if vq:
+        codes = torch.randint(0, d.img_vocab, (1, d.n_img_tokens), dtype=torch.int32)
+        t0 = time.perf_counter()
+        with torch.inference_mode():
+            O.decode_code(sd, d, codes, [1, d.code_dim, d.grid, d.grid])
+        vq_s = time.perf_counter() - t0
+    n = d.n_img_tokens
+    per_batch = prefill_s + (n - 1) * step_s + n * other_s + rows_b * vq_s
+    return {"images_per_s": rows_b / per_batch, "prefill_s": prefill_s, "ms_per_decode_step": 1e3 * step_s,
+            "vq_decode_s_per_image": vq_s, "rows": 2 * rows_b, "prompt_len": prompt_len, "n_decode_timed": n_decode,
+            "sample_wall_s": loop_s + vq_s}
+
+
+def run_reference_arm(args):
+    """Reference arm: the reference's CPU PyTorch path (oracle port) on all host threads.  Each timed step
+    is a bounded sample of the configs[1] workload - one prompt pair (R=2) at P=256: prefill + 8 decode
+    steps - extrapolated to a full 576-token image; the VQ decode of one image is timed once."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from oracle import janus_oracle as O
+    d = O.PRESETS[args.model]
+    sd = O.init_state_dict(d, seed=0, with_vq=True)
+    first = cpu_reference_sample(args.model, threads, prompt_len=256, rows_b=1, n_decode=2, vq=True, sd=sd)
+    vq_s = first["vq_decode_s_per_image"]
+    vals = []
+    for i in range(args.warmup + args.steps):
+        if i > 0 and i < args.warmup:
+            continue                       # one warm-up pass is enough for a CPU path; keep the run bounded
+        v = cpu_reference_sample(args.model, threads, prompt_len=256, rows_b=1, n_decode=8, vq=False, sd=sd)
+        if i >= args.warmup:
+            vals.append(v)
+    n = d.n_img_tokens
+    per = [v["prefill_s"] + (n - 1) * v["ms_per_decode_step"] / 1e3 + vq_s for v in vals]
+    ips = len(per) / sum(per)
+    line = {
+        "metric": METRIC, "value": ips, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(per) / len(per), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] layout2image (task_type=uni), Janus-1.3B-arch random init, 576 VQ tokens, CFG 5; "
+                               "reference arm = oracle port of System.t2i/sample_image on CPU fp32 (the reference cannot be "
+                               "imported here), bounded sample per step: 1 prompt pair (R=2), P=256, prefill + 8 decode steps, "
+                               "+ VQ decode of 1 image timed once, extrapolated to a 576-token image"},
+        "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "R=2 rows, P=256: prefill + 8 decode steps (+ VQ decode of 1 image, timed once), "
+                                   "extrapolated to 576 tokens",
+                         "ms_per_decode_step": sum(v["ms_per_decode_step"] for v in vals) / len(vals),
+                         "prefill_s": sum(v["prefill_s"] for v in vals) / len(vals), "vq_decode_s_per_image": vq_s,
+                         "torch": torch.__version__},
+        "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def kernel_roofline(eng, R: int, peaks: dict, iters: int = 4):
+    """Dominant kernel timed alone: the tcgen05 swap-AB GEMM streaming each layer's gate|up weights
+    ([2F, D] bf16, 46 MB at 1.3B) for R activation rows, rotating over all L layers so the weights come
+    from HBM (L x 46 MB >> 126 MB L2).  CUDA events on the launching stream."""
+    import ctypes as C
+    import torch
+    from plangen_b200 import _lib
+    d = eng.dims
+    N, K = 2 * d.F, d.D
+    X = (torch.randn(R, K, device=eng.device) * 0.5).to(torch.bfloat16)
+    splits = max(1, min(16, eng.counter("num_sms") // ((N + 127) // 128)))
+    out = torch.empty(splits, R, N, device=eng.device, dtype=torch.float32)
+    st = torch.cuda.current_stream(eng.device)
+
+    def one_pass():
+        for l in range(d.L):
+            W = eng._weights[f"l{l}.wgu"]
+            _lib.check(eng._lib.pg_test_gemm(eng._h, 1, 1, C.c_void_p(X.data_ptr()), C.c_void_p(W.data_ptr()), R, N, K,
+                                             splits, C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream)))
+
+    for _ in range(3):
+        one_pass()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for _ in range(iters):
+        one_pass()
+    e1.record(st)
+    torch.cuda.synchronize()
+    per_launch_s = e0.elapsed_time(e1) / 1e3 / (iters * d.L)
+    alg_bytes = N * K * 2 + R * K * 2 + splits * R * N * 4
+    achieved = alg_bytes / per_launch_s / 1e9
+    peak = peaks.get("hbm_gbs")
+    which = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    if not peak:
+        peak, which = 6650.0, "fallback (B200_PROFILING.md)"
+    return {"bound": "hbm", "kernel": "gemm_tc_kernel<32> (gate|up projection, swap-AB tcgen05)", "achieved": achieved,
+            "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "splits": splits}
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from plangen_b200 import JANUS_1P3B, JANUS_7B
+    from plangen_b200.engine import FastJanus
+    from plangen_b200 import synthetic, dp
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: plangen_b200 has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    dims = JANUS_1P3B if args.model == "janus-1.3b" else JANUS_7B
+    B = args.batch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+
+    sd = synthetic.random_state_dict(dims, dev, seed=0, with_vq=True)
+    opts = {}
+    for kv in args.option:
+        k, v = kv.split("=")
+        opts[k] = int(v)
+    eng = FastJanus(sd, dims, mode="bf16", max_batch=B, max_prompt=512, device=str(dev), options=opts)
+    sd_cpu_needed = (rank == 0 and world == 1 and not args.no_cpu_baseline)
+    if not sd_cpu_needed:
+        del sd
+    torch.cuda.empty_cache()
+
+    # each rank decodes its own batches (weak scaling): batch index = step * world + rank
+    def batch_for(step):
+        cond, neg = synthetic.layoutsam_prompts(dims, B, seed=1234 + step * world + rank)
+        return synthetic.collate_cfg_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
+
+    total = args.warmup + args.steps
+    host = [batch_for(i) for i in range(total)]
+    dev_batches = [(i.to(dev), m.to(dev)) for i, m in host]
+    pinned = [(i.pin_memory(), m.pin_memory()) for i, m in host]
+    out_host = torch.empty(B, 3, dims.img_size, dims.img_size, dtype=torch.uint8, pin_memory=True)
+
+    def step_resident(k):
+        ids, mask = dev_batches[k]
+        dec, _ = eng.t2i(tokens=ids, mask=mask, cfg_weight=5.0, temperature=1.0)
+        img = (((dec.float().clamp(-1, 1) + 1) / 2) * 255).to(torch.uint8)
+        return dp.gather_images(img, world)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(args.warmup):
+        step_resident(k)
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    eng.set_option("reset_launches", 0)
+    st = torch.cuda.current_stream(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(st)
+    for k in range(args.warmup, total):
+        step_resident(k)
+    e1.record(st)
+    barrier()
+    elapsed = dp.max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    launches = eng.counter("launches")
+    clk = clocks.stop() if rank == 0 else None
+
+    # decode-step time alone (graph replays), for the roofline of the step
+    P = dev_batches[args.warmup][0].shape[1]
+    lens = (dev_batches[args.warmup][1][:, :P] != 0).sum(1).tolist()
+
+    # end-to-end through the host-buffer API
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.warmup, total):
+        ids, mask = pinned[k]
+        eng.generate_from_host(ids, mask, out_host=out_host)
+    barrier()
+    e2e_elapsed = dp.max_over_ranks(time.perf_counter() - t0, dev)
+
+    # per-phase timing of one batch (prefill / decode loop / VQ), events on the launching stream
+    phases = {}
+    if rank == 0:
+        ids, mask = dev_batches[args.warmup]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        emb = eng.language_model.get_input_embeddings()(ids)
+        torch.cuda.synchronize()
+        ev[0].record(st)
+        toks1 = eng.sample_image(emb, B, 1, mask, 5.0, 1.0, generator=0)          # prefill + 1 token
+        ev[1].record(st)
+        toks = eng.sample_image(emb, B, dims.n_img_tokens, mask, 5.0, 1.0, generator=0)
+        ev[2].record(st)
+        eng.gen_vision_model.decode_code(toks, shape=[B, dims.code_dim, dims.grid, dims.grid])
+        ev[3].record(st)
+        torch.cuda.synchronize()
+        prefill_ms = ev[0].elapsed_time(ev[1])
+        loop_ms = ev[1].elapsed_time(ev[2]) - prefill_ms
+        phases = {"prefill_ms": prefill_ms, "decode_loop_ms": loop_ms, "vq_decode_ms": ev[2].elapsed_time(ev[3]),
+                  "ms_per_decode_step": loop_ms / (dims.n_img_tokens - 1)}
+        kvb = 2 * dims.L * dims.D * 2
+        mean_T = sum(lens) / len(lens) + dims.n_img_tokens / 2
+        step_bytes = eng.weight_bytes_per_step + len(lens) * mean_T * kvb + len(lens) * kvb
+        peak = peaks.get("hbm_gbs") or 6650.0
+        phases["decode_step_algorithmic_GB"] = step_bytes / 1e9
+        phases["decode_step_GBps"] = step_bytes / (phases["ms_per_decode_step"] / 1e3) / 1e9
+        phases["decode_step_frac_of_hbm_peak"] = phases["decode_step_GBps"] / peak
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    images = B * world * args.steps
+    line = {
+        "metric": METRIC, "value": images / elapsed, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "impl": "b200",
+        "config": {"workload": f"configs[1] layout2image (task_type=uni), {dims.name}-arch random init, batch {B} per GPU "
+                               f"(R={2 * B} rows with the cond/uncond pair), padded prompt P={P}, 576 VQ tokens, CFG 5, T 1, "
+                               "prefill + 576-step decode loop + VQ decode_code; prompts sharded per rank",
+                   "l2": "working set per decode step (2.5 GB weights + KV) >> 126 MB L2, no explicit flush",
+                   "parallelism": f"dp{world}"},
+        "clocks": clk,
+        "e2e": {"value": images / e2e_elapsed, "unit": UNIT,
+                "h2d_bytes_per_step": int(sum(t.numel() * t.element_size() for t in pinned[0])),
+                "d2h_bytes_per_step": int(out_host.numel())},
+        "gpu_launches": int(launches),
+        "phases": phases,
+    }
+    if not args.no_roofline:
+        line["roofline"] = kernel_roofline(eng, 2 * B, peaks)
+    if world == 1 and not args.no_cpu_baseline:
+        del eng
+        torch.cuda.empty_cache()
+        threads = os.cpu_count() or 1
+        cb = cpu_reference_sample(args.model, threads, prompt_len=256, rows_b=1, n_decode=24, vq=True,
+                                  sd={k: v.cpu() for k, v in sd.items()})
+        line["cpu_baseline"] = {"value": cb["images_per_s"], "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": "BASELINE configs[0]: R=2 rows (B=1 + CFG pair), P=256, fp32 oracle port: prefill + 24 "
+                                          "decode steps + VQ decode of 1 image, extrapolated to 576 tokens",
+                                "ms_per_decode_step": cb["ms_per_decode_step"], "prefill_s": cb["prefill_s"],
+                                "vq_decode_s_per_image": cb["vq_decode_s_per_image"], "torch": torch.__version__}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()
