@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 #define PG_DEVINL __device__ __forceinline__
 
@@ -94,8 +95,27 @@ PG_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-PG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+PG_DEVINL uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// Bounded spin: a protocol bug must surface as a trapped kernel (an error the host sees), never as a
+// hung GPU.  `tag` identifies the wait site in the diagnostic.
+PG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0, int info = 0) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FFFu) == 0) {                       // look at the clock only every 16K failed polls
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000ull) {
+        if ((threadIdx.x & 31) == 0)
+          printf("plangen_b200: mbarrier wait timed out (site %d, block %d,%d,%d thread %d parity %u info %d)\n", tag,
+                 blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x, parity, info);
+        __trap();
+      }
+    }
   }
 }
 

@@ -16,6 +16,7 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "lm_kernels.cuh"
+#include "attn_tma.cuh"
 #include "sample.cuh"
 #include "vq_kernels.cuh"
 
@@ -68,7 +69,7 @@ struct pg_engine {
   std::unordered_map<std::string, std::pair<const void*, size_t>> tensors;
   EncodeTiledFn encode = nullptr;
   // options
-  int use_tc = 1, use_pdl = 1, use_graph = 1, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
+  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
   int64_t launches = 0;
   bool finalized = false;
@@ -117,7 +118,10 @@ static int launch(pg_engine* e, void (*kernel)(KArgs...), dim3 grid, dim3 block,
   cfg.attrs = attr;
   cfg.numAttrs = e->use_pdl ? 1 : 0;
   e->launches++;
-  CK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+  if (le != cudaSuccess)
+    return fail("kernel launch #%lld failed (grid %u,%u,%u block %u smem %zu): %s", (long long)e->launches, grid.x, grid.y,
+                grid.z, block.x, smem, cudaGetErrorString(le));
   return 0;
 }
 
@@ -264,6 +268,7 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   if (!dims || !out) return fail("null argument");
   if (dims->head_dim != HEAD_DIM) return fail("head_dim must be %d", HEAD_DIM);
   if (dims->D % 8 || dims->F % 8 || dims->img_embed % 8) return fail("D, F, img_embed must be multiples of 8");
+  if (dims->D > RN_THREADS * RN_MAX_PER_THREAD) return fail("D > %d is not supported by the RMSNorm kernel", RN_THREADS * RN_MAX_PER_THREAD);
   if (dims->vq_nres < 1 || dims->vq_nres > 8) return fail("bad vq_nres");
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
@@ -294,6 +299,7 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
   CK(cudaFuncSetAttribute(cfg_sample_embed_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dims->img_vocab * 4));
@@ -353,6 +359,10 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "tc_stages") e->tc_stages = (int)value;
   else if (k == "vq_chunk") e->vq_chunk = (int)value;
   else if (k == "attn_splits") e->attn_splits = (int)value;
+  else if (k == "attn_impl") e->attn_impl = (int)value;
+  else if (k == "attn_ctas") e->attn_ctas = (int)value;
+  else if (k == "attn_trigger") e->attn_trigger = (int)value;
+  else if (k == "attn_attr") e->attn_attr = (int)value;
   else if (k == "gemm_splits") e->gemm_splits = (int)value;
   else if (k == "dbg_logits_ptr") e->dbg_logits = (float*)(uintptr_t)value;
   else if (k == "reset_launches") e->launches = 0;
@@ -383,10 +393,13 @@ extern "C" int pg_engine_get_counter(const pg_engine* e, const char* key, int64_
 static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t sstride, const float* w, void* xn,
                         float* y, int rows, int in_stride, int in_off, int flags, cudaStream_t st) {
   const int D = e->d.D;
+  // few rows (decode): 1024 threads so one row's split-K loads are all in flight; many rows (prefill): 256+
+  int threads = rows <= 256 ? RN_THREADS : 256;
+  while (threads * RN_MAX_PER_THREAD < D) threads *= 2;
   DISPATCH_T(e,
-             launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(256), 0, st, x, part, S, sstride, w, (bf16*)xn, y, D,
+             launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (bf16*)xn, y, D,
                     e->d.rms_eps, in_stride, in_off, flags, e->step_ctr),
-             launch(e, resid_rmsnorm_kernel<float>, dim3(rows), dim3(256), 0, st, x, part, S, sstride, w, (float*)xn, y,
+             launch(e, resid_rmsnorm_kernel<float>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (float*)xn, y,
                     D, e->d.rms_eps, in_stride, in_off, flags, e->step_ctr));
   return 0;
 }
@@ -545,13 +558,24 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     TRY(layer_weights(e, l, &w));
     if (l == 0 && !first_norm_done) TRY(k_resid_norm(e, e->x_dec, nullptr, 0, 0, w.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
     TRY(run_gemm(e, e->xn, w.wqkv, R, 3 * HD, D, e->part, e->part_bytes, &S, st));
+    if (e->bf16 && e->attn_impl == 1 && R <= AT_MAX_ROWS) {
+      const int ctas = e->attn_ctas > 0 ? e->attn_ctas : e->num_sms;
+      const int saved = e->use_pdl;
+      if (!e->attn_attr) e->use_pdl = 0;
+      int rc = launch(e, attn_decode_tma_kernel, dim3(ctas), dim3(AT_THREADS), AT_SMEM, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
+                      (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ws, e->attn_cnt,
+                      R, d.H, e->Tmax, pos_base, step_ptr, scale, 1, e->attn_trigger);
+      e->use_pdl = saved;
+      TRY(rc);
+    } else {
     DISPATCH_T(e,
-               launch(e, attn_decode_kernel<bf16>, dim3(d.H, R, nsp), dim3(128), 0, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
-                      (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ws,
-                      e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, 1),
-               launch(e, attn_decode_kernel<float>, dim3(d.H, R, nsp), dim3(128), 0, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
-                      (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), kv_start, (float*)e->attn_out, e->attn_ws,
-                      e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, 0));
+                 launch(e, attn_decode_kernel<bf16>, dim3(d.H, R, nsp), dim3(128), 0, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
+                        (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ws,
+                        e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, 1),
+                 launch(e, attn_decode_kernel<float>, dim3(d.H, R, nsp), dim3(128), 0, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
+                        (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), kv_start, (float*)e->attn_out, e->attn_ws,
+                        e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, 0));
+    }
     TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &S, st));
     TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st));
     TRY(run_gemm(e, e->xn, w.wgu, R, 2 * F, D, e->part, e->part_bytes, &S, st));
@@ -675,17 +699,27 @@ extern "C" int pg_prepare_gen_img_embeds(pg_engine* e, const int32_t* ids, int n
 }
 
 // ------------------------------------------------------------------------------ a2: the whole loop
+// step_host >= 0: the host supplies the step index (plain launches); < 0: read the device-side counter
+// (graph replays; consecutive graph launches are fully ordered, so kernels may read it before their
+// PDL wait).
 static int one_step(pg_engine* e, const int32_t* kv_start, int R, int P, int n_steps, float cfg_weight, float temperature,
                     uint64_t seed, int greedy, const int32_t* edit_region, const int32_t* gt_labels, int32_t* tokens_out,
-                    bool with_lm, cudaStream_t st) {
+                    bool with_lm, int step_host, cudaStream_t st) {
   NEED(b1, float, "head.b1");
   LayerW w0;
   TRY(layer_weights(e, 0, &w0));
   int S = 1;
   TRY(head_gemms(e, R, &S, st));
-  TRY(k_sample(e, e->part, S, (size_t)R * e->d.img_vocab, b1, R / 2, cfg_weight, temperature, seed, 0, greedy, edit_region,
-               gt_labels, 0, e->step_ctr, n_steps, tokens_out, with_lm ? e->x_dec : nullptr, w0.ln1, with_lm ? e->xn : nullptr, st));
-  if (with_lm) TRY(decode_layers(e, kv_start, R, P, e->step_ctr, true, true, P + n_steps / 2, st));
+  const bool host = step_host >= 0;
+  uint64_t per_step, stride;
+  philox_policy(e, (size_t)(R / 2) * e->d.img_vocab, &per_step, &stride);
+  TRY(k_sample(e, e->part, S, (size_t)R * e->d.img_vocab, b1, R / 2, cfg_weight, temperature, seed,
+               host ? per_step * (uint64_t)step_host : 0, greedy, edit_region, gt_labels, host ? step_host : 0,
+               host ? nullptr : e->step_ctr, n_steps, tokens_out, with_lm ? e->x_dec : nullptr, w0.ln1,
+               with_lm ? e->xn : nullptr, st));
+  if (with_lm)
+    TRY(decode_layers(e, kv_start, R, host ? P + step_host : P, host ? nullptr : e->step_ctr, true, !host,
+                      P + n_steps / 2, st));
   return 0;
 }
 
@@ -713,7 +747,7 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int64_t before = e->launches;
         int rc = one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels,
-                          tokens_out, true, st);
+                          tokens_out, true, -1, st);
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         e->graph_launches = e->launches - before;
         e->launches = before;
@@ -728,11 +762,12 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
       e->launches += e->graph_launches * (n_steps - 1);
     } else {
       for (int i = 0; i < n_steps - 1; ++i)
-        TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, true, st));
+        TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, true, i, st));
     }
   }
   // last token: head + sample only (the reference computes and drops one more embed)
-  TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, false, st));
+  TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, false,
+               n_steps - 1, st));
   CK(cudaEventRecord(e->ev_out, st));
   CK(cudaStreamWaitEvent(user, e->ev_out, 0));
   return 0;

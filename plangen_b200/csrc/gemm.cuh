@@ -90,7 +90,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       for (int i = pre; i < nkb; ++i) {
         const int s = i % num_stages;
         const uint32_t round = (uint32_t)(i / num_stages);
-        mbar_wait(&empty_bar[s], (round & 1u) ^ 1u);
+        mbar_wait(&empty_bar[s], (round & 1u) ^ 1u, 1);
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
         tma_load_2d(smem + s * Cfg::STAGE_BYTES, &map_w, &full_bar[s], (kb_begin + i) * TC_BK, n0, pol_w);
         tma_load_2d(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[s], (kb_begin + i) * TC_BK, m0, pol_x);
@@ -103,7 +103,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       for (int i = 0; i < nkb; ++i) {
         const int s = i % num_stages;
         const uint32_t round = (uint32_t)(i / num_stages);
-        mbar_wait(&full_bar[s], round & 1u);
+        mbar_wait(&full_bar[s], round & 1u, 2);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
         const uint64_t da = umma_desc_k_sw128(a_addr);
@@ -122,7 +122,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     float* out = C + (size_t)split * M * N;
     if (use_pdl) pdl_wait();
     if (nkb > 0) {
-      mbar_wait(tmem_full_bar, 0);
+      mbar_wait(tmem_full_bar, 0, 3);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < NT; c0 += 16) {

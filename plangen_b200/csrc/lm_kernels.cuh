@@ -19,9 +19,17 @@ constexpr int RN_ROUND_RESID = 1;   // keep the residual stream bf16-rounded (de
                                     // inputs_embeds there is the bf16 output of gen_aligner, so HF's residual adds are bf16)
 constexpr int RN_INC_STEP = 2;      // block 0 increments *step_ptr at the end (last kernel of a decode-step graph)
 
+// fixed-order sum over the split-K slabs; loads are issued 4 at a time so they overlap
 PG_DEVINL float reduce_splits(const float* __restrict__ part, int S, size_t split_stride, size_t idx) {
-  float a = part[idx];
-  for (int s = 1; s < S; ++s) a += part[(size_t)s * split_stride + idx];
+  const float* p = part + idx;
+  float a = p[0];
+  int s = 1;
+  for (; s + 3 < S; s += 4) {
+    const float b0 = p[(size_t)s * split_stride], b1 = p[(size_t)(s + 1) * split_stride];
+    const float b2 = p[(size_t)(s + 2) * split_stride], b3 = p[(size_t)(s + 3) * split_stride];
+    a = (((a + b0) + b1) + b2) + b3;
+  }
+  for (; s < S; ++s) a += p[(size_t)s * split_stride];
   return a;
 }
 
@@ -43,8 +51,10 @@ __global__ void embed_gather_kernel(const int32_t* __restrict__ ids, const float
 // x[tok] += rnd(sum_s part[s][tok]);  xn = w * (x * rsqrt(mean(x^2) + eps))   (HF modeling_llama.py:60-65)
 // One CTA per output row.  Input row index = blockIdx.x * in_stride + in_off (lets the final norm of
 // a prefill pick only the last position of every prompt row).
+constexpr int RN_THREADS = 1024;            // upper bound; launched with 256..1024 threads
+constexpr int RN_MAX_PER_THREAD = 8;        // D <= 8 * blockDim.x
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(RN_THREADS)
 resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int S, size_t split_stride,
                      const float* __restrict__ w, T* __restrict__ xn_out, float* __restrict__ y_out, int D,
                      float eps, int in_stride, int in_off, int flags, int* step_ptr) {
@@ -54,26 +64,38 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
   const size_t row_in = (size_t)blockIdx.x * in_stride + in_off;
   const size_t row_out = blockIdx.x;
   float* xr = x + row_in * D;
+  float v[RN_MAX_PER_THREAD];
   float ss = 0.f;
-  // pass 1: residual update + sum of squares (values are re-read from x in pass 2; row stays in L1/L2)
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float v = xr[d];
-    if (part != nullptr) {
-      const float a = Act<T>::rnd(reduce_splits(part, S, split_stride, row_in * D + d));
-      v = v + a;
-      if (flags & RN_ROUND_RESID) v = Act<T>::rnd(v);
-      xr[d] = v;
+  // residual update + sum of squares; the row stays in registers (all split loads of a thread are
+  // independent, so they are in flight together)
+#pragma unroll
+  for (int k = 0; k < RN_MAX_PER_THREAD; ++k) {
+    const int d = threadIdx.x + k * blockDim.x;
+    v[k] = 0.f;
+    if (d < D) {
+      float t = xr[d];
+      if (part != nullptr) {
+        const float a = Act<T>::rnd(reduce_splits(part, S, split_stride, row_in * D + d));
+        t = t + a;
+        if (flags & RN_ROUND_RESID) t = Act<T>::rnd(t);
+        xr[d] = t;
+      }
+      v[k] = t;
+      ss += t * t;
     }
-    ss += v * v;
   }
   ss = block_sum(ss, red);
   const float r = rsqrtf(ss / (float)D + eps);
-  for (int d = threadIdx.x; d < D; d += blockDim.x) {
-    float hn = xr[d] * r;
-    if (flags & RN_ROUND_RESID) hn = Act<T>::rnd(hn);      // `.to(input_dtype)` with a bf16 residual stream
-    const float y = w[d] * hn;
-    if (xn_out) Act<T>::st(xn_out + row_out * D + d, y);   // autocast cast at the next Linear
-    if (y_out) y_out[row_out * D + d] = y;
+#pragma unroll
+  for (int k = 0; k < RN_MAX_PER_THREAD; ++k) {
+    const int d = threadIdx.x + k * blockDim.x;
+    if (d < D) {
+      float hn = v[k] * r;
+      if (flags & RN_ROUND_RESID) hn = Act<T>::rnd(hn);      // `.to(input_dtype)` with a bf16 residual stream
+      const float y = w[d] * hn;
+      if (xn_out) Act<T>::st(xn_out + row_out * D + d, y);   // autocast cast at the next Linear
+      if (y_out) y_out[row_out * D + d] = y;
+    }
   }
   if ((flags & RN_INC_STEP) && blockIdx.x == 0 && threadIdx.x == 0) *step_ptr += 1;
 }

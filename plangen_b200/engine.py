@@ -176,7 +176,7 @@ class FastJanus:
                 self.set_option(k, v)
             kvb, wsb = C.c_size_t(), C.c_size_t()
             _lib.check(self._lib.pg_engine_query_bytes(h, C.byref(kvb), C.byref(wsb)))
-            self._kv = torch.empty(kvb.value, dtype=torch.uint8, device=self.device)
+            self._kv = torch.zeros(kvb.value, dtype=torch.uint8, device=self.device)   # TMA tiles read past `pos`: keep it finite
             self._ws = torch.empty(wsb.value, dtype=torch.uint8, device=self.device)
             _lib.check(self._lib.pg_engine_bind_buffers(h, _ptr(self._kv), kvb.value, _ptr(self._ws), wsb.value))
             tmax = self.counter("tmax")

@@ -173,3 +173,37 @@ def test_t2i_end_to_end_small():
     assert torch.isfinite(dec.float()).all()
     img = eng.generate_from_host(ids.pin_memory(), mask.pin_memory())
     assert img.dtype == torch.uint8 and img.shape == (2, 3, d.img_size, d.img_size) and not img.is_cuda
+
+
+@pytest.mark.parametrize("attn_impl", [1, 0])
+def test_bf16_long_ragged_context(attn_impl):
+    """Long, ragged prompts (many 32-token KV tiles per row, cond/uncond lengths very different) through
+    the TMA-staged decode attention (attn_impl=1) and the plain kernel (0): CFG logits vs the autocast
+    reference on the same GPU, teacher-forced."""
+    dims = O.SMALL
+    steps = 10
+    sd = O.init_state_dict(dims, seed=0, with_vq=False)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(3)
+    lens = [211, 37, 160, 1, 97]
+    cond = [torch.randint(0, dims.vocab - 2, (n,), generator=g).tolist() for n in lens]
+    neg = [torch.randint(0, dims.vocab - 2, (29,), generator=g).tolist()] * len(lens)
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
+    trace = {}
+    ref_tok, _ = O.t2i(sdc, dims, ids.cuda(), mask.cuda(), sampler=O.greedy_sampler, mode="autocast",
+                       image_token_num_per_image=steps, decode=False, trace=trace)
+    ref_logits = torch.stack(trace["logits"]).numpy()
+    eng = get_engine(dims, "bf16", with_vq=False, max_batch=8, max_prompt=256)
+    eng.set_option("attn_impl", attn_impl)
+    dbg = torch.zeros(steps, len(lens), dims.img_vocab, device="cuda")
+    eng.set_option("dbg_logits_ptr", dbg.data_ptr())
+    try:
+        emb = eng.language_model.get_input_embeddings()(ids.cuda())
+        forced = {"edit_region": torch.zeros(len(lens), steps, dtype=torch.int32)}
+        eng.sample_image(emb, len(lens), steps, mask.cuda(), 5.0, 1.0, generator=0, batch=forced, gt_labels=ref_tok,
+                         greedy=True)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("dbg_logits_ptr", 0)
+        eng.set_option("attn_impl", 1)
+    assert_close(dbg.cpu().numpy(), ref_logits, 2e-2, 2e-2, f"bf16 long-context CFG logits (attn_impl={attn_impl})")
