@@ -17,6 +17,7 @@
 #include "gemm.cuh"
 #include "lm_kernels.cuh"
 #include "attn_tma.cuh"
+#include "step_kernel.cuh"
 #include "sample.cuh"
 #include "vq_kernels.cuh"
 
@@ -69,7 +70,7 @@ struct pg_engine {
   std::unordered_map<std::string, std::pair<const void*, size_t>> tensors;
   EncodeTiledFn encode = nullptr;
   // options
-  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
+  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 1, mega_coop = 0, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
   int64_t launches = 0;
   bool finalized = false;
@@ -82,6 +83,11 @@ struct pg_engine {
   size_t part_bytes = 0;
   int *attn_cnt = nullptr, *step_ctr = nullptr;
   void *embed_table = nullptr, *align_tmp = nullptr;
+  // persistent step kernel state
+  CUtensorMap* wmaps_dev = nullptr; CUtensorMap* amaps_dev = nullptr; float* ln_dev = nullptr;
+  unsigned long long* sk_sync = nullptr;     // [0] grid barrier counter, [1] launch epoch
+  CUtensorMap amaps_host[3];
+  int amaps_R = -1;
   void *vq_act[3] = {nullptr, nullptr, nullptr};
   void* vq_col = nullptr; float* vq_part = nullptr; float *gn_partial = nullptr, *gn_stats = nullptr;
   size_t vq_act_elems = 0, vq_col_elems = 0, vq_part_elems = 0;
@@ -225,6 +231,10 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->step_ctr = (int*)c.take(256);
   e->embed_table = c.take((size_t)d.img_vocab * d.D * es);
   e->align_tmp = c.take((size_t)d.img_vocab * d.D * es);
+  e->wmaps_dev = (CUtensorMap*)c.take((size_t)d.L * 4 * sizeof(CUtensorMap));
+  e->amaps_dev = (CUtensorMap*)c.take(3 * sizeof(CUtensorMap));
+  e->ln_dev = (float*)c.take((size_t)d.L * 2 * d.D * 4);
+  e->sk_sync = (unsigned long long*)c.take(256);
   // VQ decoder scratch, per chunk of images
   const int Bc = vq_chunk_of(e);
   size_t act = 0, col = 0, part = 0;
@@ -300,6 +310,7 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+  CK(cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
   CK(cudaFuncSetAttribute(cfg_sample_embed_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dims->img_vocab * 4));
@@ -362,6 +373,8 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "attn_ctas") e->attn_ctas = (int)value;
   else if (k == "attn_trigger") e->attn_trigger = (int)value;
+  else if (k == "use_mega") e->use_mega = (int)value;
+  else if (k == "mega_coop") e->mega_coop = (int)value;
   else if (k == "attn_attr") e->attn_attr = (int)value;
   else if (k == "gemm_splits") e->gemm_splits = (int)value;
   else if (k == "dbg_logits_ptr") e->dbg_logits = (float*)(uintptr_t)value;
@@ -417,6 +430,16 @@ static int check_ready(pg_engine* e) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------ LM layer weights
+struct LayerW { const float *ln1, *ln2; const void *wqkv, *wo, *wgu, *wd; };
+static int layer_weights(pg_engine* e, int l, LayerW* w) {
+  const std::string p = "l" + std::to_string(l) + ".";
+  w->ln1 = (const float*)T_(e, p + "ln1"); w->ln2 = (const float*)T_(e, p + "ln2");
+  w->wqkv = T_(e, p + "wqkv"); w->wo = T_(e, p + "wo"); w->wgu = T_(e, p + "wgu"); w->wd = T_(e, p + "wd");
+  if (!w->ln1 || !w->ln2 || !w->wqkv || !w->wo || !w->wgu || !w->wd) return fail("layer %d weights missing", l);
+  return 0;
+}
+
 // ------------------------------------------------------------------------------ finalize
 extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
   if (!e) return fail("null engine");
@@ -449,6 +472,23 @@ extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
   if (rc) return rc;
   CK(cudaMemsetAsync(e->attn_cnt, 0, (size_t)d.max_rows * d.H * 4, st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 256, st));
+  CK(cudaMemsetAsync(e->sk_sync, 0, 256, st));
+  if (e->bf16) {
+    // per-layer weight tensor maps and norm scales for the persistent step kernel
+    std::vector<CUtensorMap> maps((size_t)d.L * 4);
+    for (int l = 0; l < d.L; ++l) {
+      LayerW w;
+      TRY(layer_weights(e, l, &w));
+      TRY(make_map_2d(e, &maps[(size_t)l * 4 + 0], w.wqkv, (uint64_t)3 * e->HD, (uint64_t)d.D, TC_BM));
+      TRY(make_map_2d(e, &maps[(size_t)l * 4 + 1], w.wo, (uint64_t)d.D, (uint64_t)e->HD, TC_BM));
+      TRY(make_map_2d(e, &maps[(size_t)l * 4 + 2], w.wgu, (uint64_t)2 * d.F, (uint64_t)d.D, TC_BM));
+      TRY(make_map_2d(e, &maps[(size_t)l * 4 + 3], w.wd, (uint64_t)d.D, (uint64_t)d.F, TC_BM));
+      CK(cudaMemcpyAsync(e->ln_dev + ((size_t)l * 2 + 0) * d.D, w.ln1, (size_t)d.D * 4, cudaMemcpyDeviceToDevice, st));
+      CK(cudaMemcpyAsync(e->ln_dev + ((size_t)l * 2 + 1) * d.D, w.ln2, (size_t)d.D * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaMemcpyAsync(e->wmaps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+  }
   CK(cudaStreamSynchronize(st));
   e->finalized = true;
   return 0;
@@ -463,15 +503,6 @@ extern "C" int pg_embed_tokens(pg_engine* e, const int32_t* ids, int n_tokens, f
 }
 
 // ------------------------------------------------------------------------------ LM layers
-struct LayerW { const float *ln1, *ln2; const void *wqkv, *wo, *wgu, *wd; };
-static int layer_weights(pg_engine* e, int l, LayerW* w) {
-  const std::string p = "l" + std::to_string(l) + ".";
-  w->ln1 = (const float*)T_(e, p + "ln1"); w->ln2 = (const float*)T_(e, p + "ln2");
-  w->wqkv = T_(e, p + "wqkv"); w->wo = T_(e, p + "wo"); w->wgu = T_(e, p + "wgu"); w->wd = T_(e, p + "wd");
-  if (!w->ln1 || !w->ln2 || !w->wqkv || !w->wo || !w->wgu || !w->wd) return fail("layer %d weights missing", l);
-  return 0;
-}
-
 static int elementwise_blocks(pg_engine* e, size_t total) {
   return (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)e->num_sms * 16));
 }
@@ -542,9 +573,99 @@ static int attn_split_count(pg_engine* e, int R, int T) {
 }
 
 // one decode step over e->x_dec (fp32 [R, D]); xn for layer 0 already in e->xn when first_norm_done
+static GemmSched sched_for(int N, int K, int G) {
+  GemmSched g;
+  g.n_tiles = (N + TC_BM - 1) / TC_BM;
+  g.num_kb = (K + TC_BK - 1) / TC_BK;
+  int best_s = 1;
+  double best_eff = -1.0;
+  for (int s = 1; s <= std::min(16, g.num_kb); ++s) {
+    const int kb_per = (g.num_kb + s - 1) / s;
+    if ((s - 1) * kb_per >= g.num_kb) continue;            // an empty split
+    const long items = (long)g.n_tiles * s;
+    const long waves = (items + G - 1) / G;
+    // time ~ waves * kb_per (longest item) ; ideal ~ n_tiles * num_kb / G
+    const double eff = ((double)g.n_tiles * g.num_kb / G) / ((double)waves * kb_per);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
+  }
+  g.splits = best_s;
+  g.kb_per_split = (g.num_kb + best_s - 1) / best_s;
+  return g;
+}
+
+static bool mega_ok(const pg_engine* e, int R) {
+  const pg_dims& d = e->d;
+  return e->bf16 && e->use_mega && e->use_tc && R <= SK_NT && R <= AT_MAX_ROWS && d.D <= SK_RNK * SK_WTHREADS &&
+         d.D % 8 == 0 && d.F % 8 == 0;
+}
+
+// activation tensor maps of the step kernel depend on the row count of the batch; refreshed outside any
+// stream capture
+static int prepare_amaps(pg_engine* e, int R, cudaStream_t st) {
+  const pg_dims& d = e->d;
+  if (e->amaps_R == R) return 0;
+  TRY(make_map_2d(e, &e->amaps_host[0], e->xn, (uint64_t)R, (uint64_t)d.D, SK_NT));
+  TRY(make_map_2d(e, &e->amaps_host[1], e->attn_out, (uint64_t)R, (uint64_t)e->HD, SK_NT));
+  TRY(make_map_2d(e, &e->amaps_host[2], e->hbuf, (uint64_t)R, (uint64_t)d.F, SK_NT));
+  CK(cudaMemcpyAsync(e->amaps_dev, e->amaps_host, sizeof(e->amaps_host), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  e->amaps_R = R;
+  return 0;
+}
+
+// all layers of one decode step in ONE persistent kernel (step_kernel.cuh); xn of layer 0 must be ready
+static int decode_layers_mega(pg_engine* e, const int32_t* kv_start, int R, int pos_base, int* step_ptr, bool inc_step,
+                              cudaStream_t st) {
+  const pg_dims& d = e->d;
+  NEED(cosT, float, "rope_cos");
+  NEED(sinT, float, "rope_sin");
+  NEED(normw, float, "norm");
+  const int G = e->num_sms;
+  StepParams p = {};
+  p.R = R; p.H = d.H; p.D = d.D; p.HD = e->HD; p.F = d.F; p.L = d.L; p.Tmax = e->Tmax;
+  p.eps = d.rms_eps; p.scale = 1.0f / sqrtf((float)HEAD_DIM);
+  p.wmaps = e->wmaps_dev; p.amaps = e->amaps_dev; p.ln = e->ln_dev; p.norm_w = normw;
+  p.x = e->x_dec; p.xn = (bf16*)e->xn; p.attn_out = (bf16*)e->attn_out; p.h = (bf16*)e->hbuf;
+  p.hidden_t = (bf16*)e->hidden_t; p.hidden_f = e->hidden_f;
+  p.g_qkv = sched_for(3 * e->HD, d.D, G); p.g_o = sched_for(d.D, e->HD, G);
+  p.g_gu = sched_for(2 * d.F, d.D, G); p.g_d = sched_for(d.D, d.F, G);
+  size_t off = 0;
+  auto carve = [&](size_t floats) { float* q = e->part + off; off += (floats + 255) / 256 * 256; return q; };
+  p.part_qkv = carve((size_t)p.g_qkv.splits * R * 3 * e->HD);
+  p.part_o = carve((size_t)p.g_o.splits * R * d.D);
+  p.part_gu = carve((size_t)p.g_gu.splits * R * 2 * d.F);
+  p.part_d = carve((size_t)p.g_d.splits * R * d.D);
+  if (off * 4 > e->part_bytes) return fail("internal: split-K scratch too small for the step kernel");
+  p.kv = (bf16*)e->kv; p.kv_start = kv_start; p.cosT = cosT; p.sinT = sinT;
+  p.attn_ws = e->attn_ws; p.attn_cnt = e->attn_cnt;
+  p.grid_bar = e->sk_sync; p.epoch = e->sk_sync + 1;
+  p.pos_base = pos_base; p.step_ptr = step_ptr; p.inc_step = inc_step ? 1 : 0;
+  if (e->amaps_R != R) return fail("internal: activation tensor maps were not prepared for R=%d", R);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(G); cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = SK_SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = e->mega_coop ? 1 : 0;
+  e->launches++;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, decode_step_kernel, p);
+  if (le != cudaSuccess) return fail("decode_step_kernel launch failed: %s", cudaGetErrorString(le));
+  return 0;
+}
+
 static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_base, const int* step_ptr,
                          bool first_norm_done, bool inc_step, int T_hint, cudaStream_t st) {
   const pg_dims& d = e->d;
+  if (mega_ok(e, R)) {
+    TRY(prepare_amaps(e, R, st));          // no-op when already prepared (must be, inside a capture)
+    if (!first_norm_done) {
+      LayerW w0;
+      TRY(layer_weights(e, 0, &w0));
+      TRY(k_resid_norm(e, e->x_dec, nullptr, 0, 0, w0.ln1, e->xn, nullptr, R, 1, 0, RN_ROUND_RESID, st));
+    }
+    return decode_layers_mega(e, kv_start, R, pos_base, const_cast<int*>(step_ptr), inc_step, st);
+  }
   NEED(cosT, float, "rope_cos");
   NEED(sinT, float, "rope_sin");
   NEED(normw, float, "norm");
@@ -734,13 +855,14 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
   CK(cudaEventRecord(e->ev_in, user));
   CK(cudaStreamWaitEvent(st, e->ev_in, 0));
   TRY(pg_prefill(e, x_prompt, kv_start, R, P, nullptr, 0, (void*)st));
+  if (mega_ok(e, R)) TRY(prepare_amaps(e, R, st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 4, st));
   if (n_steps > 1) {
     if (e->use_graph) {
       char key[512];
-      snprintf(key, sizeof(key), "%d/%d/%d/%a/%a/%llu/%d/%p/%p/%p/%p/%d/%d/%d", R, P, n_steps, cfg_weight, temperature,
+      snprintf(key, sizeof(key), "%d/%d/%d/%a/%a/%llu/%d/%p/%p/%p/%p/%d/%d/%d/%d", R, P, n_steps, cfg_weight, temperature,
                (unsigned long long)seed, greedy, (const void*)kv_start, (const void*)edit_region, (const void*)gt_labels,
-               (void*)tokens_out, e->use_pdl, e->use_tc, e->bf16 ? 1 : 0);
+               (void*)tokens_out, e->use_pdl, e->use_tc, e->bf16 ? 1 : 0, e->use_mega);
       if (!e->graph_exec || e->graph_key != key) {
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
         cudaGraph_t graph = nullptr;
@@ -967,7 +1089,24 @@ extern "C" int pg_vq_decode_code(pg_engine* e, const int32_t* codes, int B, int 
   return 0;
 }
 
-// ------------------------------------------------------------------------------ unit-test hook
+// ------------------------------------------------------------------------------ debug / test hooks
+extern "C" int pg_debug_copy(pg_engine* e, const char* name, void* dst_dev, size_t nbytes, void* stream) {
+  if (!e || !name || !dst_dev) return fail("null argument");
+  const std::string k(name);
+  const void* src = nullptr;
+  if (k == "x_dec") src = e->x_dec;
+  else if (k == "xn") src = e->xn;
+  else if (k == "attn_out") src = e->attn_out;
+  else if (k == "hbuf") src = e->hbuf;
+  else if (k == "hidden_f") src = e->hidden_f;
+  else if (k == "part") src = e->part;
+  else if (k == "qbuf") src = e->qbuf;
+  else return fail("unknown debug buffer '%s'", name);
+  CK(cudaMemcpyAsync(dst_dev, src, nbytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+
 extern "C" int pg_test_gemm(pg_engine* e, int impl, int is_bf16, const void* X, const void* W, int M, int N, int K,
                             int splits, float* C, void* stream) {
   if (!e) return fail("null engine");
