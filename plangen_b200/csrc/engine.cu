@@ -72,6 +72,7 @@ struct pg_engine {
   // options
   int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 1, mega_coop = 0, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
+  unsigned long long* sk_prof = nullptr;
   int64_t launches = 0;
   bool finalized = false;
   // bound buffers
@@ -378,6 +379,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_attr") e->attn_attr = (int)value;
   else if (k == "gemm_splits") e->gemm_splits = (int)value;
   else if (k == "dbg_logits_ptr") e->dbg_logits = (float*)(uintptr_t)value;
+  else if (k == "sk_prof_ptr") e->sk_prof = (unsigned long long*)(uintptr_t)value;
   else if (k == "reset_launches") e->launches = 0;
   else return fail("unknown option '%s'", key);
   if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
@@ -640,6 +642,7 @@ static int decode_layers_mega(pg_engine* e, const int32_t* kv_start, int R, int 
   p.attn_ws = e->attn_ws; p.attn_cnt = e->attn_cnt;
   p.grid_bar = e->sk_sync; p.epoch = e->sk_sync + 1;
   p.pos_base = pos_base; p.step_ptr = step_ptr; p.inc_step = inc_step ? 1 : 0;
+  p.prof = e->sk_prof;
   if (e->amaps_R != R) return fail("internal: activation tensor maps were not prepared for R=%d", R);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(G); cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = SK_SMEM; cfg.stream = st;

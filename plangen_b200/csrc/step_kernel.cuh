@@ -66,6 +66,7 @@ struct StepParams {
   int* step_ptr;                 // nullable: pos = pos_base + *step_ptr
   int inc_step;
   GemmSched g_qkv, g_o, g_gu, g_d;
+  unsigned long long* prof;      // nullable: [gridDim][L*8+1] phase-end timestamps (ns) of each CTA's worker thread 0
 };
 
 PG_DEVINL unsigned long long ld_acquire_u64(const unsigned long long* p) {
@@ -290,11 +291,17 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
     // =========================================================== workers (16 warps)
     int ja = 0, ji = 0;                                        // mirrors of the A-ring / accumulator counters
     const float LOG2E = 1.4426950408889634f;
+    int prof_i = 0;
+    unsigned long long* prof = p.prof ? p.prof + (size_t)c * (SK_PHASES * L + 1) : nullptr;
+    if (prof && tid == 0) prof[prof_i++] = global_timer_ns();
     auto phase_done = [&]() {                                  // all of this CTA's global writes of the phase are done
       fence_proxy_async_global();                              // generic-proxy stores -> later TMA (async-proxy) reads
       __threadfence();
       named_bar_sync(1, SK_WTHREADS);
-      if (tid == 0) atomicAdd(p.grid_bar, 1ull);
+      if (tid == 0) {
+        atomicAdd(p.grid_bar, 1ull);
+        if (prof) prof[prof_i++] = global_timer_ns();
+      }
     };
     auto phase_wait = [&](int phase_index) {                   // previous phase complete on every CTA
       if (tid == 0) grid_wait(p.grid_bar, bar_target(phase_index - 1), 32);
