@@ -70,7 +70,7 @@ struct pg_engine {
   std::unordered_map<std::string, std::pair<const void*, size_t>> tensors;
   EncodeTiledFn encode = nullptr;
   // options
-  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 1, mega_coop = 0, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
+  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
   unsigned long long* sk_prof = nullptr;
   int64_t launches = 0;
@@ -144,6 +144,26 @@ static int make_map_2d(pg_engine* e, CUtensorMap* m, const void* ptr, uint64_t r
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (%d) rows=%llu K=%llu ptr=%p", (int)r,
                                      (unsigned long long)rows, (unsigned long long)K, ptr);
   return 0;
+}
+
+static GemmSched sched_for(int N, int K, int G) {
+  GemmSched g;
+  g.n_tiles = (N + TC_BM - 1) / TC_BM;
+  g.num_kb = (K + TC_BK - 1) / TC_BK;
+  int best_s = 1;
+  double best_eff = -1.0;
+  for (int s = 1; s <= std::min(16, g.num_kb); ++s) {
+    const int kb_per = (g.num_kb + s - 1) / s;
+    if ((s - 1) * kb_per >= g.num_kb) continue;            // an empty split
+    const long items = (long)g.n_tiles * s;
+    const long waves = (items + G - 1) / G;
+    // time ~ waves * kb_per (longest item) ; ideal ~ n_tiles * num_kb / G
+    const double eff = ((double)g.n_tiles * g.num_kb / G) / ((double)waves * kb_per);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
+  }
+  g.splits = best_s;
+  g.kb_per_split = (g.num_kb + best_s - 1) / best_s;
+  return g;
 }
 
 template <int NT>
@@ -575,26 +595,6 @@ static int attn_split_count(pg_engine* e, int R, int T) {
 }
 
 // one decode step over e->x_dec (fp32 [R, D]); xn for layer 0 already in e->xn when first_norm_done
-static GemmSched sched_for(int N, int K, int G) {
-  GemmSched g;
-  g.n_tiles = (N + TC_BM - 1) / TC_BM;
-  g.num_kb = (K + TC_BK - 1) / TC_BK;
-  int best_s = 1;
-  double best_eff = -1.0;
-  for (int s = 1; s <= std::min(16, g.num_kb); ++s) {
-    const int kb_per = (g.num_kb + s - 1) / s;
-    if ((s - 1) * kb_per >= g.num_kb) continue;            // an empty split
-    const long items = (long)g.n_tiles * s;
-    const long waves = (items + G - 1) / G;
-    // time ~ waves * kb_per (longest item) ; ideal ~ n_tiles * num_kb / G
-    const double eff = ((double)g.n_tiles * g.num_kb / G) / ((double)waves * kb_per);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
-  }
-  g.splits = best_s;
-  g.kb_per_split = (g.num_kb + best_s - 1) / best_s;
-  return g;
-}
-
 static bool mega_ok(const pg_engine* e, int R) {
   const pg_dims& d = e->d;
   return e->bf16 && e->use_mega && e->use_tc && R <= SK_NT && R <= AT_MAX_ROWS && d.D <= SK_RNK * SK_WTHREADS &&

@@ -209,5 +209,5 @@ def test_bf16_long_ragged_context(path):
     finally:
         eng.set_option("dbg_logits_ptr", 0)
         eng.set_option("attn_impl", 1)
-        eng.set_option("use_mega", 1)
+        eng.set_option("use_mega", 0)
     assert_close(dbg.cpu().numpy(), ref_logits, 2e-2, 2e-2, f"bf16 long-context CFG logits ({path})")

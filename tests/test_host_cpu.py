@@ -1,0 +1,120 @@
+"""CPU tests of the host-side mirror: C-ABI exports, mask encoding, prompt layout, DP sharding (gloo)."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from oracle import janus_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from plangen_b200 import _lib, build
+    lib = build.build()
+    cdll = ctypes.CDLL(lib)
+    header = open(os.path.join(ROOT, "include", "plangen_b200.h")).read()
+    declared = set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(cdll, name), f"{name} declared in include/plangen_b200.h but not exported"
+    assert declared == set(_lib.EXPORTS), "ctypes table and header disagree"
+    assert cdll.pg_abi_version() == 1
+
+
+def test_engine_fails_loudly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from plangen_b200.config import Dims
+    from plangen_b200.engine import FastJanus
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FastJanus({}, Dims.from_any(O.TINY))
+    # and the C-ABI itself refuses too
+    from plangen_b200 import _lib
+    lib = _lib.load()
+    pd = _lib.PgDims(); pd.head_dim = 128; pd.vq_nres = 1
+    h = ctypes.c_void_p()
+    assert lib.pg_engine_create(ctypes.byref(pd), 0, ctypes.byref(h)) != 0
+    assert lib.pg_last_error()
+
+
+def test_kv_start_from_mask_contract():
+    from plangen_b200.engine import kv_start_from_mask
+    m = torch.tensor([[0, 0, 1, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1, 1], [0, 0, 0, 0, 1, 1, 1]], dtype=torch.int32)
+    assert kv_start_from_mask(m, 4).tolist() == [2, 0, 4]          # row 2: empty prompt
+    with pytest.raises(ValueError):
+        kv_start_from_mask(torch.tensor([[1, 0, 1, 1, 1]]), 3)      # hole: not LEFT padded
+    with pytest.raises(ValueError):
+        kv_start_from_mask(torch.tensor([[0, 1, 1, 1, 0]]), 3)      # image part must be all ones
+
+
+def test_collate_mirror_matches_oracle():
+    from plangen_b200 import synthetic
+    from plangen_b200.config import Dims
+    d = Dims.from_any(O.SMALL)
+    cond, neg = synthetic.layoutsam_prompts(d, 5, seed=3, lo=9, hi=40, neg_len=11)
+    ids, mask = synthetic.collate_cfg_batch(cond, neg, d.pad_id, d.n_img_tokens)
+    ids2, mask2 = O.t2i_infer_collate_batch(cond, neg, d.pad_id, d.n_img_tokens)
+    assert torch.equal(ids, ids2) and torch.equal(mask, mask2)
+    assert all(d.pad_id not in c for c in cond)
+    # ragged + empty rows
+    ids, mask = synthetic.collate_cfg_batch([[1, 2, 3], []], [[4], [5, 6]], d.pad_id, 4)
+    assert ids.tolist() == [[1, 2, 3], [d.pad_id, d.pad_id, 4], [d.pad_id] * 3, [d.pad_id, 5, 6]]
+    assert mask[2].tolist() == [0, 0, 0, 1, 1, 1, 1]
+
+
+def test_synthetic_state_dict_names_match_oracle_specs():
+    from plangen_b200 import synthetic
+    from plangen_b200.config import Dims
+    for d in (O.TINY, O.SMALL):
+        a = [(n, s) for n, s, _ in synthetic.state_dict_names(Dims.from_any(d))]
+        b = [(n, s) for n, s, _ in O.tensor_specs(d)]
+        assert sorted(a) == sorted(b)
+
+
+def test_weight_bytes_per_step_matches_baseline_md():
+    """1 275 207 680 weight elements per decode step at 1.3B incl. gen_aligner (4 214 784),
+    which the engine replaces by a table gather."""
+    from plangen_b200.config import JANUS_1P3B as d
+    HD = d.H * d.head_dim
+    el = d.L * (3 * HD * d.D + d.D * HD + 3 * d.D * d.F + 2 * d.D) + d.D + (d.D * d.img_embed + d.img_embed + d.img_vocab * d.img_embed + d.img_vocab)
+    assert el == 1275207680 - 4214784
+
+
+def test_shard_batches_round_robin():
+    from plangen_b200 import dp
+    per_rank = [dp.shard_batches(10, r, 4) for r in range(4)]
+    assert per_rank == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
+    assert dp.interleave_results(per_rank, 4) == list(range(10))
+
+
+_WORKER = r"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from plangen_b200 import dp
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+mine = dp.shard_batches(5, rank, world)
+local = torch.full((2, 3, 4, 4), rank, dtype=torch.uint8)
+allimg = dp.gather_images(local, world)
+assert allimg.shape == (2 * world, 3, 4, 4) and allimg[2 * rank].eq(rank).all() and allimg[2 * (1 - rank)].eq(1 - rank).all()
+t = dp.max_over_ranks(1.0 + rank, torch.device("cpu"))
+assert t == float(world)
+sys.stdout.write("rank %d batches %s\n" % (rank, mine)); sys.stdout.flush()
+dist.destroy_process_group()
+"""
+
+
+def test_dp_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), ROOT],
+                       capture_output=True, text=True, env=env, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "rank 0 batches [0, 2, 4]" in r.stdout and "rank 1 batches [1, 3]" in r.stdout, r.stdout
