@@ -928,12 +928,13 @@ static int vq_im2col(VqCtx& c, const void* in, void* col, int Hi, int Wi, int C,
     if (!gamma || !beta) return fail("missing GroupNorm tensors for %s", gn_name.c_str());
   }
   if (C % 4) return fail("im2col needs C %% 4 == 0");
-  const size_t total = (size_t)c.Bc * Hi * up * Wi * up * ks * ks * (C / 4);
-  if (total * 4 > e->vq_col_elems) return fail("internal: im2col scratch too small");
+  const size_t n_pix = (size_t)c.Bc * Hi * up * Wi * up;
+  if (n_pix * ks * ks * C > e->vq_col_elems) return fail("internal: im2col scratch too small");
   const float* stats = gn ? e->gn_stats : nullptr;
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n_pix + 7) / 8, (size_t)e->num_sms * 32));
   DISPATCH_T(e,
-             launch(e, im2col_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, c.st, (const bf16*)in, (bf16*)col, stats, gamma, beta, Hi, Wi, C, ks, up, swish ? 1 : 0, total),
-             launch(e, im2col_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, c.st, (const float*)in, (float*)col, stats, gamma, beta, Hi, Wi, C, ks, up, swish ? 1 : 0, total));
+             launch(e, im2col_kernel<bf16>, dim3(blocks), dim3(256), 0, c.st, (const bf16*)in, (bf16*)col, stats, gamma, beta, Hi, Wi, C, ks, up, swish ? 1 : 0, n_pix),
+             launch(e, im2col_kernel<float>, dim3(blocks), dim3(256), 0, c.st, (const float*)in, (float*)col, stats, gamma, beta, Hi, Wi, C, ks, up, swish ? 1 : 0, n_pix));
   return 0;
 }
 

@@ -99,43 +99,68 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __r
 // ----------------------------------------------------- im2col (+ GroupNorm + swish + upsample x2)
 // in:  [B][Hi][Wi][C] (T), out col: [B*Ho*Wo][ks*ks*C] (T), Ho = Hi * up, pad = ks / 2.
 // stats == nullptr -> no normalisation; swish only applies together with stats.
+// One warp per output pixel; a lane owns 4 consecutive channels of every 128-channel slab, so each tap is
+// one coalesced 256-byte read and one coalesced 256-byte write per warp and the GroupNorm scale/shift of
+// the lane's channels are loaded once per pixel.
+template <typename T> struct Ch4;
+template <> struct Ch4<float> {
+  static PG_DEVINL void ld(const float* p, float (&v)[4]) { const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+  static PG_DEVINL void st(float* p, const float (&v)[4]) { *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]); }
+};
+template <> struct Ch4<bf16> {
+  static PG_DEVINL void ld(const bf16* p, float (&v)[4]) { const uint2 t = *reinterpret_cast<const uint2*>(p); v[0] = bf16lo(t.x); v[1] = bf16hi(t.x); v[2] = bf16lo(t.y); v[3] = bf16hi(t.y); }
+  static PG_DEVINL void st(bf16* p, const float (&v)[4]) {
+    const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 t; t.x = *reinterpret_cast<const uint32_t*>(&a); t.y = *reinterpret_cast<const uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = t;
+  }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const T* __restrict__ in, T* __restrict__ col, const float* __restrict__ stats,
               const float* __restrict__ gamma, const float* __restrict__ beta, int Hi, int Wi, int C, int ks, int up,
-              int swish, size_t total /* B*Ho*Wo*ks*ks*(C/4) */) {
+              int swish, size_t n_pix /* B*Ho*Wo */) {
   pdl_launch_dependents();
   pdl_wait();
-  const int Ho = Hi * up, Wo = Wi * up, C4 = C / 4, pad = ks / 2, cpg = C / 32;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i % C4);
-    size_t t = i / C4;
-    const int tap = (int)(t % (ks * ks));
-    t /= (ks * ks);
-    const int ox = (int)(t % Wo);
-    t /= Wo;
-    const int oy = (int)(t % Ho);
-    const int b = (int)(t / Ho);
-    const int iy = oy + tap / ks - pad, ix = ox + tap % ks - pad;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (iy >= 0 && iy < Ho && ix >= 0 && ix < Wo) {
-      const T* src = in + (((size_t)b * Hi + iy / up) * Wi + ix / up) * C + c4 * 4;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = Act<T>::ld(src + j);
+  const int lane = threadIdx.x & 31;
+  const int Ho = Hi * up, Wo = Wi * up, pad = ks / 2, cpg = C / 32, taps = ks * ks;
+  const size_t warp_id = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t pix = warp_id; pix < n_pix; pix += n_warps) {
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int b = (int)(pix / ((size_t)Wo * Ho));
+    T* dst_row = col + pix * (size_t)taps * C;
+    for (int c0 = lane * 4; c0 < C; c0 += 128) {
+      float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
       if (stats) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const int c = c4 * 4 + j;
+          const int c = c0 + j;
           const float mean = stats[((size_t)b * 32 + c / cpg) * 2], rstd = stats[((size_t)b * 32 + c / cpg) * 2 + 1];
-          float y = (v[j] - mean) * rstd * gamma[c] + beta[c];      // group_norm runs in fp32 under autocast
-          if (swish) y = y / (1.0f + expf(-y));                     // x * sigmoid(x)
-          v[j] = y;
+          sc[j] = rstd * gamma[c];                        // y = (x - mean) * rstd * gamma + beta  (fp32, as group_norm under autocast)
+          sh[j] = beta[c] - mean * sc[j];
         }
       }
-    }
-    T* dst = col + i * 4;
+      for (int tap = 0; tap < taps; ++tap) {
+        const int iy = oy + tap / ks - pad, ix = ox + tap % ks - pad;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (iy >= 0 && iy < Ho && ix >= 0 && ix < Wo) {
+          Ch4<T>::ld(in + (((size_t)b * Hi + iy / up) * Wi + ix / up) * C + c0, v);
+          if (stats) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) Act<T>::st(dst + j, v[j]);
+            for (int j = 0; j < 4; ++j) {
+              // same operation order as the reference: ((x - mean) * rstd) * gamma + beta
+              float y = fmaf(v[j], sc[j], sh[j]);
+              if (swish) y = y / (1.0f + expf(-y));       // x * sigmoid(x)
+              v[j] = y;
+            }
+          }
+        }
+        Ch4<T>::st(dst_row + (size_t)tap * C + c0, v);
+      }
+    }
   }
 }
 
