@@ -503,6 +503,8 @@ def sample_image(sd, d: JanusDims, inputs_embeds: torch.Tensor, num_gen: int,
                           past_key_values=outputs.past_key_values if i != 0 else None)
             hidden_states = outputs.last_hidden_state
             logits = gen_head(sd, hidden_states[:, -1, :])
+            if trace is not None:
+                trace.setdefault("raw_logits", []).append(logits.float().cpu())
             logit_cond = logits[0::2, :]
             logit_uncond = logits[1::2, :]
             logits = logit_uncond + cfg_weight * (logit_cond - logit_uncond)

@@ -64,11 +64,14 @@ def load(build_if_missing: bool = True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    if build_if_missing:
-        _build.build()
-    if not os.path.exists(_build.LIB):
-        raise PgError(f"{_build.LIB} is missing: build it with `python -m plangen_b200.build`; there is no fallback path")
-    lib = C.CDLL(_build.LIB)
+    path = os.environ.get("PG_LIB_PATH")          # A/B testing of kernel variants
+    if not path:
+        if build_if_missing:
+            _build.build()
+        path = _build.LIB
+    if not os.path.exists(path):
+        raise PgError(f"{path} is missing: build it with `python -m plangen_b200.build`; there is no fallback path")
+    lib = C.CDLL(path)
     for name, (res, args) in EXPORTS.items():
         fn = getattr(lib, name)      # AttributeError if the symbol is not exported
         fn.restype = res

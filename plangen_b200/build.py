@@ -30,6 +30,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
            "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+    cmd[1:1] = os.environ.get("PG_NVCC_FLAGS", "").split()
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -30,7 +30,10 @@ constexpr int AT_GW = 4;                                // warps per group
 constexpr int AT_GT = AT_GW * 32;                       // threads per group
 constexpr int AT_NW = AT_NG * AT_GW;
 constexpr int AT_TW = AT_TILE / AT_GW;                  // tokens per warp per tile (8)
-constexpr int AT_SPG = 3;                               // ring stages per group
+#ifndef PG_AT_SPG
+#define PG_AT_SPG 3
+#endif
+constexpr int AT_SPG = PG_AT_SPG;                      // ring stages per group
 constexpr int AT_STAGES = AT_NG * AT_SPG;
 constexpr int AT_THREADS = 32 * (AT_NW + AT_NG);      // 16 consumer warps + one producer warp per group
 constexpr int AT_MAX_ROWS = 256;
@@ -335,7 +338,7 @@ attn_decode_tma_kernel(const float* __restrict__ part, int S, size_t split_strid
                        const float* __restrict__ sinT, bf16* __restrict__ kcache, bf16* __restrict__ vcache,
                        const int32_t* __restrict__ kv_start, bf16* __restrict__ out, float* __restrict__ ws_part,
                        int* __restrict__ ws_count, int R, int H, int Tmax, int pos_base,
-                       const int* __restrict__ step_ptr, float scale, int bf16_trig, int early_trigger) {
+                       const int* __restrict__ step_ptr, float scale, int bf16_trig, int early_trigger, Prof prof) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[AT_STAGES], empty_bar[AT_STAGES];
@@ -345,6 +348,7 @@ attn_decode_tma_kernel(const float* __restrict__ part, int S, size_t split_strid
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (early_trigger & 1) pdl_launch_dependents();
+  prof_begin(prof);
   // The step counter is only written by the last kernel of a decode step; graph replays are fully ordered,
   // and with plain launches the host passes the position explicitly (step_ptr == nullptr), so reading it
   // before the PDL wait is safe.
@@ -386,6 +390,7 @@ attn_decode_tma_kernel(const float* __restrict__ part, int S, size_t split_strid
   attn_group_stream<AT_SPG>(tg, gb, ge, cut, row_units, R, H, Tmax, pos, part, S, split_stride, cosT, sinT, kcache,
                             vcache, kv_start, out, ws_part, ws_count, scale, bf16_trig != 0, ring, 2 * AT_TILE_BYTES,
                             stage_tab + g * AT_SPG, full_bar, empty_bar, kc, gsm[g], c * AT_NG + g, 1 + g, early_trigger & 2);
+  prof_end(prof);
 }
 
 }  // namespace pg

@@ -119,6 +119,15 @@ PG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0, int info =
   }
 }
 
+// Optional in-situ timeline: every CTA stamps kernel begin (min) / end (max) into buf[2*slot], buf[2*slot+1]
+struct Prof { unsigned long long* buf; int slot; };
+PG_DEVINL void prof_begin(const Prof& p) {
+  if (p.buf && threadIdx.x == 0) atomicMin(&p.buf[2 * p.slot], (unsigned long long)global_timer_ns());
+}
+PG_DEVINL void prof_end(const Prof& p) {
+  if (p.buf && threadIdx.x == 0) atomicMax(&p.buf[2 * p.slot + 1], (unsigned long long)global_timer_ns());
+}
+
 // generic-proxy writes (st.shared) made visible to the async proxy (TMA / tcgen05)
 PG_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -158,6 +167,14 @@ PG_DEVINL void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
       " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(dst)),
       "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
+
+// contiguous global -> shared bulk copy (TMA, no tensor map), completion on an mbarrier
+PG_DEVINL void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
       : "memory");
 }
 

@@ -73,6 +73,9 @@ struct pg_engine {
   int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
   unsigned long long* sk_prof = nullptr;
+  unsigned long long* prof_buf = nullptr;   // per-kernel timeline of ONE decode step (plain-launch mode)
+  int prof_step = -1, prof_slot = 0;
+  bool prof_active = false;
   int64_t launches = 0;
   bool finalized = false;
   // bound buffers
@@ -112,6 +115,13 @@ static const void* T_(pg_engine* e, const std::string& name, size_t* nbytes = nu
 #define NEED(var, type, name)                                        \
   const type* var = (const type*)T_(e, (name));                      \
   if (!var) return fail("tensor '%s' was not registered", std::string(name).c_str());
+
+static Prof next_prof(pg_engine* e) {
+  Prof p;
+  p.buf = (e->prof_active && e->prof_buf) ? e->prof_buf : nullptr;
+  p.slot = p.buf ? e->prof_slot++ : 0;
+  return p;
+}
 
 // ------------------------------------------------------------------------------ launch helper
 template <typename... KArgs, typename... Args>
@@ -168,7 +178,7 @@ static GemmSched sched_for(int N, int K, int G) {
 
 template <int NT>
 static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx, float* C, int M, int N, int K,
-                     int splits, int kb_per_split, bool w_const, cudaStream_t st) {
+                     int splits, int kb_per_split, bool w_const, const void* w_tiled, cudaStream_t st) {
   using Cfg = TcCfg<NT>;
   int stages = e->tc_stages > 0 ? e->tc_stages : (200 * 1024) / Cfg::STAGE_BYTES;
   stages = std::max(2, std::min(stages, 12));
@@ -176,12 +186,13 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   const size_t smem = Cfg::smem_bytes(stages);
   dim3 grid((N + TC_BM - 1) / TC_BM, (M + NT - 1) / NT, splits);
   return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
-                e->use_pdl ? (w_const ? 3 : 1) : 0);
+                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e));
 }
 
 // C[splits][M][N] fp32 = X[M][K] * W[N][K]^T.  Returns the number of splits used through *splits_out.
 static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, int K, float* C, size_t c_bytes,
-                    int* splits_out, cudaStream_t st, int force_impl = -1, int force_splits = 0, bool w_const = true) {
+                    int* splits_out, cudaStream_t st, int force_impl = -1, int force_splits = 0, bool w_const = true,
+                    const void* w_tiled = nullptr) {
   const bool tc = e->bf16 && ((force_impl == 1) || (force_impl < 0 && e->use_tc)) && (K % 8 == 0) &&
                   (((uintptr_t)X & 15) == 0) && (((uintptr_t)W & 15) == 0);
   if (force_impl == 1 && !tc) return fail("tcgen05 GEMM needs bf16 operands, K %% 8 == 0 and 16-byte aligned pointers");
@@ -200,11 +211,11 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     TRY(make_map_2d(e, &mw, W, (uint64_t)N, (uint64_t)K, TC_BM));
     TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
     switch (NT) {
-      case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
-      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
-      case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
-      case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
-      default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, st)); break;
+      case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
+      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
+      case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
+      case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
+      default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
     }
   } else {
     if (K % 4 != 0) return fail("SIMT GEMM needs K %% 4 == 0 (K=%d)", K);
@@ -400,6 +411,8 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "gemm_splits") e->gemm_splits = (int)value;
   else if (k == "dbg_logits_ptr") e->dbg_logits = (float*)(uintptr_t)value;
   else if (k == "sk_prof_ptr") e->sk_prof = (unsigned long long*)(uintptr_t)value;
+  else if (k == "prof_ptr") e->prof_buf = (unsigned long long*)(uintptr_t)value;
+  else if (k == "prof_step") e->prof_step = (int)value;
   else if (k == "reset_launches") e->launches = 0;
   else return fail("unknown option '%s'", key);
   if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
@@ -433,9 +446,9 @@ static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t
   while (threads * RN_MAX_PER_THREAD < D) threads *= 2;
   DISPATCH_T(e,
              launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (bf16*)xn, y, D,
-                    e->d.rms_eps, in_stride, in_off, flags, e->step_ctr),
+                    e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e)),
              launch(e, resid_rmsnorm_kernel<float>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (float*)xn, y,
-                    D, e->d.rms_eps, in_stride, in_off, flags, e->step_ctr));
+                    D, e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e)));
   return 0;
 }
 
@@ -565,8 +578,8 @@ extern "C" int pg_prefill(pg_engine* e, float* x, const int32_t* kv_start, int R
     {
       const size_t total = (size_t)tok * F;
       DISPATCH_T(e,
-                 launch(e, swiglu_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (bf16*)e->hbuf, F, total),
-                 launch(e, swiglu_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (float*)e->hbuf, F, total));
+                 launch(e, swiglu_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (bf16*)e->hbuf, F, total, next_prof(e)),
+                 launch(e, swiglu_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (float*)e->hbuf, F, total, next_prof(e)));
     }
     TRY(run_gemm(e, e->hbuf, w.wd, tok, D, F, e->part, e->part_bytes, &S, st));
     if (l + 1 < d.L) {
@@ -688,7 +701,7 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
       if (!e->attn_attr) e->use_pdl = 0;
       int rc = launch(e, attn_decode_tma_kernel, dim3(ctas), dim3(AT_THREADS), AT_SMEM, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
                       (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ws, e->attn_cnt,
-                      R, d.H, e->Tmax, pos_base, step_ptr, scale, 1, e->attn_trigger);
+                      R, d.H, e->Tmax, pos_base, step_ptr, scale, 1, e->attn_trigger, next_prof(e));
       e->use_pdl = saved;
       TRY(rc);
     } else {
@@ -706,8 +719,8 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     {
       const size_t total = (size_t)R * F;
       DISPATCH_T(e,
-                 launch(e, swiglu_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)R * 2 * F, (bf16*)e->hbuf, F, total),
-                 launch(e, swiglu_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)R * 2 * F, (float*)e->hbuf, F, total));
+                 launch(e, swiglu_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)R * 2 * F, (bf16*)e->hbuf, F, total, next_prof(e)),
+                 launch(e, swiglu_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)R * 2 * F, (float*)e->hbuf, F, total, next_prof(e)));
     }
     TRY(run_gemm(e, e->hbuf, w.wd, R, D, F, e->part, e->part_bytes, &S, st));
     if (l + 1 < d.L) {
@@ -886,8 +899,13 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
       for (int i = 0; i < n_steps - 1; ++i) CK(cudaGraphLaunch(e->graph_exec, st));
       e->launches += e->graph_launches * (n_steps - 1);
     } else {
-      for (int i = 0; i < n_steps - 1; ++i)
-        TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, true, i, st));
+      for (int i = 0; i < n_steps - 1; ++i) {
+        e->prof_active = (i == e->prof_step);
+        e->prof_slot = 0;
+        int rc = one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, true, i, st);
+        e->prof_active = false;
+        TRY(rc);
+      }
     }
   }
   // last token: head + sample only (the reference computes and drops one more embed)

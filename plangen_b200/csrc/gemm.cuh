@@ -34,7 +34,8 @@ struct TcCfg {
 template <int NT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
-               float* __restrict__ C, int M, int N, int K, int kb_per_split, int num_stages, int use_pdl) {
+               float* __restrict__ C, int M, int N, int K, int kb_per_split, int num_stages, int use_pdl,
+               const uint8_t* __restrict__ w_tiled, Prof prof) {
   using Cfg = TcCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -53,7 +54,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const int kb_end = min(kb_begin + kb_per_split, num_kb);
   const int nkb = max(kb_end - kb_begin, 0);
 
-  if (use_pdl) pdl_launch_dependents();
+  if (use_pdl & 1) pdl_launch_dependents();
+  prof_begin(prof);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
@@ -79,12 +81,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       const int pre = min(nkb, num_stages);
       // use_pdl bit 1: the W operand is a constant weight, so its tiles may be requested before the
       // previous kernel has finished (it is an activation in the VQ attention contractions)
-      if (use_pdl == 1) pdl_wait();
+      // A tile source: TMA tensor load from the row-major weight, or - when the weight was packed tile-major
+      // and pre-swizzled (w_tiled) - ONE contiguous 16 KB bulk copy per tile (full DRAM bursts, one issue).
+      auto load_a = [&](int stage, int kb) {
+        if (w_tiled)
+          bulk_copy_g2s(smem + stage * Cfg::STAGE_BYTES, w_tiled + ((size_t)blockIdx.x * num_kb + kb) * TC_A_BYTES, TC_A_BYTES,
+                        &full_bar[stage], pol_w);
+        else
+          tma_load_2d(smem + stage * Cfg::STAGE_BYTES, &map_w, &full_bar[stage], kb * TC_BK, n0, pol_w);
+      };
+      if ((use_pdl & 3) == 1) pdl_wait();
       for (int i = 0; i < pre; ++i) {
         mbar_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
-        tma_load_2d(smem + i * Cfg::STAGE_BYTES, &map_w, &full_bar[i], (kb_begin + i) * TC_BK, n0, pol_w);
+        load_a(i, kb_begin + i);
       }
-      if (use_pdl == 3) pdl_wait();
+      if ((use_pdl & 3) == 3) pdl_wait();
       for (int i = 0; i < pre; ++i)
         tma_load_2d(smem + i * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[i], (kb_begin + i) * TC_BK, m0, pol_x);
       for (int i = pre; i < nkb; ++i) {
@@ -92,7 +103,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         const uint32_t round = (uint32_t)(i / num_stages);
         mbar_wait(&empty_bar[s], (round & 1u) ^ 1u, 1);
         mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        tma_load_2d(smem + s * Cfg::STAGE_BYTES, &map_w, &full_bar[s], (kb_begin + i) * TC_BK, n0, pol_w);
+        load_a(s, kb_begin + i);
         tma_load_2d(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[s], (kb_begin + i) * TC_BK, m0, pol_x);
       }
     }
@@ -120,7 +131,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int quarter = warp & 3;              // a warp may only touch TMEM lanes 32*(warp%4)..+31
     const int n = n0 + quarter * 32 + lane;
     float* out = C + (size_t)split * M * N;
-    if (use_pdl) pdl_wait();
+    if (use_pdl & 1) pdl_wait();
     if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0, 3);
       tc_fence_after();
@@ -146,6 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  prof_end(prof);
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 

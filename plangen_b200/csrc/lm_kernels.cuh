@@ -57,9 +57,10 @@ template <typename T>
 __global__ void __launch_bounds__(RN_THREADS)
 resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int S, size_t split_stride,
                      const float* __restrict__ w, T* __restrict__ xn_out, float* __restrict__ y_out, int D,
-                     float eps, int in_stride, int in_off, int flags, int* step_ptr) {
+                     float eps, int in_stride, int in_off, int flags, int* step_ptr, Prof prof) {
   __shared__ float red[32];
   pdl_launch_dependents();
+  prof_begin(prof);
   pdl_wait();
   const size_t row_in = (size_t)blockIdx.x * in_stride + in_off;
   const size_t row_out = blockIdx.x;
@@ -98,6 +99,7 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
     }
   }
   if ((flags & RN_INC_STEP) && blockIdx.x == 0 && threadIdx.x == 0) *step_ptr += 1;
+  prof_end(prof);
 }
 
 // plain RMSNorm of externally supplied rows (used for the first layer of a decode step when the
@@ -160,8 +162,10 @@ qkv_rope_store_kernel(const float* __restrict__ part, int S, size_t split_stride
 // h = silu(gate) * up   (HF LlamaMLP :182-184); partial layout [S][tok][2F] = [gate | up]
 template <typename T>
 __global__ void __launch_bounds__(256)
-swiglu_kernel(const float* __restrict__ part, int S, size_t split_stride, T* __restrict__ h, int F, size_t total) {
+swiglu_kernel(const float* __restrict__ part, int S, size_t split_stride, T* __restrict__ h, int F, size_t total,
+              Prof prof) {
   pdl_launch_dependents();
+  prof_begin(prof);
   pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t tok = i / F, f = i % F;
@@ -170,6 +174,7 @@ swiglu_kernel(const float* __restrict__ part, int S, size_t split_stride, T* __r
     const float sg = Act<T>::rnd(g / (1.0f + expf(-g)));
     Act<T>::st(h + i, sg * u);
   }
+  prof_end(prof);
 }
 
 // ------------------------------------------------------- bias (+ exact GELU) epilogue
