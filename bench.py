@@ -12,7 +12,7 @@ cond/uncond pair, synthetic LayoutSAM-shaped prompts with 4-8 boxes).  Prints ON
   value     images/s, whole job, inputs already resident in HBM (CUDA-event timed, max over ranks)
   e2e       same metric through the public host-buffer API (pinned-host ids/mask -> uint8 images in
             host memory; H2D and D2H inside the timed region)
-  roofline  the dominant kernel (tcgen05 weight-streaming GEMM) timed alone with CUDA events
+  roofline  the dominant kernel (TMA-staged KV-cache decode attention) timed alone with CUDA events
   cpu_baseline  the oracle port of the reference PyTorch path on the box's host cores (bounded sample)
 
 `--impl reference` times the reference's own CPU implementation of the path: the oracle restatement
@@ -187,25 +187,24 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- B200 arm
-def kernel_roofline(eng, R: int, peaks: dict, iters: int = 4):
-    """Dominant kernel timed alone: the tcgen05 swap-AB GEMM streaming each layer's gate|up weights
-    ([2F, D] bf16, 46 MB at 1.3B) for R activation rows, rotating over all L layers so the weights come
-    from HBM (L x 46 MB >> 126 MB L2).  CUDA events on the launching stream."""
+def kernel_roofline(eng, kv_start, lens, P: int, peaks: dict, iters: int = 6):
+    """Dominant kernel of the decode step timed alone (38 % of a mid-sequence step, profiles/): the KV-cache
+    decode attention `attn_decode_tma_kernel`, one launch per layer, rotating over all L layers so the K/V
+    tiles come from HBM (L x ~130 MB >> 126 MB L2).  Position = the middle of the 576-token loop.
+    achieved = algorithmic K+V bytes per launch / CUDA-event time per launch on the launching stream."""
     import ctypes as C
     import torch
     from plangen_b200 import _lib
     d = eng.dims
-    N, K = 2 * d.F, d.D
-    X = (torch.randn(R, K, device=eng.device) * 0.5).to(torch.bfloat16)
-    splits = max(1, min(16, eng.counter("num_sms") // ((N + 127) // 128)))
-    out = torch.empty(splits, R, N, device=eng.device, dtype=torch.float32)
+    R = len(lens)
+    pos = P + d.n_img_tokens // 2
     st = torch.cuda.current_stream(eng.device)
+    sp = C.c_void_p(st.cuda_stream)
+    _lib.check(eng._lib.pg_debug_zero_part(eng._h, R * 3 * d.H * d.head_dim * 4, sp))
 
     def one_pass():
         for l in range(d.L):
-            W = eng._weights[f"l{l}.wgu"]
-            _lib.check(eng._lib.pg_test_gemm(eng._h, 1, 1, C.c_void_p(X.data_ptr()), C.c_void_p(W.data_ptr()), R, N, K,
-                                             splits, C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream)))
+            _lib.check(eng._lib.pg_test_attn_decode(eng._h, C.c_void_p(kv_start.data_ptr()), R, pos, l, sp))
 
     for _ in range(3):
         one_pass()
@@ -217,15 +216,18 @@ def kernel_roofline(eng, R: int, peaks: dict, iters: int = 4):
     e1.record(st)
     torch.cuda.synchronize()
     per_launch_s = e0.elapsed_time(e1) / 1e3 / (iters * d.L)
-    alg_bytes = N * K * 2 + R * K * 2 + splits * R * N * 4
+    kv_tok = 2 * d.H * d.head_dim * 2                      # K and V bytes per cached token per row per layer (bf16)
+    alg_bytes = sum((ln + d.n_img_tokens // 2) * kv_tok for ln in lens) + R * kv_tok
     achieved = alg_bytes / per_launch_s / 1e9
     peak = peaks.get("hbm_gbs")
     which = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     if not peak:
         peak, which = 6650.0, "fallback (B200_PROFILING.md)"
-    return {"bound": "hbm", "kernel": "gemm_tc_kernel<32> (gate|up projection, swap-AB tcgen05)", "achieved": achieved,
-            "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "splits": splits}
+    return {"bound": "hbm", "kernel": "attn_decode_tma_kernel (KV-cache decode attention, paired CFG batch, 1 launch/layer)",
+            "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": 141221376 + 6263552, "traffic_note": "dram read+write per launch from ncu --set full at step 300 of the "
+            "same workload (profiles/r01_attn_decode.full.txt); algorithmic K+V bytes there: 133.5 MB",
+            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "position": pos}
 
 
 def run_b200_arm(args):
@@ -367,7 +369,8 @@ def run_b200_arm(args):
         "phases": phases,
     }
     if not args.no_roofline:
-        line["roofline"] = kernel_roofline(eng, 2 * B, peaks)
+        kvs = (dev_batches[args.warmup][1][:, :P] == 0).sum(1).to(torch.int32).contiguous()
+        line["roofline"] = kernel_roofline(eng, kvs, lens, P, peaks)
     if world == 1 and not args.no_cpu_baseline:
         del eng
         torch.cuda.empty_cache()

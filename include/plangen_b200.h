@@ -115,6 +115,11 @@ int pg_engine_get_counter(const pg_engine* e, const char* key, int64_t* value);
 /* Copy an internal workspace buffer (x_dec, xn, attn_out, hbuf, hidden_f, part, qbuf) for debugging. */
 int pg_debug_copy(pg_engine* e, const char* name, void* dst_dev, size_t nbytes, void* stream);
 
+/* Decode-attention kernel of one layer alone on the current KV cache (bench roofline leg); the QKV partial
+ * buffer must have been zeroed with pg_debug_zero_part. */
+int pg_test_attn_decode(pg_engine* e, const int32_t* kv_start, int R, int pos, int layer, void* stream);
+int pg_debug_zero_part(pg_engine* e, size_t nbytes, void* stream);
+
 /* Plain GEMM exposed for unit tests:  C[m,n] = sum_k X[m,k] * W[n,k]
  * impl 0 = SIMT (fp32 or bf16 inputs), 1 = tcgen05 (bf16 inputs).  C fp32 [splits][M][N]. */
 int pg_test_gemm(pg_engine* e, int impl, int is_bf16, const void* X, const void* W, int M, int N,

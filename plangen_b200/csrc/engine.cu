@@ -1112,6 +1112,34 @@ extern "C" int pg_vq_decode_code(pg_engine* e, const int32_t* codes, int B, int 
 }
 
 // ------------------------------------------------------------------------------ debug / test hooks
+// Launch the decode-attention kernel of one layer alone on the current KV cache (bench roofline leg).
+// The QKV partial buffer is zero-filled, so the arithmetic is a uniform softmax over the cached tokens;
+// bytes moved and control flow are those of a real step at column `pos`.
+extern "C" int pg_test_attn_decode(pg_engine* e, const int32_t* kv_start, int R, int pos, int layer, void* stream) {
+  TRY(check_ready(e));
+  if (!e->bf16) return fail("pg_test_attn_decode: bf16 mode only");
+  if (R < 1 || R > e->d.max_rows || R > AT_MAX_ROWS || pos < 1 || pos >= e->Tmax || layer < 0 || layer >= e->d.L)
+    return fail("pg_test_attn_decode: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  NEED(cosT, float, "rope_cos");
+  NEED(sinT, float, "rope_sin");
+  const int HD = e->HD;
+  const int ctas = e->attn_ctas > 0 ? e->attn_ctas : e->num_sms;
+  const int saved = e->use_pdl;
+  e->use_pdl = 0;
+  int rc = launch(e, attn_decode_tma_kernel, dim3(ctas), dim3(AT_THREADS), AT_SMEM, st, (const float*)e->part, 1, (size_t)R * 3 * HD,
+                  cosT, sinT, (bf16*)kv_ptr(e, layer, 0, R), (bf16*)kv_ptr(e, layer, 1, R), kv_start, (bf16*)e->attn_out,
+                  e->attn_ws, e->attn_cnt, R, e->d.H, e->Tmax, pos, (const int*)nullptr, 1.0f / sqrtf((float)HEAD_DIM), 1, 0,
+                  next_prof(e));
+  e->use_pdl = saved;
+  return rc;
+}
+extern "C" int pg_debug_zero_part(pg_engine* e, size_t nbytes, void* stream) {
+  if (!e || !e->part) return fail("null engine");
+  CK(cudaMemsetAsync(e->part, 0, std::min(nbytes, e->part_bytes), (cudaStream_t)stream));
+  return 0;
+}
+
 extern "C" int pg_debug_copy(pg_engine* e, const char* name, void* dst_dev, size_t nbytes, void* stream) {
   if (!e || !name || !dst_dev) return fail("null argument");
   const std::string k(name);
