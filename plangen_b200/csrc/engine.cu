@@ -156,13 +156,13 @@ static int make_map_2d(pg_engine* e, CUtensorMap* m, const void* ptr, uint64_t r
   return 0;
 }
 
-static GemmSched sched_for(int N, int K, int G) {
+static GemmSched sched_for(int N, int K, int G, int max_splits = 16) {
   GemmSched g;
   g.n_tiles = (N + TC_BM - 1) / TC_BM;
   g.num_kb = (K + TC_BK - 1) / TC_BK;
   int best_s = 1;
   double best_eff = -1.0;
-  for (int s = 1; s <= std::min(16, g.num_kb); ++s) {
+  for (int s = 1; s <= std::min(max_splits, g.num_kb); ++s) {
     const int kb_per = (g.num_kb + s - 1) / s;
     if ((s - 1) * kb_per >= g.num_kb) continue;            // an empty split
     const long items = (long)g.n_tiles * s;
@@ -642,8 +642,8 @@ static int decode_layers_mega(pg_engine* e, const int32_t* kv_start, int R, int 
   p.wmaps = e->wmaps_dev; p.amaps = e->amaps_dev; p.ln = e->ln_dev; p.norm_w = normw;
   p.x = e->x_dec; p.xn = (bf16*)e->xn; p.attn_out = (bf16*)e->attn_out; p.h = (bf16*)e->hbuf;
   p.hidden_t = (bf16*)e->hidden_t; p.hidden_f = e->hidden_f;
-  p.g_qkv = sched_for(3 * e->HD, d.D, G); p.g_o = sched_for(d.D, e->HD, G);
-  p.g_gu = sched_for(2 * d.F, d.D, G); p.g_d = sched_for(d.D, d.F, G);
+  p.g_qkv = sched_for(3 * e->HD, d.D, G, SK_MAXS); p.g_o = sched_for(d.D, e->HD, G, SK_MAXS);
+  p.g_gu = sched_for(2 * d.F, d.D, G, SK_MAXS); p.g_d = sched_for(d.D, d.F, G, SK_MAXS);
   size_t off = 0;
   auto carve = [&](size_t floats) { float* q = e->part + off; off += (floats + 255) / 256 * 256; return q; };
   p.part_qkv = carve((size_t)p.g_qkv.splits * R * 3 * e->HD);

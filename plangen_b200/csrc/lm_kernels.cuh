@@ -19,17 +19,33 @@ constexpr int RN_ROUND_RESID = 1;   // keep the residual stream bf16-rounded (de
                                     // inputs_embeds there is the bf16 output of gen_aligner, so HF's residual adds are bf16)
 constexpr int RN_INC_STEP = 2;      // block 0 increments *step_ptr at the end (last kernel of a decode-step graph)
 
-// fixed-order sum over the split-K slabs; loads are issued 4 at a time so they overlap
+// Fixed-order (left to right) sum over the split-K slabs.  ALL slab loads are issued before the first add:
+// a load-add-load-add loop serialises one L2 round trip (~0.45 us) per split on the in-order pipe.
+constexpr int MAX_SPLITS = 16;
+template <int MAXS>
+PG_DEVINL void load_splits(const float* __restrict__ p, int S, size_t split_stride, float (&b)[MAXS]) {
+#pragma unroll
+  for (int s = 0; s < MAXS; ++s) b[s] = (s < S) ? __ldcg(p + (size_t)s * split_stride) : 0.f;
+}
+template <int MAXS>
+PG_DEVINL float sum_loaded(const float (&b)[MAXS], int S) {
+  float a = b[0];
+#pragma unroll
+  for (int s = 1; s < MAXS; ++s) if (s < S) a += b[s];
+  return a;
+}
+// single element: slabs in chunks of 8 loads in flight (same left-to-right order)
 PG_DEVINL float reduce_splits(const float* __restrict__ part, int S, size_t split_stride, size_t idx) {
   const float* p = part + idx;
-  float a = p[0];
-  int s = 1;
-  for (; s + 3 < S; s += 4) {
-    const float b0 = p[(size_t)s * split_stride], b1 = p[(size_t)(s + 1) * split_stride];
-    const float b2 = p[(size_t)(s + 2) * split_stride], b3 = p[(size_t)(s + 3) * split_stride];
-    a = (((a + b0) + b1) + b2) + b3;
+  float b[8];
+  load_splits(p, S, split_stride, b);
+  float a = sum_loaded(b, S);
+  if (S > 8) {
+    load_splits(p + (size_t)8 * split_stride, S - 8, split_stride, b);
+    a += b[0];
+#pragma unroll
+    for (int s = 1; s < 8; ++s) if (s < S - 8) a += b[s];
   }
-  for (; s < S; ++s) a += p[(size_t)s * split_stride];
   return a;
 }
 
@@ -70,19 +86,30 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
   // residual update + sum of squares; the row stays in registers (all split loads of a thread are
   // independent, so they are in flight together)
 #pragma unroll
-  for (int k = 0; k < RN_MAX_PER_THREAD; ++k) {
-    const int d = threadIdx.x + k * blockDim.x;
-    v[k] = 0.f;
-    if (d < D) {
-      float t = xr[d];
-      if (part != nullptr) {
-        const float a = Act<T>::rnd(reduce_splits(part, S, split_stride, row_in * D + d));
-        t = t + a;
-        if (flags & RN_ROUND_RESID) t = Act<T>::rnd(t);
-        xr[d] = t;
+  for (int k0 = 0; k0 < RN_MAX_PER_THREAD; k0 += 2) {       // two elements (<= 34 loads) in flight at a time
+    float b[2][MAX_SPLITS];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int d = threadIdx.x + (k0 + j) * blockDim.x;
+      v[k0 + j] = 0.f;
+      if (d < D) {
+        v[k0 + j] = xr[d];
+        if (part != nullptr) load_splits(part + row_in * D + d, S, split_stride, b[j]);
       }
-      v[k] = t;
-      ss += t * t;
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int d = threadIdx.x + (k0 + j) * blockDim.x;
+      if (d < D) {
+        float t = v[k0 + j];
+        if (part != nullptr) {
+          t = t + Act<T>::rnd(sum_loaded(b[j], S));
+          if (flags & RN_ROUND_RESID) t = Act<T>::rnd(t);
+          xr[d] = t;
+        }
+        v[k0 + j] = t;
+        ss += t * t;
+      }
     }
   }
   ss = block_sum(ss, red);

@@ -5,18 +5,19 @@
 // kernel boundary (~8 per layer x 24 layers) and each op pays its own launch / prologue / epilogue
 // latency.  Here every SM runs a warp-specialised CTA for the whole step:
 //
-//   warp 16  producer A : streams THIS CTA's share of every op's weight tiles (TMA tensor loads,
-//                         SWIZZLE_128B) and KV-cache tiles (TMA bulk copies) through one ring of 16 KB
-//                         stages, in program order, for ALL layers.  Weights and cached K/V do not
-//                         depend on the step's activations, so this warp never waits for a grid barrier:
-//                         while the other warps wait for a dependency, it keeps the ring (and HBM) busy.
-//   warp 17  producer B : streams the small activation operand tiles (L2-resident) of the contractions
-//                         through a second ring, after the grid barrier of the producing phase.
+//   warp 16  weight producer : streams THIS CTA's share of every contraction's weight tiles (TMA tensor
+//                         loads, SWIZZLE_128B) through a ring of 16 KB stages, in program order, for ALL
+//                         layers.  Weights do not depend on the step's activations, so this warp never waits
+//                         for a grid barrier: while the others wait for a dependency it keeps HBM busy.
+//   warp 17  operand producer: streams the small activation operand tiles (L2-resident) of the
+//                         contractions through a second ring, after the grid barrier of the producing phase.
 //   warp 18  MMA issuer : tcgen05.mma (swap-AB: weight tile = M 128, token tile = N 32), fp32 accumulators
 //                         double-buffered in TMEM.
-//   warps 0-15 workers  : TMEM epilogues (warps 0-3), the KV-cache attention (4 groups x 4 warps, fp32
-//                         online softmax on CUDA cores straight from the ring), split-K reductions fused
-//                         with residual + RMSNorm and SwiGLU.
+//   warp 19  K/V producers (lanes 0-3, one per attention group): the cached K/V tiles of the group's share
+//                         of the attention, TMA bulk copies into the group's private stages; cached tokens are
+//                         step-independent too, so they are prefetched during the QKV contraction.
+//   warps 0-15 workers  : TMEM epilogues (warps 0-3), the KV-cache attention (4 independent groups x 4 warps,
+//                         attn_tma.cuh), split-K reductions fused with residual + RMSNorm and SwiGLU.
 //
 // Phases per layer (grid barrier after each; arithmetic identical to the per-op kernels):
 //   0 QKV contraction -> 1 attention (+RoPE, KV append) -> 2 O contraction -> 3 residual + RMSNorm
@@ -28,18 +29,20 @@
 
 namespace pg {
 
-constexpr int SK_NSA = 8;                       // A ring: weight / KV stages of 16 KB
-constexpr int SK_NSB = 8;                       // B ring: activation tiles
+constexpr int SK_NSA = 4;                       // weight ring: stages of 16 KB
+constexpr int SK_NSB = 4;                       // operand ring: activation tiles
+constexpr int SK_SPG = 2;                       // K/V stages per attention group
+constexpr int SK_NKV = AT_NG * SK_SPG;          // K/V ring stages of 16 KB
 constexpr int SK_NT = 32;                       // token tile (rows R <= 32)
 constexpr int SK_WORKERS = 16;
 constexpr int SK_WTHREADS = SK_WORKERS * 32;
-constexpr int SK_THREADS = 32 * (SK_WORKERS + 3);
+constexpr int SK_THREADS = 32 * (SK_WORKERS + 4);
 constexpr int SK_A_BYTES = 16384;
 constexpr int SK_B_BYTES = SK_NT * TC_BK * 2;   // 4 KB
-constexpr int SK_SMEM = SK_NSA * SK_A_BYTES + SK_NSB * SK_B_BYTES + 1024;
+constexpr int SK_SMEM = (SK_NSA + SK_NKV) * SK_A_BYTES + SK_NSB * SK_B_BYTES + 1024;
 constexpr int SK_PHASES = 8;
+constexpr int SK_MAXS = 10;                     // split-K slabs per contraction in the step kernel (sched_for cap)
 constexpr int SK_RNK = 8;                       // RMSNorm elements per worker thread: D <= 8 * 512
-static_assert(SK_NSA % AT_NG == 0, "attention stage ownership");
 static_assert(SK_A_BYTES == 2 * AT_TILE_BYTES && SK_A_BYTES == TC_A_BYTES, "one ring serves weights and K/V");
 
 struct GemmSched { int n_tiles, splits, kb_per_split, num_kb; };
@@ -93,22 +96,20 @@ PG_DEVINL void grid_wait(const unsigned long long* bar, unsigned long long targe
   }
 }
 
-PG_DEVINL void umma_commit4(uint64_t* bar) {   // the A ring's empty barriers expect 4 arrivals (see attention groups)
-  umma_commit(bar); umma_commit(bar); umma_commit(bar); umma_commit(bar);
-}
 
 __global__ void __launch_bounds__(SK_THREADS, 1)
 decode_step_kernel(const __grid_constant__ StepParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ringA = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* ringB = ringA + SK_NSA * SK_A_BYTES;
+  uint8_t* ringKV = ringA + SK_NSA * SK_A_BYTES;
+  uint8_t* ringB = ringKV + SK_NKV * SK_A_BYTES;
   __shared__ uint64_t fullA[SK_NSA], emptyA[SK_NSA], fullB[SK_NSB], emptyB[SK_NSB], tmem_full[2], tmem_empty[2];
+  __shared__ uint64_t kv_full[SK_NKV], kv_empty[SK_NKV];
   __shared__ uint32_t tmem_slot;
   __shared__ int row_units[AT_MAX_ROWS + 1];
-  __shared__ float q_s[HEAD_DIM], k_s[HEAD_DIM], v_s[HEAD_DIM];
-  __shared__ float m_s[SK_WORKERS], l_s[SK_WORKERS], o_s[SK_WORKERS][HEAD_DIM];
+  __shared__ int stage_tab[AT_NG * SK_SPG];
+  __shared__ AttnGroupSmem gsm[AT_NG];
   __shared__ float red_s[32];
-  __shared__ int is_last_s;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int G = gridDim.x, c = blockIdx.x;
@@ -119,40 +120,26 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
   auto bar_target = [&](int phase_index) { return bar_base + (unsigned long long)(phase_index + 1) * (unsigned long long)G; };
 
   if (tid == 0) {
-    for (int i = 0; i < SK_NSA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], AT_GW); }
+    for (int i = 0; i < SK_NSA; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
     for (int i = 0; i < SK_NSB; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+    for (int i = 0; i < SK_NKV; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], AT_GW); }
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     mbar_fence_init();
   }
+  if (tid < SK_NKV) stage_tab[(tid % AT_NG) * SK_SPG + tid / AT_NG] = tid;     // group g owns K/V stages g, g+4
   if (warp == SK_WORKERS + 2) { tmem_alloc(&tmem_slot, 2 * SK_NT); tmem_relinquish(); }
-  // attention schedule of this step (same for every layer): units per row -> exclusive prefix
-  if (warp == 0) {
-    int carry = 0;
-    for (int r0 = 0; r0 < R; r0 += 32) {
-      const int r = r0 + lane;
-      int u = (r < R) ? row_tiles(p.kv_start[r], pos) + 1 : 0;
-      int incl = u;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      if (r < R) row_units[r] = carry + incl - u;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) row_units[R] = carry;
-  }
+  if (warp == 0) build_row_units(row_units, p.kv_start, R, pos, lane);     // attention schedule (same for every layer)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
-  const int U = row_units[R] * H;
-  const int per = (U + G - 1) / G;
-  const int u_begin = min(c * per, U), u_end = min(u_begin + per, U);
+  AttnCut cut;
+  cut.U = row_units[R] * H;
+  cut.per = max(1, (cut.U + G - 1) / G);
+  cut.sub = (cut.per + AT_NG - 1) / AT_NG;
   const size_t kv_layer = (size_t)2 * R * H * p.Tmax * HEAD_DIM;     // elements per layer (k then v)
   const size_t kv_half = (size_t)R * H * p.Tmax * HEAD_DIM;
 
-  // ------------------------------------------------------------------ helpers shared by the roles
   // contraction items of this CTA: it = c, c + G, ...; tile = it / splits, split = it % splits
   struct Item { int tile, split, kb0, kb1; };
   auto item_of = [&](const GemmSched& g, int it) {
@@ -163,23 +150,17 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
   };
 
   if (warp == SK_WORKERS) {
-    // =========================================================== producer A: weights + cached K/V
+    // =========================================================== weight producer
     if (lane == 0) {
       const uint64_t pol = policy_evict_first();
-      int ja = 0;                                              // A-ring tile counter of this CTA
-      auto stage_acquire = [&]() {
-        const int s = ja % SK_NSA;
-        const uint32_t round = (uint32_t)(ja / SK_NSA);
-        mbar_wait(&emptyA[s], (round & 1u) ^ 1u, 21, ja);
-        mbar_expect_tx(&fullA[s], SK_A_BYTES);
-        ++ja;
-        return s;
-      };
+      int ja = 0;
       auto stream_weights = [&](const GemmSched& g, const CUtensorMap* map) {
         for (int it = c; it < g.n_tiles * g.splits; it += G) {
           const Item im = item_of(g, it);
-          for (int kb = im.kb0; kb < im.kb1; ++kb) {
-            const int s = stage_acquire();
+          for (int kb = im.kb0; kb < im.kb1; ++kb, ++ja) {
+            const int s = ja % SK_NSA;
+            mbar_wait(&emptyA[s], (((uint32_t)(ja / SK_NSA)) & 1u) ^ 1u, 21, ja);
+            mbar_expect_tx(&fullA[s], SK_A_BYTES);
             tma_load_2d(ringA + (size_t)s * SK_A_BYTES, map, &fullA[s], kb * TC_BK, im.tile * TC_BM, pol);
           }
         }
@@ -187,32 +168,13 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
       for (int l = 0; l < L; ++l) {
         const CUtensorMap* wm = p.wmaps + (size_t)l * 4;
         stream_weights(p.g_qkv, wm + 0);
-        // cached K/V tiles of this CTA's attention units
-        {
-          const bf16* kc = p.kv + (size_t)l * kv_layer;
-          const bf16* vc = kc + kv_half;
-          int r = 0;
-          while (r + 1 < R && row_units[r + 1] * H <= u_begin) ++r;
-          for (int u = u_begin; u < u_end; ++u) {
-            while (row_units[r + 1] * H <= u) ++r;
-            const int ur = row_units[r + 1] - row_units[r];
-            const int local = u - row_units[r] * H;
-            const int h = local / ur, k = local % ur;
-            if (k == ur - 1) continue;
-            const int t0 = (p.kv_start[r] / AT_TILE + k) * AT_TILE;
-            const int s = stage_acquire();
-            const size_t off = (((size_t)r * H + h) * p.Tmax + t0) * HEAD_DIM;
-            bulk_load(ringA + (size_t)s * SK_A_BYTES, kc + off, AT_TILE_BYTES, &fullA[s], pol);
-            bulk_load(ringA + (size_t)s * SK_A_BYTES + AT_TILE_BYTES, vc + off, AT_TILE_BYTES, &fullA[s], pol);
-          }
-        }
         stream_weights(p.g_o, wm + 1);
         stream_weights(p.g_gu, wm + 2);
         stream_weights(p.g_d, wm + 3);
       }
     }
   } else if (warp == SK_WORKERS + 1) {
-    // =========================================================== producer B: activation operand tiles
+    // =========================================================== operand producer: activation tiles
     if (lane == 0) {
       const uint64_t pol = policy_evict_last();
       int jb = 0;
@@ -221,13 +183,11 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
         fence_proxy_async_global();                            // generic-proxy stores of other CTAs -> TMA reads
         for (int it = c; it < g.n_tiles * g.splits; it += G) {
           const Item im = item_of(g, it);
-          for (int kb = im.kb0; kb < im.kb1; ++kb) {
+          for (int kb = im.kb0; kb < im.kb1; ++kb, ++jb) {
             const int s = jb % SK_NSB;
-            const uint32_t round = (uint32_t)(jb / SK_NSB);
-            mbar_wait(&emptyB[s], (round & 1u) ^ 1u, 22, jb);
+            mbar_wait(&emptyB[s], (((uint32_t)(jb / SK_NSB)) & 1u) ^ 1u, 22, jb);
             mbar_expect_tx(&fullB[s], SK_B_BYTES);
             tma_load_2d(ringB + (size_t)s * SK_B_BYTES, map, &fullB[s], kb * TC_BK, 0, pol);
-            ++jb;
           }
         }
       };
@@ -250,10 +210,8 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
           mbar_wait(&tmem_empty[buf], (((uint32_t)(ji >> 1)) & 1u) ^ 1u, 23, ji);   // epilogue drained this buffer
           tc_fence_after();
           const uint32_t tacc = tmem_base + (uint32_t)(buf * SK_NT);
-          for (int kb = im.kb0; kb < im.kb1; ++kb) {
+          for (int kb = im.kb0; kb < im.kb1; ++kb, ++ja, ++jb) {
             const int sb = jb % SK_NSB, sa = ja % SK_NSA;
-            // B first: its arrival implies this CTA finished the previous phase, hence every earlier use of
-            // the A stage (possibly by an attention group) has completed -> no parity aliasing on fullA
             mbar_wait(&fullB[sb], (uint32_t)(jb / SK_NSB) & 1u, 24, jb);
             mbar_wait(&fullA[sa], (uint32_t)(ja / SK_NSA) & 1u, 25, ja);
             tc_fence_after();
@@ -262,9 +220,8 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)
               umma_bf16(tacc, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb > im.kb0) | (k > 0)));
-            umma_commit4(&emptyA[sa]);
+            umma_commit(&emptyA[sa]);
             umma_commit(&emptyB[sb]);
-            ++ja; ++jb;
           }
           umma_commit(&tmem_full[buf]);
           ++ji;
@@ -272,31 +229,35 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
       };
       for (int l = 0; l < L; ++l) {
         run_gemm(p.g_qkv);
-        // the attention phase consumes this CTA's K/V tiles from the A ring: skip over them
-        {
-          int r = 0;
-          while (r + 1 < R && row_units[r + 1] * H <= u_begin) ++r;
-          for (int u = u_begin; u < u_end; ++u) {
-            while (row_units[r + 1] * H <= u) ++r;
-            const int ur = row_units[r + 1] - row_units[r];
-            if ((u - row_units[r] * H) % ur != ur - 1) ++ja;
-          }
-        }
         run_gemm(p.g_o);
         run_gemm(p.g_gu);
         run_gemm(p.g_d);
       }
     }
+  } else if (warp == SK_WORKERS + 3) {
+    // =========================================================== K/V producers: lane g feeds attention group g
+    if (lane < AT_NG) {
+      const int g = lane;
+      int gb, ge;
+      cut.group_range(c, g, gb, ge);
+      int kload = 0;
+      const uint64_t pol = policy_evict_first();
+      for (int l = 0; l < L; ++l) {
+        const bf16* kc = p.kv + (size_t)l * kv_layer;
+        attn_produce_group<SK_SPG>(gb, ge, row_units, R, H, p.Tmax, p.kv_start, kc, kc + kv_half, ringKV, SK_A_BYTES,
+                                   stage_tab + g * SK_SPG, kv_full, kv_empty, kload, SK_A_BYTES, pol);
+      }
+    }
   } else {
     // =========================================================== workers (16 warps)
-    int ja = 0, ji = 0;                                        // mirrors of the A-ring / accumulator counters
-    const float LOG2E = 1.4426950408889634f;
+    int ji = 0;                                                // mirror of the accumulator-buffer counter
+    int kc_att = 0;                                            // K/V tiles consumed by this warp's attention group
     int prof_i = 0;
     unsigned long long* prof = p.prof ? p.prof + (size_t)c * (SK_PHASES * L + 1) : nullptr;
     if (prof && tid == 0) prof[prof_i++] = global_timer_ns();
     auto phase_done = [&]() {                                  // all of this CTA's global writes of the phase are done
       fence_proxy_async_global();                              // generic-proxy stores -> later TMA (async-proxy) reads
-      __threadfence();
+      __threadfence();                                         // (also invalidates L1: next phase re-reads from L2)
       named_bar_sync(1, SK_WTHREADS);
       if (tid == 0) {
         atomicAdd(p.grid_bar, 1ull);
@@ -332,24 +293,47 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[buf]);
         }
-        ja += im.kb1 - im.kb0;
         ++ji;
       }
     };
+    // fixed-order split-K sum with L2 (cache-global) loads: the slabs were written by other CTAs
+
     // residual + RMSNorm of row `c` (CTAs >= R idle): x += rnd(sum part); xn = w * (x * r)
+    unsigned long long* fine = (p.prof && c == 0) ? p.prof + (size_t)G * (SK_PHASES * L + 1) : nullptr;
+    int fine_on = 0;
+    auto stamp = [&](int i) { if (fine && fine_on && tid == 0) fine[i] = global_timer_ns(); };
     auto resid_norm = [&](const float* part, int S, const float* w, bf16* xn_out, float* y_out, bf16* y_out_t) {
       if (c < R) {
+        stamp(1);
         float* xr = p.x + (size_t)c * D;
-        float v[SK_RNK];
+        float v[SK_RNK], a[SK_RNK];
+        // all loads of two elements first (the row and every split slab), so they are in flight together
+#pragma unroll
+        for (int k0 = 0; k0 < SK_RNK; k0 += 2) {
+          float b[2][SK_MAXS];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int d = tid + (k0 + j) * SK_WTHREADS;
+            v[k0 + j] = 0.f;
+            if (d < D) { v[k0 + j] = __ldcg(xr + d); load_splits(part + (size_t)c * D + d, S, (size_t)R * D, b[j]); }
+          }
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int d = tid + (k0 + j) * SK_WTHREADS;
+            a[k0 + j] = (d < D) ? sum_loaded(b[j], S) : 0.f;
+          }
+        }
         float ss = 0.f;
+        if (fine && fine_on) { float keep = 0.f;
+#pragma unroll
+          for (int k = 0; k < SK_RNK; ++k) keep += a[k] + v[k];
+          if (keep == 123.456f) red_s[31] = keep;               // force the loads to complete before the stamp
+          stamp(2); }
 #pragma unroll
         for (int k = 0; k < SK_RNK; ++k) {
           const int d = tid + k * SK_WTHREADS;
-          v[k] = 0.f;
           if (d < D) {
-            float t = xr[d];
-            const float a = bf16_round(reduce_splits(part, S, (size_t)R * D, (size_t)c * D + d));
-            t = bf16_round(t + a);                              // bf16 residual stream of the decode steps
+            const float t = bf16_round(v[k] + bf16_round(a[k]));   // bf16 residual stream of the decode steps
             xr[d] = t;
             v[k] = t;
             ss += t * t;
@@ -361,6 +345,7 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
         float tot = (lane < SK_WORKERS) ? red_s[lane] : 0.f;
         tot = warp_sum(tot);
         const float r = rsqrtf(tot / (float)D + p.eps);
+        stamp(3);
 #pragma unroll
         for (int k = 0; k < SK_RNK; ++k) {
           const int d = tid + k * SK_WTHREADS;
@@ -375,6 +360,9 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
       }
     };
 
+    const int grp = warp / AT_GW, tg = tid - grp * AT_GT;
+    int gb, ge;
+    cut.group_range(c, grp, gb, ge);
     for (int l = 0; l < L; ++l) {
       const int pb = l * SK_PHASES;
       bf16* kc = p.kv + (size_t)l * kv_layer;
@@ -386,180 +374,26 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
       if (l > 0) phase_wait(pb + 0);
       epilogue(p.g_qkv, p.part_qkv, 3 * HD);
       phase_done();
-      // ---------------- phase 1: attention over this CTA's units
+      // ---------------- phase 1: attention, 4 independent group streams
       phase_wait(pb + 1);
-      {
-        const int S = p.g_qkv.splits;
-        const size_t sstride = (size_t)R * 3 * HD;
-        int u = u_begin;
-        int r = 0;
-        while (r + 1 < R && row_units[r + 1] * H <= u_begin) ++r;
-        while (u < u_end) {
-          while (row_units[r + 1] * H <= u) ++r;
-          const int ur = row_units[r + 1] - row_units[r];
-          const int item_base = row_units[r] * H;
-          const int h = (u - item_base) / ur;
-          const int item_lo = item_base + h * ur, item_hi = item_lo + ur;
-          const int seg_lo = u, seg_hi = min(item_hi, u_end);
-          const int start = p.kv_start[r];
-          const bool owns_new = (seg_hi == item_hi);
-          const int n_tiles_seg = (seg_hi - seg_lo) - (owns_new ? 1 : 0);
-          {
-            const float* row = p.part_qkv + (size_t)r * 3 * HD;
-            const int jj = tid & 63;
-            const float cs = p.cosT[pos * 64 + jj], sn = p.sinT[pos * 64 + jj];
-            if (tid < 64) {
-              const float x1 = bf16_round(reduce_splits(row, S, sstride, (size_t)h * HEAD_DIM + jj));
-              const float x2 = bf16_round(reduce_splits(row, S, sstride, (size_t)h * HEAD_DIM + jj + 64));
-              float a, b;
-              rope_pair<bf16>(x1, x2, cs, sn, true, a, b);
-              q_s[jj] = a * (p.scale * LOG2E); q_s[jj + 64] = b * (p.scale * LOG2E);
-            } else if (owns_new && tid < 128) {
-              const float x1 = bf16_round(reduce_splits(row, S, sstride, (size_t)HD + h * HEAD_DIM + jj));
-              const float x2 = bf16_round(reduce_splits(row, S, sstride, (size_t)HD + h * HEAD_DIM + jj + 64));
-              float a, b;
-              rope_pair<bf16>(x1, x2, cs, sn, true, a, b);
-              const float v1 = bf16_round(reduce_splits(row, S, sstride, (size_t)2 * HD + h * HEAD_DIM + jj));
-              const float v2 = bf16_round(reduce_splits(row, S, sstride, (size_t)2 * HD + h * HEAD_DIM + jj + 64));
-              k_s[jj] = a; k_s[jj + 64] = b; v_s[jj] = v1; v_s[jj + 64] = v2;
-              const size_t cidx = (((size_t)r * H + h) * p.Tmax + pos) * HEAD_DIM + jj;
-              kc[cidx] = __float2bfloat16_rn(a); kc[cidx + 64] = __float2bfloat16_rn(b);
-              vc[cidx] = __float2bfloat16_rn(v1); vc[cidx + 64] = __float2bfloat16_rn(v2);
-            }
-          }
-          named_bar_sync(1, SK_WTHREADS);
-          float qv[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) qv[i] = q_s[lane * 4 + i];
-          float m = -INFINITY, lsum = 0.f, o[4] = {0.f, 0.f, 0.f, 0.f};
-          const int first_tile_k = seg_lo - item_lo;
-          const int grp = warp / AT_GW, wig = warp % AT_GW;
-          for (int jt = ja + ((grp - ja) % AT_NG + AT_NG) % AT_NG; jt < ja + n_tiles_seg; jt += AT_NG) {
-            const int t = jt - ja;
-            const int s = jt % SK_NSA;
-            mbar_wait(&fullA[s], (uint32_t)(jt / SK_NSA) & 1u, 27, jt);
-            const uint8_t* kt = ringA + (size_t)s * SK_A_BYTES + wig * AT_TW * (HEAD_DIM * 2);
-            const uint8_t* vt = kt + AT_TILE_BYTES;
-            const int t0 = (start / AT_TILE + first_tile_k + t) * AT_TILE + wig * AT_TW;
-            float sc[AT_TW];
-#pragma unroll
-            for (int i = 0; i < AT_TW; ++i) {
-              const uint2 kk = *reinterpret_cast<const uint2*>(kt + i * (HEAD_DIM * 2) + lane * 8);
-              float d = bf16lo(kk.x) * qv[0];
-              d = fmaf(bf16hi(kk.x), qv[1], d); d = fmaf(bf16lo(kk.y), qv[2], d); d = fmaf(bf16hi(kk.y), qv[3], d);
-              sc[i] = d;
-            }
-#pragma unroll
-            for (int off = 16, n = AT_TW; off >= 4; off >>= 1, n >>= 1) {
-              const bool upper = (lane & off) != 0;
-#pragma unroll
-              for (int i = 0; i < n / 2; ++i) {
-                const float send = upper ? sc[i] : sc[i + n / 2];
-                const float recv = __shfl_xor_sync(0xffffffffu, send, off);
-                sc[i] = (upper ? sc[i + n / 2] : sc[i]) + recv;
-              }
-            }
-            sc[0] += __shfl_xor_sync(0xffffffffu, sc[0], 2);
-            sc[0] += __shfl_xor_sync(0xffffffffu, sc[0], 1);
-            const int tok = t0 + (lane >> 2);
-            const bool valid = (tok >= start) && (tok < pos);
-            const float sv = valid ? sc[0] : -INFINITY;
-            const float mx = fmaxf(m, warp_max(sv));
-            const float pr = valid ? exp2f(sv - mx) : 0.f;
-            const float corr = (mx == -INFINITY) ? 1.f : exp2f(m - mx);
-            lsum = lsum * corr + 0.25f * warp_sum(pr);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] *= corr;
-#pragma unroll
-            for (int i = 0; i < AT_TW; ++i) {
-              const float pi = __shfl_sync(0xffffffffu, pr, i * 4);
-              const uint2 vv = *reinterpret_cast<const uint2*>(vt + i * (HEAD_DIM * 2) + lane * 8);
-              o[0] = fmaf(pi, bf16lo(vv.x), o[0]); o[1] = fmaf(pi, bf16hi(vv.x), o[1]);
-              o[2] = fmaf(pi, bf16lo(vv.y), o[2]); o[3] = fmaf(pi, bf16hi(vv.y), o[3]);
-            }
-            m = mx;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&emptyA[s]);
-          }
-          if (owns_new && warp == 0) {
-            float d = 0.f;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) d = fmaf(k_s[lane * 4 + i], qv[i], d);
-            d = warp_sum(d);
-            const float mx = fmaxf(m, d);
-            const float corr = (m == -INFINITY) ? 0.f : exp2f(m - mx);
-            const float pr = exp2f(d - mx);
-            lsum = lsum * corr + pr;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) o[i] = fmaf(pr, v_s[lane * 4 + i], o[i] * corr);
-            m = mx;
-          }
-          if (lane == 0) { m_s[warp] = m; l_s[warp] = lsum; }
-#pragma unroll
-          for (int i = 0; i < 4; ++i) o_s[warp][lane * 4 + i] = o[i];
-          named_bar_sync(1, SK_WTHREADS);
-          const int c_first = item_lo / per, c_last = (item_hi - 1) / per;
-          const int n_contrib = c_last - c_first + 1;
-          const int it = r * H + h;
-          const bool out_thread = tid < HEAD_DIM;
-          float M = -INFINITY, Ltot = 0.f, acc = 0.f;
-          if (out_thread) {
-#pragma unroll
-            for (int w = 0; w < SK_WORKERS; ++w) M = fmaxf(M, m_s[w]);
-#pragma unroll
-            for (int w = 0; w < SK_WORKERS; ++w) {
-              const float f = (m_s[w] == -INFINITY) ? 0.f : exp2f(m_s[w] - M);
-              Ltot += l_s[w] * f;
-              acc += o_s[w][tid] * f;
-            }
-          }
-          const size_t oidx = (size_t)r * HD + h * HEAD_DIM + tid;
-          if (n_contrib == 1) {
-            if (out_thread) p.attn_out[oidx] = __float2bfloat16_rn(acc / Ltot);
-            named_bar_sync(1, SK_WTHREADS);
-          } else {
-            if (out_thread) {
-              float* wp = p.attn_ws + ((size_t)it * AT_MAX_SLOTS + (c - c_first)) * (HEAD_DIM + 2);
-              wp[tid] = acc;
-              if (tid == 0) { wp[HEAD_DIM] = M; wp[HEAD_DIM + 1] = Ltot; }
-              __threadfence();
-            }
-            named_bar_sync(1, SK_WTHREADS);
-            if (tid == 0) {
-              const int prev = atomicAdd(p.attn_cnt + it, 1);
-              is_last_s = (prev == n_contrib - 1);
-            }
-            named_bar_sync(1, SK_WTHREADS);
-            if (is_last_s && out_thread) {
-              __threadfence();
-              const float* wb = p.attn_ws + (size_t)it * AT_MAX_SLOTS * (HEAD_DIM + 2);
-              float Mg = -INFINITY;
-              for (int s2 = 0; s2 < n_contrib; ++s2) Mg = fmaxf(Mg, __ldcg(wb + (size_t)s2 * (HEAD_DIM + 2) + HEAD_DIM));
-              float Lg = 0.f, og = 0.f;
-              for (int s2 = 0; s2 < n_contrib; ++s2) {
-                const float ms = __ldcg(wb + (size_t)s2 * (HEAD_DIM + 2) + HEAD_DIM);
-                const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - Mg);
-                Lg += __ldcg(wb + (size_t)s2 * (HEAD_DIM + 2) + HEAD_DIM + 1) * f;
-                og += __ldcg(wb + (size_t)s2 * (HEAD_DIM + 2) + tid) * f;
-              }
-              p.attn_out[oidx] = __float2bfloat16_rn(og / Lg);
-              if (tid == 0) p.attn_cnt[it] = 0;
-            }
-            named_bar_sync(1, SK_WTHREADS);
-          }
-          ja += n_tiles_seg;
-          u = seg_hi;
-        }
-      }
+      attn_group_stream<SK_SPG>(tg, gb, ge, cut, row_units, R, H, p.Tmax, pos, p.part_qkv, p.g_qkv.splits,
+                                (size_t)R * 3 * HD, p.cosT, p.sinT, kc, vc, p.kv_start, p.attn_out, p.attn_ws, p.attn_cnt,
+                                p.scale, true, ringKV, SK_A_BYTES, stage_tab + grp * SK_SPG, kv_full, kv_empty, kc_att,
+                                gsm[grp], c * AT_NG + grp, 2 + grp);
       phase_done();
       // ---------------- phase 2: O contraction
       phase_wait(pb + 2);
       epilogue(p.g_o, p.part_o, D);
       phase_done();
       // ---------------- phase 3: residual + post-attention RMSNorm
+      fine_on = (l == 12);
+      stamp(0);
       phase_wait(pb + 3);
       resid_norm(p.part_o, p.g_o.splits, p.ln + ((size_t)l * 2 + 1) * D, p.xn, nullptr, nullptr);
+      stamp(4);
       phase_done();
+      stamp(5);
+      fine_on = 0;
       // ---------------- phase 4: gate|up contraction
       phase_wait(pb + 4);
       epilogue(p.g_gu, p.part_gu, 2 * F);
@@ -569,12 +403,34 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
       {
         const int S = p.g_gu.splits;
         const size_t sstride = (size_t)R * 2 * F, total = (size_t)R * F;
-        for (size_t i = (size_t)c * SK_WTHREADS + tid; i < total; i += (size_t)G * SK_WTHREADS) {
-          const size_t tok = i / F, f = i % F;
-          const float g = bf16_round(reduce_splits(p.part_gu, S, sstride, tok * 2 * F + f));
-          const float uu = bf16_round(reduce_splits(p.part_gu, S, sstride, tok * 2 * F + F + f));
-          const float sg = bf16_round(g / (1.0f + expf(-g)));
-          p.h[i] = __float2bfloat16_rn(sg * uu);
+        constexpr int UN = 2;
+        for (size_t i0 = (size_t)c * SK_WTHREADS + tid; i0 < total; i0 += (size_t)G * SK_WTHREADS * UN) {
+          float gsum[UN], usum[UN];
+          float bg[UN][SK_MAXS], bu[UN][SK_MAXS];
+#pragma unroll
+          for (int q = 0; q < UN; ++q) {                        // every load of the UN elements before any add / store
+            const size_t i = i0 + (size_t)q * G * SK_WTHREADS;
+            if (i < total) {
+              const size_t tok = i / F, f = i % F;
+              load_splits(p.part_gu + tok * 2 * F + f, S, sstride, bg[q]);
+              load_splits(p.part_gu + tok * 2 * F + F + f, S, sstride, bu[q]);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < UN; ++q) {
+            const size_t i = i0 + (size_t)q * G * SK_WTHREADS;
+            gsum[q] = (i < total) ? sum_loaded(bg[q], S) : 0.f;
+            usum[q] = (i < total) ? sum_loaded(bu[q], S) : 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < UN; ++q) {
+            const size_t i = i0 + (size_t)q * G * SK_WTHREADS;
+            if (i < total) {
+              const float g = bf16_round(gsum[q]), uu = bf16_round(usum[q]);
+              const float sg = bf16_round(g / (1.0f + expf(-g)));
+              p.h[i] = __float2bfloat16_rn(sg * uu);
+            }
+          }
         }
       }
       phase_done();

@@ -6,18 +6,19 @@ from plangen_b200 import JANUS_1P3B, synthetic
 from plangen_b200.engine import FastJanus
 B = 16; dims = JANUS_1P3B; dev = torch.device("cuda", 0)
 sd = synthetic.random_state_dict(dims, dev, seed=0, with_vq=False)
-eng = FastJanus(sd, dims, mode="bf16", max_batch=B, max_prompt=512, with_vq=False)
+eng = FastJanus(sd, dims, mode="bf16", max_batch=B, max_prompt=512, with_vq=False, options={"use_mega": 1})
 del sd
 cond, neg = synthetic.layoutsam_prompts(dims, B, seed=1234)
 ids, mask = synthetic.collate_cfg_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
 emb = eng.language_model.get_input_embeddings()(ids.to(dev))
 n = int(os.environ.get("PG_STEPS", "300"))
 G = eng.counter("num_sms"); NP = dims.L * 8 + 1
-prof = torch.zeros(G, NP, dtype=torch.int64, device=dev)
+prof = torch.zeros(G * NP + 16, dtype=torch.int64, device=dev)
 eng.set_option("sk_prof_ptr", prof.data_ptr())
 eng.sample_image(emb, B, n, mask.to(dev), 5.0, 1.0, generator=0)
 torch.cuda.synchronize()
-t = prof.cpu().double()          # stamps of the LAST launch
+fine = prof[G * NP:].cpu().double()
+t = prof[:G * NP].view(G, NP).cpu().double()          # stamps of the LAST launch
 t0 = t[:, 0].min()
 end = t[:, 1:]                   # [G, L*8] phase end per CTA
 # phase duration measured globally: max over CTAs of phase end - max over CTAs of previous phase end
@@ -41,3 +42,5 @@ g_end = end[:, lay * 8 + 4]; g_start = end[:, lay * 8 + 3].max()
 print("gu per-CTA us:", [round(float(x), 1) for x in ((g_end - g_start) / 1e3)[::8]])
 n_end = end[:, lay * 8 + 3]; n_start = end[:, lay * 8 + 2].max()
 print("norm1 per-CTA us:", [round(float(x), 1) for x in ((n_end - n_start) / 1e3)[::8]])
+
+print("norm1 fine (CTA 0, layer 12) us: wait %.2f loads %.2f reduce %.2f stores %.2f done(fence+bar+atomic) %.2f" % tuple(float(fine[i + 1] - fine[i]) / 1e3 for i in range(5)))
