@@ -119,13 +119,15 @@ PG_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity, int tag = 0, int info =
   }
 }
 
-// Optional in-situ timeline: every CTA stamps kernel begin (min) / end (max) into buf[2*slot], buf[2*slot+1]
+// Optional in-situ timeline: every CTA stamps kernel begin (min) into buf[slot] and end (max) into
+// buf[PROF_SLOTS + slot]; buf[2*PROF_SLOTS ..] receives a snapshot after the profiled step.
+constexpr int PROF_SLOTS = 256;
 struct Prof { unsigned long long* buf; int slot; };
 PG_DEVINL void prof_begin(const Prof& p) {
-  if (p.buf && threadIdx.x == 0) atomicMin(&p.buf[2 * p.slot], (unsigned long long)global_timer_ns());
+  if (p.buf && threadIdx.x == 0) atomicMin(&p.buf[p.slot], (unsigned long long)global_timer_ns());
 }
 PG_DEVINL void prof_end(const Prof& p) {
-  if (p.buf && threadIdx.x == 0) atomicMax(&p.buf[2 * p.slot + 1], (unsigned long long)global_timer_ns());
+  if (p.buf && threadIdx.x == 0) atomicMax(&p.buf[PROF_SLOTS + p.slot], (unsigned long long)global_timer_ns());
 }
 
 // generic-proxy writes (st.shared) made visible to the async proxy (TMA / tcgen05)

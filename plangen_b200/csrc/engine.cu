@@ -70,7 +70,7 @@ struct pg_engine {
   std::unordered_map<std::string, std::pair<const void*, size_t>> tensors;
   EncodeTiledFn encode = nullptr;
   // options
-  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
+  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, fuse_swiglu = 1, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
   unsigned long long* sk_prof = nullptr;
   unsigned long long* prof_buf = nullptr;   // per-kernel timeline of ONE decode step (plain-launch mode)
@@ -119,7 +119,7 @@ static const void* T_(pg_engine* e, const std::string& name, size_t* nbytes = nu
 static Prof next_prof(pg_engine* e) {
   Prof p;
   p.buf = (e->prof_active && e->prof_buf) ? e->prof_buf : nullptr;
-  p.slot = p.buf ? e->prof_slot++ : 0;
+  p.slot = p.buf ? std::min(e->prof_slot++, PROF_SLOTS - 1) : 0;
   return p;
 }
 
@@ -178,7 +178,7 @@ static GemmSched sched_for(int N, int K, int G, int max_splits = 16) {
 
 template <int NT>
 static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx, float* C, int M, int N, int K,
-                     int splits, int kb_per_split, bool w_const, const void* w_tiled, cudaStream_t st) {
+                     int splits, int kb_per_split, bool w_const, const void* w_tiled, void* swiglu_out, cudaStream_t st) {
   using Cfg = TcCfg<NT>;
   int stages = e->tc_stages > 0 ? e->tc_stages : (200 * 1024) / Cfg::STAGE_BYTES;
   stages = std::max(2, std::min(stages, 12));
@@ -186,13 +186,13 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   const size_t smem = Cfg::smem_bytes(stages);
   dim3 grid((N + TC_BM - 1) / TC_BM, (M + NT - 1) / NT, splits);
   return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
-                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e));
+                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out);
 }
 
 // C[splits][M][N] fp32 = X[M][K] * W[N][K]^T.  Returns the number of splits used through *splits_out.
 static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, int K, float* C, size_t c_bytes,
                     int* splits_out, cudaStream_t st, int force_impl = -1, int force_splits = 0, bool w_const = true,
-                    const void* w_tiled = nullptr) {
+                    const void* w_tiled = nullptr, void* swiglu_out = nullptr) {
   const bool tc = e->bf16 && ((force_impl == 1) || (force_impl < 0 && e->use_tc)) && (K % 8 == 0) &&
                   (((uintptr_t)X & 15) == 0) && (((uintptr_t)W & 15) == 0);
   if (force_impl == 1 && !tc) return fail("tcgen05 GEMM needs bf16 operands, K %% 8 == 0 and 16-byte aligned pointers");
@@ -202,6 +202,7 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     const int tiles = ((N + TC_BM - 1) / TC_BM) * ((M + NT - 1) / NT);
     const int num_kb = (K + TC_BK - 1) / TC_BK;
     int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : std::max(1, e->num_sms / tiles));
+    if (swiglu_out) want = 1;                               // the SwiGLU epilogue is non-linear: whole K in one CTA
     want = std::min(std::min(want, 16), num_kb);
     while (want > 1 && (size_t)want * M * N * 4 > c_bytes) --want;
     const int kb_per_split = (num_kb + want - 1) / want;
@@ -211,13 +212,14 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     TRY(make_map_2d(e, &mw, W, (uint64_t)N, (uint64_t)K, TC_BM));
     TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
     switch (NT) {
-      case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
-      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
-      case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
-      case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
-      default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, st)); break;
+      case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
+      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
+      case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
+      case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
+      default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
     }
   } else {
+    if (swiglu_out) return fail("internal: fused SwiGLU epilogue needs the tcgen05 path");
     if (K % 4 != 0) return fail("SIMT GEMM needs K %% 4 == 0 (K=%d)", K);
     const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
     int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : std::max(1, (2 * e->num_sms) / tiles));
@@ -406,6 +408,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_ctas") e->attn_ctas = (int)value;
   else if (k == "attn_trigger") e->attn_trigger = (int)value;
   else if (k == "use_mega") e->use_mega = (int)value;
+  else if (k == "fuse_swiglu") e->fuse_swiglu = (int)value;
   else if (k == "mega_coop") e->mega_coop = (int)value;
   else if (k == "attn_attr") e->attn_attr = (int)value;
   else if (k == "gemm_splits") e->gemm_splits = (int)value;
@@ -542,6 +545,24 @@ static int elementwise_blocks(pg_engine* e, size_t total) {
   return (int)std::max<size_t>(1, std::min<size_t>((total + 255) / 256, (size_t)e->num_sms * 16));
 }
 
+// gate|up projection + SwiGLU -> hbuf.  bf16 + tcgen05: one kernel (fused epilogue, interleaved weight rows);
+// otherwise the contraction followed by swiglu_kernel.
+// (decode-sized token counts only: with 256-token tiles the two gate warps' expf work would outlast the MMAs)
+static bool fused_swiglu_ok(const pg_engine* e, int tok) { return e->bf16 && e->use_tc && e->fuse_swiglu && e->d.F % 64 == 0 && tok <= 128; }
+static int k_gate_up(pg_engine* e, const LayerW& w, int tok, cudaStream_t st) {
+  const pg_dims& d = e->d;
+  const int F = d.F, D = d.D;
+  int S = 1;
+  if (fused_swiglu_ok(e, tok)) return run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, e->hbuf);
+  TRY(run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st));
+  const size_t total = (size_t)tok * F;
+  const int il = (e->bf16 && F % 64 == 0) ? 1 : 0;         // bf16 weights are packed interleaved when F % 64 == 0 (weights.py)
+  DISPATCH_T(e,
+             launch(e, swiglu_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (bf16*)e->hbuf, F, total, il, next_prof(e)),
+             launch(e, swiglu_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (float*)e->hbuf, F, total, il, next_prof(e)));
+  return 0;
+}
+
 // a3: prompt prefill.  x fp32 [R*P, D] in place.
 extern "C" int pg_prefill(pg_engine* e, float* x, const int32_t* kv_start, int R, int P, float* hidden_out,
                           int all_positions, void* stream) {
@@ -574,13 +595,7 @@ extern "C" int pg_prefill(pg_engine* e, float* x, const int32_t* kv_start, int R
                       (float*)e->attn_out, P, d.H, e->Tmax, scale));
     TRY(run_gemm(e, e->attn_out, w.wo, tok, D, HD, e->part, e->part_bytes, &S, st));
     TRY(k_resid_norm(e, x, e->part, S, (size_t)tok * D, w.ln2, e->xn, nullptr, tok, 1, 0, 0, st));
-    TRY(run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st));
-    {
-      const size_t total = (size_t)tok * F;
-      DISPATCH_T(e,
-                 launch(e, swiglu_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (bf16*)e->hbuf, F, total, next_prof(e)),
-                 launch(e, swiglu_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)tok * 2 * F, (float*)e->hbuf, F, total, next_prof(e)));
-    }
+    TRY(k_gate_up(e, w, tok, st));
     TRY(run_gemm(e, e->hbuf, w.wd, tok, D, F, e->part, e->part_bytes, &S, st));
     if (l + 1 < d.L) {
       LayerW wn;
@@ -611,7 +626,7 @@ static int attn_split_count(pg_engine* e, int R, int T) {
 static bool mega_ok(const pg_engine* e, int R) {
   const pg_dims& d = e->d;
   return e->bf16 && e->use_mega && e->use_tc && R <= SK_NT && R <= AT_MAX_ROWS && d.D <= SK_RNK * SK_WTHREADS &&
-         d.D % 8 == 0 && d.F % 8 == 0;
+         d.D % 8 == 0 && d.F % 64 == 0;
 }
 
 // activation tensor maps of the step kernel depend on the row count of the batch; refreshed outside any
@@ -715,13 +730,7 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     }
     TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &S, st));
     TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st));
-    TRY(run_gemm(e, e->xn, w.wgu, R, 2 * F, D, e->part, e->part_bytes, &S, st));
-    {
-      const size_t total = (size_t)R * F;
-      DISPATCH_T(e,
-                 launch(e, swiglu_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)R * 2 * F, (bf16*)e->hbuf, F, total, next_prof(e)),
-                 launch(e, swiglu_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->part, S, (size_t)R * 2 * F, (float*)e->hbuf, F, total, next_prof(e)));
-    }
+    TRY(k_gate_up(e, w, R, st));
     TRY(run_gemm(e, e->hbuf, w.wd, R, D, F, e->part, e->part_bytes, &S, st));
     if (l + 1 < d.L) {
       LayerW wn;
@@ -878,14 +887,17 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
       char key[512];
       snprintf(key, sizeof(key), "%d/%d/%d/%a/%a/%llu/%d/%p/%p/%p/%p/%d/%d/%d/%d", R, P, n_steps, cfg_weight, temperature,
                (unsigned long long)seed, greedy, (const void*)kv_start, (const void*)edit_region, (const void*)gt_labels,
-               (void*)tokens_out, e->use_pdl, e->use_tc, e->bf16 ? 1 : 0, e->use_mega);
+               (void*)tokens_out, e->use_pdl, e->use_tc, e->bf16 ? 1 : 0, e->use_mega + 2 * (e->prof_buf && e->prof_step >= 0 ? 1 : 0));
       if (!e->graph_exec || e->graph_key != key) {
         if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
         cudaGraph_t graph = nullptr;
         CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         const int64_t before = e->launches;
+        e->prof_active = (e->prof_buf != nullptr && e->prof_step >= 0);
+        e->prof_slot = 0;
         int rc = one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels,
                           tokens_out, true, -1, st);
+        e->prof_active = false;
         cudaError_t ce = cudaStreamEndCapture(st, &graph);
         e->graph_launches = e->launches - before;
         e->launches = before;
@@ -896,13 +908,28 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
         if (ce != cudaSuccess) { e->graph_exec = nullptr; return fail("graph instantiate failed: %s", cudaGetErrorString(ce)); }
         e->graph_key = key;
       }
-      for (int i = 0; i < n_steps - 1; ++i) CK(cudaGraphLaunch(e->graph_exec, st));
+      for (int i = 0; i < n_steps - 1; ++i) {
+        const bool prof_now = e->prof_buf && i == e->prof_step;
+        if (prof_now) {
+          CK(cudaMemsetAsync(e->prof_buf, 0xFF, PROF_SLOTS * 8, st));
+          CK(cudaMemsetAsync(e->prof_buf + PROF_SLOTS, 0, PROF_SLOTS * 8, st));
+        }
+        CK(cudaGraphLaunch(e->graph_exec, st));
+        if (prof_now)
+          CK(cudaMemcpyAsync(e->prof_buf + 2 * PROF_SLOTS, e->prof_buf, 2 * PROF_SLOTS * 8, cudaMemcpyDeviceToDevice, st));
+      }
       e->launches += e->graph_launches * (n_steps - 1);
     } else {
       for (int i = 0; i < n_steps - 1; ++i) {
-        e->prof_active = (i == e->prof_step);
+        e->prof_active = (e->prof_buf && i == e->prof_step);
         e->prof_slot = 0;
+        if (e->prof_active) {
+          CK(cudaMemsetAsync(e->prof_buf, 0xFF, PROF_SLOTS * 8, st));
+          CK(cudaMemsetAsync(e->prof_buf + PROF_SLOTS, 0, PROF_SLOTS * 8, st));
+        }
         int rc = one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, true, i, st);
+        if (e->prof_active)
+          CK(cudaMemcpyAsync(e->prof_buf + 2 * PROF_SLOTS, e->prof_buf, 2 * PROF_SLOTS * 8, cudaMemcpyDeviceToDevice, st));
         e->prof_active = false;
         TRY(rc);
       }
@@ -927,10 +954,11 @@ static int vq_gn_stats(VqCtx& c, const void* x, int HW, int C) {
   chunk_pix = std::max(chunk_pix, (HW + 255) / 256);
   const int nchunks = (HW + chunk_pix - 1) / chunk_pix;
   if (nchunks > e->gn_chunks_max) return fail("internal: gn chunks");
-  if (C % 32) return fail("GroupNorm(32) needs C %% 32 == 0 (C=%d)", C);
+  if (C % 32 || C > 512) return fail("GroupNorm(32) needs C %% 32 == 0 and C <= 512 (C=%d)", C);
+  const int gn_threads = C > 256 ? 512 : 256;
   DISPATCH_T(e,
-             launch(e, gn_partial_kernel<bf16>, dim3(nchunks, c.Bc), dim3(256), 0, c.st, (const bf16*)x, e->gn_partial, HW, C, chunk_pix),
-             launch(e, gn_partial_kernel<float>, dim3(nchunks, c.Bc), dim3(256), 0, c.st, (const float*)x, e->gn_partial, HW, C, chunk_pix));
+             launch(e, gn_partial_kernel<bf16>, dim3(nchunks, c.Bc), dim3(gn_threads), 0, c.st, (const bf16*)x, e->gn_partial, HW, C, chunk_pix),
+             launch(e, gn_partial_kernel<float>, dim3(nchunks, c.Bc), dim3(gn_threads), 0, c.st, (const float*)x, e->gn_partial, HW, C, chunk_pix));
   TRY(launch(e, gn_finalize_kernel, dim3(c.Bc), dim3(32), 0, c.st, (const float*)e->gn_partial, e->gn_stats, nchunks,
              1.0 / ((double)HW * (C / 32)), 1e-6f));
   return 0;

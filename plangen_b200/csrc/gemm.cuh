@@ -35,7 +35,7 @@ template <int NT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                float* __restrict__ C, int M, int N, int K, int kb_per_split, int num_stages, int use_pdl,
-               const uint8_t* __restrict__ w_tiled, Prof prof) {
+               const uint8_t* __restrict__ w_tiled, Prof prof, bf16* __restrict__ swiglu_out) {
   using Cfg = TcCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -132,7 +132,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int n = n0 + quarter * 32 + lane;
     float* out = C + (size_t)split * M * N;
     if (use_pdl & 1) pdl_wait();
-    if (nkb > 0) {
+    if (swiglu_out != nullptr) {
+      // Fused SwiGLU epilogue (no split-K): the weight rows are interleaved in blocks of 64, so lanes 0-63 of
+      // the tile hold gate(f0 .. f0+63) and lanes 64-127 hold up(f0 .. f0+63).  The two "up" warps park
+      // their accumulators in the (now idle) first pipeline stage, the two "gate" warps combine
+      //   h = rnd(rnd(silu(rnd(g))) * rnd(u))        (HF LlamaMLP :182-184, bf16 rounding points of autocast)
+      // and store h[m][f] directly as the bf16 operand of the down projection.
+      mbar_wait(tmem_full_bar, 0, 3);
+      tc_fence_after();
+      float* xch = reinterpret_cast<float*>(smem);            // [64 lanes][17] fp32 per 16-column chunk
+      const int F = N / 2;
+      const int f = blockIdx.x * 64 + (quarter & 1) * 32 + lane;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (quarter >= 2) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) xch[((quarter - 2) * 32 + lane) * 17 + j] = __uint_as_float(v[j]);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (quarter < 2 && f < F) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int m = m0 + c0 + j;
+            if (m < M) {
+              const float g = bf16_round(__uint_as_float(v[j]));
+              const float u = bf16_round(xch[(quarter * 32 + lane) * 17 + j]);
+              const float sg = bf16_round(g / (1.0f + expf(-g)));
+              swiglu_out[(size_t)m * F + f] = __float2bfloat16_rn(sg * u);
+            }
+          }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+    } else if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0, 3);
       tc_fence_after();
 #pragma unroll 1

@@ -186,18 +186,21 @@ qkv_rope_store_kernel(const float* __restrict__ part, int S, size_t split_stride
 }
 
 // ---------------------------------------------------------------- a4.3: SwiGLU
-// h = silu(gate) * up   (HF LlamaMLP :182-184); partial layout [S][tok][2F] = [gate | up]
+// h = silu(gate) * up   (HF LlamaMLP :182-184); partial layout [S][tok][2F]: [gate | up], or - when the
+// weight rows were packed for the fused tcgen05 epilogue - interleaved in blocks of 64 (g0-63, u0-63, g64-127, ...)
 template <typename T>
 __global__ void __launch_bounds__(256)
 swiglu_kernel(const float* __restrict__ part, int S, size_t split_stride, T* __restrict__ h, int F, size_t total,
-              Prof prof) {
+              int interleaved, Prof prof) {
   pdl_launch_dependents();
   prof_begin(prof);
   pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t tok = i / F, f = i % F;
-    const float g = Act<T>::rnd(reduce_splits(part, S, split_stride, tok * 2 * F + f));
-    const float u = Act<T>::rnd(reduce_splits(part, S, split_stride, tok * 2 * F + F + f));
+    const size_t gi = interleaved ? (f / 64) * 128 + f % 64 : f;
+    const size_t ui = interleaved ? gi + 64 : F + f;
+    const float g = Act<T>::rnd(reduce_splits(part, S, split_stride, tok * 2 * F + gi));
+    const float u = Act<T>::rnd(reduce_splits(part, S, split_stride, tok * 2 * F + ui));
     const float sg = Act<T>::rnd(g / (1.0f + expf(-g)));
     Act<T>::st(h + i, sg * u);
   }

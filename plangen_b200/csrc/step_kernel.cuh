@@ -412,8 +412,9 @@ decode_step_kernel(const __grid_constant__ StepParams p) {
             const size_t i = i0 + (size_t)q * G * SK_WTHREADS;
             if (i < total) {
               const size_t tok = i / F, f = i % F;
-              load_splits(p.part_gu + tok * 2 * F + f, S, sstride, bg[q]);
-              load_splits(p.part_gu + tok * 2 * F + F + f, S, sstride, bu[q]);
+              const size_t gi = (f / 64) * 128 + f % 64;       // gate|up rows interleaved in blocks of 64 (weights.py)
+              load_splits(p.part_gu + tok * 2 * F + gi, S, sstride, bg[q]);
+              load_splits(p.part_gu + tok * 2 * F + gi + 64, S, sstride, bu[q]);
             }
           }
 #pragma unroll

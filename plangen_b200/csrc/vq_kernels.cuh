@@ -38,44 +38,43 @@ __global__ void vq_codebook_pqc_kernel(const int32_t* __restrict__ codes, const 
 // ------------------------------------------------------------------------- GroupNorm statistics
 // stage 1: per (image, pixel chunk) partial sum / sum of squares for all 32 groups.
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 gn_partial_kernel(const T* __restrict__ x, float* __restrict__ partial, int HW, int C, int chunk_pix) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float s_sum[32], s_sq[32];
+  __shared__ float t_sum[512], t_sq[512];
   const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-  if (threadIdx.x < 32) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
   const int cpg = C / 32;
   const int p0 = chunk * chunk_pix, p1 = min(HW, p0 + chunk_pix);
-  // thread -> fixed channel (so its group is fixed), strided over pixels
-  const int c = threadIdx.x % C;
-  const int prow = threadIdx.x / C, pstride = max(1, (int)blockDim.x / C);
-  if (C <= (int)blockDim.x) {
-    float a = 0.f, q = 0.f;
+  // thread -> a fixed channel residue (tid % min(C,256)); pixels strided; every thread's (sum, sumsq) goes to
+  // shared memory and the 32 group totals are formed in a FIXED order (deterministic, batch-independent)
+  const int nt = (int)blockDim.x;
+  const int cols = min(C, nt);                     // distinct channels handled per pass
+  const int cidx = threadIdx.x % cols, prow = threadIdx.x / cols, pstride = max(1, nt / cols);
+  float a = 0.f, q = 0.f;
+  int my_group = -1;
+  if (C <= nt) {
+    my_group = cidx / cpg;
     if (prow < pstride)
       for (int p = p0 + prow; p < p1; p += pstride) {
-        const float v = Act<T>::ld(x + ((size_t)b * HW + p) * C + c);
+        const float v = Act<T>::ld(x + ((size_t)b * HW + p) * C + cidx);
         a += v; q += v * v;
       }
-    atomicAdd(&s_sum[c / cpg], a);
-    atomicAdd(&s_sq[c / cpg], q);
-  } else {
-    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
-      float a = 0.f, q = 0.f;
-      for (int p = p0; p < p1; ++p) {
-        const float v = Act<T>::ld(x + ((size_t)b * HW + p) * C + cc);
-        a += v; q += v * v;
+  }
+  t_sum[threadIdx.x] = a; t_sq[threadIdx.x] = q;
+  __syncthreads();
+  if (C <= nt) {
+    if (threadIdx.x < 32) {
+      const int g = threadIdx.x;
+      float sa = 0.f, sq = 0.f;
+      for (int t = 0; t < nt; ++t) {
+        if ((t % cols) / cpg == g && t / cols < pstride) { sa += t_sum[t]; sq += t_sq[t]; }
       }
-      atomicAdd(&s_sum[cc / cpg], a);
-      atomicAdd(&s_sq[cc / cpg], q);
+      float* o = partial + (((size_t)b * nchunks + chunk) * 32 + g) * 2;
+      o[0] = sa; o[1] = sq;
     }
   }
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float* o = partial + (((size_t)b * nchunks + chunk) * 32 + threadIdx.x) * 2;
-    o[0] = s_sum[threadIdx.x]; o[1] = s_sq[threadIdx.x];
-  }
+  (void)my_group;
 }
 // stage 2: combine chunks in double -> (mean, rstd) per (image, group)
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nchunks,

@@ -2,7 +2,8 @@
 registers through `pg_engine_set_tensor`.
 
   language_model.model.layers.{i}.self_attn.{q,k,v}_proj.weight -> l{i}.wqkv  [3*H*128, D]  (rows q | k | v)
-  ...mlp.{gate,up}_proj.weight                                   -> l{i}.wgu   [2*F, D]      (rows gate | up)
+  ...mlp.{gate,up}_proj.weight                                   -> l{i}.wgu   [2*F, D]      (fp32: rows gate | up;
+                                                                    bf16: interleaved in blocks of 64 rows)
   conv weights [Cout, Cin, kh, kw]                               -> [Cout, kh*kw*Cin]        (channels-last taps)
 
 Weights are stored in the engine's operand type: bf16 (round-to-nearest-even of the fp32 master
@@ -47,7 +48,14 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, mode: str, device, 
         out[f"l{i}.wqkv"] = w(torch.cat([sd[p + "self_attn.q_proj.weight"], sd[p + "self_attn.k_proj.weight"],
                                          sd[p + "self_attn.v_proj.weight"]], dim=0))
         out[f"l{i}.wo"] = w(sd[p + "self_attn.o_proj.weight"])
-        out[f"l{i}.wgu"] = w(torch.cat([sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]], dim=0))
+        g_, u_ = sd[p + "mlp.gate_proj.weight"], sd[p + "mlp.up_proj.weight"]
+        if mode == "bf16" and dims.F % 64 == 0:
+            # rows interleaved in blocks of 64 (g[0:64], u[0:64], g[64:128], ...): one 128-row MMA tile then holds
+            # gate AND up of the same 64 features, which the tcgen05 epilogue combines (fused SwiGLU)
+            gu = torch.stack([g_.reshape(dims.F // 64, 64, dims.D), u_.reshape(dims.F // 64, 64, dims.D)], dim=1)
+            out[f"l{i}.wgu"] = w(gu.reshape(2 * dims.F, dims.D))
+        else:
+            out[f"l{i}.wgu"] = w(torch.cat([g_, u_], dim=0))
         out[f"l{i}.wd"] = w(sd[p + "mlp.down_proj.weight"])
     out["norm"] = f(sd[lm + "norm.weight"])
     out["head.w0"] = w(sd["gen_head.output_mlp_projector.weight"])
