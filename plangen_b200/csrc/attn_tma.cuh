@@ -67,15 +67,23 @@ PG_DEVINL bool mbar_test_wait(uint64_t* bar, uint32_t parity) {       // non-blo
   return ok != 0;
 }
 
+// debug timeline: stamp k of group g of this CTA (16 stamps per group); dbg == nullptr in production
+PG_DEVINL void at_stamp(unsigned long long* dbg, int g, int k) {
+  if (dbg) dbg[((size_t)blockIdx.x * AT_NG + g) * 16 + k] = global_timer_ns();
+}
+
 // units of one row: tiles covering cached tokens [start, pos) on a 32-token grid, plus the new token
 PG_DEVINL int row_tiles(int start, int pos) { return pos > start ? ((pos - 1) / AT_TILE - start / AT_TILE + 1) : 0; }
 
 // exclusive prefix of units per row into row_units[0..R] (one warp)
-PG_DEVINL void build_row_units(int* row_units, const int32_t* kv_start, int R, int pos, int lane) {
+PG_DEVINL void build_row_units(int* row_units, const int32_t* kv_start, int R, int pos, int lane,
+                                int* row_start = nullptr, int new_token_unit = 1) {
   int carry = 0;
   for (int r0 = 0; r0 < R; r0 += 32) {
     const int r = r0 + lane;
-    int u = (r < R) ? row_tiles(kv_start[r], pos) + 1 : 0;
+    const int st = (r < R) ? kv_start[r] : 0;
+    if (row_start && r < R) row_start[r] = st;
+    int u = (r < R) ? row_tiles(st, pos) + new_token_unit : 0;
     int incl = u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -121,7 +129,7 @@ PG_DEVINL void attn_group_stream(int tg, int gb, int ge, const AttnCut& cut, con
                                  float* __restrict__ ws_part, int* __restrict__ ws_count, float scale, bool bf16_trig,
                                  uint8_t* ring, int stage_stride_bytes, const int* stage_of, uint64_t* full_bar,
                                  uint64_t* empty_bar, int& kc, AttnGroupSmem& sm, int my_slot, int bar_id,
-                                 int dbg_skip_math = 0) {
+                                 int dbg_skip_math = 0, unsigned long long* dbg = nullptr) {
   const int lane = tg & 31, wig = tg >> 5;
   const int HD = H * HEAD_DIM;
   const float LOG2E = 1.4426950408889634f;
@@ -164,6 +172,7 @@ PG_DEVINL void attn_group_stream(int tg, int gb, int ge, const AttnCut& cut, con
       }
     }
     named_bar_sync(bar_id, AT_GT);
+    if (tg == 0 && u == gb) at_stamp(dbg, bar_id - 1, 2);
     float qv[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) qv[i] = sm.q[lane * 4 + i];
@@ -172,6 +181,7 @@ PG_DEVINL void attn_group_stream(int tg, int gb, int ge, const AttnCut& cut, con
     for (int t = 0; t < n_tiles_seg; ++t, ++kc) {
       const int s = stage_of[kc % SPG];
       mbar_wait(&full_bar[s], (uint32_t)(kc / SPG) & 1u, 12, kc);
+      if (tg == 0 && kc == 0) at_stamp(dbg, bar_id - 1, 3);
       if (dbg_skip_math) {                                                // profiling aid: measure the pure stream rate
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -222,6 +232,7 @@ PG_DEVINL void attn_group_stream(int tg, int gb, int ge, const AttnCut& cut, con
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);                          // AT_GW arrivals free the stage
     }
+    if (tg == 0 && seg_hi == ge) at_stamp(dbg, bar_id - 1, 4);
     // ---- the token being decoded (owner, warp 0 of the group), straight from shared memory
     if (owns_new && wig == 0) {
       float d = 0.f;
@@ -299,19 +310,19 @@ PG_DEVINL void attn_group_stream(int tg, int gb, int ge, const AttnCut& cut, con
 // copies of the group's K/V tiles into its private stages.  A single thread feeding all four groups
 // (~1300 cycles of address arithmetic, barrier probe and two bulk-copy issues per tile) was the bottleneck
 // of the kernel; four independent issuers are not.
-template <int SPG>
+template <int SPG, bool NEW_TOKEN_UNIT = true>
 PG_DEVINL void attn_produce_group(int gb, int ge, const int* row_units, int R, int H, int Tmax,
                                   const int32_t* __restrict__ kv_start, const bf16* __restrict__ kcache,
                                   const bf16* __restrict__ vcache, uint8_t* ring, int stage_stride_bytes,
                                   const int* stage_of, uint64_t* full_bar, uint64_t* empty_bar, int& kload,
-                                  uint32_t tx_bytes, uint64_t pol) {
-  int r = 0;
+                                  uint32_t tx_bytes, uint64_t pol, int r_hint = 0) {
+  int r = r_hint;
   while (r + 1 < R && row_units[r + 1] * H <= gb) ++r;
   int ur = row_units[r + 1] - row_units[r];
   int local = gb - row_units[r] * H;
   int h = local / ur, k = local % ur;
   for (int u = gb; u < ge; ++u) {
-    if (k != ur - 1) {                                   // the new-token unit has no cached tile
+    if (!NEW_TOKEN_UNIT || k != ur - 1) {                // the new-token unit has no cached tile
       const int s = stage_of[kload % SPG];
       mbar_wait(&empty_bar[s], (((uint32_t)(kload / SPG)) & 1u) ^ 1u, 11, kload);
       mbar_expect_tx(&full_bar[s], tx_bytes);
@@ -338,7 +349,8 @@ attn_decode_tma_kernel(const float* __restrict__ part, int S, size_t split_strid
                        const float* __restrict__ sinT, bf16* __restrict__ kcache, bf16* __restrict__ vcache,
                        const int32_t* __restrict__ kv_start, bf16* __restrict__ out, float* __restrict__ ws_part,
                        int* __restrict__ ws_count, int R, int H, int Tmax, int pos_base,
-                       const int* __restrict__ step_ptr, float scale, int bf16_trig, int early_trigger, Prof prof) {
+                       const int* __restrict__ step_ptr, float scale, int bf16_trig, int early_trigger, Prof prof,
+                       unsigned long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full_bar[AT_STAGES], empty_bar[AT_STAGES];
@@ -347,6 +359,7 @@ attn_decode_tma_kernel(const float* __restrict__ part, int S, size_t split_strid
   __shared__ int stage_tab[AT_NG * AT_SPG];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < AT_NG) at_stamp(dbg, tid, 0);
   if (early_trigger & 1) pdl_launch_dependents();
   prof_begin(prof);
   // The step counter is only written by the last kernel of a decode step; graph replays are fully ordered,
@@ -361,6 +374,7 @@ attn_decode_tma_kernel(const float* __restrict__ part, int S, size_t split_strid
   if (tid < AT_STAGES) stage_tab[(tid % AT_NG) * AT_SPG + tid / AT_NG] = tid;   // group g owns stages g, g+4, g+8
   if (warp == 0) build_row_units(row_units, kv_start, R, pos, lane);
   __syncthreads();
+  if (tid < AT_NG) at_stamp(dbg, tid, 1);
   AttnCut cut;
   cut.U = row_units[R] * H;
   cut.per = max(1, (cut.U + (int)gridDim.x - 1) / (int)gridDim.x);
@@ -377,6 +391,7 @@ attn_decode_tma_kernel(const float* __restrict__ part, int S, size_t split_strid
       attn_produce_group<AT_SPG>(gb, ge, row_units, R, H, Tmax, kv_start, kcache, vcache, ring, 2 * AT_TILE_BYTES,
                                  stage_tab + g * AT_SPG, full_bar, empty_bar, kload, 2 * AT_TILE_BYTES,
                                  policy_evict_first());
+      at_stamp(dbg, g, 7);
     }
     pdl_wait();
     return;
@@ -389,7 +404,8 @@ attn_decode_tma_kernel(const float* __restrict__ part, int S, size_t split_strid
   int kc = 0;
   attn_group_stream<AT_SPG>(tg, gb, ge, cut, row_units, R, H, Tmax, pos, part, S, split_stride, cosT, sinT, kcache,
                             vcache, kv_start, out, ws_part, ws_count, scale, bf16_trig != 0, ring, 2 * AT_TILE_BYTES,
-                            stage_tab + g * AT_SPG, full_bar, empty_bar, kc, gsm[g], c * AT_NG + g, 1 + g, early_trigger & 2);
+                            stage_tab + g * AT_SPG, full_bar, empty_bar, kc, gsm[g], c * AT_NG + g, 1 + g, early_trigger & 2, dbg);
+  if (tg == 0) at_stamp(dbg, g, 5);
   prof_end(prof);
 }
 

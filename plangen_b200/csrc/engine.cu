@@ -17,6 +17,8 @@
 #include "gemm.cuh"
 #include "lm_kernels.cuh"
 #include "attn_tma.cuh"
+#include "attn_v4.cuh"
+#include "attn_v5.cuh"
 #include "step_kernel.cuh"
 #include "sample.cuh"
 #include "vq_kernels.cuh"
@@ -70,7 +72,9 @@ struct pg_engine {
   std::unordered_map<std::string, std::pair<const void*, size_t>> tensors;
   EncodeTiledFn encode = nullptr;
   // options
-  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 1, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, fuse_swiglu = 1, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
+  uint64_t attn_dbg_ptr = 0;
+  int64_t attn_test_flags = 0;
+  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 3, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, fuse_swiglu = 1, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
   unsigned long long* sk_prof = nullptr;
   unsigned long long* prof_buf = nullptr;   // per-kernel timeline of ONE decode step (plain-launch mode)
@@ -85,7 +89,7 @@ struct pg_engine {
   void *xn = nullptr, *qbuf = nullptr, *attn_out = nullptr, *hbuf = nullptr, *hidden_t = nullptr, *head_h = nullptr;
   float *part = nullptr, *x_dec = nullptr, *hidden_f = nullptr, *attn_ws = nullptr;
   size_t part_bytes = 0;
-  int *attn_cnt = nullptr, *step_ctr = nullptr;
+  int *attn_cnt = nullptr, *attn_flag = nullptr, *step_ctr = nullptr;
   void *embed_table = nullptr, *align_tmp = nullptr;
   // persistent step kernel state
   CUtensorMap* wmaps_dev = nullptr; CUtensorMap* amaps_dev = nullptr; float* ln_dev = nullptr;
@@ -262,6 +266,7 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->head_h = c.take(R * d.img_embed * es);
   e->attn_ws = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 4);
   e->attn_cnt = (int*)c.take(R * d.H * 4);
+  e->attn_flag = (int*)c.take(R * d.H * 64 * 4);
   e->step_ctr = (int*)c.take(256);
   e->embed_table = c.take((size_t)d.img_vocab * d.D * es);
   e->align_tmp = c.take((size_t)d.img_vocab * d.D * es);
@@ -344,6 +349,8 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
+  CK(cudaFuncSetAttribute(attn_decode_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM));
+  CK(cudaFuncSetAttribute(attn_decode_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM));
   CK(cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
@@ -405,6 +412,8 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "vq_chunk") e->vq_chunk = (int)value;
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
+  else if (k == "attn_dbg_ptr") e->attn_dbg_ptr = (uint64_t)value;
+  else if (k == "attn_test_flags") e->attn_test_flags = value;
   else if (k == "attn_ctas") e->attn_ctas = (int)value;
   else if (k == "attn_trigger") e->attn_trigger = (int)value;
   else if (k == "use_mega") e->use_mega = (int)value;
@@ -509,6 +518,7 @@ extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
   e->use_pdl = saved_pdl;
   if (rc) return rc;
   CK(cudaMemsetAsync(e->attn_cnt, 0, (size_t)d.max_rows * d.H * 4, st));
+  CK(cudaMemsetAsync(e->attn_flag, 0, (size_t)d.max_rows * d.H * 64 * 4, st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 256, st));
   CK(cudaMemsetAsync(e->sk_sync, 0, 256, st));
   if (e->bf16) {
@@ -643,6 +653,16 @@ static int prepare_amaps(pg_engine* e, int R, cudaStream_t st) {
   return 0;
 }
 
+// The TMA-staged decode-attention generations share one signature (attn_impl: 1 = generation 3 with a
+// last-arriver counter, 2 = helper-warp variant, 3 = generation 5, the default)
+using AttnKernel = decltype(&attn_decode_tma_kernel);
+struct AttnVariant { AttnKernel fn; int threads; int smem; int* sync; };
+static AttnVariant attn_variant(const pg_engine* e) {
+  if (e->attn_impl >= 3) return {attn_decode_v5_kernel, AT_THREADS, A5_SMEM, e->attn_flag};
+  if (e->attn_impl == 2) return {attn_decode_v4_kernel, A4_THREADS, A4_SMEM, e->attn_flag};
+  return {attn_decode_tma_kernel, AT_THREADS, AT_SMEM, e->attn_cnt};
+}
+
 // all layers of one decode step in ONE persistent kernel (step_kernel.cuh); xn of layer 0 must be ready
 static int decode_layers_mega(pg_engine* e, const int32_t* kv_start, int R, int pos_base, int* step_ptr, bool inc_step,
                               cudaStream_t st) {
@@ -710,13 +730,14 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     TRY(layer_weights(e, l, &w));
     if (l == 0 && !first_norm_done) TRY(k_resid_norm(e, e->x_dec, nullptr, 0, 0, w.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
     TRY(run_gemm(e, e->xn, w.wqkv, R, 3 * HD, D, e->part, e->part_bytes, &S, st));
-    if (e->bf16 && e->attn_impl == 1 && R <= AT_MAX_ROWS) {
+    if (e->bf16 && e->attn_impl >= 1 && R <= AT_MAX_ROWS) {
       const int ctas = e->attn_ctas > 0 ? e->attn_ctas : e->num_sms;
       const int saved = e->use_pdl;
       if (!e->attn_attr) e->use_pdl = 0;
-      int rc = launch(e, attn_decode_tma_kernel, dim3(ctas), dim3(AT_THREADS), AT_SMEM, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
-                      (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ws, e->attn_cnt,
-                      R, d.H, e->Tmax, pos_base, step_ptr, scale, 1, e->attn_trigger, next_prof(e));
+      const AttnVariant av = attn_variant(e);
+      int rc = launch(e, av.fn, dim3(ctas), dim3(av.threads), av.smem, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
+                      (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ws, av.sync,
+                      R, d.H, e->Tmax, pos_base, step_ptr, scale, 1, e->attn_trigger, next_prof(e), (unsigned long long*)nullptr);
       e->use_pdl = saved;
       TRY(rc);
     } else {
@@ -1155,10 +1176,11 @@ extern "C" int pg_test_attn_decode(pg_engine* e, const int32_t* kv_start, int R,
   const int ctas = e->attn_ctas > 0 ? e->attn_ctas : e->num_sms;
   const int saved = e->use_pdl;
   e->use_pdl = 0;
-  int rc = launch(e, attn_decode_tma_kernel, dim3(ctas), dim3(AT_THREADS), AT_SMEM, st, (const float*)e->part, 1, (size_t)R * 3 * HD,
+  const AttnVariant av = attn_variant(e);
+  int rc = launch(e, av.fn, dim3(ctas), dim3(av.threads), av.smem, st, (const float*)e->part, 1, (size_t)R * 3 * HD,
                   cosT, sinT, (bf16*)kv_ptr(e, layer, 0, R), (bf16*)kv_ptr(e, layer, 1, R), kv_start, (bf16*)e->attn_out,
-                  e->attn_ws, e->attn_cnt, R, e->d.H, e->Tmax, pos, (const int*)nullptr, 1.0f / sqrtf((float)HEAD_DIM), 1, 0,
-                  next_prof(e));
+                  e->attn_ws, av.sync, R, e->d.H, e->Tmax, pos, (const int*)nullptr, 1.0f / sqrtf((float)HEAD_DIM), 1,
+                  (int)e->attn_test_flags, next_prof(e), (unsigned long long*)e->attn_dbg_ptr);
   e->use_pdl = saved;
   return rc;
 }
