@@ -12,9 +12,11 @@
 //   * the token being decoded rides on the item's last tile (no unit of its own): no empty segments;
 //   * the partials of the NEXT segment's q / k / v are loaded into registers before the current segment's
 //     tile loop and only consumed at the boundary: the round trip overlaps the stream;
-//   * hand-off without waiting: a contributor stores its record and a release flag and moves on.  The LAST
-//     contributor of an item (it meets the item first in its range, and only ever waits for earlier groups)
-//     keeps its own record in registers and merges all records in rank order at the end of its stream;
+//   * hand-off without waiting: a contributor stores its record as 64-bit words {value, valid flag} (one
+//     atomic store per word, no fence, no counter) and moves on.  The LAST contributor of an item (it meets
+//     the item first in its range, and only ever waits for earlier groups) keeps its own record in
+//     registers and, at the end of its stream, polls the other records word by word - data and flag arrive
+//     in the same load - merges in rank order and clears the words for the next launch;
 //   * 2 ring stages per group instead of 3: 19 MB in flight still covers bandwidth x latency and shortens
 //     every queue; warp-parallel row lookup in the prologue.
 // Arithmetic per tile and merge formulas are those of generation 3; results are deterministic.
@@ -29,7 +31,25 @@ namespace pg {
 constexpr int A5_SPG = PG_A5_SPG;
 constexpr int A5_STAGES = AT_NG * A5_SPG;
 constexpr int A5_SMEM = A5_STAGES * 2 * AT_TILE_BYTES + 128;
-constexpr int A5_REC = HEAD_DIM + 2;                       // (o[128], M, L) per contributor
+constexpr int A5_REC = HEAD_DIM + 2;                       // (o[128], M, L) per contributor, one 64-bit word each
+
+PG_DEVINL void a5_post(unsigned long long* p, float v) {   // {valid = 1, value} in one single-copy-atomic store
+  const unsigned long long w = (1ull << 32) | (unsigned long long)__float_as_uint(v);
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+PG_DEVINL float a5_take(const unsigned long long* p, int tag) {      // spin until the word is valid (bounded)
+  unsigned long long w, t0 = 0;
+  for (;;) {
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+    if (w >> 32) break;
+    if (t0 == 0) t0 = global_timer_ns();
+    else if (global_timer_ns() - t0 > 4000000000ull) {
+      printf("attn v5: hand-off word timeout (tag %d, cta %d, thread %d)\n", tag, (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+  return __uint_as_float((unsigned)w);
+}
 constexpr int A5_PF = 4;                                   // split-K slabs that can be prefetched in registers
 
 struct A5Seg {
@@ -104,7 +124,7 @@ PG_DEVINL void a5_group_stream(int tg, int gb, int ge, int r0, const AttnCut& cu
                                const int* row_start, int H, int Tmax, int pos, const float* __restrict__ part, int S,
                                size_t split_stride, const float* __restrict__ cosT, const float* __restrict__ sinT,
                                bf16* __restrict__ kcache, bf16* __restrict__ vcache, bf16* __restrict__ out,
-                               float* __restrict__ ws_part, int* __restrict__ flags, float scale, bool bf16_trig,
+                               unsigned long long* __restrict__ ws_ll, float scale, bool bf16_trig,
                                uint8_t* ring, int stage_stride_bytes, const int* stage_of, uint64_t* full_bar,
                                uint64_t* empty_bar, A5GroupSmem& sm, int my_slot, int bar_id, int dbg_skip_math,
                                unsigned long long* dbg) {
@@ -256,61 +276,49 @@ PG_DEVINL void a5_group_stream(int tg, int gb, int ge, int r0, const AttnCut& cu
     } else if (my_rank == n_contrib - 1) {
       dfM = M; dfL = Ltot; dfacc = acc; df_it = it; df_n = n_contrib;     // only possible for the first segment
     } else {
-      float* wp = ws_part + ((size_t)it * AT_MAX_SLOTS + my_rank) * A5_REC;
-      wp[tg] = acc;
-      if (tg == 0) { wp[HEAD_DIM] = M; wp[HEAD_DIM + 1] = Ltot; }
+      unsigned long long* wp = ws_ll + ((size_t)it * AT_MAX_SLOTS + my_rank) * A5_REC;
+      a5_post(wp + tg, acc);
+      if (tg == 0) { a5_post(wp + HEAD_DIM, M); a5_post(wp + HEAD_DIM + 1, Ltot); }
     }
-    named_bar_sync(bar_id, AT_GT);                                        // record complete; sm.* free for the next segment
-    if (n_contrib > 1 && my_rank != n_contrib - 1 && tg == 0) {           // release, cumulative over the group's stores
-      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + (size_t)it * AT_MAX_SLOTS + my_rank), "r"(1) : "memory");
-    }
+    named_bar_sync(bar_id, AT_GT);                                        // sm.* free for the next segment
     if (!has_next) break;
     cur = nxt;
   }
-  // ---- deferred merge: wait for the records of ranks 0 .. n-2, combine in rank order (own record last)
+  // ---- deferred merge: take the records of ranks 0 .. n-2 as they become valid, combine in rank order
+  //      (own record last), clear the words for the next launch
   if (df_it >= 0) {
     const int n_other = df_n - 1;
-    int* fl = flags + (size_t)df_it * AT_MAX_SLOTS;
-    if (tg < n_other) {
-      unsigned long long t0 = 0;
-      for (;;) {
-        int f;
-        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(f) : "l"(fl + tg) : "memory");
-        if (f != 0) break;
-        if (t0 == 0) t0 = global_timer_ns();
-        else if (global_timer_ns() - t0 > 4000000000ull) {
-          printf("attn v5: hand-off flag timeout item %d rank %d (cta %d)\n", df_it, tg, (int)blockIdx.x);
-          __trap();
-        }
-      }
-      fl[tg] = 0;                                                         // re-arm for the next launch
-    }
-    named_bar_sync(bar_id, AT_GT);
-    const float* wb = ws_part + (size_t)df_it * AT_MAX_SLOTS * A5_REC;
+    unsigned long long* wb = ws_ll + (size_t)df_it * AT_MAX_SLOTS * A5_REC;
     float Mg = dfM;
-    for (int s2 = 0; s2 < n_other; ++s2) Mg = fmaxf(Mg, __ldcg(wb + (size_t)s2 * A5_REC + HEAD_DIM));
+    for (int s2 = 0; s2 < n_other; ++s2) Mg = fmaxf(Mg, a5_take(wb + (size_t)s2 * A5_REC + HEAD_DIM, 1));
     float Lg = 0.f, og = 0.f;
     for (int s2 = 0; s2 < n_other; ++s2) {
-      const float ms = __ldcg(wb + (size_t)s2 * A5_REC + HEAD_DIM);
+      const float ms = a5_take(wb + (size_t)s2 * A5_REC + HEAD_DIM, 2);
+      const float ls = a5_take(wb + (size_t)s2 * A5_REC + HEAD_DIM + 1, 3);
+      const float os = a5_take(wb + (size_t)s2 * A5_REC + tg, 4);
       const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - Mg);
-      Lg += __ldcg(wb + (size_t)s2 * A5_REC + HEAD_DIM + 1) * f;
-      og += __ldcg(wb + (size_t)s2 * A5_REC + tg) * f;
+      Lg += ls * f;
+      og += os * f;
+      wb[(size_t)s2 * A5_REC + tg] = 0ull;
     }
     const float f = (dfM == -INFINITY) ? 0.f : exp2f(dfM - Mg);
     Lg += dfL * f;
     og += dfacc * f;
     out[(size_t)df_it * HEAD_DIM + tg] = __float2bfloat16_rn(og / Lg);
+    named_bar_sync(bar_id, AT_GT);                                        // everyone has read M and L
+    if (tg < n_other) { wb[(size_t)tg * A5_REC + HEAD_DIM] = 0ull; wb[(size_t)tg * A5_REC + HEAD_DIM + 1] = 0ull; }
   }
 }
 
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_decode_v5_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ cosT,
                       const float* __restrict__ sinT, bf16* __restrict__ kcache, bf16* __restrict__ vcache,
-                      const int32_t* __restrict__ kv_start, bf16* __restrict__ out, float* __restrict__ ws_part,
-                      int* __restrict__ flags, int R, int H, int Tmax, int pos_base,
+                      const int32_t* __restrict__ kv_start, bf16* __restrict__ out, float* __restrict__ ws_ll_f,
+                      int* __restrict__ /*unused*/, int R, int H, int Tmax, int pos_base,
                       const int* __restrict__ step_ptr, float scale, int bf16_trig, int early_trigger, Prof prof,
                       unsigned long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
+  unsigned long long* ws_ll = reinterpret_cast<unsigned long long*>(ws_ll_f);   // zero-initialised {flag, value} words
   uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
   __shared__ uint64_t full_bar[A5_STAGES], empty_bar[A5_STAGES];
   __shared__ int row_units[AT_MAX_ROWS + 1], row_start[AT_MAX_ROWS];
@@ -357,7 +365,7 @@ attn_decode_v5_kernel(const float* __restrict__ part, int S, size_t split_stride
   pdl_wait();                                             // QKV partials of this step are now visible
   const int tg = tid - g * AT_GT;
   a5_group_stream<A5_SPG>(tg, gb, ge, r0, cut, row_units, row_start, H, Tmax, pos, part, S, split_stride, cosT, sinT,
-                          kcache, vcache, out, ws_part, flags, scale, bf16_trig != 0, ring, 2 * AT_TILE_BYTES,
+                          kcache, vcache, out, ws_ll, scale, bf16_trig != 0, ring, 2 * AT_TILE_BYTES,
                           stage_tab + g * A5_SPG, full_bar, empty_bar, gsm[g], c * AT_NG + g, 1 + g, early_trigger & 2, dbg);
   if (tg == 0) at_stamp(dbg, g, 5);
   prof_end(prof);

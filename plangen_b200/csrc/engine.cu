@@ -87,7 +87,7 @@ struct pg_engine {
   void* ws = nullptr; size_t ws_bytes = 0;
   // workspace carve-outs
   void *xn = nullptr, *qbuf = nullptr, *attn_out = nullptr, *hbuf = nullptr, *hidden_t = nullptr, *head_h = nullptr;
-  float *part = nullptr, *x_dec = nullptr, *hidden_f = nullptr, *attn_ws = nullptr;
+  float *part = nullptr, *x_dec = nullptr, *hidden_f = nullptr, *attn_ws = nullptr, *attn_ll = nullptr;
   size_t part_bytes = 0;
   int *attn_cnt = nullptr, *attn_flag = nullptr, *step_ctr = nullptr;
   void *embed_table = nullptr, *align_tmp = nullptr;
@@ -267,6 +267,7 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->attn_ws = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 4);
   e->attn_cnt = (int*)c.take(R * d.H * 4);
   e->attn_flag = (int*)c.take(R * d.H * 64 * 4);
+  e->attn_ll = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 8);
   e->step_ctr = (int*)c.take(256);
   e->embed_table = c.take((size_t)d.img_vocab * d.D * es);
   e->align_tmp = c.take((size_t)d.img_vocab * d.D * es);
@@ -519,6 +520,7 @@ extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
   if (rc) return rc;
   CK(cudaMemsetAsync(e->attn_cnt, 0, (size_t)d.max_rows * d.H * 4, st));
   CK(cudaMemsetAsync(e->attn_flag, 0, (size_t)d.max_rows * d.H * 64 * 4, st));
+  CK(cudaMemsetAsync(e->attn_ll, 0, (size_t)d.max_rows * d.H * 64 * (HEAD_DIM + 2) * 8, st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 256, st));
   CK(cudaMemsetAsync(e->sk_sync, 0, 256, st));
   if (e->bf16) {
@@ -656,11 +658,11 @@ static int prepare_amaps(pg_engine* e, int R, cudaStream_t st) {
 // The TMA-staged decode-attention generations share one signature (attn_impl: 1 = generation 3 with a
 // last-arriver counter, 2 = helper-warp variant, 3 = generation 5, the default)
 using AttnKernel = decltype(&attn_decode_tma_kernel);
-struct AttnVariant { AttnKernel fn; int threads; int smem; int* sync; };
+struct AttnVariant { AttnKernel fn; int threads; int smem; int* sync; float* ws; };
 static AttnVariant attn_variant(const pg_engine* e) {
-  if (e->attn_impl >= 3) return {attn_decode_v5_kernel, AT_THREADS, A5_SMEM, e->attn_flag};
-  if (e->attn_impl == 2) return {attn_decode_v4_kernel, A4_THREADS, A4_SMEM, e->attn_flag};
-  return {attn_decode_tma_kernel, AT_THREADS, AT_SMEM, e->attn_cnt};
+  if (e->attn_impl >= 3) return {attn_decode_v5_kernel, AT_THREADS, A5_SMEM, e->attn_flag, e->attn_ll};
+  if (e->attn_impl == 2) return {attn_decode_v4_kernel, A4_THREADS, A4_SMEM, e->attn_flag, e->attn_ws};
+  return {attn_decode_tma_kernel, AT_THREADS, AT_SMEM, e->attn_cnt, e->attn_ws};
 }
 
 // all layers of one decode step in ONE persistent kernel (step_kernel.cuh); xn of layer 0 must be ready
@@ -736,7 +738,7 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
       if (!e->attn_attr) e->use_pdl = 0;
       const AttnVariant av = attn_variant(e);
       int rc = launch(e, av.fn, dim3(ctas), dim3(av.threads), av.smem, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
-                      (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ws, av.sync,
+                      (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, av.ws, av.sync,
                       R, d.H, e->Tmax, pos_base, step_ptr, scale, 1, e->attn_trigger, next_prof(e), (unsigned long long*)nullptr);
       e->use_pdl = saved;
       TRY(rc);
@@ -1179,7 +1181,7 @@ extern "C" int pg_test_attn_decode(pg_engine* e, const int32_t* kv_start, int R,
   const AttnVariant av = attn_variant(e);
   int rc = launch(e, av.fn, dim3(ctas), dim3(av.threads), av.smem, st, (const float*)e->part, 1, (size_t)R * 3 * HD,
                   cosT, sinT, (bf16*)kv_ptr(e, layer, 0, R), (bf16*)kv_ptr(e, layer, 1, R), kv_start, (bf16*)e->attn_out,
-                  e->attn_ws, av.sync, R, e->d.H, e->Tmax, pos, (const int*)nullptr, 1.0f / sqrtf((float)HEAD_DIM), 1,
+                  av.ws, av.sync, R, e->d.H, e->Tmax, pos, (const int*)nullptr, 1.0f / sqrtf((float)HEAD_DIM), 1,
                   (int)e->attn_test_flags, next_prof(e), (unsigned long long*)e->attn_dbg_ptr);
   e->use_pdl = saved;
   return rc;
