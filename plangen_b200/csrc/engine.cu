@@ -70,6 +70,10 @@ struct pg_engine {
   size_t esz = 2;                 // bytes per activation / weight element
   int Tmax = 0, HD = 0;
   std::unordered_map<std::string, std::pair<const void*, size_t>> tensors;
+  struct Tiled { const uint8_t* ptr; int N, K; };
+  std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
+  uint8_t* tiled_buf = nullptr;
+  int use_tiled = 1;
   EncodeTiledFn encode = nullptr;
   // options
   uint64_t attn_dbg_ptr = 0;
@@ -212,6 +216,10 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     const int kb_per_split = (num_kb + want - 1) / want;
     splits = (num_kb + kb_per_split - 1) / kb_per_split;
     if ((size_t)splits * M * N * 4 > c_bytes) return fail("GEMM partial buffer too small (%d x %d x %d)", splits, M, N);
+    if (!w_tiled && w_const && e->use_tiled) {             // stream the tile-major copy when the weight has one
+      auto it = e->tiled.find(W);
+      if (it != e->tiled.end() && it->second.N == N && it->second.K == K) w_tiled = it->second.ptr;
+    }
     CUtensorMap mw, mx;
     TRY(make_map_2d(e, &mw, W, (uint64_t)N, (uint64_t)K, TC_BM));
     TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
@@ -364,6 +372,7 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
 extern "C" int pg_engine_destroy(pg_engine* e) {
   if (!e) return 0;
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  if (e->tiled_buf) cudaFree(e->tiled_buf);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
@@ -413,7 +422,10 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "vq_chunk") e->vq_chunk = (int)value;
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
+  else if (k == "use_tiled") e->use_tiled = (int)value;
   else if (k == "attn_dbg_ptr") e->attn_dbg_ptr = (uint64_t)value;
+  else if (k == "gemm_dbg_ptr") { unsigned long long* p = (unsigned long long*)value; CK(cudaMemcpyToSymbol(g_gemm_dbg, &p, sizeof(p))); }
+  else if (k == "gemm_dbg_n") { int n = (int)value; CK(cudaMemcpyToSymbol(g_gemm_dbg_n, &n, sizeof(n))); }
   else if (k == "attn_test_flags") e->attn_test_flags = value;
   else if (k == "attn_ctas") e->attn_ctas = (int)value;
   else if (k == "attn_trigger") e->attn_trigger = (int)value;
@@ -538,6 +550,35 @@ extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
     }
     CK(cudaMemcpyAsync(e->wmaps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
+  }
+  if (e->bf16 && !e->tiled_buf) {
+    // tile-major copies of the weights that are streamed once per step (see tile_weight_kernel)
+    struct Item { const void* w; int N, K; };
+    std::vector<Item> items;
+    for (int l = 0; l < d.L; ++l) {
+      LayerW w;
+      TRY(layer_weights(e, l, &w));
+      items.push_back({w.wqkv, 3 * e->HD, d.D});
+      items.push_back({w.wo, d.D, e->HD});
+      items.push_back({w.wgu, 2 * d.F, d.D});
+      items.push_back({w.wd, d.D, d.F});
+    }
+    if (const void* hw0 = T_(e, "head.w0")) items.push_back({hw0, d.img_embed, d.D});
+    if (const void* hw1 = T_(e, "head.w1")) items.push_back({hw1, d.img_vocab, d.img_embed});
+    size_t total_bytes = 0;
+    auto tiles_of = [](const Item& it) { return (size_t)((it.N + TC_BM - 1) / TC_BM) * ((it.K + TC_BK - 1) / TC_BK); };
+    for (const Item& it : items) if (it.K % 8 == 0) total_bytes += tiles_of(it) * TC_A_BYTES;
+    CK(cudaMalloc(&e->tiled_buf, std::max<size_t>(total_bytes, 16)));
+    size_t off = 0;
+    for (const Item& it : items) {
+      if (it.K % 8 != 0 || (((uintptr_t)it.w) & 15) != 0) continue;
+      const size_t n_chunks = tiles_of(it) * (TC_A_BYTES / 16);
+      const int blocks = (int)std::min<size_t>((n_chunks + 255) / 256, (size_t)e->num_sms * 16);
+      tile_weight_kernel<<<blocks, 256, 0, st>>>((const bf16*)it.w, e->tiled_buf + off, it.N, it.K, (it.K + TC_BK - 1) / TC_BK, n_chunks);
+      CK(cudaGetLastError());
+      e->tiled[it.w] = {e->tiled_buf + off, it.N, it.K};
+      off += tiles_of(it) * TC_A_BYTES;
+    }
   }
   CK(cudaStreamSynchronize(st));
   e->finalized = true;

@@ -8,7 +8,8 @@
 //                      operand (N = NT tokens, 16..256), so a decode step with R = 2..128 rows
 //                      streams weights at full TMA rate without padding rows to 128.
 //                      TMA (SWIZZLE_128B) -> smem ring -> tcgen05.mma (fp32 accum in TMEM) ->
-//                      tcgen05.ld epilogue.  Warp-specialised: warp0 TMA, warp1 MMA, warps2-5 epilogue.
+//                      tcgen05.ld epilogue.  Warp-specialised: warp0 TMA, warp1 MMA, warps2-5 epilogue
+//                      (warps 2 and 3 double as the second weight producer and the token-tile producer).
 //                      With PDL the weight tiles of all stages are requested BEFORE
 //                      griddepcontrol.wait, so the HBM stream does not drain at kernel boundaries.
 //   gemm_simt_kernel : fp32 (check mode) / bf16 CUDA-core fallback used for parity tests and for
@@ -23,13 +24,64 @@ constexpr int TC_BM = 128;   // weight rows per CTA (MMA M)
 constexpr int TC_BK = 64;    // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 
+// 16 accumulator columns of this warp's 32 TMEM lanes, summed over the NACC column blocks (block 0 first)
+template <int NACC, int NT>
+PG_DEVINL void tmem_ld_acc_sum(uint32_t taddr, uint32_t (&v)[16], int n_used) {
+  tmem_ld_32x32b_x16(taddr, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int a = 1; a < NACC; ++a) {
+    if (a >= n_used) break;
+    uint32_t w[16];
+    tmem_ld_32x32b_x16(taddr + (uint32_t)(a * NT), w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+  }
+}
+
 template <int NT>
 struct TcCfg {
   static constexpr int B_BYTES = NT * TC_BK * 2;
   static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-  static constexpr int TMEM_COLS = NT <= 32 ? 32 : NT <= 64 ? 64 : NT <= 128 ? 128 : 256;
+  // Successive tcgen05.mma into ONE accumulator form a dependent chain: with N <= 64 an MMA occupies the
+  // tensor pipe for 8-32 cycles but each link of the chain costs the full pipeline latency (~180 cycles,
+  // measured: 0.38 us per 4-MMA k-block), which paced every weight-streaming contraction of the decode step.
+  // The K-steps of a k-block therefore go round-robin into NACC independent accumulators (TMEM column
+  // blocks) that the epilogue adds up in a fixed order.
+  static constexpr int NACC = NT <= 64 ? 4 : NT <= 128 ? 2 : 1;
+  static constexpr int ACC_COLS = NACC * NT;
+  static constexpr int TMEM_COLS = ACC_COLS <= 32 ? 32 : ACC_COLS <= 64 ? 64 : ACC_COLS <= 128 ? 128 : ACC_COLS <= 256 ? 256 : 512;
   static constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/; }
 };
+
+// Tile-major weight copy for the streaming contractions: tile (nt, kb) = rows nt*128.., k kb*64.. as one
+// contiguous 16 KB block already in the SWIZZLE_128B shared-memory layout (16-byte chunk c of row r sits at
+// r*128 + ((c ^ (r & 7)) * 16)), zero-padded at the edges.  A row-major weight makes every TMA tile 128
+// separate 128-byte pieces at a stride of K*2 bytes (a different DRAM page each); measured on the gate|up
+// contraction that holds the stream at ~2.6 TB/s.
+__global__ void __launch_bounds__(256)
+tile_weight_kernel(const bf16* __restrict__ W, uint8_t* __restrict__ out, int N, int K, int num_kb, size_t n_chunks) {
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_chunks; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx & 7), r = (int)((idx >> 3) & 127);
+    const size_t tile = idx >> 10;
+    const int kb = (int)(tile % num_kb);
+    const size_t nt = tile / num_kb;
+    const size_t n = nt * TC_BM + r;
+    const int k = kb * TC_BK + c * 8;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (n < (size_t)N && k + 8 <= K) v = *reinterpret_cast<const uint4*>(W + n * K + k);
+    *reinterpret_cast<uint4*>(out + tile * TC_A_BYTES + r * 128 + ((c ^ (r & 7)) * 16)) = v;
+  }
+}
+
+// debug timeline (tools/gemm_timeline.py): 8 %globaltimer stamps per CTA for launches whose weight-row count
+// equals g_gemm_dbg_n; nullptr in production
+__device__ unsigned long long* g_gemm_dbg = nullptr;
+__device__ int g_gemm_dbg_n = 0;
+PG_DEVINL void gemm_stamp(unsigned long long* dbg, int k) {
+  if (dbg) dbg[((size_t)(blockIdx.z * gridDim.x + blockIdx.x)) * 8 + k] = global_timer_ns();
+}
 
 template <int NT>
 __global__ void __launch_bounds__(192, 1)
@@ -56,12 +108,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 
   if (use_pdl & 1) pdl_launch_dependents();
   prof_begin(prof);
+  unsigned long long* dbg = (g_gemm_dbg_n == N && blockIdx.y == 0) ? g_gemm_dbg : nullptr;
+  if (threadIdx.x == 0) gemm_stamp(dbg, 0);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
     tma_prefetch_desc(&map_x);
-    for (int i = 0; i < num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(tmem_full_bar, 1);
+    for (int i = 0; i < num_stages; ++i) { mbar_init(&full_bar[i], 2); mbar_init(&empty_bar[i], 1); }   // full: W + X producer
+    mbar_init(tmem_full_bar, Cfg::NACC >= 2 ? 2 : 1);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -73,64 +127,85 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================== TMA producer (one thread) =====================
-    if (lane == 0) {
-      const uint64_t pol_w = policy_evict_first();   // weights are streamed once per step
-      const uint64_t pol_x = policy_evict_last();    // activations are re-read by every CTA
-      const int pre = min(nkb, num_stages);
-      // use_pdl bit 1: the W operand is a constant weight, so its tiles may be requested before the
-      // previous kernel has finished (it is an activation in the VQ attention contractions)
-      // A tile source: TMA tensor load from the row-major weight, or - when the weight was packed tile-major
-      // and pre-swizzled (w_tiled) - ONE contiguous 16 KB bulk copy per tile (full DRAM bursts, one issue).
-      auto load_a = [&](int stage, int kb) {
-        if (w_tiled)
-          bulk_copy_g2s(smem + stage * Cfg::STAGE_BYTES, w_tiled + ((size_t)blockIdx.x * num_kb + kb) * TC_A_BYTES, TC_A_BYTES,
-                        &full_bar[stage], pol_w);
-        else
-          tma_load_2d(smem + stage * Cfg::STAGE_BYTES, &map_w, &full_bar[stage], kb * TC_BK, n0, pol_w);
-      };
-      if ((use_pdl & 3) == 1) pdl_wait();
-      for (int i = 0; i < pre; ++i) {
-        mbar_expect_tx(&full_bar[i], Cfg::STAGE_BYTES);
-        load_a(i, kb_begin + i);
-      }
-      if ((use_pdl & 3) == 3) pdl_wait();
-      for (int i = 0; i < pre; ++i)
-        tma_load_2d(smem + i * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[i], (kb_begin + i) * TC_BK, m0, pol_x);
-      for (int i = pre; i < nkb; ++i) {
-        const int s = i % num_stages;
-        const uint32_t round = (uint32_t)(i / num_stages);
-        mbar_wait(&empty_bar[s], (round & 1u) ^ 1u, 1);
-        mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-        load_a(s, kb_begin + i);
-        tma_load_2d(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[s], (kb_begin + i) * TC_BK, m0, pol_x);
-      }
+  // ===================== TMA producers (three threads) =====================
+  // One thread issuing cp.async.bulk / TMA tensor loads sustains only ~3.6 operations/us (measured,
+  // tools/micro/stream_bench.cu: 16 KB copies from one thread top out at 59 GB/s per CTA whatever the ring
+  // depth), which bounded every weight-streaming contraction at ~30 GB/s per CTA with one producer doing
+  // W + X per k-block.  The W tiles are therefore split over two issuing threads (even / odd k-blocks: warp 0
+  // and epilogue warp 2, idle until the accumulator is complete) and the X tiles over two or three (warps 3-5).
+  // Each stage's full barrier takes two arrive.expect_tx (W bytes, X bytes).
+  // use_pdl bit 1: the W operand is a constant weight, so its tiles may be requested before the previous
+  // kernel has finished (it is an activation in the VQ attention contractions).
+  constexpr bool DUAL = Cfg::NACC >= 2;        // two MMA issuers (below)
+  auto produce_w = [&](int first) {
+    const uint64_t pol_w = policy_evict_first();     // weights are streamed once per step
+    if ((use_pdl & 3) == 1) pdl_wait();
+    for (int i = first; i < nkb; i += 2) {
+      const int s = i % num_stages;
+      mbar_wait(&empty_bar[s], (((uint32_t)(i / num_stages)) & 1u) ^ 1u, 1);
+      if (dbg && blockIdx.x == 5 && blockIdx.z == 0 && i < 64) dbg[16384 + 64 + i] = global_timer_ns();
+      mbar_expect_tx(&full_bar[s], TC_A_BYTES);
+      if (w_tiled)   // weight packed tile-major and pre-swizzled: one contiguous 16 KB bulk copy per tile
+        bulk_copy_g2s(smem + s * Cfg::STAGE_BYTES, w_tiled + ((size_t)blockIdx.x * num_kb + kb_begin + i) * TC_A_BYTES, TC_A_BYTES,
+                      &full_bar[s], pol_w);
+      else
+        tma_load_2d(smem + s * Cfg::STAGE_BYTES, &map_w, &full_bar[s], (kb_begin + i) * TC_BK, n0, pol_w);
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16(TC_BM, NT);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % num_stages;
-        const uint32_t round = (uint32_t)(i / num_stages);
-        mbar_wait(&full_bar[s], round & 1u, 2);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
-        const uint64_t da = umma_desc_k_sw128(a_addr);
-        const uint64_t db = umma_desc_k_sw128(a_addr + TC_A_BYTES);
+  };
+  auto produce_x = [&](int first) {
+    const uint64_t pol_x = policy_evict_last();      // activations are re-read by every CTA
+    if (use_pdl & 1) pdl_wait();
+    if (first == 0) gemm_stamp(dbg, 1);
+    for (int i = first; i < nkb; i += (DUAL ? 2 : 3)) {
+      const int s = i % num_stages;
+      mbar_wait(&empty_bar[s], (((uint32_t)(i / num_stages)) & 1u) ^ 1u, 1);
+      if (dbg && blockIdx.x == 5 && blockIdx.z == 0 && i < 64) dbg[16384 + 128 + i] = global_timer_ns();
+      mbar_expect_tx(&full_bar[s], Cfg::B_BYTES);
+      tma_load_2d(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[s], (kb_begin + i) * TC_BK, m0, pol_x);
+    }
+  };
+  // ===================== MMA issuers (one or two threads) =====================
+  // Measured (clock64 around the issue loop): one thread spends 256 cycles issuing the four K=16 MMAs of a
+  // k-block (the tensor pipe reads the 4 KB A slice of each from shared memory at 64 B/clk - that is the
+  // floor of streaming weights as the A operand), then 115 cycles in tcgen05.commit and ~100 in the next
+  // full-barrier wait during which the pipe drains: ~50% utilisation, 0.25-0.38 us per k-block.  Two
+  // issuers on alternate k-blocks, each with its own accumulator blocks, keep the pipe fed.
+  auto issue_mma = [&](int first, int stride, int acc0, int nacc) {
+    const uint32_t idesc = umma_idesc_bf16(TC_BM, NT);
+    for (int i = first; i < nkb; i += stride) {
+      const int s = i % num_stages;
+      mbar_wait(&full_bar[s], ((uint32_t)(i / num_stages)) & 1u, 2);
+      if (i == 0) gemm_stamp(dbg, 2);
+      if (i == nkb - 1) gemm_stamp(dbg, 3);
+      if (dbg && blockIdx.x == 5 && blockIdx.z == 0 && i < 64) dbg[16384 + i] = global_timer_ns();
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + s * Cfg::STAGE_BYTES);
+      const uint64_t da = umma_desc_k_sw128(a_addr);
+      const uint64_t db = umma_desc_k_sw128(a_addr + TC_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)   // UMMA_K = 16 bf16 = 32 bytes = +2 in the encoded address
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
-        umma_commit(&empty_bar[s]);            // frees the smem stage once these MMAs retire
-      }
-      umma_commit(tmem_full_bar);              // accumulator complete -> epilogue
+      for (int k = 0; k < TC_BK / 16; ++k)     // UMMA_K = 16 bf16 = 32 bytes = +2 in the encoded address
+        umma_bf16(tmem_base + (uint32_t)((acc0 + k % nacc) * NT), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                  (uint32_t)((i != first) || (k / nacc != 0)));
+      umma_commit(&empty_bar[s]);              // frees the smem stage once these MMAs retire
     }
+    umma_commit(tmem_full_bar);                // this issuer's accumulators complete -> epilogue
+  };
+  if (warp == 0) {
+    if (lane == 0) produce_w(0);
+  } else if (warp == 1) {
+    if (lane == 0) issue_mma(0, DUAL ? 2 : 1, 0, DUAL ? Cfg::NACC / 2 : Cfg::NACC);
   } else {
     // ===================== epilogue: TMEM -> registers -> global (4 warps) =====================
     const int quarter = warp & 3;              // a warp may only touch TMEM lanes 32*(warp%4)..+31
     const int n = n0 + quarter * 32 + lane;
     float* out = C + (size_t)split * M * N;
+    const int acc_used = (DUAL && nkb < 2) ? Cfg::NACC / 2 : Cfg::NACC;   // the second issuer's blocks stay unwritten
+    if (lane == 0) {                            // producer / second issuer duty first (see above), then the epilogue
+      if (warp == 2) produce_w(1);
+      else if (DUAL && warp == 5) issue_mma(1, 2, Cfg::NACC / 2, Cfg::NACC / 2);
+      else produce_x(warp - 3);
+    }
+    __syncwarp();
     if (use_pdl & 1) pdl_wait();
     if (swiglu_out != nullptr) {
       // Fused SwiGLU epilogue (no split-K): the weight rows are interleaved in blocks of 64, so lanes 0-63 of
@@ -139,6 +214,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       //   h = rnd(rnd(silu(rnd(g))) * rnd(u))        (HF LlamaMLP :182-184, bf16 rounding points of autocast)
       // and store h[m][f] directly as the bf16 operand of the down projection.
       mbar_wait(tmem_full_bar, 0, 3);
+      if (warp == 2 && lane == 0) gemm_stamp(dbg, 4);
       tc_fence_after();
       float* xch = reinterpret_cast<float*>(smem);            // [64 lanes][17] fp32 per 16-column chunk
       const int F = N / 2;
@@ -146,8 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 #pragma unroll 1
       for (int c0 = 0; c0 < NT; c0 += 16) {
         uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
+        tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
         if (quarter >= 2) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) xch[((quarter - 2) * 32 + lane) * 17 + j] = __uint_as_float(v[j]);
@@ -169,12 +244,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       }
     } else if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0, 3);
+      if (warp == 2 && lane == 0) gemm_stamp(dbg, 4);
       tc_fence_after();
 #pragma unroll 1
       for (int c0 = 0; c0 < NT; c0 += 16) {
         uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v);
-        tmem_ld_wait();
+        tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
         if (n < N) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -190,8 +265,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       }
     }
   }
+  if (warp == 2 && lane == 0) gemm_stamp(dbg, 5);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) gemm_stamp(dbg, 6);
   prof_end(prof);
   if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }

@@ -50,7 +50,7 @@ int main(int argc, char** argv) {
   const int copy_bytes = argc > 1 ? atoi(argv[1]) : 8192, stages = argc > 2 ? atoi(argv[2]) : 3, producers = argc > 3 ? atoi(argv[3]) : 4;
   const int ctas_per_sm = argc > 4 ? atoi(argv[4]) : 1, mode = argc > 5 ? atoi(argv[5]) : 0;
   cudaDeviceProp prop; cudaGetDeviceProperties(&prop, 0);
-  const int G = prop.multiProcessorCount * ctas_per_sm;
+  const int G = argc > 6 ? atoi(argv[6]) : prop.multiProcessorCount * ctas_per_sm;   // optional: grid size override
   const int stage_bytes = mode ? 2 * copy_bytes : copy_bytes;
   const size_t per_prod = ((size_t)4 << 30) / ((size_t)G * producers) / stage_bytes * stage_bytes;   // ~4 GB total
   const size_t total = per_prod * G * producers;
@@ -68,7 +68,7 @@ int main(int argc, char** argv) {
     float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
   }
   cudaError_t err = cudaGetLastError();
-  printf("copy %6d B x%d stages x%d producers x%d cta/sm mode %d smem %zu KB: %.1f GB/s (%s)\n", copy_bytes, stages, producers, ctas_per_sm, mode,
-         smem / 1024, total / (best * 1e-3) / 1e9, cudaGetErrorString(err));
+  printf("copy %6d B x%d stages x%d producers grid %d mode %d smem %zu KB: %.1f GB/s = %.1f GB/s per CTA (%s)\n", copy_bytes, stages, producers, G, mode,
+         smem / 1024, total / (best * 1e-3) / 1e9, total / (best * 1e-3) / 1e9 / G, cudaGetErrorString(err));
   return 0;
 }
