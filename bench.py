@@ -223,7 +223,7 @@ def kernel_roofline(eng, kv_start, lens, P: int, peaks: dict, iters: int = 6):
     which = "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
     if not peak:
         peak, which = 6650.0, "fallback (B200_PROFILING.md)"
-    return {"bound": "hbm", "kernel": "attn_decode_tma_kernel (KV-cache decode attention, paired CFG batch, 1 launch/layer)",
+    return {"bound": "hbm", "kernel": "attn_decode_v5_kernel (KV-cache decode attention, paired CFG batch, 1 launch/layer)",
             "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak,
             "traffic": 141221376 + 6263552, "traffic_note": "dram read+write per launch from ncu --set full at step 300 of the "
             "same workload (profiles/r01_attn_decode.full.txt); algorithmic K+V bytes there: 133.5 MB",

@@ -27,16 +27,23 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 // 16 accumulator columns of this warp's 32 TMEM lanes, summed over the NACC column blocks (block 0 first)
 template <int NACC, int NT>
 PG_DEVINL void tmem_ld_acc_sum(uint32_t taddr, uint32_t (&v)[16], int n_used) {
-  tmem_ld_32x32b_x16(taddr, v);
-  tmem_ld_wait();
+  if constexpr (NACC == 1) {
+    tmem_ld_32x32b_x16(taddr, v);
+    tmem_ld_wait();
+  } else {
+    // all column blocks are requested before the single wait (a tcgen05.ld round trip is ~100+ cycles)
+    uint32_t w[NACC - 1][16];
+    tmem_ld_32x32b_x16(taddr, v);
 #pragma unroll
-  for (int a = 1; a < NACC; ++a) {
-    if (a >= n_used) break;
-    uint32_t w[16];
-    tmem_ld_32x32b_x16(taddr + (uint32_t)(a * NT), w);
+    for (int a = 1; a < NACC; ++a)
+      if (a < n_used) tmem_ld_32x32b_x16(taddr + (uint32_t)(a * NT), w[a - 1]);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+    for (int a = 1; a < NACC; ++a) {
+      if (a >= n_used) break;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[a - 1][j]));
+    }
   }
 }
 
@@ -209,35 +216,48 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     if (use_pdl & 1) pdl_wait();
     if (swiglu_out != nullptr) {
       // Fused SwiGLU epilogue (no split-K): the weight rows are interleaved in blocks of 64, so lanes 0-63 of
-      // the tile hold gate(f0 .. f0+63) and lanes 64-127 hold up(f0 .. f0+63).  The two "up" warps park
-      // their accumulators in the (now idle) first pipeline stage, the two "gate" warps combine
+      // the tile hold gate(f0 .. f0+63) and lanes 64-127 hold up(f0 .. f0+63).  Gate and up warps swap half of
+      // their accumulators through the (now idle) first pipeline stage and combine
       //   h = rnd(rnd(silu(rnd(g))) * rnd(u))        (HF LlamaMLP :182-184, bf16 rounding points of autocast)
-      // and store h[m][f] directly as the bf16 operand of the down projection.
+      // storing h[m][f] directly as the bf16 operand of the down projection.
       mbar_wait(tmem_full_bar, 0, 3);
       if (warp == 2 && lane == 0) gemm_stamp(dbg, 4);
       tc_fence_after();
-      float* xch = reinterpret_cast<float*>(smem);            // [64 lanes][17] fp32 per 16-column chunk
+      // Each gate warp (quarters 0, 1) pairs with the up warp two quarters above it.  Per 16-column chunk the
+      // gate warp hands g of columns 8..15 to the up warp and receives u of columns 0..7, so all four warps
+      // compute (8 tokens each) and the 8 results of a thread are independent chains the scheduler can overlap.
+      float* xch = reinterpret_cast<float*>(smem);            // [128 lanes][9] fp32 per 16-column chunk
       const int F = N / 2;
-      const int f = blockIdx.x * 64 + (quarter & 1) * 32 + lane;
+      const int pair = quarter & 1;                           // f-block within the tile
+      const int f = blockIdx.x * 64 + pair * 32 + lane;
+      const bool is_gate = quarter < 2;
+      const int jbase = is_gate ? 0 : 8;                      // columns this warp finishes
 #pragma unroll 1
       for (int c0 = 0; c0 < NT; c0 += 16) {
         uint32_t v[16];
         tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
-        if (quarter >= 2) {
+        float* mine = xch + (size_t)(quarter * 32 + lane) * 9;                   // what I give away
+        const float* theirs = xch + (size_t)((quarter ^ 2) * 32 + lane) * 9;     // what my partner gives me
 #pragma unroll
-          for (int j = 0; j < 16; ++j) xch[((quarter - 2) * 32 + lane) * 17 + j] = __uint_as_float(v[j]);
-        }
+        for (int j = 0; j < 8; ++j) mine[j] = __uint_as_float(v[(is_gate ? 8 : 0) + j]);
         asm volatile("bar.sync 2, 128;" ::: "memory");
-        if (quarter < 2 && f < F) {
+        float h[8];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m0 + c0 + j;
-            if (m < M) {
-              const float g = bf16_round(__uint_as_float(v[j]));
-              const float u = bf16_round(xch[(quarter * 32 + lane) * 17 + j]);
-              const float sg = bf16_round(g / (1.0f + expf(-g)));
-              swiglu_out[(size_t)m * F + f] = __float2bfloat16_rn(sg * u);
-            }
+        for (int j = 0; j < 8; ++j) {
+          const float own = __uint_as_float(v[jbase + j]), other = theirs[j];
+          const float g = bf16_round(is_gate ? own : other);
+          const float u = bf16_round(is_gate ? other : own);
+          // ex2.approx / rcp-based division: ~1e-6 relative error against a result kept to 8 mantissa bits;
+          // the exact expf + IEEE division cost ~100 dependent instructions per element on warps that have
+          // their scheduler to themselves (measured 1.4 us per 16-column chunk)
+          const float sg = bf16_round(__fdividef(g, 1.0f + __expf(-g)));
+          h[j] = sg * u;
+        }
+        if (f < F) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int m = m0 + c0 + jbase + j;
+            if (m < M) swiglu_out[(size_t)m * F + f] = __float2bfloat16_rn(h[j]);
           }
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");

@@ -77,6 +77,13 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
   __shared__ float red[32];
   pdl_launch_dependents();
   prof_begin(prof);
+  // the norm weight is a constant: fetch it before the dependency wait instead of after the reduction
+  float wv[RN_MAX_PER_THREAD];
+#pragma unroll
+  for (int k = 0; k < RN_MAX_PER_THREAD; ++k) {
+    const int d = threadIdx.x + k * blockDim.x;
+    wv[k] = (d < D) ? w[d] : 0.f;
+  }
   pdl_wait();
   const size_t row_in = (size_t)blockIdx.x * in_stride + in_off;
   const size_t row_out = blockIdx.x;
@@ -120,7 +127,7 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
     if (d < D) {
       float hn = v[k] * r;
       if (flags & RN_ROUND_RESID) hn = Act<T>::rnd(hn);      // `.to(input_dtype)` with a bf16 residual stream
-      const float y = w[d] * hn;
+      const float y = wv[k] * hn;
       if (xn_out) Act<T>::st(xn_out + row_out * D + d, y);   // autocast cast at the next Linear
       if (y_out) y_out[row_out * D + d] = y;
     }
