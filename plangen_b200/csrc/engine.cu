@@ -73,7 +73,7 @@ struct pg_engine {
   struct Tiled { const uint8_t* ptr; int N, K; };
   std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
   uint8_t* tiled_buf = nullptr;
-  int use_tiled = 1;
+  int use_tiled = 1, use_implicit_conv = 1;
   EncodeTiledFn encode = nullptr;
   // options
   uint64_t attn_dbg_ptr = 0;
@@ -186,15 +186,54 @@ static GemmSched sched_for(int N, int K, int G, int max_splits = 16) {
 
 template <int NT>
 static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx, float* C, int M, int N, int K,
-                     int splits, int kb_per_split, bool w_const, const void* w_tiled, void* swiglu_out, cudaStream_t st) {
+                     int splits, int kb_per_split, bool w_const, const void* w_tiled, void* swiglu_out, cudaStream_t st,
+                     const ConvGeom* conv = nullptr, int grid_y = 0) {
   using Cfg = TcCfg<NT>;
   int stages = e->tc_stages > 0 ? e->tc_stages : (200 * 1024) / Cfg::STAGE_BYTES;
   stages = std::max(2, std::min(stages, 12));
   stages = std::min(stages, std::max(2, kb_per_split));
   const size_t smem = Cfg::smem_bytes(stages);
-  dim3 grid((N + TC_BM - 1) / TC_BM, (M + NT - 1) / NT, splits);
+  dim3 grid((N + TC_BM - 1) / TC_BM, conv ? grid_y : (M + NT - 1) / NT, splits);
+  ConvGeom cg = {};
+  if (conv) cg = *conv;
   return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
-                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out);
+                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out, cg);
+}
+
+// 3x3 convolution (pad 1) as an implicit GEMM on the tcgen05 path: act bf16 NHWC [B][H][W][Cin], Wc bf16
+// [Cout][9*Cin] (k = tap*Cin + cin), C fp32 [B*H*W][Cout].  Returns 1 through *taken when the shape qualifies
+// (bf16, Cin % 64 == 0, W or a 192-pixel part of it tiles a 192-pixel block), 0 -> caller uses im2col.
+constexpr int CONV_NT = 192;
+static int run_conv_gemm(pg_engine* e, const void* act, const void* Wc, int B, int H, int W, int Cin, int Cout, float* C,
+                         size_t c_bytes, cudaStream_t st, int* taken) {
+  *taken = 0;
+  if (!e->bf16 || !e->use_tc || !e->use_implicit_conv || Cin % TC_BK != 0) return 0;
+  if ((((uintptr_t)act) & 15) || (((uintptr_t)Wc) & 15)) return 0;
+  int bw = 0;
+  if (W <= CONV_NT && CONV_NT % W == 0) bw = W;
+  else if (W % CONV_NT == 0) bw = CONV_NT;
+  if (!bw) return 0;
+  const int bh = CONV_NT / bw;
+  const size_t pixels = (size_t)B * H * W;
+  if (pixels * Cout * 4 > c_bytes) return fail("conv partial buffer too small");
+  ConvGeom cg;
+  cg.enabled = 1; cg.H = H; cg.W = W; cg.Cin = Cin; cg.bw = bw; cg.bh = bh;
+  cg.tiles_x = W / bw; cg.tiles_y = (H + bh - 1) / bh;
+  CUtensorMap mw, mx;
+  TRY(make_map_2d(e, &mw, Wc, (uint64_t)Cout, (uint64_t)9 * Cin, TC_BM));
+  cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t gstr[3] = {(cuuint64_t)Cin * 2, (cuuint64_t)W * Cin * 2, (cuuint64_t)H * W * Cin * 2};
+  cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = e->encode(&mx, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(act), gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (conv activation) failed (%d) B=%d H=%d W=%d C=%d", (int)r, B, H, W, Cin);
+  const int num_kb = 9 * Cin / TC_BK;
+  TRY(launch_tc<CONV_NT>(e, mw, mx, C, (int)pixels, Cout, 9 * Cin, 1, num_kb, true, nullptr, nullptr, st, &cg,
+                         B * cg.tiles_x * cg.tiles_y));
+  *taken = 1;
+  return 0;
 }
 
 // C[splits][M][N] fp32 = X[M][K] * W[N][K]^T.  Returns the number of splits used through *splits_out.
@@ -357,6 +396,7 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
   CK(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM));
@@ -423,6 +463,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "use_tiled") e->use_tiled = (int)value;
+  else if (k == "use_implicit_conv") e->use_implicit_conv = (int)value;
   else if (k == "attn_dbg_ptr") e->attn_dbg_ptr = (uint64_t)value;
   else if (k == "gemm_dbg_ptr") { unsigned long long* p = (unsigned long long*)value; CK(cudaMemcpyToSymbol(g_gemm_dbg, &p, sizeof(p))); }
   else if (k == "gemm_dbg_n") { int n = (int)value; CK(cudaMemcpyToSymbol(g_gemm_dbg_n, &n, sizeof(n))); }
@@ -1069,6 +1110,25 @@ static int vq_conv(VqCtx& c, const void* in, int Hi, int Wi, int Cin, const std:
   const size_t pixels = (size_t)c.Bc * Ho * Wo;
   const void* X = in;
   if (gn_name) TRY(vq_gn_stats(c, in, Hi * Wi, Cin));
+  if (ks == 3) {
+    // implicit GEMM: only the (normalised, activated, upsampled) activation is materialised, not its 9 taps
+    const void* act = in;
+    const bool qualifies = e->bf16 && e->use_tc && e->use_implicit_conv && Cin % TC_BK == 0 &&
+                           ((Wo <= CONV_NT && CONV_NT % Wo == 0) || Wo % CONV_NT == 0);
+    if (qualifies) {
+      if (gn_name || up != 1) {
+        TRY(vq_im2col(c, in, e->vq_col, Hi, Wi, Cin, 1, up, gn_name != nullptr, gn_name ? gn_name : "", swish));
+        act = e->vq_col;
+      }
+      if (pixels * Cout > e->vq_part_elems) return fail("internal: vq partial buffer too small");
+      int taken = 0;
+      TRY(run_conv_gemm(e, act, W, c.Bc, Ho, Wo, Cin, Cout, e->vq_part, e->vq_part_elems * 4, c.st, &taken));
+      if (taken) {
+        TRY(vq_epilogue(c, e->vq_part, bias, residual, out, out_nchw, Cout, Ho * Wo, pixels, 0));
+        return 0;
+      }
+    }
+  }
   if (ks != 1 || gn_name || up != 1) {
     TRY(vq_im2col(c, in, e->vq_col, Hi, Wi, Cin, ks, up, gn_name != nullptr, gn_name ? gn_name : "", swish));
     X = e->vq_col;

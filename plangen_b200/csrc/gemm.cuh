@@ -90,11 +90,19 @@ PG_DEVINL void gemm_stamp(unsigned long long* dbg, int k) {
   if (dbg) dbg[((size_t)(blockIdx.z * gridDim.x + blockIdx.x)) * 8 + k] = global_timer_ns();
 }
 
+// Implicit-GEMM 3x3 convolution (pad 1) over a channels-last activation [B][H][W][Cin]: the "token" tile of
+// CTA y is a bw x bh block of output pixels of one image, and the operand tile of k-block kb = (tap, cin0)
+// is that pixel block shifted by the tap offset - one 4-D TMA box {64 channels, bw, bh, 1} whose
+// out-of-bounds rows/columns are zero-filled by the hardware (the conv padding).  No im2col matrix exists.
+struct ConvGeom {
+  int enabled, H, W, Cin, bw, bh, tiles_x, tiles_y;
+};
+
 template <int NT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                float* __restrict__ C, int M, int N, int K, int kb_per_split, int num_stages, int use_pdl,
-               const uint8_t* __restrict__ w_tiled, Prof prof, bf16* __restrict__ swiglu_out) {
+               const uint8_t* __restrict__ w_tiled, Prof prof, bf16* __restrict__ swiglu_out, ConvGeom cg) {
   using Cfg = TcCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -107,6 +115,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.x * TC_BM;
   const int m0 = blockIdx.y * NT;
+  int cv_b = 0, cv_y0 = 0, cv_x0 = 0;
+  if (cg.enabled) {
+    const int per_img = cg.tiles_x * cg.tiles_y;
+    cv_b = blockIdx.y / per_img;
+    const int r = blockIdx.y % per_img;
+    cv_y0 = (r / cg.tiles_x) * cg.bh;
+    cv_x0 = (r % cg.tiles_x) * cg.bw;
+  }
   const int split = blockIdx.z;
   const int num_kb = (K + TC_BK - 1) / TC_BK;
   const int kb_begin = split * kb_per_split;
@@ -168,7 +184,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       mbar_wait(&empty_bar[s], (((uint32_t)(i / num_stages)) & 1u) ^ 1u, 1);
       if (dbg && blockIdx.x == 5 && blockIdx.z == 0 && i < 64) dbg[16384 + 128 + i] = global_timer_ns();
       mbar_expect_tx(&full_bar[s], Cfg::B_BYTES);
-      tma_load_2d(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[s], (kb_begin + i) * TC_BK, m0, pol_x);
+      if (cg.enabled) {
+        const int k0 = (kb_begin + i) * TC_BK, tap = k0 / cg.Cin;
+        tma_load_4d(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[s], k0 - tap * cg.Cin, cv_x0 + tap % 3 - 1,
+                    cv_y0 + tap / 3 - 1, cv_b, pol_x);
+      } else {
+        tma_load_2d(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[s], (kb_begin + i) * TC_BK, m0, pol_x);
+      }
     }
   };
   // ===================== MMA issuers (one or two threads) =====================
@@ -273,7 +295,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (n < N) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int m = m0 + c0 + j;
+            int m = m0 + c0 + j;
+            if (cg.enabled) {                    // pixel (c0 + j) of the bw x bh block -> flat NHWC pixel index
+              const int yy = (c0 + j) / cg.bw, y = cv_y0 + yy;
+              m = (y < cg.H) ? (cv_b * cg.H + y) * cg.W + cv_x0 + (c0 + j) - yy * cg.bw : M;
+            }
             if (m < M) out[(size_t)m * N + n] = __uint_as_float(v[j]);   // 32 lanes -> 128 B contiguous
           }
         }
