@@ -1061,6 +1061,9 @@ static int vq_gn_stats(VqCtx& c, const void* x, int HW, int C) {
   if (nchunks > e->gn_chunks_max) return fail("internal: gn chunks");
   if (C % 32 || C > 512) return fail("GroupNorm(32) needs C %% 32 == 0 and C <= 512 (C=%d)", C);
   const int gn_threads = C > 256 ? 512 : 256;
+  if (e->bf16 && C % 128 == 0) {
+    TRY(launch(e, gn_partial_vec_kernel, dim3(nchunks, c.Bc), dim3(256), 0, c.st, (const bf16*)x, e->gn_partial, HW, C, chunk_pix));
+  } else
   DISPATCH_T(e,
              launch(e, gn_partial_kernel<bf16>, dim3(nchunks, c.Bc), dim3(gn_threads), 0, c.st, (const bf16*)x, e->gn_partial, HW, C, chunk_pix),
              launch(e, gn_partial_kernel<float>, dim3(nchunks, c.Bc), dim3(gn_threads), 0, c.st, (const float*)x, e->gn_partial, HW, C, chunk_pix));
@@ -1077,6 +1080,13 @@ static int vq_im2col(VqCtx& c, const void* in, void* col, int Hi, int Wi, int C,
     gamma = (const float*)T_(e, "vq." + gn_name + ".weight");
     beta = (const float*)T_(e, "vq." + gn_name + ".bias");
     if (!gamma || !beta) return fail("missing GroupNorm tensors for %s", gn_name.c_str());
+  }
+  if (ks == 1 && e->bf16 && C % 8 == 0 && C <= 2048 && 256 % (C / 8) == 0) {   // activation only: vectorised apply
+    const int Ho = Hi * up, Wo = Wi * up, PL = 256 / (C / 8);
+    if ((size_t)c.Bc * Ho * Wo * C > e->vq_col_elems) return fail("internal: im2col scratch too small");
+    const int blocks = std::max(1, std::min((Ho * Wo + PL - 1) / PL, (e->num_sms * 8 + c.Bc - 1) / c.Bc));
+    return launch(e, gn_apply_kernel, dim3(blocks, c.Bc), dim3(256), 0, c.st, (const bf16*)in, (bf16*)col,
+                  gn ? (const float*)e->gn_stats : (const float*)nullptr, gamma, beta, Hi, Wi, C, up, swish ? 1 : 0);
   }
   if (C % 4) return fail("im2col needs C %% 4 == 0");
   const size_t n_pix = (size_t)c.Bc * Hi * up * Wi * up;

@@ -202,6 +202,35 @@ swiglu_kernel(const float* __restrict__ part, int S, size_t split_stride, T* __r
   pdl_launch_dependents();
   prof_begin(prof);
   pdl_wait();
+  if (S == 1 && F % 64 == 0 && total < (size_t)1 << 31) {
+    // prefill-sized inputs: 4 outputs per thread, 16-byte loads, 32-bit index arithmetic
+    const int F4 = F / 4, n4 = (int)(total / 4);
+    for (int i4 = blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += gridDim.x * blockDim.x) {
+      const int tok = i4 / F4, f = (i4 - tok * F4) * 4;
+      const int gi = interleaved ? (f >> 6) * 128 + (f & 63) : f;
+      const int ui = interleaved ? gi + 64 : F + f;
+      const float* row = part + (size_t)tok * 2 * F;
+      const float4 g4 = __ldcs(reinterpret_cast<const float4*>(row + gi));
+      const float4 u4 = __ldcs(reinterpret_cast<const float4*>(row + ui));
+      const float gs[4] = {g4.x, g4.y, g4.z, g4.w}, us[4] = {u4.x, u4.y, u4.z, u4.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float g = Act<T>::rnd(gs[j]), u = Act<T>::rnd(us[j]);
+        o[j] = Act<T>::rnd(g / (1.0f + expf(-g))) * u;
+      }
+      T* dst = h + (size_t)tok * F + f;
+      if constexpr (sizeof(T) == 2) {
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(o[0], o[1]), hi = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(dst) = pk;
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+    }
+    prof_end(prof);
+    return;
+  }
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t tok = i / F, f = i % F;
     const size_t gi = interleaved ? (f / 64) * 128 + f % 64 : f;

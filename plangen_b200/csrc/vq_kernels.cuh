@@ -115,6 +115,89 @@ template <> struct Ch4<bf16> {
   }
 };
 
+// bf16 fast path of stage 1 (C % 128 == 0: a thread owns 4 consecutive channels of one group, 8-byte
+// loads, four pixels in flight): same output layout and a fixed summation order, so results do not depend on
+// the batch composition.
+__global__ void __launch_bounds__(256)
+gn_partial_vec_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int HW, int C, int chunk_pix) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float t_sum[256], t_sq[256];
+  const int b = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int cvn = C / 4;                               // channel vectors per pixel (32 .. 128)
+  const int cv = threadIdx.x % cvn, pl = threadIdx.x / cvn, PL = 256 / cvn;
+  const int p0 = chunk * chunk_pix, p1 = min(HW, p0 + chunk_pix);
+  const bf16* base = x + (size_t)b * HW * C + cv * 4;
+  float a = 0.f, q = 0.f;
+  int p = p0 + pl;
+  for (; p + 3 * PL < p1; p += 4 * PL) {
+    float v[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) Ch4<bf16>::ld(base + (size_t)(p + u * PL) * C, v[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a += v[u][j]; q += v[u][j] * v[u][j]; }
+  }
+  for (; p < p1; p += PL) {
+    float v[4];
+    Ch4<bf16>::ld(base + (size_t)p * C, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a += v[j]; q += v[j] * v[j]; }
+  }
+  t_sum[threadIdx.x] = a; t_sq[threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int g = threadIdx.x, vpg = cvn / 32;         // channel vectors per group
+    float sa = 0.f, sq = 0.f;
+    for (int l = 0; l < PL; ++l)
+      for (int j = 0; j < vpg; ++j) { sa += t_sum[l * cvn + g * vpg + j]; sq += t_sq[l * cvn + g * vpg + j]; }
+    float* o = partial + (((size_t)b * nchunks + chunk) * 32 + g) * 2;
+    o[0] = sa; o[1] = sq;
+  }
+}
+
+// GroupNorm apply (+ swish) (+ nearest x2 upsample), channels-last bf16 -> bf16, 16 bytes per thread.  The
+// activation a 3x3 implicit-GEMM convolution reads (engine.cu run_conv_gemm); same arithmetic as im2col_kernel.
+__global__ void __launch_bounds__(256)
+gn_apply_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, const float* __restrict__ stats,
+                const float* __restrict__ gamma, const float* __restrict__ beta, int Hi, int Wi, int C, int up, int swish) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.y;
+  const int cvn = C / 8, cv = threadIdx.x % cvn, pl = threadIdx.x / cvn, PL = 256 / cvn;
+  const int Ho = Hi * up, Wo = Wi * up, cpg = C / 32;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = cv * 8 + j;
+    sc[j] = 1.f; sh[j] = 0.f;
+    if (stats) {
+      const float mean = stats[((size_t)b * 32 + c / cpg) * 2], rstd = stats[((size_t)b * 32 + c / cpg) * 2 + 1];
+      sc[j] = rstd * gamma[c];
+      sh[j] = beta[c] - mean * sc[j];
+    }
+  }
+  const int n_pix = Ho * Wo;
+  for (int p = blockIdx.x * PL + pl; p < n_pix; p += gridDim.x * PL) {
+    const int oy = p / Wo, ox = p - oy * Wo;
+    const uint4 t = *reinterpret_cast<const uint4*>(in + (((size_t)b * Hi + oy / up) * Wi + ox / up) * C + cv * 8);
+    const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float y0 = bf16lo(w[k]), y1 = bf16hi(w[k]);
+      if (stats) {
+        y0 = fmaf(y0, sc[2 * k], sh[2 * k]); y1 = fmaf(y1, sc[2 * k + 1], sh[2 * k + 1]);
+        if (swish) { y0 = y0 / (1.0f + expf(-y0)); y1 = y1 / (1.0f + expf(-y1)); }
+      }
+      const __nv_bfloat162 o = __floats2bfloat162_rn(y0, y1);
+      r[k] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+    *reinterpret_cast<uint4*>(out + ((size_t)b * n_pix + p) * C + cv * 8) = make_uint4(r[0], r[1], r[2], r[3]);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const T* __restrict__ in, T* __restrict__ col, const float* __restrict__ stats,

@@ -146,11 +146,24 @@ def test_fullsize_vq_decode_vs_autocast_reference():
     codes = torch.randint(0, d.img_vocab, (2, 576), generator=g, dtype=torch.int32).cuda()
     with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
         want = O.decode_code(sd, d, codes, [2, 8, 24, 24]).float()
+    with torch.inference_mode():
+        want32 = O.decode_code(sd, d, codes, [2, 8, 24, 24]).float()
     out = eng.gen_vision_model.decode_code(codes, shape=[2, 8, 24, 24]).float()
     assert out.shape == (2, 3, 384, 384)
-    a, b = out.cpu().numpy(), want.cpu().numpy()
-    assert_close(a, b, 2e-2, 6e-2, "VQ-16 bf16 384x384")
+    a, b, b32 = out.cpu().numpy(), want.cpu().numpy(), want32.cpu().numpy()
+    # Same reasoning as the LM test above: ~60 bf16 layers with GroupNorm do not agree element-wise in the
+    # tail between any two bf16 evaluations (a single pixel of 884 736 moved across the fixed tolerance when
+    # only the GroupNorm summation order changed).  So: (1) >= 99.99 % of the pixels within rtol 2e-2 +
+    # 6e-2 * max|ref| of the reference bf16 path, (2) mean error small, (3) the engine's error against the
+    # fp32 reference decoder no larger than 1.25x the reference bf16 path's own error against fp32.
+    tol = 2e-2 * np.abs(b) + 6e-2 * np.abs(b).max()
+    frac_ok = float((np.abs(a - b) <= tol).mean())
+    assert frac_ok >= 0.9999, f"VQ-16 bf16 384x384: only {frac_ok:.6f} of the pixels within tolerance"
     assert np.abs(a - b).mean() < 1e-2 * np.abs(b).max()
+    e_mine, e_ref = np.abs(a - b32), np.abs(b - b32)
+    assert e_mine.mean() <= 1.25 * e_ref.mean(), (e_mine.mean(), e_ref.mean())
+    assert np.quantile(e_mine, 0.9999) <= 1.25 * np.quantile(e_ref, 0.9999), (np.quantile(e_mine, 0.9999), np.quantile(e_ref, 0.9999))
+    assert e_mine.max() <= 1.5 * e_ref.max(), (e_mine.max(), e_ref.max())
     # idempotence / batch independence: decoding image 0 alone gives the same pixels
     solo = eng.gen_vision_model.decode_code(codes[:1], shape=[1, 8, 24, 24]).float()
     assert torch.equal(solo[0], out[0])
