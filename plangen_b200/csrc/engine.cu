@@ -73,7 +73,7 @@ struct pg_engine {
   struct Tiled { const uint8_t* ptr; int N, K; };
   std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
   uint8_t* tiled_buf = nullptr;
-  int use_tiled = 1, use_implicit_conv = 1;
+  int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2;
   EncodeTiledFn encode = nullptr;
   // options
   uint64_t attn_dbg_ptr = 0;
@@ -189,9 +189,14 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
                      int splits, int kb_per_split, bool w_const, const void* w_tiled, void* swiglu_out, cudaStream_t st,
                      const ConvGeom* conv = nullptr, int grid_y = 0) {
   using Cfg = TcCfg<NT>;
-  int stages = e->tc_stages > 0 ? e->tc_stages : (200 * 1024) / Cfg::STAGE_BYTES;
+  // wide token tiles (prefill, VQ convolutions) are tensor-bound: a shallow ring leaves room for two CTAs per SM,
+  // whose epilogues overlap each other's main loops (measured: prefill 75.6 -> 68 ms); the weight-streaming decode
+  // shapes want the deepest ring (1.64 ms/step at 8-10 stages, 1.76 at 4)
+  int stages = NT >= 192 ? e->tc_wide_stages : (200 * 1024) / Cfg::STAGE_BYTES;
+  if (e->tc_stages > 0) stages = std::min(stages, e->tc_stages);   // option: cap the ring depth
   stages = std::max(2, std::min(stages, 12));
   stages = std::min(stages, std::max(2, kb_per_split));
+  if (stages < kb_per_split && (stages & 1)) --stages;   // reused rings must be even (see the invariant in gemm_tc_kernel)
   const size_t smem = Cfg::smem_bytes(stages);
   dim3 grid((N + TC_BM - 1) / TC_BM, conv ? grid_y : (M + NT - 1) / NT, splits);
   ConvGeom cg = {};
@@ -463,6 +468,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "use_tiled") e->use_tiled = (int)value;
+  else if (k == "tc_wide_stages") e->tc_wide_stages = std::max(2, (int)value);
   else if (k == "use_implicit_conv") e->use_implicit_conv = (int)value;
   else if (k == "attn_dbg_ptr") e->attn_dbg_ptr = (uint64_t)value;
   else if (k == "gemm_dbg_ptr") { unsigned long long* p = (unsigned long long*)value; CK(cudaMemcpyToSymbol(g_gemm_dbg, &p, sizeof(p))); }

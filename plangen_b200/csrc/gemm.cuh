@@ -155,8 +155,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
   // tools/micro/stream_bench.cu: 16 KB copies from one thread top out at 59 GB/s per CTA whatever the ring
   // depth), which bounded every weight-streaming contraction at ~30 GB/s per CTA with one producer doing
   // W + X per k-block.  The W tiles are therefore split over two issuing threads (even / odd k-blocks: warp 0
-  // and epilogue warp 2, idle until the accumulator is complete) and the X tiles over two or three (warps 3-5).
+  // and epilogue warp 2, idle until the accumulator is complete) and the X tiles over two (warps 3, 4).
   // Each stage's full barrier takes two arrive.expect_tx (W bytes, X bytes).
+  // INVARIANT: every role that is split over two threads strides the k-blocks by 2 and the ring depth is EVEN
+  // whenever stages are reused (launch_tc), so a stage always belongs to the same thread of each role and
+  // that thread observes every phase of the stage's barriers - a thread that skipped a phase would see the
+  // parity of an older phase as "complete" (mbarrier parity aliasing) and run ahead of the data.
   // use_pdl bit 1: the W operand is a constant weight, so its tiles may be requested before the previous
   // kernel has finished (it is an activation in the VQ attention contractions).
   constexpr bool DUAL = Cfg::NACC >= 2;        // two MMA issuers (below)
@@ -179,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const uint64_t pol_x = policy_evict_last();      // activations are re-read by every CTA
     if (use_pdl & 1) pdl_wait();
     if (first == 0) gemm_stamp(dbg, 1);
-    for (int i = first; i < nkb; i += (DUAL ? 2 : 3)) {
+    for (int i = first; i < nkb; i += 2) {
       const int s = i % num_stages;
       mbar_wait(&empty_bar[s], (((uint32_t)(i / num_stages)) & 1u) ^ 1u, 1);
       if (dbg && blockIdx.x == 5 && blockIdx.z == 0 && i < 64) dbg[16384 + 128 + i] = global_timer_ns();
@@ -231,7 +235,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int acc_used = (DUAL && nkb < 2) ? Cfg::NACC / 2 : Cfg::NACC;   // the second issuer's blocks stay unwritten
     if (lane == 0) {                            // producer / second issuer duty first (see above), then the epilogue
       if (warp == 2) produce_w(1);
-      else if (DUAL && warp == 5) issue_mma(1, 2, Cfg::NACC / 2, Cfg::NACC / 2);
+      else if (warp == 5) { if (DUAL) issue_mma(1, 2, Cfg::NACC / 2, Cfg::NACC / 2); }
       else produce_x(warp - 3);
     }
     __syncwarp();

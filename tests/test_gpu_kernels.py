@@ -28,6 +28,8 @@ def _gemm(eng, impl, X, W, splits):
     (2, 128, 64, 1), (2, 256, 256, 1), (16, 256, 512, 2), (32, 384, 2048, 3), (5, 130, 72, 1),
     (64, 1024, 1408, 4), (128, 512, 512, 1), (200, 256, 320, 1), (576, 576, 512, 1), (1000, 3, 1152, 1),
     (32, 6144, 2048, 3), (32, 2048, 5632, 9),
+    # ring reuse with every token-tile width (the ring depth must stay even, see gemm_tc_kernel's invariant)
+    (8, 256, 4096, 1), (16, 384, 5632, 1), (48, 256, 4096, 1), (100, 256, 2048, 1), (192, 256, 2304, 1), (300, 128, 4096, 1),
 ])
 def test_gemm_tcgen05_matches_torch(M, N, K, splits):
     eng = get_engine(O.TINY, "bf16")
