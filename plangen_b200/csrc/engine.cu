@@ -73,7 +73,7 @@ struct pg_engine {
   struct Tiled { const uint8_t* ptr; int N, K; };
   std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
   uint8_t* tiled_buf = nullptr;
-  int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2;
+  int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2, sample_cluster = 1;
   EncodeTiledFn encode = nullptr;
   // options
   uint64_t attn_dbg_ptr = 0;
@@ -468,10 +468,12 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "use_tiled") e->use_tiled = (int)value;
+  else if (k == "sample_cluster") e->sample_cluster = (int)value;
   else if (k == "tc_wide_stages") e->tc_wide_stages = std::max(2, (int)value);
   else if (k == "use_implicit_conv") e->use_implicit_conv = (int)value;
   else if (k == "attn_dbg_ptr") e->attn_dbg_ptr = (uint64_t)value;
   else if (k == "gemm_dbg_ptr") { unsigned long long* p = (unsigned long long*)value; CK(cudaMemcpyToSymbol(g_gemm_dbg, &p, sizeof(p))); }
+  else if (k == "sample_dbg_ptr") { unsigned long long* p = (unsigned long long*)value; CK(cudaMemcpyToSymbol(g_sample_dbg, &p, sizeof(p))); }
   else if (k == "gemm_dbg_n") { int n = (int)value; CK(cudaMemcpyToSymbol(g_gemm_dbg_n, &n, sizeof(n))); }
   else if (k == "attn_test_flags") e->attn_test_flags = value;
   else if (k == "attn_ctas") e->attn_ctas = (int)value;
@@ -922,6 +924,19 @@ static int k_sample(pg_engine* e, const float* part, int S, size_t sstride, cons
   uint64_t per_step, stride;
   philox_policy(e, (size_t)B * d.img_vocab, &per_step, &stride);
   const size_t smem = (size_t)d.img_vocab * 4;
+  if (e->sample_cluster) {
+    const size_t csm = (size_t)((d.img_vocab + SAMPLE_CLUSTER - 1) / SAMPLE_CLUSTER) * 4;
+    DISPATCH_T(e,
+               launch(e, cfg_sample_embed_cluster_kernel<bf16>, dim3(B * SAMPLE_CLUSTER), dim3(SAMPLE_CL_THREADS), csm, st, part, S, sstride, bias, B, d.img_vocab,
+                      cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, edit_region, gt_labels, step_base,
+                      step_ptr, n_steps, tokens_out, (const bf16*)e->embed_table, d.D, x_next, next_norm_w, (bf16*)xn_next,
+                      d.rms_eps, 1, e->dbg_logits),
+               launch(e, cfg_sample_embed_cluster_kernel<float>, dim3(B * SAMPLE_CLUSTER), dim3(SAMPLE_CL_THREADS), csm, st, part, S, sstride, bias, B, d.img_vocab,
+                      cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, edit_region, gt_labels, step_base,
+                      step_ptr, n_steps, tokens_out, (const float*)e->embed_table, d.D, x_next, next_norm_w, (float*)xn_next,
+                      d.rms_eps, 0, e->dbg_logits));
+    return 0;
+  }
   DISPATCH_T(e,
              launch(e, cfg_sample_embed_kernel<bf16>, dim3(B), dim3(SAMPLE_THREADS), smem, st, part, S, sstride, bias, B, d.img_vocab,
                     cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, edit_region, gt_labels, step_base,

@@ -30,7 +30,9 @@ PG_DEVINL PhiloxOut philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_
 
 // q for element li, exactly as torch's exponential_ kernel computes it
 PG_DEVINL float torch_exponential_at(uint64_t li, uint64_t stride, uint64_t seed, uint64_t offset) {
-  const uint64_t idx = li % stride, slot = li / stride;
+  uint64_t idx, slot;
+  if ((li | stride) >> 32) { idx = li % stride; slot = li / stride; }
+  else { const uint32_t l32 = (uint32_t)li, s32 = (uint32_t)stride; slot = l32 / s32; idx = l32 - (uint32_t)slot * s32; }   // 64-bit division is ~10x the cost
   const uint32_t comp = (uint32_t)(slot & 3);
   const uint64_t ctr = offset / 4 + (slot >> 2);
   const PhiloxOut r = philox4x32_10((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)idx, (uint32_t)(idx >> 32),
@@ -46,6 +48,9 @@ constexpr int SAMPLE_THREADS = 1024;
 
 // logits: fp32 split partials [S][2B][V] of gen_head's second Linear (+ bias added here), or, when
 // bias == nullptr and S == 1, final logits handed in through the drop-in API.
+__device__ unsigned long long* g_sample_dbg = nullptr;   // debug timeline (tools/sample_timeline.py); nullptr in production
+#define SAMPLE_STAMP(k) do { if (g_sample_dbg && threadIdx.x == 0) g_sample_dbg[blockIdx.x * 16 + (k)] = global_timer_ns(); } while (0)
+
 template <typename T>
 __global__ void __launch_bounds__(SAMPLE_THREADS)
 cfg_sample_embed_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ bias,
@@ -62,27 +67,47 @@ cfg_sample_embed_kernel(const float* __restrict__ part, int S, size_t split_stri
   __shared__ int besti[32];
   __shared__ int tok_s;
   pdl_launch_dependents();
+  SAMPLE_STAMP(0);
   pdl_wait();
+  SAMPLE_STAMP(1);
   const int b = blockIdx.x, tid = threadIdx.x;
   const int step = step_base + (step_ptr ? *step_ptr : 0);
   const uint64_t offset = offset_base + offset_per_step * (uint64_t)(step - step_base);
   const size_t rc = (size_t)(2 * b) * V, ru = (size_t)(2 * b + 1) * V;
   float mx = -INFINITY;
-  for (int v = tid; v < V; v += SAMPLE_THREADS) {
-    float c = reduce_splits(part, S, split_stride, rc + v);
-    float u = reduce_splits(part, S, split_stride, ru + v);
-    if (bias) { c += bias[v]; u += bias[v]; }
-    c = Act<T>::rnd(c); u = Act<T>::rnd(u);
-    // logits = uncond + w * (cond - uncond); / temperature     (plangen_base.py:587-588); each op
-    // is a separate rounded elementwise kernel in the reference (bf16 under autocast)
-    float t = Act<T>::rnd(__fsub_rn(c, u));
-    t = Act<T>::rnd(__fmul_rn(cfg_weight, t));
-    t = Act<T>::rnd(__fadd_rn(u, t));
-    t = Act<T>::rnd(__fdiv_rn(t, temperature));
-    sh[v] = t;
-    if (dbg_logits) dbg_logits[((size_t)step * B + b) * V + v] = t;
-    mx = fmaxf(mx, t);
+  // eight elements (16 independent loads) in flight per thread: one element per iteration cost a full L2
+  // round trip each (measured 22 us for this loop at V = 16384)
+  for (int v0 = tid; v0 < V; v0 += 8 * SAMPLE_THREADS) {
+    float cs[8], us[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int v = v0 + j * SAMPLE_THREADS;
+      cs[j] = us[j] = 0.f;
+      if (v < V) {
+        if (S == 1) { cs[j] = __ldcg(part + rc + v); us[j] = __ldcg(part + ru + v); }
+        else { cs[j] = reduce_splits(part, S, split_stride, rc + v); us[j] = reduce_splits(part, S, split_stride, ru + v); }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int v = v0 + j * SAMPLE_THREADS;
+      if (v < V) {
+        float c = cs[j], u = us[j];
+        if (bias) { const float bb = bias[v]; c += bb; u += bb; }
+        c = Act<T>::rnd(c); u = Act<T>::rnd(u);
+        // logits = uncond + w * (cond - uncond); / temperature     (plangen_base.py:587-588); each op
+        // is a separate rounded elementwise kernel in the reference (bf16 under autocast)
+        float t = Act<T>::rnd(__fsub_rn(c, u));
+        t = Act<T>::rnd(__fmul_rn(cfg_weight, t));
+        t = Act<T>::rnd(__fadd_rn(u, t));
+        t = Act<T>::rnd(__fdiv_rn(t, temperature));
+        sh[v] = t;
+        if (dbg_logits) dbg_logits[((size_t)step * B + b) * V + v] = t;
+        mx = fmaxf(mx, t);
+      }
+    }
   }
+  SAMPLE_STAMP(2);
   mx = block_max(mx, red);
   float sum = 0.f;
   for (int v = tid; v < V; v += SAMPLE_THREADS) {
@@ -90,6 +115,7 @@ cfg_sample_embed_kernel(const float* __restrict__ part, int S, size_t split_stri
     sh[v] = e;
     sum += e;
   }
+  SAMPLE_STAMP(3);
   sum = block_sum(sum, red);
   // argmax over p/q (first index wins ties, like torch.argmax)
   float bv = -INFINITY;
@@ -103,6 +129,7 @@ cfg_sample_embed_kernel(const float* __restrict__ part, int S, size_t split_stri
     }
     if (score > bv || (score == bv && v < bi)) { bv = score; bi = v; }
   }
+  SAMPLE_STAMP(4);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
@@ -129,6 +156,7 @@ cfg_sample_embed_kernel(const float* __restrict__ part, int S, size_t split_stri
     }
   }
   __syncthreads();
+  SAMPLE_STAMP(5);
   if (x_next == nullptr) return;
   // next input = gen_aligner(gen_embed(tok)) duplicated to the cond and uncond rows (:602-604),
   // plus (optionally) the first decoder layer's input RMSNorm of those rows
@@ -141,6 +169,7 @@ cfg_sample_embed_kernel(const float* __restrict__ part, int S, size_t split_stri
     ss += v * v;
   }
   if (xn_next == nullptr) return;
+  SAMPLE_STAMP(6);
   ss = block_sum(ss, red);
   const float r = rsqrtf(ss / (float)D + eps);
   for (int d = tid; d < D; d += SAMPLE_THREADS) {
@@ -150,6 +179,196 @@ cfg_sample_embed_kernel(const float* __restrict__ part, int S, size_t split_stri
     Act<T>::st(xn_next + (size_t)(2 * b) * D + d, y);
     Act<T>::st(xn_next + (size_t)(2 * b + 1) * D + d, y);
   }
+  SAMPLE_STAMP(7);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Same operation on a thread-block CLUSTER: 8 CTAs per image, each owning an eighth of the vocabulary (and
+// of the embedding row).  One CTA per image kept a single SM busy for ~40 us per decode step (16 Philox
+// evaluations + logf + two IEEE divisions per thread, behind 16 dependent logit loads); the cluster spreads
+// the arithmetic over 128 SMs and combines max / sum / arg-max / sum of squares through distributed shared
+// memory in rank order (deterministic).  Per-element arithmetic is that of cfg_sample_embed_kernel; the
+// arg-max is order independent (value, then lowest index), so tokens only differ where the softmax
+// denominator's last bit decides.
+constexpr int SAMPLE_CLUSTER = 8;
+#ifndef PG_SAMPLE_CL_THREADS
+#define PG_SAMPLE_CL_THREADS 256
+#endif
+constexpr int SAMPLE_CL_THREADS = PG_SAMPLE_CL_THREADS;   // light CTAs: a cluster needs 8 co-scheduled SMs of one GPC
+
+struct SampleXchg {
+  float mx, sum, bv, ss;
+  int bi;
+};
+
+PG_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+PG_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a 32-bit word of CTA `rank`'s copy of a shared-memory variable
+PG_DEVINL uint32_t dsmem_ld_u32(const void* my_smem_ptr, uint32_t rank) {
+  uint32_t remote, v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(my_smem_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+template <typename T>
+__global__ void __cluster_dims__(SAMPLE_CLUSTER, 1, 1) __launch_bounds__(SAMPLE_CL_THREADS)
+cfg_sample_embed_cluster_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ bias,
+                                int B, int V, float cfg_weight, float temperature, uint64_t seed, uint64_t offset_base,
+                                uint64_t offset_per_step, uint64_t philox_stride, int greedy,
+                                const int32_t* __restrict__ edit_region, const int32_t* __restrict__ gt_labels,
+                                int step_base, const int* __restrict__ step_ptr, int n_steps,
+                                int32_t* __restrict__ tokens_out, const T* __restrict__ embed_table, int D,
+                                float* __restrict__ x_next, const float* __restrict__ next_norm_w, T* __restrict__ xn_next,
+                                float eps, int round_resid, float* __restrict__ dbg_logits) {
+  extern __shared__ float sh[];      // this CTA's slice of the CFG logits -> unnormalised probabilities
+  __shared__ float red[32];
+  __shared__ float bestv[32];
+  __shared__ int besti[32];
+  __shared__ SampleXchg xc;          // read by the other CTAs of the cluster
+  pdl_launch_dependents();
+  SAMPLE_STAMP(0);
+  pdl_wait();
+  SAMPLE_STAMP(1);
+  const int tid = threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  const int b = blockIdx.x / SAMPLE_CLUSTER;
+  const int chunk = (V + SAMPLE_CLUSTER - 1) / SAMPLE_CLUSTER;
+  const int v_lo = (int)rank * chunk, v_hi = min(V, v_lo + chunk);
+  const int step = step_base + (step_ptr ? *step_ptr : 0);
+  const uint64_t offset = offset_base + offset_per_step * (uint64_t)(step - step_base);
+  const size_t rc = (size_t)(2 * b) * V, ru = (size_t)(2 * b + 1) * V;
+  float mx = -INFINITY;
+  for (int v0 = v_lo + tid; v0 < v_hi; v0 += 4 * SAMPLE_CL_THREADS) {
+    float cs[4], us[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int v = v0 + j * SAMPLE_CL_THREADS;
+      cs[j] = us[j] = 0.f;
+      if (v < v_hi) {
+        if (S == 1) { cs[j] = __ldcg(part + rc + v); us[j] = __ldcg(part + ru + v); }
+        else { cs[j] = reduce_splits(part, S, split_stride, rc + v); us[j] = reduce_splits(part, S, split_stride, ru + v); }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int v = v0 + j * SAMPLE_CL_THREADS;
+      if (v < v_hi) {
+        float c = cs[j], u = us[j];
+        if (bias) { const float bb = bias[v]; c += bb; u += bb; }
+        c = Act<T>::rnd(c); u = Act<T>::rnd(u);
+        float t = Act<T>::rnd(__fsub_rn(c, u));           // plangen_base.py:587-588, one rounded op each
+        t = Act<T>::rnd(__fmul_rn(cfg_weight, t));
+        t = Act<T>::rnd(__fadd_rn(u, t));
+        t = Act<T>::rnd(__fdiv_rn(t, temperature));
+        sh[v - v_lo] = t;
+        if (dbg_logits) dbg_logits[((size_t)step * B + b) * V + v] = t;
+        mx = fmaxf(mx, t);
+      }
+    }
+  }
+  SAMPLE_STAMP(2);
+  mx = block_max(mx, red);
+  if (tid == 0) xc.mx = mx;
+  cluster_sync_all();
+#pragma unroll
+  for (uint32_t r = 0; r < SAMPLE_CLUSTER; ++r) mx = fmaxf(mx, __uint_as_float(dsmem_ld_u32(&xc.mx, r)));
+  float sum = 0.f;
+  for (int v = v_lo + tid; v < v_hi; v += SAMPLE_CL_THREADS) {
+    const float e = expf(sh[v - v_lo] - mx);
+    sh[v - v_lo] = e;
+    sum += e;
+  }
+  SAMPLE_STAMP(3);
+  sum = block_sum(sum, red);
+  if (tid == 0) xc.sum = sum;
+  cluster_sync_all();
+  sum = 0.f;
+#pragma unroll
+  for (uint32_t r = 0; r < SAMPLE_CLUSTER; ++r) sum += __uint_as_float(dsmem_ld_u32(&xc.sum, r));   // rank order
+  // argmax over p/q (first index wins ties, like torch.argmax)
+  float bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int v = v_lo + tid; v < v_hi; v += SAMPLE_CL_THREADS) {
+    const float p = __fdiv_rn(sh[v - v_lo], sum);
+    float score = p;
+    if (!greedy) {
+      const float q = torch_exponential_at((uint64_t)b * V + v, philox_stride, seed, offset);
+      score = __fdiv_rn(p, q);
+    }
+    if (score > bv || (score == bv && v < bi)) { bv = score; bi = v; }
+  }
+  SAMPLE_STAMP(4);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((tid & 31) == 0) { bestv[tid >> 5] = bv; besti[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid < 32) {
+    bv = bestv[tid]; bi = besti[tid];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (tid == 0) { xc.bv = bv; xc.bi = bi; }
+  }
+  cluster_sync_all();
+  bv = -INFINITY; bi = 0x7fffffff;
+#pragma unroll
+  for (uint32_t r = 0; r < SAMPLE_CLUSTER; ++r) {
+    const float ov = __uint_as_float(dsmem_ld_u32(&xc.bv, r));
+    const int oi = (int)dsmem_ld_u32(&xc.bi, r);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  int tok = bi;
+  // teacher forcing (plangen_base.py:593-598): outside the edit region keep the ground truth
+  if (edit_region != nullptr && edit_region[(size_t)b * n_steps + step] == 0) tok = gt_labels[(size_t)b * n_steps + step];
+  tok = min(max(tok, 0), V - 1);
+  if (rank == 0 && tid == 0) tokens_out[(size_t)b * n_steps + step] = tok;
+  SAMPLE_STAMP(5);
+  if (x_next == nullptr) { cluster_sync_all(); return; }   // nobody may exit while its xc can still be read
+  // next input = gen_aligner(gen_embed(tok)) duplicated to the cond and uncond rows (:602-604), plus
+  // (optionally) the first decoder layer's input RMSNorm of those rows; each CTA handles an eighth of the row
+  const T* erow = embed_table + (size_t)tok * D;
+  const int dchunk = (D + SAMPLE_CLUSTER - 1) / SAMPLE_CLUSTER;
+  const int d_lo = (int)rank * dchunk, d_hi = min(D, d_lo + dchunk);
+  float ss = 0.f;
+  for (int d = d_lo + tid; d < d_hi; d += SAMPLE_CL_THREADS) {
+    const float v = Act<T>::ld(erow + d);
+    x_next[(size_t)(2 * b) * D + d] = v;
+    x_next[(size_t)(2 * b + 1) * D + d] = v;
+    ss += v * v;
+  }
+  SAMPLE_STAMP(6);
+  ss = block_sum(ss, red);
+  if (tid == 0) xc.ss = ss;
+  cluster_sync_all();
+  if (xn_next != nullptr) {
+    ss = 0.f;
+#pragma unroll
+    for (uint32_t r = 0; r < SAMPLE_CLUSTER; ++r) ss += __uint_as_float(dsmem_ld_u32(&xc.ss, r));
+    const float rs = rsqrtf(ss / (float)D + eps);
+    for (int d = d_lo + tid; d < d_hi; d += SAMPLE_CL_THREADS) {
+      float hn = Act<T>::ld(erow + d) * rs;
+      if (round_resid) hn = Act<T>::rnd(hn);
+      const float y = next_norm_w[d] * hn;
+      Act<T>::st(xn_next + (size_t)(2 * b) * D + d, y);
+      Act<T>::st(xn_next + (size_t)(2 * b + 1) * D + d, y);
+    }
+  }
+  cluster_sync_all();                                       // keep xc alive until every peer has read it
+  SAMPLE_STAMP(7);
 }
 
 // prepare_gen_img_embeds through the precomputed table (modeling_vlm.py:270-271)

@@ -9,9 +9,9 @@ mkdir -p gpurun_out
 timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
 tail -c 400 gpurun_out/${R}_bench.err
 PG_STEPS=300 PG_GRAPH=0 timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-  -k regex:"^(gemm_tc|gemm_simt|attn_|resid_rmsnorm|swiglu|bias_act|cfg_sample|qkv_rope|embed_gather|decode_step)" -s 57061 -c 196 \
+  -k regex:"^(gemm_tc|gemm_simt|attn_|resid_rmsnorm|swiglu|bias_act|cfg_sample|qkv_rope|embed_gather|decode_step)" -s 43300 -c 180 \
   --csv --log-file gpurun_out/${R}_launches_decode_step.csv python tools/profile_step.py > gpurun_out/p_a.log 2>&1
-PG_STEPS=300 PG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"attn_decode_tma" -s 7000 -c 1 \
+PG_STEPS=300 PG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"attn_decode_v5" -s 7000 -c 1 \
   -o gpurun_out/${R}_attn_decode python tools/profile_step.py > gpurun_out/p_b.log 2>&1
 PG_STEPS=300 PG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel" -s 28900 -c 4 \
   -o gpurun_out/${R}_gemm_tc python tools/profile_step.py > gpurun_out/p_c.log 2>&1

@@ -45,3 +45,9 @@ for k in ["head0", "head1"] + per_layer:
 npl = len(per_layer)
 for name, b, e in rows[2 + npl * 10: 2 + npl * 11]:
     print(f"  {name:12s} begin {b:9.2f} end {e:9.2f} dur {e-b:7.2f}")
+print("first rows of the step (head gemms, then layer 0):")
+for name, b, e in rows[:6]:
+    print(f"  {name:12s} begin {b:9.2f} end {e:9.2f} dur {e-b:7.2f}")
+print("last rows:")
+for name, b, e in rows[-3:]:
+    print(f"  {name:12s} begin {b:9.2f} end {e:9.2f} dur {e-b:7.2f}")
