@@ -314,7 +314,8 @@ cfg_sample_embed_cluster_kernel(const float* __restrict__ part, int S, size_t sp
   if ((tid & 31) == 0) { bestv[tid >> 5] = bv; besti[tid >> 5] = bi; }
   __syncthreads();
   if (tid < 32) {
-    bv = bestv[tid]; bi = besti[tid];
+    const bool have = tid < SAMPLE_CL_THREADS / 32;          // one entry per warp of this CTA
+    bv = have ? bestv[tid] : -INFINITY; bi = have ? besti[tid] : 0x7fffffff;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
