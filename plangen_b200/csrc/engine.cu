@@ -73,7 +73,7 @@ struct pg_engine {
   struct Tiled { const uint8_t* ptr; int N, K; };
   std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
   uint8_t* tiled_buf = nullptr;
-  int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2, sample_cluster = 1;
+  int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2, sample_cluster = 1, fuse_conv_epilogue = 0;   // fused conv epilogue measured slower (VQ 57 vs 42.5 ms): 2-byte scattered stores on the GEMM critical path
   EncodeTiledFn encode = nullptr;
   // options
   uint64_t attn_dbg_ptr = 0;
@@ -210,7 +210,8 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
 // (bf16, Cin % 64 == 0, W or a 192-pixel part of it tiles a 192-pixel block), 0 -> caller uses im2col.
 constexpr int CONV_NT = 192;
 static int run_conv_gemm(pg_engine* e, const void* act, const void* Wc, int B, int H, int W, int Cin, int Cout, float* C,
-                         size_t c_bytes, cudaStream_t st, int* taken) {
+                         size_t c_bytes, cudaStream_t st, int* taken, const float* bias = nullptr,
+                         const void* residual = nullptr, void* out_bf16 = nullptr) {
   *taken = 0;
   if (!e->bf16 || !e->use_tc || !e->use_implicit_conv || Cin % TC_BK != 0) return 0;
   if ((((uintptr_t)act) & 15) || (((uintptr_t)Wc) & 15)) return 0;
@@ -224,6 +225,7 @@ static int run_conv_gemm(pg_engine* e, const void* act, const void* Wc, int B, i
   ConvGeom cg;
   cg.enabled = 1; cg.H = H; cg.W = W; cg.Cin = Cin; cg.bw = bw; cg.bh = bh;
   cg.tiles_x = W / bw; cg.tiles_y = (H + bh - 1) / bh;
+  cg.bias = bias; cg.residual = (const bf16*)residual; cg.out_bf16 = (bf16*)out_bf16;
   CUtensorMap mw, mx;
   TRY(make_map_2d(e, &mw, Wc, (uint64_t)Cout, (uint64_t)9 * Cin, TC_BM));
   cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -469,6 +471,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "use_tiled") e->use_tiled = (int)value;
   else if (k == "sample_cluster") e->sample_cluster = (int)value;
+  else if (k == "fuse_conv_epilogue") e->fuse_conv_epilogue = (int)value;
   else if (k == "tc_wide_stages") e->tc_wide_stages = std::max(2, (int)value);
   else if (k == "use_implicit_conv") e->use_implicit_conv = (int)value;
   else if (k == "attn_dbg_ptr") e->attn_dbg_ptr = (uint64_t)value;
@@ -1153,9 +1156,11 @@ static int vq_conv(VqCtx& c, const void* in, int Hi, int Wi, int Cin, const std:
       }
       if (pixels * Cout > e->vq_part_elems) return fail("internal: vq partial buffer too small");
       int taken = 0;
-      TRY(run_conv_gemm(e, act, W, c.Bc, Ho, Wo, Cin, Cout, e->vq_part, e->vq_part_elems * 4, c.st, &taken));
+      const bool fuse = out != nullptr && out_nchw == nullptr && e->fuse_conv_epilogue;   // bias (+ residual) -> bf16 in the GEMM epilogue
+      TRY(run_conv_gemm(e, act, W, c.Bc, Ho, Wo, Cin, Cout, e->vq_part, e->vq_part_elems * 4, c.st, &taken,
+                        fuse ? bias : nullptr, fuse ? residual : nullptr, fuse ? out : nullptr));
       if (taken) {
-        TRY(vq_epilogue(c, e->vq_part, bias, residual, out, out_nchw, Cout, Ho * Wo, pixels, 0));
+        if (!fuse) TRY(vq_epilogue(c, e->vq_part, bias, residual, out, out_nchw, Cout, Ho * Wo, pixels, 0));
         return 0;
       }
     }

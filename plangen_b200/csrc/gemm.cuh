@@ -96,6 +96,11 @@ PG_DEVINL void gemm_stamp(unsigned long long* dbg, int k) {
 // out-of-bounds rows/columns are zero-filled by the hardware (the conv padding).  No im2col matrix exists.
 struct ConvGeom {
   int enabled, H, W, Cin, bw, bh, tiles_x, tiles_y;
+  // optional fused epilogue (no split-K): out[m][n] = rnd(rnd(acc + bias[n]) + residual[m][n]) as bf16, the
+  // rounding points of conv_epilogue_kernel; saves the fp32 partial round trip and a launch per convolution
+  const float* bias;
+  const bf16* residual;
+  bf16* out_bf16;
 };
 
 template <int NT>
@@ -292,19 +297,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       mbar_wait(tmem_full_bar, 0, 3);
       if (warp == 2 && lane == 0) gemm_stamp(dbg, 4);
       tc_fence_after();
+      if (!cg.enabled) {
+        // plain split-K partial store (the decode step's hot epilogue: keep it branch-free)
 #pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
-        if (n < N) {
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
+          if (n < N) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            int m = m0 + c0 + j;
-            if (cg.enabled) {                    // pixel (c0 + j) of the bw x bh block -> flat NHWC pixel index
-              const int yy = (c0 + j) / cg.bw, y = cv_y0 + yy;
-              m = (y < cg.H) ? (cv_b * cg.H + y) * cg.W + cv_x0 + (c0 + j) - yy * cg.bw : M;
+            for (int j = 0; j < 16; ++j) {
+              const int m = m0 + c0 + j;
+              if (m < M) out[(size_t)m * N + n] = __uint_as_float(v[j]);   // 32 lanes -> 128 B contiguous
             }
-            if (m < M) out[(size_t)m * N + n] = __uint_as_float(v[j]);   // 32 lanes -> 128 B contiguous
+          }
+        }
+      } else {
+        // convolution: pixel (c0 + j) of the bw x bh block -> flat NHWC pixel index; optional fused bias/residual
+        const float bias_n = (cg.out_bf16 && n < N) ? cg.bias[n] : 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
+          if (n < N) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int yy = (c0 + j) / cg.bw, y = cv_y0 + yy;
+              if (y < cg.H) {
+                const size_t o = (size_t)((cv_b * cg.H + y) * cg.W + cv_x0 + (c0 + j) - yy * cg.bw) * N + n;
+                if (cg.out_bf16) {
+                  float r = bf16_round(__uint_as_float(v[j]) + bias_n);
+                  if (cg.residual) r = bf16_round(r + __bfloat162float(cg.residual[o]));
+                  cg.out_bf16[o] = __float2bfloat16_rn(r);
+                } else {
+                  out[o] = __uint_as_float(v[j]);
+                }
+              }
+            }
           }
         }
       }
