@@ -285,28 +285,59 @@ PG_DEVINL void a5_group_stream(int tg, int gb, int ge, int r0, const AttnCut& cu
     cur = nxt;
   }
   // ---- deferred merge: take the records of ranks 0 .. n-2 as they become valid, combine in rank order
-  //      (own record last), clear the words for the next launch
+  //      (own record last), clear the words for the next launch.  With few rows an item is cut over many
+  //      groups (n-1 up to 63): the (M, L) words are fetched by 2(n-1) threads at once into shared memory and
+  //      the output words eight records at a time, instead of one dependent round trip per record.
   if (df_it >= 0) {
     const int n_other = df_n - 1;
     unsigned long long* wb = ws_ll + (size_t)df_it * AT_MAX_SLOTS * A5_REC;
+    float* ml = sm.o[0];                                                  // [n_other][2], free since the last barrier
+    if (tg < 2 * n_other) {
+      unsigned long long* w = wb + (size_t)(tg >> 1) * A5_REC + HEAD_DIM + (tg & 1);
+      ml[tg] = a5_take(w, 1);
+      *w = 0ull;
+    }
+    named_bar_sync(bar_id, AT_GT);
     float Mg = dfM;
-    for (int s2 = 0; s2 < n_other; ++s2) Mg = fmaxf(Mg, a5_take(wb + (size_t)s2 * A5_REC + HEAD_DIM, 1));
+    for (int s2 = 0; s2 < n_other; ++s2) Mg = fmaxf(Mg, ml[2 * s2]);
     float Lg = 0.f, og = 0.f;
-    for (int s2 = 0; s2 < n_other; ++s2) {
-      const float ms = a5_take(wb + (size_t)s2 * A5_REC + HEAD_DIM, 2);
-      const float ls = a5_take(wb + (size_t)s2 * A5_REC + HEAD_DIM + 1, 3);
-      const float os = a5_take(wb + (size_t)s2 * A5_REC + tg, 4);
-      const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - Mg);
-      Lg += ls * f;
-      og += os * f;
-      wb[(size_t)s2 * A5_REC + tg] = 0ull;
+    for (int s0 = 0; s0 < n_other; s0 += 8) {
+      unsigned long long w[8];
+      bool ok;
+      unsigned long long t0 = 0;
+      do {                                                                // eight loads in flight, retried until all valid
+        ok = true;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          w[k] = 1ull << 32;
+          if (s0 + k < n_other)
+            asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w[k]) : "l"(wb + (size_t)(s0 + k) * A5_REC + tg) : "memory");
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ok = ok && (w[k] >> 32) != 0;
+        if (!ok) {
+          if (t0 == 0) t0 = global_timer_ns();
+          else if (global_timer_ns() - t0 > 4000000000ull) {
+            printf("attn v5: hand-off record timeout (item %d, cta %d, thread %d)\n", df_it, (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+          }
+        }
+      } while (!ok);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (s0 + k < n_other) {
+          const float ms = ml[2 * (s0 + k)];
+          const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - Mg);
+          Lg += ml[2 * (s0 + k) + 1] * f;
+          og += __uint_as_float((unsigned)w[k]) * f;
+          wb[(size_t)(s0 + k) * A5_REC + tg] = 0ull;
+        }
+      }
     }
     const float f = (dfM == -INFINITY) ? 0.f : exp2f(dfM - Mg);
     Lg += dfL * f;
     og += dfacc * f;
     out[(size_t)df_it * HEAD_DIM + tg] = __float2bfloat16_rn(og / Lg);
-    named_bar_sync(bar_id, AT_GT);                                        // everyone has read M and L
-    if (tg < n_other) { wb[(size_t)tg * A5_REC + HEAD_DIM] = 0ull; wb[(size_t)tg * A5_REC + HEAD_DIM + 1] = 0ull; }
   }
 }
 

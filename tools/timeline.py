@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from plangen_b200 import JANUS_1P3B, synthetic
 from plangen_b200.engine import FastJanus
-B = 16; dims = JANUS_1P3B; dev = torch.device("cuda", 0)
+B = int(os.environ.get("PG_B", "16")); dims = JANUS_1P3B; dev = torch.device("cuda", 0)
 sd = synthetic.random_state_dict(dims, dev, seed=0, with_vq=False)
 eng = FastJanus(sd, dims, mode="bf16", max_batch=B, max_prompt=512, with_vq=False, options={"use_graph": int(os.environ.get("PG_GRAPH", "1")), "fuse_swiglu": int(os.environ.get("PG_FUSE", "1"))})
 del sd
