@@ -225,9 +225,27 @@ def kernel_roofline(eng, kv_start, lens, P: int, peaks: dict, iters: int = 6):
         peak, which = 6650.0, "fallback (B200_PROFILING.md)"
     return {"bound": "hbm", "kernel": "attn_decode_v5_kernel (KV-cache decode attention, paired CFG batch, 1 launch/layer)",
             "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": 141221376 + 6263552, "traffic_note": "dram read+write per launch from ncu --set full at step 300 of the "
-            "same workload (profiles/r01_attn_decode.full.txt); algorithmic K+V bytes there: 133.5 MB",
+            "traffic": _ncu_traffic_bytes(), "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
+            "at step ~290 of the same workload (profiles/r01_attn_decode.full.txt); algorithmic K+V bytes there ~128 MB, the excess "
+            "is the 32-token tile granularity (rows start mid-tile)",
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "position": pos}
+
+
+def _ncu_traffic_bytes():
+    """DRAM bytes of one attention launch from the committed ncu extract (None if the file is missing)."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_attn_decode.full.txt")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, seen = 0.0, 0
+    try:
+        with open(path) as f:
+            for line in f:
+                parts = line.split()
+                if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[2] in scale:
+                    total += float(parts[1]) * scale[parts[2]]
+                    seen += 1
+    except OSError:
+        return None
+    return int(total) if seen == 2 else None
 
 
 def run_b200_arm(args):
