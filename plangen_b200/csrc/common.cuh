@@ -130,6 +130,24 @@ PG_DEVINL void prof_end(const Prof& p) {
   if (p.buf && threadIdx.x == 0) atomicMax(&p.buf[PROF_SLOTS + p.slot], (unsigned long long)global_timer_ns());
 }
 
+// ------------------------------------------------------------------------------ thread-block clusters
+PG_DEVINL uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+PG_DEVINL void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// read a 32-bit word of CTA `rank`'s copy of a shared-memory variable
+PG_DEVINL uint32_t dsmem_ld_u32(const void* my_smem_ptr, uint32_t rank) {
+  uint32_t remote, v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(my_smem_ptr)), "r"(rank));
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
+  return v;
+}
+
+
 // generic-proxy writes (st.shared) made visible to the async proxy (TMA / tcgen05)
 PG_DEVINL void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

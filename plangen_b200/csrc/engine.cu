@@ -73,6 +73,12 @@ struct pg_engine {
   struct Tiled { const uint8_t* ptr; int N, K; };
   std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
   uint8_t* tiled_buf = nullptr;
+  int cluster_z = 0;
+  // resid+RMSNorm folded into the contractions (gemm.cuh NormFuse): parity-green but measured slower (2.13 vs 1.62 ms per
+  // step): two converter warps cannot build the normalised token tile at the MMA cadence, and cluster launches lose the
+  // early residency / weight prefetch that PDL gives plain launches.  Off by default; kept for round 2.
+  int fuse_norm = 0;
+  float* ssq_o = nullptr; float* ssq_d = nullptr;
   int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2, sample_cluster = 1, fuse_conv_epilogue = 0;   // fused conv epilogue measured slower (VQ 57 vs 42.5 ms): 2-byte scattered stores on the GEMM critical path
   EncodeTiledFn encode = nullptr;
   // options
@@ -137,11 +143,21 @@ static int launch(pg_engine* e, void (*kernel)(KArgs...), dim3 grid, dim3 block,
                   Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (e->use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (e->cluster_z > 1) {                       // one-shot: thread-block cluster along z for the next launch
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = (unsigned)e->cluster_z;
+    ++na;
+  }
+  e->cluster_z = 0;
   cfg.attrs = attr;
-  cfg.numAttrs = e->use_pdl ? 1 : 0;
+  cfg.numAttrs = na;
   e->launches++;
   cudaError_t le = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
   if (le != cudaSuccess)
@@ -187,7 +203,7 @@ static GemmSched sched_for(int N, int K, int G, int max_splits = 16) {
 template <int NT>
 static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx, float* C, int M, int N, int K,
                      int splits, int kb_per_split, bool w_const, const void* w_tiled, void* swiglu_out, cudaStream_t st,
-                     const ConvGeom* conv = nullptr, int grid_y = 0) {
+                     const ConvGeom* conv = nullptr, int grid_y = 0, const NormFuse* nfp = nullptr) {
   using Cfg = TcCfg<NT>;
   // wide token tiles (prefill, VQ convolutions) are tensor-bound: a shallow ring leaves room for two CTAs per SM,
   // whose epilogues overlap each other's main loops (measured: prefill 75.6 -> 68 ms); the weight-streaming decode
@@ -197,12 +213,16 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   stages = std::max(2, std::min(stages, 12));
   stages = std::min(stages, std::max(2, kb_per_split));
   if (stages < kb_per_split && (stages & 1)) --stages;   // reused rings must be even (see the invariant in gemm_tc_kernel)
-  const size_t smem = Cfg::smem_bytes(stages);
+  if (nfp && nfp->xsrc) stages = std::min(stages, 6);      // room for the fp32 staging rings of the normalising producers
+  const size_t smem = Cfg::smem_bytes(stages) + ((nfp && nfp->xsrc) ? NF_STAGING_BYTES : 0);
   dim3 grid((N + TC_BM - 1) / TC_BM, conv ? grid_y : (M + NT - 1) / NT, splits);
   ConvGeom cg = {};
   if (conv) cg = *conv;
+  NormFuse nf = {};
+  if (nfp) nf = *nfp;
+  if (nf.xres) e->cluster_z = splits;            // the split-K CTAs of a tile reduce through distributed shared memory
   return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
-                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out, cg);
+                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out, cg, nf);
 }
 
 // 3x3 convolution (pad 1) as an implicit GEMM on the tcgen05 path: act bf16 NHWC [B][H][W][Cin], Wc bf16
@@ -246,18 +266,20 @@ static int run_conv_gemm(pg_engine* e, const void* act, const void* Wc, int B, i
 // C[splits][M][N] fp32 = X[M][K] * W[N][K]^T.  Returns the number of splits used through *splits_out.
 static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, int K, float* C, size_t c_bytes,
                     int* splits_out, cudaStream_t st, int force_impl = -1, int force_splits = 0, bool w_const = true,
-                    const void* w_tiled = nullptr, void* swiglu_out = nullptr) {
+                    const void* w_tiled = nullptr, void* swiglu_out = nullptr, const NormFuse* nf = nullptr) {
   const bool tc = e->bf16 && ((force_impl == 1) || (force_impl < 0 && e->use_tc)) && (K % 8 == 0) &&
                   (((uintptr_t)X & 15) == 0) && (((uintptr_t)W & 15) == 0);
   if (force_impl == 1 && !tc) return fail("tcgen05 GEMM needs bf16 operands, K %% 8 == 0 and 16-byte aligned pointers");
   int splits = 1;
   if (tc) {
-    const int NT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+    const int NT = (nf && M <= 32) ? 32 : M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     const int tiles = ((N + TC_BM - 1) / TC_BM) * ((M + NT - 1) / NT);
     const int num_kb = (K + TC_BK - 1) / TC_BK;
     int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : std::max(1, e->num_sms / tiles));
     if (swiglu_out) want = 1;                               // the SwiGLU epilogue is non-linear: whole K in one CTA
     want = std::min(std::min(want, 16), num_kb);
+    if (nf && nf->xres) want = std::min(want, 8);          // portable cluster size
+    if (nf && NT != 32) return fail("internal: fused norm needs the 32-token tile");
     while (want > 1 && (size_t)want * M * N * 4 > c_bytes) --want;
     const int kb_per_split = (num_kb + want - 1) / want;
     splits = (num_kb + kb_per_split - 1) / kb_per_split;
@@ -269,9 +291,22 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     CUtensorMap mw, mx;
     TRY(make_map_2d(e, &mw, W, (uint64_t)N, (uint64_t)K, TC_BM));
     TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
+    NormFuse nf_local;
+    if (nf && nf->xsrc) {
+      nf_local = *nf;
+      cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+      cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
+      cuuint32_t box[2] = {(cuuint32_t)TC_BK, 32};
+      cuuint32_t estr[2] = {1, 1};
+      CUresult r = e->encode(&nf_local.map_xf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(nf->xsrc), gdim, gstr, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (residual stream) failed (%d)", (int)r);
+      nf = &nf_local;
+    }
     switch (NT) {
       case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
-      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
+      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st, nullptr, 0, nf)); break;
       case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
       case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
       default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
@@ -321,6 +356,8 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->attn_ws = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 4);
   e->attn_cnt = (int*)c.take(R * d.H * 4);
   e->attn_flag = (int*)c.take(R * d.H * 64 * 4);
+  e->ssq_o = (float*)c.take((size_t)((d.D + TC_BM - 1) / TC_BM) * 32 * 4);
+  e->ssq_d = (float*)c.take((size_t)((d.D + TC_BM - 1) / TC_BM) * 32 * 4);
   e->attn_ll = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 8);
   e->step_ctr = (int*)c.take(256);
   e->embed_table = c.take((size_t)d.img_vocab * d.D * es);
@@ -398,12 +435,12 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
-  CK(cudaFuncSetAttribute(gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CK(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  CK(cudaFuncSetAttribute(gemm_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+  CK(cudaFuncSetAttribute(gemm_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   CK(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM));
@@ -470,6 +507,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "use_tiled") e->use_tiled = (int)value;
+  else if (k == "fuse_norm") e->fuse_norm = (int)value;
   else if (k == "sample_cluster") e->sample_cluster = (int)value;
   else if (k == "fuse_conv_epilogue") e->fuse_conv_epilogue = (int)value;
   else if (k == "tc_wide_stages") e->tc_wide_stages = std::max(2, (int)value);
@@ -654,11 +692,12 @@ static int elementwise_blocks(pg_engine* e, size_t total) {
 // otherwise the contraction followed by swiglu_kernel.
 // (decode-sized token counts only: with 256-token tiles the two gate warps' expf work would outlast the MMAs)
 static bool fused_swiglu_ok(const pg_engine* e, int tok) { return e->bf16 && e->use_tc && e->fuse_swiglu && e->d.F % 64 == 0 && tok <= 128; }
-static int k_gate_up(pg_engine* e, const LayerW& w, int tok, cudaStream_t st) {
+static int k_gate_up(pg_engine* e, const LayerW& w, int tok, cudaStream_t st, const NormFuse* nf = nullptr) {
   const pg_dims& d = e->d;
   const int F = d.F, D = d.D;
   int S = 1;
-  if (fused_swiglu_ok(e, tok)) return run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, e->hbuf);
+  if (fused_swiglu_ok(e, tok)) return run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, e->hbuf, nf);
+  if (nf) return fail("internal: fused norm needs the fused SwiGLU epilogue");
   TRY(run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st));
   const size_t total = (size_t)tok * F;
   const int il = (e->bf16 && F % 64 == 0) ? 1 : 0;         // bf16 weights are packed interleaved when F % 64 == 0 (weights.py)
@@ -820,11 +859,24 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
   const int rflag = e->bf16 ? RN_ROUND_RESID : 0;
   const int nsp = attn_split_count(e, R, T_hint);
   int S = 1;
+  bool fused_tail = false;
   for (int l = 0; l < d.L; ++l) {
     LayerW w;
     TRY(layer_weights(e, l, &w));
     if (l == 0 && !first_norm_done) TRY(k_resid_norm(e, e->x_dec, nullptr, 0, 0, w.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
-    TRY(run_gemm(e, e->xn, w.wqkv, R, 3 * HD, D, e->part, e->part_bytes, &S, st));
+    // fused path: resid + RMSNorm live inside the contractions around them (gemm.cuh NormFuse), 5 kernels per layer
+    const bool fuse = e->bf16 && e->use_tc && e->fuse_norm && R <= 32 && fused_swiglu_ok(e, R) && D % 8 == 0 && HD % 8 == 0 &&
+                      F % 8 == 0 && D <= 32 * TC_BM * 8;
+    NormFuse nf_qkv = {}, nf_o = {}, nf_gu = {}, nf_d = {};
+    if (fuse) {
+      const int nt = (D + TC_BM - 1) / TC_BM;
+      nf_qkv.xsrc = e->x_dec; nf_qkv.ssq = e->ssq_d; nf_qkv.normw = w.ln1; nf_qkv.n_ssq_tiles = nt; nf_qkv.eps = d.rms_eps;
+      nf_gu.xsrc = e->x_dec; nf_gu.ssq = e->ssq_o; nf_gu.normw = w.ln2; nf_gu.n_ssq_tiles = nt; nf_gu.eps = d.rms_eps;
+      nf_o.xres = e->x_dec; nf_o.ssq_out = e->ssq_o;
+      nf_d.xres = e->x_dec; nf_d.ssq_out = e->ssq_d;
+    }
+    TRY(run_gemm(e, e->xn, w.wqkv, R, 3 * HD, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr,
+                 (fuse && l > 0) ? &nf_qkv : nullptr));
     if (e->bf16 && e->attn_impl >= 1 && R <= AT_MAX_ROWS) {
       const int ctas = e->attn_ctas > 0 ? e->attn_ctas : e->num_sms;
       const int saved = e->use_pdl;
@@ -844,6 +896,15 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
                         (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), kv_start, (float*)e->attn_out, e->attn_ws,
                         e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, 0));
     }
+    if (fuse) {
+      int So = 1;
+      TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &So, st, -1, 0, true, nullptr, nullptr, &nf_o));
+      TRY(k_gate_up(e, w, R, st, &nf_gu));
+      TRY(run_gemm(e, e->hbuf, w.wd, R, D, F, e->part, e->part_bytes, &So, st, -1, 0, true, nullptr, nullptr, &nf_d));
+      fused_tail = true;
+      continue;
+    }
+    fused_tail = false;
     TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &S, st));
     TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st));
     TRY(k_gate_up(e, w, R, st));
@@ -854,7 +915,8 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
       TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, wn.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
     }
   }
-  TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, normw, e->hidden_t, e->hidden_f, R, 1, 0,
+  // final norm: the fused path has already folded the last down projection into the residual stream
+  TRY(k_resid_norm(e, e->x_dec, fused_tail ? nullptr : e->part, S, (size_t)R * D, normw, e->hidden_t, e->hidden_f, R, 1, 0,
                    rflag | (inc_step ? RN_INC_STEP : 0), st));
   return 0;
 }

@@ -201,22 +201,6 @@ struct SampleXchg {
   int bi;
 };
 
-PG_DEVINL uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-PG_DEVINL void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// read a 32-bit word of CTA `rank`'s copy of a shared-memory variable
-PG_DEVINL uint32_t dsmem_ld_u32(const void* my_smem_ptr, uint32_t rank) {
-  uint32_t remote, v;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(my_smem_ptr)), "r"(rank));
-  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(remote) : "memory");
-  return v;
-}
-
 template <typename T>
 __global__ void __cluster_dims__(SAMPLE_CLUSTER, 1, 1) __launch_bounds__(SAMPLE_CL_THREADS)
 cfg_sample_embed_cluster_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ bias,
