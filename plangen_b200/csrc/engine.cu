@@ -73,7 +73,7 @@ struct pg_engine {
   struct Tiled { const uint8_t* ptr; int N, K; };
   std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
   uint8_t* tiled_buf = nullptr;
-  int cluster_z = 0;
+  int cluster_z = 0, rn_threads = 0;
   // resid+RMSNorm folded into the contractions (gemm.cuh NormFuse): parity-green but measured slower (2.13 vs 1.62 ms per
   // step): two converter warps cannot build the normalised token tile at the MMA cadence, and cluster launches lose the
   // early residency / weight prefetch that PDL gives plain launches.  Off by default; kept for round 2.
@@ -508,6 +508,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "use_tiled") e->use_tiled = (int)value;
   else if (k == "fuse_norm") e->fuse_norm = (int)value;
+  else if (k == "rn_threads") e->rn_threads = (int)value;
   else if (k == "sample_cluster") e->sample_cluster = (int)value;
   else if (k == "fuse_conv_epilogue") e->fuse_conv_epilogue = (int)value;
   else if (k == "tc_wide_stages") e->tc_wide_stages = std::max(2, (int)value);
@@ -557,7 +558,7 @@ static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t
                         float* y, int rows, int in_stride, int in_off, int flags, cudaStream_t st) {
   const int D = e->d.D;
   // few rows (decode): 1024 threads so one row's split-K loads are all in flight; many rows (prefill): 256+
-  int threads = rows <= 256 ? RN_THREADS : 256;
+  int threads = rows <= 256 ? (e->rn_threads > 0 ? e->rn_threads : RN_THREADS) : 256;
   while (threads * RN_MAX_PER_THREAD < D) threads *= 2;
   DISPATCH_T(e,
              launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (bf16*)xn, y, D,
