@@ -74,6 +74,9 @@ struct pg_engine {
   std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
   uint8_t* tiled_buf = nullptr;
   int cluster_z = 0, rn_threads = 0;
+  // L2 prefetch of the next attention launch's KV tiles from the decode-step norm kernels (lm_kernels.cuh KvPrefetch):
+  // tiles with (index mod kvpf_den) < kvpf1 by the post-attention norm, the next kvpf2 residues by the post-MLP norm
+  int kvpf_den = 8, kvpf1 = 0, kvpf2 = 0;
   // resid+RMSNorm folded into the contractions (gemm.cuh NormFuse): parity-green but measured slower (2.13 vs 1.62 ms per
   // step): two converter warps cannot build the normalised token tile at the MMA cadence, and cluster launches lose the
   // early residency / weight prefetch that PDL gives plain launches.  Off by default; kept for round 2.
@@ -84,7 +87,7 @@ struct pg_engine {
   // options
   uint64_t attn_dbg_ptr = 0;
   int64_t attn_test_flags = 0;
-  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 3, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, fuse_swiglu = 1, tc_stages = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
+  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 3, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, fuse_swiglu = 1, tc_stages = 0, tc_stages_gu = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
   unsigned long long* sk_prof = nullptr;
   unsigned long long* prof_buf = nullptr;   // per-kernel timeline of ONE decode step (plain-launch mode)
@@ -209,7 +212,9 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   // whose epilogues overlap each other's main loops (measured: prefill 75.6 -> 68 ms); the weight-streaming decode
   // shapes want the deepest ring (1.64 ms/step at 8-10 stages, 1.76 at 4)
   int stages = NT >= 192 ? e->tc_wide_stages : (200 * 1024) / Cfg::STAGE_BYTES;
-  if (e->tc_stages > 0) stages = std::min(stages, e->tc_stages);   // option: cap the ring depth
+  // options: cap the ring depth of the split-K contractions / of the (unsplit, long-stream) gate|up contraction
+  if (e->tc_stages > 0 && !swiglu_out) stages = std::min(stages, e->tc_stages);
+  if (e->tc_stages_gu > 0 && swiglu_out) stages = std::min(stages, e->tc_stages_gu);
   stages = std::max(2, std::min(stages, 12));
   stages = std::min(stages, std::max(2, kb_per_split));
   if (stages < kb_per_split && (stages & 1)) --stages;   // reused rings must be even (see the invariant in gemm_tc_kernel)
@@ -503,12 +508,16 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "use_pdl") e->use_pdl = (int)value;
   else if (k == "use_graph") e->use_graph = (int)value;
   else if (k == "tc_stages") e->tc_stages = (int)value;
+  else if (k == "tc_stages_gu") e->tc_stages_gu = (int)value;
   else if (k == "vq_chunk") e->vq_chunk = (int)value;
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "use_tiled") e->use_tiled = (int)value;
   else if (k == "fuse_norm") e->fuse_norm = (int)value;
   else if (k == "rn_threads") e->rn_threads = (int)value;
+  else if (k == "kvpf_den") e->kvpf_den = std::max(1, (int)value);
+  else if (k == "kvpf1") e->kvpf1 = (int)value;
+  else if (k == "kvpf2") e->kvpf2 = (int)value;
   else if (k == "sample_cluster") e->sample_cluster = (int)value;
   else if (k == "fuse_conv_epilogue") e->fuse_conv_epilogue = (int)value;
   else if (k == "tc_wide_stages") e->tc_wide_stages = std::max(2, (int)value);
@@ -555,16 +564,19 @@ extern "C" int pg_engine_get_counter(const pg_engine* e, const char* key, int64_
   } while (0)
 
 static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t sstride, const float* w, void* xn,
-                        float* y, int rows, int in_stride, int in_off, int flags, cudaStream_t st) {
+                        float* y, int rows, int in_stride, int in_off, int flags, cudaStream_t st,
+                        const KvPrefetch* pfp = nullptr) {
   const int D = e->d.D;
+  KvPrefetch pf = {};
+  if (pfp) pf = *pfp;
   // few rows (decode): 1024 threads so one row's split-K loads are all in flight; many rows (prefill): 256+
   int threads = rows <= 256 ? (e->rn_threads > 0 ? e->rn_threads : RN_THREADS) : 256;
   while (threads * RN_MAX_PER_THREAD < D) threads *= 2;
   DISPATCH_T(e,
              launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (bf16*)xn, y, D,
-                    e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e)),
+                    e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e), pf),
              launch(e, resid_rmsnorm_kernel<float>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (float*)xn, y,
-                    D, e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e)));
+                    D, e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e), pf));
   return 0;
 }
 
@@ -861,6 +873,19 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
   const int nsp = attn_split_count(e, R, T_hint);
   int S = 1;
   bool fused_tail = false;
+  // KV tiles of attention launch (layer tl) prefetched into L2 by the norm kernels in front of it; tl == L means layer 0
+  // of the NEXT step (one more token in the cache)
+  const bool kvpf_on = e->bf16 && e->attn_impl >= 1 && R <= AT_MAX_ROWS && (e->kvpf1 > 0 || e->kvpf2 > 0);
+  auto kv_prefetch = [&](int tl, int lo, int hi) {
+    KvPrefetch pf = {};
+    if (!kvpf_on || hi <= lo) return pf;
+    const int layer = tl % d.L;
+    pf.k = (const uint8_t*)kv_ptr(e, layer, 0, R); pf.v = (const uint8_t*)kv_ptr(e, layer, 1, R);
+    pf.kv_start = kv_start; pf.step_ptr = step_ptr; pf.H = d.H; pf.Tmax = e->Tmax;
+    pf.pos = pos_base + (tl >= d.L ? 1 : 0);
+    pf.lo = lo; pf.hi = hi; pf.den = e->kvpf_den; pf.tile_bytes = 32 * HEAD_DIM * e->esz;
+    return pf;
+  };
   for (int l = 0; l < d.L; ++l) {
     LayerW w;
     TRY(layer_weights(e, l, &w));
@@ -907,18 +932,21 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     }
     fused_tail = false;
     TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &S, st));
-    TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st));
+    const KvPrefetch pf1 = kv_prefetch(l + 1, 0, e->kvpf1);
+    TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st, &pf1));
     TRY(k_gate_up(e, w, R, st));
     TRY(run_gemm(e, e->hbuf, w.wd, R, D, F, e->part, e->part_bytes, &S, st));
     if (l + 1 < d.L) {
       LayerW wn;
       TRY(layer_weights(e, l + 1, &wn));
-      TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, wn.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
+      const KvPrefetch pf2 = kv_prefetch(l + 1, e->kvpf1, e->kvpf1 + e->kvpf2);
+      TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, wn.ln1, e->xn, nullptr, R, 1, 0, rflag, st, &pf2));
     }
   }
+  const KvPrefetch pf_last = kv_prefetch(d.L, e->kvpf1, e->kvpf1 + e->kvpf2);
   // final norm: the fused path has already folded the last down projection into the residual stream
   TRY(k_resid_norm(e, e->x_dec, fused_tail ? nullptr : e->part, S, (size_t)R * D, normw, e->hidden_t, e->hidden_f, R, 1, 0,
-                   rflag | (inc_step ? RN_INC_STEP : 0), st));
+                   rflag | (inc_step ? RN_INC_STEP : 0), st, &pf_last));
   return 0;
 }
 
