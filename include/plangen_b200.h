@@ -102,6 +102,18 @@ int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_start, int 
                     const int32_t* edit_region, const int32_t* gt_labels,
                     int32_t* tokens_out, void* stream);
 
+/* replaces: System.x2t (plangen_base.py:513-523) = vl_gpt.language_model.generate(inputs_embeds=,
+ *           attention_mask=, pad_token_id=, eos_token_id=, max_new_tokens=, do_sample=False, use_cache=True),
+ *           HF GenerationMixin greedy search with position_ids derived from the attention mask.
+ * Stage-1 layout-text decode.  Needs the optional tensor "lm_head" [vocab, D].
+ * x_prompt fp32 [R,P,D] (consumed); kv_start int32 [R] = leading pad columns per row.
+ * tokens_out int32 [R, max_new_tokens] (device): rows that produced eos continue with pad_id, as in HF.
+ * *n_generated (HOST int) = number of valid columns: HF stops after the step at which every row has finished.
+ * Synchronises `stream` before returning (generate() is synchronous in the reference too). */
+int pg_generate_greedy(pg_engine* e, float* x_prompt, const int32_t* kv_start, int R, int P,
+                       int max_new_tokens, int eos_id, int pad_id, int32_t* tokens_out,
+                       int* n_generated, void* stream);
+
 /* replaces: gen_vision_model.decode_code(code_b, shape=[B,8,g,g], channel_first=True)
  *           three_party/Janus/janus/models/vq_model.py:505-508
  * codes int32 [B, gh*gw] -> image fp32 NCHW [B,3,16*gh,16*gw] (unclamped). */

@@ -142,11 +142,14 @@ def _vq_decoder_shapes(d: JanusDims) -> List[Tuple[str, Tuple[int, ...], str]]:
     return out
 
 
-def tensor_specs(d: JanusDims, with_vq: bool = True) -> List[Tuple[str, Tuple[int, ...], str]]:
-    """All state-dict tensors the decode path touches, reference naming."""
+def tensor_specs(d: JanusDims, with_vq: bool = True, with_lm_head: bool = False) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """All state-dict tensors the decode path touches, reference naming.  `with_lm_head` adds the
+    untied text head used by the stage-1 layout-text decode (x2t, §8f rank 1)."""
     s: List[Tuple[str, Tuple[int, ...], str]] = []
     lm = "language_model.model."
     s.append((lm + "embed_tokens.weight", (d.vocab, d.D), "lm"))
+    if with_lm_head:
+        s.append(("language_model.lm_head.weight", (d.vocab, d.D), "lm"))
     HD = d.H * d.head_dim
     for i in range(d.L):
         l = lm + f"layers.{i}."
@@ -175,7 +178,7 @@ def tensor_specs(d: JanusDims, with_vq: bool = True) -> List[Tuple[str, Tuple[in
 
 
 def init_state_dict(d: JanusDims, seed: int = 0, with_vq: bool = True,
-                    lm_std: float = 0.02, only: Optional[str] = None) -> Dict[str, torch.Tensor]:
+                    lm_std: float = 0.02, only: Optional[str] = None, with_lm_head: bool = False) -> Dict[str, torch.Tensor]:
     """Deterministic random-init fp32 weights (CPU generator; identical on every
     box with the same torch build).  Every tensor has its own generator seeded
     from (seed, crc32(name)), so any subset (`only` = name prefix) reproduces the
@@ -186,7 +189,7 @@ def init_state_dict(d: JanusDims, seed: int = 0, with_vq: bool = True,
     them is caught."""
     import zlib
     sd: Dict[str, torch.Tensor] = {}
-    for name, shape, kind in tensor_specs(d, with_vq):
+    for name, shape, kind in tensor_specs(d, with_vq, with_lm_head):
         if only is not None and not name.startswith(only):
             continue
         g = torch.Generator(device="cpu").manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
@@ -278,17 +281,21 @@ class LMOutput:
 def llama_model_forward(sd: Dict[str, torch.Tensor], d: JanusDims, inputs_embeds: torch.Tensor,
                         attention_mask: Optional[torch.Tensor] = None,
                         past_key_values: Optional[List[Tuple[torch.Tensor, torch.Tensor]]] = None,
-                        use_cache: bool = True) -> LMOutput:
+                        use_cache: bool = True, position_ids: Optional[torch.Tensor] = None) -> LMOutput:
     """LlamaModel.forward (HF :375-427) as the reference calls it
     (plangen_base.py:571-576): inputs_embeds + full-length 0/1 mask, no
-    position_ids => positions = past_len + arange(q)."""
+    position_ids => positions = past_len + arange(q).  `position_ids` (R, q) is what
+    generate() passes (x2t): they only feed the rotary embedding; the causal mask is
+    built from the cache positions either way (HF :394-400)."""
     lm = "language_model.model."
     R, q_len, _ = inputs_embeds.shape
     past_len = 0 if not past_key_values else past_key_values[0][0].shape[2]
-    position_ids = (torch.arange(q_len, device=inputs_embeds.device) + past_len).unsqueeze(0)
+    cache_position = (torch.arange(q_len, device=inputs_embeds.device) + past_len).unsqueeze(0)
+    rope_position = cache_position if position_ids is None else position_ids
+    position_ids = cache_position
     kv_len = past_len + q_len
     h = inputs_embeds
-    cos, sin = rope_cos_sin(position_ids, d, h.dtype)
+    cos, sin = rope_cos_sin(rope_position, d, h.dtype)
     new_cache: List[Tuple[torch.Tensor, torch.Tensor]] = []
     scaling = d.head_dim ** -0.5
     mask4 = None
@@ -342,6 +349,51 @@ def prepare_gen_img_embeds(sd, image_ids: torch.Tensor) -> torch.Tensor:
 
 def embed_tokens(sd, ids: torch.Tensor) -> torch.Tensor:
     return F.embedding(ids.long(), sd["language_model.model.embed_tokens.weight"])
+
+
+# --------------------------------------------------- stage-1 layout-text decode (x2t)
+def generate_greedy(sd, d: JanusDims, inputs_embeds: torch.Tensor, attention_mask: torch.Tensor,
+                    max_new_tokens: int, eos_token_id: int, pad_token_id: int, mode: str = "fp32",
+                    return_logits: bool = False):
+    """System.x2t (plangen_base.py:513-523): `language_model.generate(inputs_embeds=, attention_mask=,
+    pad_token_id=eos, bos_token_id=, eos_token_id=eos, max_new_tokens=512, do_sample=False, use_cache=True)`
+    = HF GenerationMixin greedy search (third-party `transformers`, pinned ==4.48.3, generation/utils.py
+    `_sample` with do_sample=False; `prepare_inputs_for_generation`):
+      * position_ids = attention_mask.cumsum(-1) - 1, pads filled with 1; one more per generated token;
+      * next_token_logits = logits[:, -1, :].float(); next_tokens = argmax;
+      * finished rows keep emitting pad_token_id; a row finishes when it emits eos_token_id;
+      * the loop stops when every row has finished or after max_new_tokens;
+      * with inputs_embeds and no input_ids the returned sequences hold the NEW tokens only.
+    Returns int64 (R, n_generated) [, list of per-step fp32 logits]."""
+    dev = inputs_embeds.device
+    R = inputs_embeds.shape[0]
+    mask = attention_mask.to(dev).long()
+    head = sd["language_model.lm_head.weight"]
+    logits_all = []
+    with torch.inference_mode(), _autocast_ctx(mode, dev):
+        pos = (mask.cumsum(-1) - 1).masked_fill(mask == 0, 1)
+        out = llama_model_forward(sd, d, inputs_embeds, attention_mask=mask, position_ids=pos)
+        pkv = out.past_key_values
+        hidden = out.last_hidden_state[:, -1, :]
+        unfinished = torch.ones(R, dtype=torch.long, device=dev)
+        seq = torch.zeros(R, 0, dtype=torch.long, device=dev)
+        for i in range(max_new_tokens):
+            logits = F.linear(hidden, head).float()
+            if return_logits:
+                logits_all.append(logits.clone())
+            nxt = torch.argmax(logits, dim=-1)
+            nxt = nxt * unfinished + pad_token_id * (1 - unfinished)
+            seq = torch.cat([seq, nxt[:, None]], dim=-1)
+            unfinished = unfinished & (nxt != eos_token_id).long()
+            if int(unfinished.max()) == 0 or i == max_new_tokens - 1:
+                break
+            mask = torch.cat([mask, torch.ones(R, 1, dtype=torch.long, device=dev)], dim=-1)
+            pos = mask.sum(-1, keepdim=True) - 1
+            out = llama_model_forward(sd, d, embed_tokens(sd, nxt)[:, None, :], attention_mask=mask,
+                                      past_key_values=pkv, position_ids=pos)
+            pkv = out.past_key_values
+            hidden = out.last_hidden_state[:, -1, :]
+    return (seq, logits_all) if return_logits else seq
 
 
 # ------------------------------------------------------------------- VQ decode side

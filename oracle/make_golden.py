@@ -116,14 +116,61 @@ def golden_vq_tiny(name: str, d: O.JanusDims, batch: int):
     print(name, tuple(out.shape), float(out.abs().mean()))
 
 
+def hf_llama_causal(d: O.JanusDims, sd):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=d.D, intermediate_size=d.F, num_hidden_layers=d.L,
+                      num_attention_heads=d.H, num_key_value_heads=d.H, head_dim=d.head_dim,
+                      vocab_size=d.vocab, rms_norm_eps=d.rms_eps, rope_theta=d.rope_theta, tie_word_embeddings=False,
+                      max_position_embeddings=4096, attn_implementation="eager")
+    m = LlamaForCausalLM(cfg).eval()
+    pre = "language_model."
+    missing, unexpected = m.load_state_dict({k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}, strict=True)
+    assert not missing and not unexpected
+    return m
+
+
+def golden_x2t(name: str, d: O.JanusDims, batch: int, max_new: int, lo: int, hi: int, eos_from=(0, 3)):
+    """Stage-1 layout-text decode (System.x2t, plangen_base.py:513-523): the REAL HF `generate` on left-padded
+    prompts.  eos_token_id is chosen as the token row eos_from[0] emits at step eos_from[1] in a free run, so
+    that row finishes early and the pad-fill / early-stop bookkeeping is exercised."""
+    sd = O.init_state_dict(d, seed=0, with_vq=False, with_lm_head=True)
+    hf = hf_llama_causal(d, sd)
+    cond, _ = O.synthetic_prompts(d, batch, seed=4321, lo=lo, hi=hi, neg_len=4)
+    ids, mask = O.pad_input_ids(cond, d.pad_id)
+    kw = dict(bos_token_id=1, max_new_tokens=max_new, do_sample=False, use_cache=True, output_logits=True,
+              return_dict_in_generate=True)
+    with torch.inference_mode():
+        emb = hf.get_input_embeddings()(ids.long())
+        free = hf.generate(inputs_embeds=emb, attention_mask=mask.long(), pad_token_id=d.vocab - 1,
+                           eos_token_id=d.vocab - 1, **kw)
+        row = free.sequences[eos_from[0]].tolist()
+        # first step >= eos_from[1] whose token did not occur earlier in that row: the row then finishes exactly there
+        k = next((j for j in range(eos_from[1], len(row)) if row[j] not in row[:j]), eos_from[1])
+        eos = int(row[k])
+        out = hf.generate(inputs_embeds=emb, attention_mask=mask.long(), pad_token_id=eos, eos_token_id=eos, **kw)
+        # second case: every row finishes early (eos = most frequent first token is not guaranteed; use per-run stop)
+    np.savez_compressed(os.path.join(OUT, name), dims=np.array(d.name), ids=ids.numpy(), mask=mask.numpy(), eos=eos,
+                        max_new=max_new, tokens=out.sequences.numpy(), free_tokens=free.sequences.numpy(),
+                        logits=torch.stack(out.logits, 0)[:4].numpy(), versions=versions())
+    print(name, "eos", eos, "tokens", out.sequences.tolist())
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(sys.argv) > 1 and sys.argv[1] == "x2t":     # only the stage-1 text-decode vectors
+        golden_x2t("x2t_tiny_fp32.npz", O.TINY, batch=3, max_new=24, lo=5, hi=14)
+        golden_x2t("x2t_small_fp32.npz", O.SMALL, batch=4, max_new=20, lo=9, hi=40, eos_from=(1, 5))
+        golden_x2t("x2t_tiny_stop_fp32.npz", O.TINY, batch=1, max_new=24, lo=11, hi=11, eos_from=(0, 6))   # all rows finish early
+        return
     golden_lm("lm_tiny_fp32.npz", O.TINY, batch=2, steps=8, lo=5, hi=12, neg_len=7)
     golden_lm("lm_small_fp32.npz", O.SMALL, batch=3, steps=6, lo=9, hi=40, neg_len=13)
     golden_vq_tiny("vq_tiny.npz", O.TINY, batch=2)
     golden_vq_tiny("vq_small.npz", O.SMALL, batch=1)
     golden_vq_ref_class("vq16_grid4.npz")
+    golden_x2t("x2t_tiny_fp32.npz", O.TINY, batch=3, max_new=24, lo=5, hi=14)
+    golden_x2t("x2t_small_fp32.npz", O.SMALL, batch=4, max_new=20, lo=9, hi=40, eos_from=(1, 5))
+    golden_x2t("x2t_tiny_stop_fp32.npz", O.TINY, batch=1, max_new=24, lo=11, hi=11, eos_from=(0, 6))
 
 
 if __name__ == "__main__":

@@ -403,7 +403,7 @@ attn_decode_tma_kernel(const float* __restrict__ part, int S, size_t split_strid
   cut.group_range(c, g, gb, ge);
   int kc = 0;
   attn_group_stream<AT_SPG>(tg, gb, ge, cut, row_units, R, H, Tmax, pos, part, S, split_stride, cosT, sinT, kcache,
-                            vcache, kv_start, out, ws_part, ws_count, scale, bf16_trig != 0, ring, 2 * AT_TILE_BYTES,
+                            vcache, kv_start, out, ws_part, ws_count, scale, (bf16_trig & 1) != 0, ring, 2 * AT_TILE_BYTES,
                             stage_tab + g * AT_SPG, full_bar, empty_bar, kc, gsm[g], c * AT_NG + g, 1 + g, early_trigger & 2, dbg);
   if (tg == 0) at_stamp(dbg, g, 5);
   prof_end(prof);

@@ -470,7 +470,7 @@ attn_decode_v4_kernel(const float* __restrict__ part, int S, size_t split_stride
     int jq = 0;                                             // queue entries published so far (segments, then the end marker)
     bool ended = false;
     if (n0 > 0) {
-      a4_produce_batch(lane, G, 0, n0, sg, H, Tmax, pos, part, S, split_stride, cs, sn, kcache, vcache, scale, bf16_trig != 0,
+      a4_produce_batch(lane, G, 0, n0, sg, H, Tmax, pos, part, S, split_stride, cs, sn, kcache, vcache, scale, (bf16_trig & 1) != 0,
                        hold_stream ? &G.start : nullptr);
       jq = n0;
     } else if (hold_stream) {
@@ -489,7 +489,7 @@ attn_decode_v4_kernel(const float* __restrict__ part, int S, size_t split_stride
         if (w.u >= ge) { a4_publish_end(lane, G, jq); ended = true; }
         else {
           sg[0] = a4_next_segment(w, ge, row_units, H, row_start);
-          a4_produce_batch(lane, G, jq, 1, sg, H, Tmax, pos, part, S, split_stride, cs, sn, kcache, vcache, scale, bf16_trig != 0);
+          a4_produce_batch(lane, G, jq, 1, sg, H, Tmax, pos, part, S, split_stride, cs, sn, kcache, vcache, scale, (bf16_trig & 1) != 0);
         }
         ++jq;
       }

@@ -124,7 +124,7 @@ PG_DEVINL void a5_group_stream(int tg, int gb, int ge, int r0, const AttnCut& cu
                                const int* row_start, int H, int Tmax, int pos, const float* __restrict__ part, int S,
                                size_t split_stride, const float* __restrict__ cosT, const float* __restrict__ sinT,
                                bf16* __restrict__ kcache, bf16* __restrict__ vcache, bf16* __restrict__ out,
-                               unsigned long long* __restrict__ ws_ll, float scale, bool bf16_trig,
+                               unsigned long long* __restrict__ ws_ll, float scale, int trig_flags,
                                uint8_t* ring, int stage_stride_bytes, const int* stage_of, uint64_t* full_bar,
                                uint64_t* empty_bar, A5GroupSmem& sm, int my_slot, int bar_id, int dbg_skip_math,
                                unsigned long long* dbg) {
@@ -133,7 +133,8 @@ PG_DEVINL void a5_group_stream(int tg, int gb, int ge, int r0, const AttnCut& cu
   const int HD = H * HEAD_DIM;
   const float LOG2E = 1.4426950408889634f;
   const uint32_t ring_s = smem_u32(ring);
-  const float c = cosT[pos * 64 + jj], sn = sinT[pos * 64 + jj];
+  const bool bf16_trig = (trig_flags & 1) != 0, rope_rel = (trig_flags & ROPE_REL) != 0;
+  float c = cosT[pos * 64 + jj], sn = sinT[pos * 64 + jj];
   int u = gb, r = r0, kc = 0;
   A5Seg cur = a5_next_segment(u, r, ge, row_units, H, row_start);
   A5Pref pf;
@@ -145,6 +146,10 @@ PG_DEVINL void a5_group_stream(int tg, int gb, int ge, int r0, const AttnCut& cu
     // ---- q (all), k/v of the new token (owner) from the prefetched partials
     {
       const float* p = part + (size_t)cur.r * 3 * HD + cur.h * HEAD_DIM + jj;
+      if (rope_rel) {                       // text decode: position relative to the row's first valid column
+        const int pr = max(pos - cur.start, 0);
+        c = cosT[pr * 64 + jj]; sn = sinT[pr * 64 + jj];
+      }
       if (tg < 64) {
         const float x1 = bf16_round(a5_sum(pf, 0, S, p, split_stride));
         const float x2 = bf16_round(a5_sum(pf, 1, S, p + 64, split_stride));
@@ -396,7 +401,7 @@ attn_decode_v5_kernel(const float* __restrict__ part, int S, size_t split_stride
   pdl_wait();                                             // QKV partials of this step are now visible
   const int tg = tid - g * AT_GT;
   a5_group_stream<A5_SPG>(tg, gb, ge, r0, cut, row_units, row_start, H, Tmax, pos, part, S, split_stride, cosT, sinT,
-                          kcache, vcache, out, ws_ll, scale, bf16_trig != 0, ring, 2 * AT_TILE_BYTES,
+                          kcache, vcache, out, ws_ll, scale, bf16_trig, ring, 2 * AT_TILE_BYTES,
                           stage_tab + g * A5_SPG, full_bar, empty_bar, gsm[g], c * AT_NG + g, 1 + g, early_trigger & 2, dbg);
   if (tg == 0) at_stamp(dbg, g, 5);
   prof_end(prof);

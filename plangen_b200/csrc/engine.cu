@@ -21,6 +21,7 @@
 #include "attn_v5.cuh"
 #include "step_kernel.cuh"
 #include "sample.cuh"
+#include "text_decode.cuh"
 #include "vq_kernels.cuh"
 
 using namespace pg;
@@ -89,6 +90,7 @@ struct pg_engine {
   int64_t attn_test_flags = 0;
   int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 3, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, fuse_swiglu = 1, tc_stages = 0, tc_stages_gu = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
+  float* dbg_text_logits = nullptr;
   unsigned long long* sk_prof = nullptr;
   unsigned long long* prof_buf = nullptr;   // per-kernel timeline of ONE decode step (plain-launch mode)
   int prof_step = -1, prof_slot = 0;
@@ -102,7 +104,11 @@ struct pg_engine {
   void *xn = nullptr, *qbuf = nullptr, *attn_out = nullptr, *hbuf = nullptr, *hidden_t = nullptr, *head_h = nullptr;
   float *part = nullptr, *x_dec = nullptr, *hidden_f = nullptr, *attn_ws = nullptr, *attn_ll = nullptr;
   size_t part_bytes = 0;
-  int *attn_cnt = nullptr, *attn_flag = nullptr, *step_ctr = nullptr;
+  int *attn_cnt = nullptr, *attn_flag = nullptr, *step_ctr = nullptr, *greedy_state = nullptr;
+  cudaGraphExec_t txt_graph_exec = nullptr;          // one text-decode step (pg_generate_greedy)
+  std::string txt_graph_key;
+  int64_t txt_graph_launches = 0;
+  int* poll_host = nullptr;                          // pinned: early-exit poll of the greedy loop
   void *embed_table = nullptr, *align_tmp = nullptr;
   // persistent step kernel state
   CUtensorMap* wmaps_dev = nullptr; CUtensorMap* amaps_dev = nullptr; float* ln_dev = nullptr;
@@ -365,6 +371,7 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->ssq_d = (float*)c.take((size_t)((d.D + TC_BM - 1) / TC_BM) * 32 * 4);
   e->attn_ll = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 8);
   e->step_ctr = (int*)c.take(256);
+  e->greedy_state = (int*)c.take(256 + R * 4);      // [0] rows unfinished, [1] steps generated, [64..] per-row flags
   e->embed_table = c.take((size_t)d.img_vocab * d.D * es);
   e->align_tmp = c.take((size_t)d.img_vocab * d.D * es);
   e->wmaps_dev = (CUtensorMap*)c.take((size_t)d.L * 4 * sizeof(CUtensorMap));
@@ -461,6 +468,8 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
 extern "C" int pg_engine_destroy(pg_engine* e) {
   if (!e) return 0;
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  if (e->txt_graph_exec) cudaGraphExecDestroy(e->txt_graph_exec);
+  if (e->poll_host) cudaFreeHost(e->poll_host);
   if (e->tiled_buf) cudaFree(e->tiled_buf);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -535,12 +544,14 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_attr") e->attn_attr = (int)value;
   else if (k == "gemm_splits") e->gemm_splits = (int)value;
   else if (k == "dbg_logits_ptr") e->dbg_logits = (float*)(uintptr_t)value;
+  else if (k == "dbg_text_logits_ptr") e->dbg_text_logits = (float*)(uintptr_t)value;   // [max_new][R][vocab] fp32
   else if (k == "sk_prof_ptr") e->sk_prof = (unsigned long long*)(uintptr_t)value;
   else if (k == "prof_ptr") e->prof_buf = (unsigned long long*)(uintptr_t)value;
   else if (k == "prof_step") e->prof_step = (int)value;
   else if (k == "reset_launches") e->launches = 0;
   else return fail("unknown option '%s'", key);
   if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
+  if (e->txt_graph_exec) { cudaGraphExecDestroy(e->txt_graph_exec); e->txt_graph_exec = nullptr; e->txt_graph_key.clear(); }
   return 0;
 }
 
@@ -668,6 +679,7 @@ extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
     }
     if (const void* hw0 = T_(e, "head.w0")) items.push_back({hw0, d.img_embed, d.D});
     if (const void* hw1 = T_(e, "head.w1")) items.push_back({hw1, d.img_vocab, d.img_embed});
+    if (const void* lmh = T_(e, "lm_head")) items.push_back({lmh, d.vocab, d.D});      // stage-1 text decode (optional)
     size_t total_bytes = 0;
     auto tiles_of = [](const Item& it) { return (size_t)((it.N + TC_BM - 1) / TC_BM) * ((it.K + TC_BK - 1) / TC_BK); };
     for (const Item& it : items) if (it.K % 8 == 0) total_bytes += tiles_of(it) * TC_A_BYTES;
@@ -721,8 +733,16 @@ static int k_gate_up(pg_engine* e, const LayerW& w, int tok, cudaStream_t st, co
 }
 
 // a3: prompt prefill.  x fp32 [R*P, D] in place.
+static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, int P, float* hidden_out, int all_positions,
+                        bool rope_rel, void* stream);
 extern "C" int pg_prefill(pg_engine* e, float* x, const int32_t* kv_start, int R, int P, float* hidden_out,
                           int all_positions, void* stream) {
+  return prefill_impl(e, x, kv_start, R, P, hidden_out, all_positions, false, stream);
+}
+// rope_rel: RoPE positions = column - kv_start[row] (what HF generate() derives from the attention mask, x2t);
+// otherwise absolute columns (the image loop calls LlamaModel.forward without position_ids)
+static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, int P, float* hidden_out, int all_positions,
+                        bool rope_rel, void* stream) {
   TRY(check_ready(e));
   const pg_dims& d = e->d;
   if (R < 1 || R > d.max_rows || P < 1 || P > d.max_prompt) return fail("prefill shape R=%d P=%d exceeds engine limits", R, P);
@@ -740,9 +760,11 @@ extern "C" int pg_prefill(pg_engine* e, float* x, const int32_t* kv_start, int R
     TRY(run_gemm(e, e->xn, w.wqkv, tok, 3 * HD, D, e->part, e->part_bytes, &S, st));
     DISPATCH_T(e,
                launch(e, qkv_rope_store_kernel<bf16>, dim3(tok), dim3(256), 0, st, e->part, S, (size_t)tok * 3 * HD, cosT, sinT,
-                      (bf16*)e->qbuf, (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax),
+                      (bf16*)e->qbuf, (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax,
+                      rope_rel ? kv_start : (const int32_t*)nullptr),
                launch(e, qkv_rope_store_kernel<float>, dim3(tok), dim3(256), 0, st, e->part, S, (size_t)tok * 3 * HD, cosT, sinT,
-                      (float*)e->qbuf, (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax));
+                      (float*)e->qbuf, (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax,
+                      rope_rel ? kv_start : (const int32_t*)nullptr));
     DISPATCH_T(e,
                launch(e, attn_prefill_kernel<bf16>, dim3((P + 63) / 64, d.H, R), dim3(256), ATTN_PREFILL_SMEM, st,
                       (const bf16*)e->qbuf, (const bf16*)kv_ptr(e, l, 0, R), (const bf16*)kv_ptr(e, l, 1, R), kv_start,
@@ -852,10 +874,13 @@ static int decode_layers_mega(pg_engine* e, const int32_t* kv_start, int R, int 
   return 0;
 }
 
+// regime 0: image-token decode (inputs_embeds = bf16 gen_aligner output => bf16 residual stream, bf16 trig, absolute
+// positions); regime 1: text decode inside generate() (fp32 embed_tokens rows => fp32 residual stream, fp32 trig,
+// mask-aware positions) - the rounding points HF's autocast produces for each input dtype
 static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_base, const int* step_ptr,
-                         bool first_norm_done, bool inc_step, int T_hint, cudaStream_t st) {
+                         bool first_norm_done, bool inc_step, int T_hint, cudaStream_t st, int regime = 0) {
   const pg_dims& d = e->d;
-  if (mega_ok(e, R)) {
+  if (regime == 0 && mega_ok(e, R)) {
     TRY(prepare_amaps(e, R, st));          // no-op when already prepared (must be, inside a capture)
     if (!first_norm_done) {
       LayerW w0;
@@ -869,7 +894,8 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
   NEED(normw, float, "norm");
   const int D = d.D, HD = e->HD, F = d.F;
   const float scale = 1.0f / sqrtf((float)HEAD_DIM);
-  const int rflag = e->bf16 ? RN_ROUND_RESID : 0;
+  const int rflag = (e->bf16 && regime == 0) ? RN_ROUND_RESID : 0;
+  const int trig = regime == 0 ? (e->bf16 ? 1 : 0) : ROPE_REL;
   const int nsp = attn_split_count(e, R, T_hint);
   int S = 1;
   bool fused_tail = false;
@@ -891,7 +917,7 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     TRY(layer_weights(e, l, &w));
     if (l == 0 && !first_norm_done) TRY(k_resid_norm(e, e->x_dec, nullptr, 0, 0, w.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
     // fused path: resid + RMSNorm live inside the contractions around them (gemm.cuh NormFuse), 5 kernels per layer
-    const bool fuse = e->bf16 && e->use_tc && e->fuse_norm && R <= 32 && fused_swiglu_ok(e, R) && D % 8 == 0 && HD % 8 == 0 &&
+    const bool fuse = regime == 0 && e->bf16 && e->use_tc && e->fuse_norm && R <= 32 && fused_swiglu_ok(e, R) && D % 8 == 0 && HD % 8 == 0 &&
                       F % 8 == 0 && D <= 32 * TC_BM * 8;
     NormFuse nf_qkv = {}, nf_o = {}, nf_gu = {}, nf_d = {};
     if (fuse) {
@@ -903,24 +929,24 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     }
     TRY(run_gemm(e, e->xn, w.wqkv, R, 3 * HD, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr,
                  (fuse && l > 0) ? &nf_qkv : nullptr));
-    if (e->bf16 && e->attn_impl >= 1 && R <= AT_MAX_ROWS) {
+    if (e->bf16 && e->attn_impl >= 1 && R <= AT_MAX_ROWS && (regime == 0 || e->attn_impl >= 3)) {
       const int ctas = e->attn_ctas > 0 ? e->attn_ctas : e->num_sms;
       const int saved = e->use_pdl;
       if (!e->attn_attr) e->use_pdl = 0;
       const AttnVariant av = attn_variant(e);
       int rc = launch(e, av.fn, dim3(ctas), dim3(av.threads), av.smem, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
                       (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, av.ws, av.sync,
-                      R, d.H, e->Tmax, pos_base, step_ptr, scale, 1, e->attn_trigger, next_prof(e), (unsigned long long*)nullptr);
+                      R, d.H, e->Tmax, pos_base, step_ptr, scale, trig, e->attn_trigger, next_prof(e), (unsigned long long*)nullptr);
       e->use_pdl = saved;
       TRY(rc);
     } else {
     DISPATCH_T(e,
                  launch(e, attn_decode_kernel<bf16>, dim3(d.H, R, nsp), dim3(128), 0, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
                         (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ws,
-                        e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, 1),
+                        e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, trig),
                  launch(e, attn_decode_kernel<float>, dim3(d.H, R, nsp), dim3(128), 0, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
                         (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), kv_start, (float*)e->attn_out, e->attn_ws,
-                        e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, 0));
+                        e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, trig));
     }
     if (fuse) {
       int So = 1;
@@ -1158,6 +1184,95 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
   // last token: head + sample only (the reference computes and drops one more embed)
   TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, false,
                n_steps - 1, st));
+  CK(cudaEventRecord(e->ev_out, st));
+  CK(cudaStreamWaitEvent(user, e->ev_out, 0));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ f1: stage-1 text decode (x2t)
+// One greedy step: lm_head contraction -> argmax / eos bookkeeping / embed_tokens / first RMSNorm -> decoder layers.
+static int text_step(pg_engine* e, const int32_t* kv_start, int R, int P, int max_new, int eos_id, int pad_id,
+                     int32_t* tokens_out, bool with_lm, int step_host, cudaStream_t st) {
+  const pg_dims& d = e->d;
+  NEED(lm_head, void, "lm_head");
+  NEED(table, float, "embed_tokens");
+  LayerW w0;
+  TRY(layer_weights(e, 0, &w0));
+  int S = 1;
+  TRY(run_gemm(e, e->hidden_t, lm_head, R, d.vocab, d.D, e->part, e->part_bytes, &S, st));
+  const bool host = step_host >= 0;
+  GreedyState gs = {e->greedy_state + 64, e->greedy_state, e->greedy_state + 1};
+  DISPATCH_T(e,
+             launch(e, lm_argmax_embed_kernel<bf16>, dim3(R), dim3(TXT_THREADS), 0, st, e->part, S, (size_t)R * d.vocab, d.vocab, eos_id, pad_id, gs,
+                    host ? step_host : 0, host ? (const int*)nullptr : e->step_ctr, max_new, tokens_out, table, d.vocab, d.D,
+                    with_lm ? e->x_dec : (float*)nullptr, w0.ln1, with_lm ? (bf16*)e->xn : (bf16*)nullptr, d.rms_eps, e->dbg_text_logits),
+             launch(e, lm_argmax_embed_kernel<float>, dim3(R), dim3(TXT_THREADS), 0, st, e->part, S, (size_t)R * d.vocab, d.vocab, eos_id, pad_id, gs,
+                    host ? step_host : 0, host ? (const int*)nullptr : e->step_ctr, max_new, tokens_out, table, d.vocab, d.D,
+                    with_lm ? e->x_dec : (float*)nullptr, w0.ln1, with_lm ? (float*)e->xn : (float*)nullptr, d.rms_eps, e->dbg_text_logits));
+  if (with_lm)
+    TRY(decode_layers(e, kv_start, R, host ? P + step_host : P, host ? nullptr : e->step_ctr, true, !host, P + max_new / 2, st, 1));
+  return 0;
+}
+
+// language_model.generate(inputs_embeds=, attention_mask=, pad_token_id=, eos_token_id=, max_new_tokens=, do_sample=False,
+// use_cache=True)  (plangen_base.py:513-523; HF GenerationMixin greedy search).  x_prompt fp32 [R][P][D] (overwritten),
+// tokens_out int32 [R][max_new_tokens] on the device; *n_generated (host) = number of columns that are valid = the
+// step after which every row had produced eos (HF stops there), or max_new_tokens.  Synchronises the stream.
+extern "C" int pg_generate_greedy(pg_engine* e, float* x_prompt, const int32_t* kv_start, int R, int P, int max_new_tokens,
+                                  int eos_id, int pad_id, int32_t* tokens_out, int* n_generated, void* stream) {
+  TRY(check_ready(e));
+  const pg_dims& d = e->d;
+  if (!n_generated || !tokens_out) return fail("null argument");
+  if (R < 1 || R > d.max_rows) return fail("generate R=%d exceeds engine limits", R);
+  if (max_new_tokens < 1 || P + max_new_tokens > e->Tmax) return fail("P + max_new_tokens = %d exceeds the KV capacity %d", P + max_new_tokens, e->Tmax);
+  if (d.D > TXT_MAX_PER_THREAD * TXT_THREADS) return fail("hidden size %d too large for the greedy-step kernel", d.D);
+  if (!T_(e, "lm_head")) return fail("tensor 'lm_head' not set: the engine was built without language_model.lm_head.weight");
+  if (!e->poll_host) CK(cudaMallocHost(&e->poll_host, 64));
+  cudaStream_t user = (cudaStream_t)stream;
+  cudaStream_t st = e->own_stream;
+  CK(cudaEventRecord(e->ev_in, user));
+  CK(cudaStreamWaitEvent(st, e->ev_in, 0));
+  TRY(prefill_impl(e, x_prompt, kv_start, R, P, nullptr, 0, true, (void*)st));
+  CK(cudaMemsetAsync(e->step_ctr, 0, 4, st));
+  GreedyState gs = {e->greedy_state + 64, e->greedy_state, e->greedy_state + 1};
+  greedy_state_init_kernel<<<(R + 127) / 128, 128, 0, st>>>(gs, R, max_new_tokens);
+  CK(cudaGetLastError());
+  const int poll_every = 16;
+  bool stopped = false;
+  if (max_new_tokens > 1 && e->use_graph) {
+    char key[384];
+    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%p/%p/%d/%d/%d", R, P, max_new_tokens, eos_id, pad_id, (const void*)kv_start,
+             (void*)tokens_out, e->use_pdl, e->use_tc, e->bf16 ? 1 : 0);
+    if (!e->txt_graph_exec || e->txt_graph_key != key) {
+      if (e->txt_graph_exec) { cudaGraphExecDestroy(e->txt_graph_exec); e->txt_graph_exec = nullptr; }
+      cudaGraph_t graph = nullptr;
+      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      const int64_t before = e->launches;
+      int rc = text_step(e, kv_start, R, P, max_new_tokens, eos_id, pad_id, tokens_out, true, -1, st);
+      cudaError_t ce = cudaStreamEndCapture(st, &graph);
+      e->txt_graph_launches = e->launches - before;
+      e->launches = before;
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) return fail("stream capture failed: %s", cudaGetErrorString(ce));
+      ce = cudaGraphInstantiate(&e->txt_graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) { e->txt_graph_exec = nullptr; return fail("graph instantiate failed: %s", cudaGetErrorString(ce)); }
+      e->txt_graph_key = key;
+    }
+  }
+  for (int i = 0; i < max_new_tokens - 1 && !stopped; ++i) {
+    if (e->use_graph) { CK(cudaGraphLaunch(e->txt_graph_exec, st)); e->launches += e->txt_graph_launches; }
+    else TRY(text_step(e, kv_start, R, P, max_new_tokens, eos_id, pad_id, tokens_out, true, i, st));
+    if ((i + 1) % poll_every == 0) {            // every row done?  (HF checks after every token, with a host sync each)
+      CK(cudaMemcpyAsync(e->poll_host, e->greedy_state, 8, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      if (e->poll_host[0] == 0) stopped = true;
+    }
+  }
+  if (!stopped) TRY(text_step(e, kv_start, R, P, max_new_tokens, eos_id, pad_id, tokens_out, false, max_new_tokens - 1, st));
+  CK(cudaMemcpyAsync(e->poll_host, e->greedy_state, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  *n_generated = e->poll_host[1];
   CK(cudaEventRecord(e->ev_out, st));
   CK(cudaStreamWaitEvent(user, e->ev_out, 0));
   return 0;

@@ -17,7 +17,10 @@ constexpr int HEAD_DIM = 128;
 // flags for resid_rmsnorm_kernel
 constexpr int RN_ROUND_RESID = 1;   // keep the residual stream bf16-rounded (decode steps in the autocast regime:
                                     // inputs_embeds there is the bf16 output of gen_aligner, so HF's residual adds are bf16)
-constexpr int RN_INC_STEP = 2;      // block 0 increments *step_ptr at the end (last kernel of a decode-step graph)
+constexpr int RN_INC_STEP = 2;
+// bit 1 of the decode-attention kernels' `bf16_trig` argument: RoPE position of the new token = column - kv_start[row]
+// (HF generate() derives position_ids from the attention mask; the image loop passes none => absolute columns)
+constexpr int ROPE_REL = 2;      // block 0 increments *step_ptr at the end (last kernel of a decode-step graph)
 
 // Fixed-order (left to right) sum over the split-K slabs.  ALL slab loads are issued before the first add:
 // a load-add-load-add loop serialises one L2 round trip (~0.45 us) per split on the in-order pipe.
@@ -193,16 +196,20 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 qkv_rope_store_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ cosT,
                       const float* __restrict__ sinT, T* __restrict__ q_out, T* __restrict__ kcache,
-                      T* __restrict__ vcache, int P, int H, int Tmax) {
+                      T* __restrict__ vcache, int P, int H, int Tmax, const int32_t* __restrict__ rope_start) {
   pdl_launch_dependents();
   pdl_wait();
   const int tok = blockIdx.x;
   const int r = tok / P, p = tok % P;
   const int HD = H * HEAD_DIM;
   const float* row = part + (size_t)tok * 3 * HD;
+  // rope_start != nullptr: HF generate() positions, cumsum(attention_mask) - 1 = column - left-pad count
+  // (GenerationMixin.prepare_inputs_for_generation); nullptr: absolute columns (LlamaModel.forward without
+  // position_ids, the image loop, plangen_base.py:571-576).  Pad columns are never attended; their position is moot.
+  const int pr = rope_start ? max(p - rope_start[r], 0) : p;
   for (int i = threadIdx.x; i < H * 64; i += blockDim.x) {
     const int h = i >> 6, j = i & 63;
-    const float c = cosT[p * 64 + j], s = sinT[p * 64 + j];
+    const float c = cosT[pr * 64 + j], s = sinT[pr * 64 + j];
     const size_t o1 = (size_t)h * HEAD_DIM + j, o2 = o1 + 64;
     float q1 = Act<T>::rnd(reduce_splits(row, S, split_stride, o1));
     float q2 = Act<T>::rnd(reduce_splits(row, S, split_stride, o2));
@@ -455,18 +462,19 @@ attn_decode_kernel(const float* __restrict__ part, int S, size_t split_stride, c
   {
     const float* row = part + (size_t)r * 3 * HD;
     const int j = tid & 63;
-    const float c = cosT[pos * 64 + j], s = sinT[pos * 64 + j];
+    const int pr = (bf16_trig & ROPE_REL) ? max(pos - start, 0) : pos;
+    const float c = cosT[pr * 64 + j], s = sinT[pr * 64 + j];
     if (tid < 64) {
       const float x1 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)h * HEAD_DIM + j));
       const float x2 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)h * HEAD_DIM + j + 64));
       float a, b;
-      rope_pair<T>(x1, x2, c, s, bf16_trig != 0, a, b);
+      rope_pair<T>(x1, x2, c, s, (bf16_trig & 1) != 0, a, b);
       q_s[j] = a * scale; q_s[j + 64] = b * scale;
     } else if (sp == nsp - 1) {
       const float x1 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)HD + h * HEAD_DIM + j));
       const float x2 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)HD + h * HEAD_DIM + j + 64));
       float a, b;
-      rope_pair<T>(x1, x2, c, s, bf16_trig != 0, a, b);
+      rope_pair<T>(x1, x2, c, s, (bf16_trig & 1) != 0, a, b);
       const float v1 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)2 * HD + h * HEAD_DIM + j));
       const float v2 = Act<T>::rnd(reduce_splits(row, S, split_stride, (size_t)2 * HD + h * HEAD_DIM + j + 64));
       k_s[j] = a; k_s[j + 64] = b; v_s[j] = v1; v_s[j + 64] = v2;

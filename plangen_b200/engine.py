@@ -119,6 +119,41 @@ class _LanguageModel:
     def get_input_embeddings(self):
         return self._emb
 
+    @torch.inference_mode()
+    def generate(self, inputs_embeds=None, attention_mask=None, pad_token_id=None, bos_token_id=None, eos_token_id=None,
+                 max_new_tokens=512, do_sample=False, use_cache=True, **kw):
+        """`LlamaForCausalLM.generate` as System.x2t calls it (plangen_base.py:513-523): greedy search from
+        `inputs_embeds` with a LEFT-padded `attention_mask`; returns the NEW token ids only, int64
+        (R, n) with n <= max_new_tokens (HF stops once every row has emitted eos; finished rows are filled
+        with pad_token_id).  The whole loop runs on the device (pg_generate_greedy)."""
+        e = self.model._e
+        if inputs_embeds is None:
+            raise ValueError("inputs_embeds is required (the reference never passes input_ids here)")
+        if do_sample or kw.get("num_beams", 1) != 1:
+            raise NotImplementedError("only greedy search (do_sample=False, num_beams=1) is implemented; x2t uses nothing else")
+        if not use_cache:
+            raise NotImplementedError("use_cache=False is not supported")
+        if eos_token_id is None:
+            raise ValueError("eos_token_id is required")
+        if isinstance(eos_token_id, (list, tuple)):
+            if len(eos_token_id) != 1:
+                raise NotImplementedError("a single eos_token_id is supported")
+            eos_token_id = eos_token_id[0]
+        pad = eos_token_id if pad_token_id is None else pad_token_id
+        R, P, D = inputs_embeds.shape
+        if attention_mask is None:
+            kv_start = torch.zeros(R, dtype=torch.int32, device=e.device)
+        else:
+            kv_start = kv_start_from_mask(attention_mask.to(e.device), P)
+        x = inputs_embeds.to(device=e.device, dtype=torch.float32).contiguous().clone()
+        tokens = torch.zeros(R, int(max_new_tokens), dtype=torch.int32, device=e.device)
+        n = C.c_int(0)
+        e._keep = (kv_start, x)
+        _lib.check(e._lib.pg_generate_greedy(e._h, _ptr(x), _ptr(kv_start), R, P, int(max_new_tokens), int(eos_token_id),
+                                             int(pad), _ptr(tokens), C.byref(n), _stream_ptr(e.device)))
+        e._serial += 1
+        return tokens[:, :n.value].to(torch.int64)
+
 
 class _GenVisionModel:
     def __init__(self, eng: "FastJanus"):

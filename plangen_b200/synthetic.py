@@ -83,10 +83,13 @@ def state_dict_names(d: Dims, with_vq: bool = True) -> List[Tuple[str, Tuple[int
     return s
 
 
-def random_state_dict(d: Dims, device, seed: int = 0, with_vq: bool = True) -> Dict[str, torch.Tensor]:
+def random_state_dict(d: Dims, device, seed: int = 0, with_vq: bool = True, with_lm_head: bool = False) -> Dict[str, torch.Tensor]:
     g = torch.Generator(device=device).manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
-    for name, shape, kind in state_dict_names(d, with_vq):
+    names = state_dict_names(d, with_vq)
+    if with_lm_head:       # untied text head, only needed by language_model.generate (stage-1 layout-text decode)
+        names = names + [("language_model.lm_head.weight", (d.vocab, d.D), "lm")]
+    for name, shape, kind in names:
         t = torch.empty(shape, device=device, dtype=torch.float32)
         if kind == "lm":
             t.normal_(0.0, 0.02, generator=g)

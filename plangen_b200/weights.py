@@ -58,6 +58,8 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, mode: str, device, 
             out[f"l{i}.wgu"] = w(torch.cat([g_, u_], dim=0))
         out[f"l{i}.wd"] = w(sd[p + "mlp.down_proj.weight"])
     out["norm"] = f(sd[lm + "norm.weight"])
+    if "language_model.lm_head.weight" in sd:      # optional: stage-1 layout-text decode (language_model.generate)
+        out["lm_head"] = w(sd["language_model.lm_head.weight"])
     out["head.w0"] = w(sd["gen_head.output_mlp_projector.weight"])
     out["head.b0"] = f(sd["gen_head.output_mlp_projector.bias"])
     out["head.w1"] = w(sd["gen_head.vision_head.weight"])

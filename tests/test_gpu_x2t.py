@@ -1,0 +1,120 @@
+"""-m gpu: stage-1 layout-text decode (System.x2t -> language_model.generate, plangen_base.py:513-523; SURVEY §8f
+rank 1) through the C-ABI (pg_generate_greedy) against the committed output of the real HF generate and the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import janus_oracle as O
+from tests.gpu_util import assert_close, product_dims
+
+pytestmark = pytest.mark.gpu
+
+_ENG = {}
+
+
+def _engine(d, mode, max_steps=64):
+    from plangen_b200.engine import FastJanus
+    key = (d.name, mode, max_steps)
+    if key not in _ENG:
+        sd = O.init_state_dict(d, seed=0, with_vq=False, with_lm_head=True)
+        _ENG[key] = FastJanus(sd, product_dims(d), mode=mode, max_batch=4, max_prompt=64, max_steps=max_steps, with_vq=False)
+    return _ENG[key]
+
+
+GOLDENS = [("x2t_tiny_fp32.npz", O.TINY), ("x2t_small_fp32.npz", O.SMALL), ("x2t_tiny_stop_fp32.npz", O.TINY)]
+
+
+@pytest.mark.parametrize("name,dims", GOLDENS)
+@pytest.mark.parametrize("graph", [1, 0])
+def test_fp32_generate_matches_hf_generate_golden(golden_dir, name, dims, graph):
+    """fp32 check mode: token ids identical to HF generate (pad fill of finished rows, early stop, number of
+    returned columns), first-step logits within 1e-4."""
+    g = np.load(os.path.join(golden_dir, name))
+    eng = _engine(dims, "fp32")
+    eng.set_option("use_graph", graph)
+    ids, mask = torch.from_numpy(g["ids"]).cuda(), torch.from_numpy(g["mask"]).cuda()
+    eos, max_new = int(g["eos"]), int(g["max_new"])
+    dbg = torch.zeros(max_new, ids.shape[0], dims.vocab, device="cuda")
+    eng.set_option("dbg_text_logits_ptr", dbg.data_ptr())
+    try:
+        emb = eng.language_model.get_input_embeddings()(ids)
+        out = eng.language_model.generate(inputs_embeds=emb, attention_mask=mask, pad_token_id=eos, bos_token_id=1,
+                                          eos_token_id=eos, max_new_tokens=max_new, do_sample=False, use_cache=True)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("dbg_text_logits_ptr", 0)
+        eng.set_option("use_graph", 1)
+    assert out.dtype == torch.int64
+    assert out.cpu().tolist() == g["tokens"].tolist()
+    n = min(g["logits"].shape[0], out.shape[1])
+    assert_close(dbg[:n].cpu().numpy(), g["logits"][:n], 1e-4, 2e-5, "lm_head logits")
+
+
+def test_fp32_generate_ragged_batch_matches_oracle():
+    """Rows with 0..many pad columns, eos hit at different steps; engine vs oracle restatement."""
+    d = O.SMALL
+    sd = O.init_state_dict(d, seed=0, with_vq=False, with_lm_head=True)
+    prompts = [[5, 6, 7], list(range(10, 45)), [9] * 17, [3], list(range(100, 140))]
+    ids, mask = O.pad_input_ids(prompts, d.pad_id)
+    free = O.generate_greedy(sd, d, O.embed_tokens(sd, ids), mask, 40, d.vocab - 1, d.vocab - 1)
+    eos = int(free[2, 9])
+    want = O.generate_greedy(sd, d, O.embed_tokens(sd, ids), mask, 40, eos, eos)
+    eng = _engine(d, "fp32")
+    emb = eng.language_model.get_input_embeddings()(ids.cuda())
+    got = eng.language_model.generate(inputs_embeds=emb, attention_mask=mask.cuda(), pad_token_id=eos, eos_token_id=eos,
+                                      max_new_tokens=40, do_sample=False)
+    assert got.cpu().tolist() == want.tolist()
+
+
+@pytest.mark.parametrize("dims", [O.TINY, O.SMALL])
+@pytest.mark.parametrize("use_tc", [1, 0])
+def test_bf16_generate_logits_match_autocast_reference(dims, use_tc):
+    """Reference regime (fp32 master weights under torch.autocast(bf16), plangen_base.py:360) on the same GPU:
+    lm_head logits of every step within rtol 2e-2 while the two greedy sequences agree (a near-tie may flip a
+    token of a random-init model, after which the sequences legitimately diverge)."""
+    sd = O.init_state_dict(dims, seed=0, with_vq=False, with_lm_head=True)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    cond, _ = O.synthetic_prompts(dims, 4, seed=99, lo=9, hi=40, neg_len=4)
+    ids, mask = O.pad_input_ids(cond, dims.pad_id)
+    ids, mask = ids.cuda(), mask.cuda()
+    steps = 10
+    ref_tok, ref_logits = O.generate_greedy(sdc, dims, O.embed_tokens(sdc, ids), mask, steps, dims.vocab - 1, dims.vocab - 1,
+                                            mode="autocast", return_logits=True)
+    eng = _engine(dims, "bf16")
+    eng.set_option("use_tc", use_tc)
+    dbg = torch.zeros(steps, ids.shape[0], dims.vocab, device="cuda")
+    eng.set_option("dbg_text_logits_ptr", dbg.data_ptr())
+    try:
+        emb = eng.language_model.get_input_embeddings()(ids)
+        got = eng.language_model.generate(inputs_embeds=emb, attention_mask=mask, pad_token_id=dims.vocab - 1,
+                                          eos_token_id=dims.vocab - 1, max_new_tokens=steps, do_sample=False)
+        torch.cuda.synchronize()
+    finally:
+        eng.set_option("dbg_text_logits_ptr", 0)
+        eng.set_option("use_tc", 1)
+    same = (got == ref_tok[:, :got.shape[1]]).long().cumprod(1)          # 1 while the sequences still agree
+    checked = 0
+    for i in range(steps):
+        rows = [r for r in range(ids.shape[0]) if i == 0 or bool(same[r, i - 1])]
+        if rows:
+            assert_close(dbg[i, rows].cpu().numpy(), ref_logits[i][rows].cpu().numpy(), 2e-2, 2e-2, f"bf16 lm_head logits step {i}")
+            checked += len(rows)
+    assert checked >= 2 * ids.shape[0]
+
+
+def test_generate_requires_lm_head_and_capacity():
+    from plangen_b200.engine import FastJanus
+    from plangen_b200 import _lib
+    d = O.TINY
+    sd = O.init_state_dict(d, seed=0, with_vq=False)
+    eng = FastJanus(sd, product_dims(d), mode="fp32", max_batch=2, max_prompt=64, with_vq=False)
+    emb = torch.zeros(2, 5, d.D, device="cuda")
+    with pytest.raises(_lib.PgError, match="lm_head"):
+        eng.language_model.generate(inputs_embeds=emb, eos_token_id=3, max_new_tokens=4)
+    eng2 = _engine(d, "fp32")
+    with pytest.raises(_lib.PgError, match="KV capacity"):
+        eng2.language_model.generate(inputs_embeds=emb, eos_token_id=3, max_new_tokens=4096)
+    with pytest.raises(NotImplementedError):
+        eng2.language_model.generate(inputs_embeds=emb, eos_token_id=3, max_new_tokens=4, do_sample=True)

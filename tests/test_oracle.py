@@ -173,3 +173,37 @@ def test_vq_oracle_matches_live_reference_bf16_autocast():
         want = dec(z)
         h = O._conv(z, sd, pre + "conv_in", 1)       # exercise the same pieces under autocast
     assert want.shape == (1, 3, d.img_size, d.img_size) and h.dtype == torch.bfloat16
+
+
+# ------------------------------------------------------- stage-1 layout-text decode (x2t)
+X2T_GOLDENS = [("x2t_tiny_fp32.npz", O.TINY), ("x2t_small_fp32.npz", O.SMALL), ("x2t_tiny_stop_fp32.npz", O.TINY)]
+
+
+@pytest.mark.parametrize("name,dims", X2T_GOLDENS)
+def test_generate_greedy_matches_hf_generate_golden(golden_dir, name, dims):
+    """The restated greedy search (System.x2t, plangen_base.py:513-523) against the committed output of the
+    real HF `LlamaForCausalLM.generate` (oracle/make_golden.py::golden_x2t): identical token ids incl. the
+    pad fill of finished rows and the early stop, logits within 1e-5."""
+    g = np.load(os.path.join(golden_dir, name))
+    sd = O.init_state_dict(dims, seed=0, with_vq=False, with_lm_head=True)
+    ids, mask = torch.from_numpy(g["ids"]), torch.from_numpy(g["mask"])
+    eos = int(g["eos"])
+    seq, logits = O.generate_greedy(sd, dims, O.embed_tokens(sd, ids), mask, int(g["max_new"]), eos, eos, return_logits=True)
+    assert seq.tolist() == g["tokens"].tolist()
+    n = min(len(logits), g["logits"].shape[0])
+    got = torch.stack(logits[:n]).numpy()
+    assert np.abs(got - g["logits"][:n]).max() <= 1e-5 * np.abs(g["logits"]).max()
+
+
+def test_generate_greedy_positions_are_mask_aware():
+    """generate() derives position_ids from the attention mask: a row's result must not depend on how many pad
+    columns sit in front of it (the image loop's absolute positions would change the rotary phases)."""
+    d = O.TINY
+    sd = O.init_state_dict(d, seed=0, with_vq=False, with_lm_head=True)
+    prompt = [11, 12, 13, 14, 15, 16, 17]
+    ids1, mask1 = O.pad_input_ids([prompt], d.pad_id)
+    ids2, mask2 = O.pad_input_ids([prompt, list(range(20, 40))], d.pad_id)
+    a = O.generate_greedy(sd, d, O.embed_tokens(sd, ids1), mask1, 6, d.vocab - 1, d.vocab - 1, return_logits=True)[1]
+    b = O.generate_greedy(sd, d, O.embed_tokens(sd, ids2), mask2, 6, d.vocab - 1, d.vocab - 1, return_logits=True)[1]
+    for x, y in zip(a, b):
+        assert torch.allclose(x[0], y[0], atol=2e-6)
