@@ -78,6 +78,11 @@ struct pg_engine {
   // L2 prefetch of the next attention launch's KV tiles from the decode-step norm kernels (lm_kernels.cuh KvPrefetch):
   // tiles with (index mod kvpf_den) < kvpf1 by the post-attention norm, the next kvpf2 residues by the post-MLP norm
   int kvpf_den = 8, kvpf1 = 0, kvpf2 = 0;
+  // dynamic shared memory requested by the decode-step norm kernels (they use none): keeps a 200 KB contraction CTA
+  // from becoming co-resident on a norm CTA's SM, where its queued weight-tile requests delay the norm's loads
+  int norm_smem_kb = 0, norm_smem_mask = 3;
+  int norm_tma = 1;
+  int tc_prefetch = 0, tc_prefetch_gu = 0;   // weight tiles a decode contraction may request before its dependency wait (0 = ring depth)
   // resid+RMSNorm folded into the contractions (gemm.cuh NormFuse): parity-green but measured slower (2.13 vs 1.62 ms per
   // step): two converter warps cannot build the normalised token tile at the MMA cadence, and cluster launches lose the
   // early residency / weight prefetch that PDL gives plain launches.  Off by default; kept for round 2.
@@ -233,7 +238,8 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   if (nfp) nf = *nfp;
   if (nf.xres) e->cluster_z = splits;            // the split-K CTAs of a tile reduce through distributed shared memory
   return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
-                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out, cg, nf);
+                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out, cg, nf,
+                NT <= 64 ? (swiglu_out ? e->tc_prefetch_gu : e->tc_prefetch) : 0);
 }
 
 // 3x3 convolution (pad 1) as an implicit GEMM on the tcgen05 path: act bf16 NHWC [B][H][W][Cin], Wc bf16
@@ -453,6 +459,10 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaFuncSetAttribute(gemm_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   CK(cudaFuncSetAttribute(gemm_tc_kernel<192>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+  CK(cudaFuncSetAttribute(resid_rmsnorm_tma_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(resid_rmsnorm_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(resid_rmsnorm_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(resid_rmsnorm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM));
@@ -524,6 +534,11 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "use_tiled") e->use_tiled = (int)value;
   else if (k == "fuse_norm") e->fuse_norm = (int)value;
   else if (k == "rn_threads") e->rn_threads = (int)value;
+  else if (k == "norm_tma") e->norm_tma = (int)value;
+  else if (k == "tc_prefetch") e->tc_prefetch = (int)value;
+  else if (k == "tc_prefetch_gu") e->tc_prefetch_gu = (int)value;
+  else if (k == "norm_smem_kb") e->norm_smem_kb = (int)value;
+  else if (k == "norm_smem_mask") e->norm_smem_mask = (int)value;
   else if (k == "kvpf_den") e->kvpf_den = std::max(1, (int)value);
   else if (k == "kvpf1") e->kvpf1 = (int)value;
   else if (k == "kvpf2") e->kvpf2 = (int)value;
@@ -534,6 +549,8 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_dbg_ptr") e->attn_dbg_ptr = (uint64_t)value;
   else if (k == "gemm_dbg_ptr") { unsigned long long* p = (unsigned long long*)value; CK(cudaMemcpyToSymbol(g_gemm_dbg, &p, sizeof(p))); }
   else if (k == "sample_dbg_ptr") { unsigned long long* p = (unsigned long long*)value; CK(cudaMemcpyToSymbol(g_sample_dbg, &p, sizeof(p))); }
+  else if (k == "norm_dbg_ptr") { unsigned long long* p = (unsigned long long*)value; CK(cudaMemcpyToSymbol(g_norm_dbg, &p, sizeof(p))); }
+  else if (k == "norm_dbg_step") { int n = (int)value; CK(cudaMemcpyToSymbol(g_norm_dbg_step, &n, sizeof(n))); }
   else if (k == "gemm_dbg_n") { int n = (int)value; CK(cudaMemcpyToSymbol(g_gemm_dbg_n, &n, sizeof(n))); }
   else if (k == "attn_test_flags") e->attn_test_flags = value;
   else if (k == "attn_ctas") e->attn_ctas = (int)value;
@@ -576,17 +593,30 @@ extern "C" int pg_engine_get_counter(const pg_engine* e, const char* key, int64_
 
 static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t sstride, const float* w, void* xn,
                         float* y, int rows, int in_stride, int in_off, int flags, cudaStream_t st,
-                        const KvPrefetch* pfp = nullptr) {
+                        const KvPrefetch* pfp = nullptr, size_t smem = 0) {
   const int D = e->d.D;
   KvPrefetch pf = {};
   if (pfp) pf = *pfp;
+  // decode steps: slabs + residual row through TMA bulk copies into shared memory (bit-identical, see lm_kernels.cuh)
+  const size_t tma_smem = (size_t)(S + 1) * D * 4 + 128;
+  const int tma_threads = std::min(RN_THREADS, std::max(128, (D / 4 + 31) / 32 * 32));   // one element quad per thread
+  if (e->norm_tma && part != nullptr && in_stride == 1 && in_off == 0 && rows <= 256 && D % 4 == 0 &&
+      D <= RN_MAX_PER_THREAD * tma_threads && tma_smem <= 200 * 1024 && (sstride * 4) % 16 == 0 &&
+      (((uintptr_t)part | (uintptr_t)x) & 15) == 0) {
+    DISPATCH_T(e,
+               launch(e, resid_rmsnorm_tma_kernel<bf16>, dim3(rows), dim3(tma_threads), tma_smem, st, x, part, S, sstride, w, (bf16*)xn, y, D,
+                      e->d.rms_eps, flags, e->step_ctr, next_prof(e), pf),
+               launch(e, resid_rmsnorm_tma_kernel<float>, dim3(rows), dim3(tma_threads), tma_smem, st, x, part, S, sstride, w, (float*)xn, y, D,
+                      e->d.rms_eps, flags, e->step_ctr, next_prof(e), pf));
+    return 0;
+  }
   // few rows (decode): 1024 threads so one row's split-K loads are all in flight; many rows (prefill): 256+
   int threads = rows <= 256 ? (e->rn_threads > 0 ? e->rn_threads : RN_THREADS) : 256;
   while (threads * RN_MAX_PER_THREAD < D) threads *= 2;
   DISPATCH_T(e,
-             launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (bf16*)xn, y, D,
+             launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(threads), smem, st, x, part, S, sstride, w, (bf16*)xn, y, D,
                     e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e), pf),
-             launch(e, resid_rmsnorm_kernel<float>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (float*)xn, y,
+             launch(e, resid_rmsnorm_kernel<float>, dim3(rows), dim3(threads), smem, st, x, part, S, sstride, w, (float*)xn, y,
                     D, e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e), pf));
   return 0;
 }
@@ -959,14 +989,16 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     fused_tail = false;
     TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &S, st));
     const KvPrefetch pf1 = kv_prefetch(l + 1, 0, e->kvpf1);
-    TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st, &pf1));
+    TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st, &pf1,
+                     (e->norm_smem_mask & 1) ? (size_t)e->norm_smem_kb * 1024 : 0));
     TRY(k_gate_up(e, w, R, st));
     TRY(run_gemm(e, e->hbuf, w.wd, R, D, F, e->part, e->part_bytes, &S, st));
     if (l + 1 < d.L) {
       LayerW wn;
       TRY(layer_weights(e, l + 1, &wn));
       const KvPrefetch pf2 = kv_prefetch(l + 1, e->kvpf1, e->kvpf1 + e->kvpf2);
-      TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, wn.ln1, e->xn, nullptr, R, 1, 0, rflag, st, &pf2));
+      TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, wn.ln1, e->xn, nullptr, R, 1, 0, rflag, st, &pf2,
+                       (e->norm_smem_mask & 2) ? (size_t)e->norm_smem_kb * 1024 : 0));
     }
   }
   const KvPrefetch pf_last = kv_prefetch(d.L, e->kvpf1, e->kvpf1 + e->kvpf2);

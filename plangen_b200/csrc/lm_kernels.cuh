@@ -100,6 +100,14 @@ PG_DEVINL void kv_prefetch_l2(const KvPrefetch& pf, int row) {
   }
 }
 
+// debug timeline (tools/norm_timeline.py): 8 %globaltimer stamps per CTA of the decode-step norm kernels of the
+// step g_norm_dbg_step, indexed by the kernel's timeline slot; nullptr in production
+__device__ unsigned long long* g_norm_dbg = nullptr;
+__device__ int g_norm_dbg_step = -1;
+PG_DEVINL void norm_stamp(unsigned long long* d, int slot, int k) {
+  if (d && threadIdx.x == 0) d[((size_t)slot * 64 + blockIdx.x) * 8 + k] = global_timer_ns();
+}
+
 constexpr int RN_THREADS = 1024;            // upper bound; launched with 256..1024 threads
 constexpr int RN_MAX_PER_THREAD = 8;        // D <= 8 * blockDim.x
 template <typename T>
@@ -110,6 +118,8 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
   __shared__ float red[32];
   pdl_launch_dependents();
   prof_begin(prof);
+  unsigned long long* nd = (prof.buf && g_norm_dbg && step_ptr && *step_ptr == g_norm_dbg_step && blockIdx.x < 64) ? g_norm_dbg : nullptr;
+  norm_stamp(nd, prof.slot, 0);
   if (pf.k != nullptr) kv_prefetch_l2(pf, blockIdx.x);
   // the norm weight is a constant: fetch it before the dependency wait instead of after the reduction
   float wv[RN_MAX_PER_THREAD];
@@ -119,6 +129,7 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
     wv[k] = (d < D) ? w[d] : 0.f;
   }
   pdl_wait();
+  norm_stamp(nd, prof.slot, 1);
   const size_t row_in = (size_t)blockIdx.x * in_stride + in_off;
   const size_t row_out = blockIdx.x;
   float* xr = x + row_in * D;
@@ -153,7 +164,9 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
       }
     }
   }
+  norm_stamp(nd, prof.slot, 2);
   ss = block_sum(ss, red);
+  norm_stamp(nd, prof.slot, 3);
   const float r = rsqrtf(ss / (float)D + eps);
 #pragma unroll
   for (int k = 0; k < RN_MAX_PER_THREAD; ++k) {
@@ -166,7 +179,124 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
       if (y_out) y_out[row_out * D + d] = y;
     }
   }
+  norm_stamp(nd, prof.slot, 4);
   if ((flags & RN_INC_STEP) && blockIdx.x == 0 && threadIdx.x == 0) *step_ptr += 1;
+  prof_end(prof);
+}
+
+// Decode-step variant: the S split-K slabs of the row and the residual row are brought into shared memory by
+// S + 1 TMA bulk copies issued by one thread, instead of 18-34 scalar loads per thread.  In-kernel stamps
+// (tools/norm_timeline.py) showed the scalar version spending 3.3-3.7 us in its single round of L2 loads whether
+// or not the neighbouring contractions were prefetching: with one CTA per row only 32 SMs take part and each is
+// bound by its own load-miss parallelism (74 KB per SM); the copy engine keeps the whole 74 KB in flight.
+// Same left-to-right summation order and rounding points as resid_rmsnorm_kernel => bit-identical results.
+PG_DEVINL float4 lds_f4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+template <typename T>
+__global__ void __launch_bounds__(RN_THREADS)
+resid_rmsnorm_tma_kernel(float* __restrict__ x, const float* __restrict__ part, int S, size_t split_stride,
+                         const float* __restrict__ w, T* __restrict__ xn_out, float* __restrict__ y_out, int D,
+                         float eps, int flags, int* step_ptr, Prof prof, KvPrefetch pf) {
+  extern __shared__ uint8_t rn_smem_raw[];
+  __shared__ float red[32];
+  __shared__ uint64_t bar;
+  const uint32_t slab_s = (smem_u32(rn_smem_raw) + 127u) & ~127u;          // [S + 1][D] fp32, shared-space address
+  pdl_launch_dependents();
+  prof_begin(prof);
+  unsigned long long* nd = (prof.buf && g_norm_dbg && step_ptr && *step_ptr == g_norm_dbg_step && blockIdx.x < 64) ? g_norm_dbg : nullptr;
+  norm_stamp(nd, prof.slot, 0);
+  if (pf.k != nullptr) kv_prefetch_l2(pf, blockIdx.x);
+  const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+  // thread t owns the element quads 4 (t + k blockDim); the norm weight is a constant: fetched before the wait
+  constexpr int NQ = RN_MAX_PER_THREAD / 4;
+  float4 wv[NQ];
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    const int d = 4 * (tid + k * blockDim.x);
+    wv[k] = (d < D) ? *reinterpret_cast<const float4*>(w + d) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+  pdl_wait();
+  norm_stamp(nd, prof.slot, 1);
+  const size_t row = blockIdx.x;
+  float* xr = x + row * D;
+  const uint32_t row_bytes = (uint32_t)D * 4;
+  if (tid == 0) {
+    const uint64_t pol = policy_evict_first();
+    mbar_expect_tx(&bar, (uint32_t)(S + 1) * row_bytes);
+    uint32_t dst = slab_s;
+    const float* src = part + row * D;
+    for (int s = 0; s < S; ++s, dst += row_bytes, src += split_stride)
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                   ::"r"(dst), "l"(src), "r"(row_bytes), "r"(smem_u32(&bar)), "l"(pol) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(xr), "r"(row_bytes), "r"(smem_u32(&bar)), "l"(pol) : "memory");
+  }
+  if (tid < 32) mbar_wait(&bar, 0, 40);          // one warp polls the barrier; bar.sync releases the rest
+  __syncthreads();
+  norm_stamp(nd, prof.slot, 2);
+  float4 v[NQ];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    const int d = 4 * (tid + k * blockDim.x);
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d < D) {
+      uint32_t a_s = slab_s + (uint32_t)d * 4;
+      float4 a = lds_f4(a_s);
+      int s = 1;
+      for (; s + 4 <= S; s += 4) {               // four independent loads in flight, adds stay left to right
+        const float4 b0 = lds_f4(a_s + (uint32_t)(s + 0) * row_bytes), b1 = lds_f4(a_s + (uint32_t)(s + 1) * row_bytes);
+        const float4 b2 = lds_f4(a_s + (uint32_t)(s + 2) * row_bytes), b3 = lds_f4(a_s + (uint32_t)(s + 3) * row_bytes);
+        a.x += b0.x; a.y += b0.y; a.z += b0.z; a.w += b0.w;
+        a.x += b1.x; a.y += b1.y; a.z += b1.z; a.w += b1.w;
+        a.x += b2.x; a.y += b2.y; a.z += b2.z; a.w += b2.w;
+        a.x += b3.x; a.y += b3.y; a.z += b3.z; a.w += b3.w;
+      }
+      for (; s < S; ++s) {
+        const float4 b = lds_f4(a_s + (uint32_t)s * row_bytes);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      const float4 xv = lds_f4(a_s + (uint32_t)S * row_bytes);
+      float4 t;
+      t.x = xv.x + Act<T>::rnd(a.x); t.y = xv.y + Act<T>::rnd(a.y); t.z = xv.z + Act<T>::rnd(a.z); t.w = xv.w + Act<T>::rnd(a.w);
+      if (flags & RN_ROUND_RESID) { t.x = Act<T>::rnd(t.x); t.y = Act<T>::rnd(t.y); t.z = Act<T>::rnd(t.z); t.w = Act<T>::rnd(t.w); }
+      *reinterpret_cast<float4*>(xr + d) = t;
+      v[k] = t;
+      ss += t.x * t.x; ss += t.y * t.y; ss += t.z * t.z; ss += t.w * t.w;
+    }
+  }
+  ss = block_sum(ss, red);
+  norm_stamp(nd, prof.slot, 3);
+  const float r = rsqrtf(ss / (float)D + eps);
+#pragma unroll
+  for (int k = 0; k < NQ; ++k) {
+    const int d = 4 * (tid + k * blockDim.x);
+    if (d < D) {
+      float h[4] = {v[k].x * r, v[k].y * r, v[k].z * r, v[k].w * r};
+      if (flags & RN_ROUND_RESID) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = Act<T>::rnd(h[j]);
+      }
+      const float y[4] = {wv[k].x * h[0], wv[k].y * h[1], wv[k].z * h[2], wv[k].w * h[3]};
+      if (xn_out) {
+        if constexpr (sizeof(T) == 2) {
+          const __nv_bfloat162 lo = __floats2bfloat162_rn(y[0], y[1]), hi = __floats2bfloat162_rn(y[2], y[3]);
+          uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(xn_out + row * D + d) = pk;
+        } else {
+          *reinterpret_cast<float4*>(xn_out + row * D + d) = make_float4(y[0], y[1], y[2], y[3]);
+        }
+      }
+      if (y_out) *reinterpret_cast<float4*>(y_out + row * D + d) = make_float4(y[0], y[1], y[2], y[3]);
+    }
+  }
+  norm_stamp(nd, prof.slot, 4);
+  if ((flags & RN_INC_STEP) && blockIdx.x == 0 && tid == 0) *step_ptr += 1;
   prof_end(prof);
 }
 
