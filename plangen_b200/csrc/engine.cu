@@ -81,7 +81,7 @@ struct pg_engine {
   // dynamic shared memory requested by the decode-step norm kernels (they use none): keeps a 200 KB contraction CTA
   // from becoming co-resident on a norm CTA's SM, where its queued weight-tile requests delay the norm's loads
   int norm_smem_kb = 0, norm_smem_mask = 3;
-  int norm_tma = 1;
+  int norm_tma = 3;      // bit 0: decode-step norms through the TMA-staged kernel, bit 1: prefill norms too
   int tc_prefetch = 0, tc_prefetch_gu = 0;   // weight tiles a decode contraction may request before its dependency wait (0 = ring depth)
   // resid+RMSNorm folded into the contractions (gemm.cuh NormFuse): parity-green but measured slower (2.13 vs 1.62 ms per
   // step): two converter warps cannot build the normalised token tile at the MMA cadence, and cluster launches lose the
@@ -600,7 +600,7 @@ static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t
   // decode steps: slabs + residual row through TMA bulk copies into shared memory (bit-identical, see lm_kernels.cuh)
   const size_t tma_smem = (size_t)(S + 1) * D * 4 + 128;
   const int tma_threads = std::min(RN_THREADS, std::max(128, (D / 4 + 31) / 32 * 32));   // one element quad per thread
-  if (e->norm_tma && part != nullptr && in_stride == 1 && in_off == 0 && rows <= 256 && D % 4 == 0 &&
+  if (e->norm_tma && part != nullptr && in_stride == 1 && in_off == 0 && (rows <= 256 || (e->norm_tma & 2)) && D % 4 == 0 &&
       D <= RN_MAX_PER_THREAD * tma_threads && tma_smem <= 200 * 1024 && (sstride * 4) % 16 == 0 &&
       (((uintptr_t)part | (uintptr_t)x) & 15) == 0) {
     DISPATCH_T(e,

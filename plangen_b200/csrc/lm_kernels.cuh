@@ -337,6 +337,41 @@ qkv_rope_store_kernel(const float* __restrict__ part, int S, size_t split_stride
   // (GenerationMixin.prepare_inputs_for_generation); nullptr: absolute columns (LlamaModel.forward without
   // position_ids, the image loop, plangen_base.py:571-576).  Pad columns are never attended; their position is moot.
   const int pr = rope_start ? max(p - rope_start[r], 0) : p;
+  if (S == 1) {
+    // prefill (one split): four rotary pairs per thread, 16-byte loads / 8-byte stores
+    for (int i = threadIdx.x; i < H * 16; i += blockDim.x) {
+      const int h = i >> 4, j = (i & 15) * 4;
+      const float4 c4 = *reinterpret_cast<const float4*>(cosT + pr * 64 + j), s4 = *reinterpret_cast<const float4*>(sinT + pr * 64 + j);
+      const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+      const size_t o1 = (size_t)h * HEAD_DIM + j, o2 = o1 + 64;
+      const size_t cidx = (((size_t)r * H + h) * Tmax + p) * HEAD_DIM + j;
+      float lo[4], hi[4], a[4], b[4];
+      auto ld4 = [&](size_t off, float (&dst)[4]) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(row + off));
+        dst[0] = t.x; dst[1] = t.y; dst[2] = t.z; dst[3] = t.w;
+      };
+      auto st4 = [&](T* dst, const float (&src)[4]) {
+        if constexpr (sizeof(T) == 2) {
+          const __nv_bfloat162 x0 = __floats2bfloat162_rn(src[0], src[1]), x1 = __floats2bfloat162_rn(src[2], src[3]);
+          uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&x0); pk.y = *reinterpret_cast<const uint32_t*>(&x1);
+          *reinterpret_cast<uint2*>(dst) = pk;
+        } else {
+          *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
+        }
+      };
+      ld4(o1, lo); ld4(o2, hi);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rope_pair<T>(Act<T>::rnd(lo[u]), Act<T>::rnd(hi[u]), cs[u], sn[u], false, a[u], b[u]);
+      st4(q_out + (size_t)tok * HD + o1, a); st4(q_out + (size_t)tok * HD + o2, b);
+      ld4(HD + o1, lo); ld4(HD + o2, hi);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) rope_pair<T>(Act<T>::rnd(lo[u]), Act<T>::rnd(hi[u]), cs[u], sn[u], false, a[u], b[u]);
+      st4(kcache + cidx, a); st4(kcache + cidx + 64, b);
+      ld4(2 * HD + o1, lo); ld4(2 * HD + o2, hi);
+      st4(vcache + cidx, lo); st4(vcache + cidx + 64, hi);
+    }
+    return;
+  }
   for (int i = threadIdx.x; i < H * 64; i += blockDim.x) {
     const int h = i >> 6, j = i & 63;
     const float c = cosT[pr * 64 + j], s = sinT[pr * 64 + j];
