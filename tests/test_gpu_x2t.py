@@ -210,3 +210,36 @@ def test_fullsize_x2t_logits_vs_autocast_reference_and_properties():
     k1 = free1[0].tolist().index(eos1)
     one = eng.language_model.generate(pad_token_id=eos1, eos_token_id=eos1, max_new_tokens=40, **kw1).cpu()
     assert one.tolist() == free1[:, :k1 + 1].tolist()
+
+
+def test_two_stage_flow_on_one_engine():
+    """BASELINE configs[2] (uni_2stage): stage-1 text decode and stage-2 image decode alternate on the SAME engine
+    (one KV cache, one workspace, two cached CUDA graphs).  Neither stage may disturb the other: results equal those of
+    an engine that only ever ran that stage."""
+    from plangen_b200.engine import FastJanus
+    d = O.SMALL
+    sd = O.init_state_dict(d, seed=0, with_vq=True, with_lm_head=True)
+    mk = lambda: FastJanus(sd, product_dims(d), mode="bf16", max_batch=4, max_prompt=64, max_steps=48, with_vq=True)
+    both, only_txt, only_img = mk(), mk(), mk()
+    prompts = [[5, 6, 7, 8], list(range(10, 45)), [9] * 17]
+    tids, tmask = O.pad_input_ids(prompts, d.pad_id)
+    tids, tmask = tids.cuda(), tmask.cuda()
+    cond, neg = O.synthetic_prompts(d, 3, seed=11, lo=9, hi=40, neg_len=13)
+    iids, imask = O.t2i_infer_collate_batch(cond, neg, d.pad_id, d.n_img_tokens)
+    iids, imask = iids.cuda(), imask.cuda()
+
+    def stage1(eng):
+        emb = eng.language_model.get_input_embeddings()(tids)
+        return eng.language_model.generate(inputs_embeds=emb, attention_mask=tmask, pad_token_id=d.vocab - 1,
+                                           eos_token_id=d.vocab - 1, max_new_tokens=30).cpu()
+
+    def stage2(eng):
+        dec, _ = eng.t2i(tokens=iids, mask=imask, cfg_weight=5.0, temperature=1.0)
+        return eng.last_tokens.cpu(), dec.float().cpu()
+
+    t_ref, (i_ref, img_ref) = stage1(only_txt), stage2(only_img)
+    for _ in range(2):
+        t = stage1(both)
+        i, img = stage2(both)
+        assert torch.equal(t, t_ref), "stage-1 tokens changed after an image decode on the same engine"
+        assert torch.equal(i, i_ref) and torch.equal(img, img_ref), "stage-2 result changed after a text decode"
