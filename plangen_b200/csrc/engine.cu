@@ -22,6 +22,7 @@
 #include "step_kernel.cuh"
 #include "sample.cuh"
 #include "text_decode.cuh"
+#include "attn_prefill_tc.cuh"
 #include "vq_kernels.cuh"
 
 using namespace pg;
@@ -81,6 +82,8 @@ struct pg_engine {
   // dynamic shared memory requested by the decode-step norm kernels (they use none): keeps a 200 KB contraction CTA
   // from becoming co-resident on a norm CTA's SM, where its queued weight-tile requests delay the norm's loads
   int norm_smem_kb = 0, norm_smem_mask = 3;
+  int prefill_attn_tc = 1;                   // prompt-prefill attention on tcgen05 (attn_prefill_tc.cuh); 0 = CUDA-core kernel
+  void* vT = nullptr;                        // [R][H][128][Ppad] key-contiguous copy of V for the prefill attention
   int norm_tma = 3;      // bit 0: decode-step norms through the TMA-staged kernel, bit 1: prefill norms too
   int tc_prefetch = 0, tc_prefetch_gu = 0;   // weight tiles a decode contraction may request before its dependency wait (0 = ring depth)
   // resid+RMSNorm folded into the contractions (gemm.cuh NormFuse): parity-green but measured slower (2.13 vs 1.62 ms per
@@ -378,6 +381,7 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->attn_ll = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 8);
   e->step_ctr = (int*)c.take(256);
   e->greedy_state = (int*)c.take(256 + R * 4);      // [0] rows unfinished, [1] steps generated, [64..] per-row flags
+  e->vT = c.take(R * d.H * HEAD_DIM * align_up((size_t)std::max(d.max_prompt, 1), 64) * 2);
   e->embed_table = c.take((size_t)d.img_vocab * d.D * es);
   e->align_tmp = c.take((size_t)d.img_vocab * d.D * es);
   e->wmaps_dev = (CUtensorMap*)c.take((size_t)d.L * 4 * sizeof(CUtensorMap));
@@ -463,6 +467,7 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaFuncSetAttribute(resid_rmsnorm_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(resid_rmsnorm_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(resid_rmsnorm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CK(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PA_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM));
@@ -535,6 +540,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "fuse_norm") e->fuse_norm = (int)value;
   else if (k == "rn_threads") e->rn_threads = (int)value;
   else if (k == "norm_tma") e->norm_tma = (int)value;
+  else if (k == "prefill_attn_tc") e->prefill_attn_tc = (int)value;
   else if (k == "tc_prefetch") e->tc_prefetch = (int)value;
   else if (k == "tc_prefetch_gu") e->tc_prefetch_gu = (int)value;
   else if (k == "norm_smem_kb") e->norm_smem_kb = (int)value;
@@ -678,6 +684,7 @@ extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
   CK(cudaMemsetAsync(e->attn_flag, 0, (size_t)d.max_rows * d.H * 64 * 4, st));
   CK(cudaMemsetAsync(e->attn_ll, 0, (size_t)d.max_rows * d.H * 64 * (HEAD_DIM + 2) * 8, st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 256, st));
+  CK(cudaMemsetAsync(e->vT, 0, (size_t)d.max_rows * d.H * HEAD_DIM * align_up((size_t)std::max(d.max_prompt, 1), 64) * 2, st));   // must stay finite
   CK(cudaMemsetAsync(e->sk_sync, 0, 256, st));
   if (e->bf16) {
     // per-layer weight tensor maps and norm scales for the persistent step kernel
@@ -795,6 +802,18 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
                launch(e, qkv_rope_store_kernel<float>, dim3(tok), dim3(256), 0, st, e->part, S, (size_t)tok * 3 * HD, cosT, sinT,
                       (float*)e->qbuf, (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax,
                       rope_rel ? kv_start : (const int32_t*)nullptr));
+    if (e->bf16 && e->use_tc && e->prefill_attn_tc) {
+      // tensor-core path: key-contiguous V copy, then one CTA per (row, head, 128-query tile)
+      const int Ppad = (int)align_up((size_t)P, 64);
+      TRY(launch(e, v_transpose_kernel, dim3(Ppad / 64, d.H, R), dim3(256), 0, st, (const bf16*)kv_ptr(e, l, 1, R), (bf16*)e->vT, P, Ppad,
+                 d.H, e->Tmax));
+      CUtensorMap mq, mk, mv;
+      TRY(make_map_2d(e, &mq, e->qbuf, (uint64_t)tok, (uint64_t)HD, PA_BQ));
+      TRY(make_map_2d(e, &mk, kv_ptr(e, l, 0, R), (uint64_t)R * d.H * e->Tmax, (uint64_t)HEAD_DIM, PA_BK));
+      TRY(make_map_2d(e, &mv, e->vT, (uint64_t)R * d.H * HEAD_DIM, (uint64_t)Ppad, HEAD_DIM));
+      TRY(launch(e, attn_prefill_tc_kernel, dim3((P + PA_BQ - 1) / PA_BQ, d.H, R), dim3(128), PA_SMEM, st, mq, mk, mv, kv_start,
+                 (bf16*)e->attn_out, P, d.H, e->Tmax, scale));
+    } else
     DISPATCH_T(e,
                launch(e, attn_prefill_kernel<bf16>, dim3((P + 63) / 64, d.H, R), dim3(256), ATTN_PREFILL_SMEM, st,
                       (const bf16*)e->qbuf, (const bf16*)kv_ptr(e, l, 0, R), (const bf16*)kv_ptr(e, l, 1, R), kv_start,
