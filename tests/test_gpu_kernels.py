@@ -100,3 +100,42 @@ def test_sampler_teacher_forcing_and_greedy():
     want = O.prepare_gen_img_embeds(sd, toks[:, 2].long())
     assert_close(x2[0::2].cpu().numpy(), want.cpu().numpy(), 1e-4, 1e-5, "embed cond rows")
     assert torch.equal(x2[0::2], x2[1::2])
+
+
+def test_prefill_attention_tensor_core_path_long_ragged_prompts():
+    """Prompt prefill through the tcgen05 attention kernel (attn_prefill_tc.cuh) on prompts that span several
+    128-query tiles and 128-key blocks: rows whose left padding ends inside the first, a middle and the last key
+    block, a row with no padding, and tiles that are all padding.  Final hidden states of the valid positions vs
+    (a) the reference PyTorch path (fp32 master weights under autocast bf16) on the same GPU within the bf16
+    tolerance and (b) the CUDA-core attention kernel of the same engine (two bf16 evaluations of the same
+    arithmetic: closer to each other than either is required to be to the reference)."""
+    import numpy as np
+    from oracle import janus_oracle as O
+    from tests.gpu_util import get_engine, assert_close
+    d = O.SMALL
+    lens = [3, 150, 290, 399, 129, 128, 257, 1]
+    g = torch.Generator().manual_seed(21)
+    prompts = [torch.randint(0, d.pad_id, (n,), generator=g).tolist() for n in lens]
+    ids, mask = O.pad_input_ids(prompts, d.pad_id)
+    P = ids.shape[1]
+    assert P == 399
+    sd = O.init_state_dict(d, seed=0, with_vq=False)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    with torch.inference_mode(), torch.autocast("cuda", dtype=torch.bfloat16):
+        ref = O.llama_model_forward(sdc, d, O.embed_tokens(sdc, ids.cuda()), attention_mask=mask.cuda()).last_hidden_state.float()
+    eng = get_engine(d, "bf16", max_batch=4, max_prompt=400, with_vq=False)
+    emb = eng.language_model.get_input_embeddings()(ids.cuda())
+    outs = {}
+    for tc in (1, 0):
+        eng.set_option("prefill_attn_tc", tc)
+        try:
+            outs[tc] = eng.language_model.model(inputs_embeds=emb, attention_mask=mask.cuda(), use_cache=True).last_hidden_state.float()
+            torch.cuda.synchronize()
+        finally:
+            eng.set_option("prefill_attn_tc", 1)
+    valid = (mask.cuda() != 0)
+    r, a, b = ref[valid].cpu().numpy(), outs[1][valid].cpu().numpy(), outs[0][valid].cpu().numpy()
+    assert np.isfinite(outs[1].cpu().numpy()).all()
+    assert_close(a, r, 2e-2, 3e-2, "prefill hidden states, tcgen05 attention vs autocast reference")
+    assert_close(b, r, 2e-2, 3e-2, "prefill hidden states, CUDA-core attention vs autocast reference")
+    assert np.abs(a - b).mean() <= 1.5 * max(np.abs(a - r).mean(), np.abs(b - r).mean())
