@@ -359,6 +359,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       for (int c0 = 0; c0 < NT; c0 += 16) {
         uint32_t v[16];
         tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
+        if (c0 == 0 && warp == 2 && lane == 0) gemm_stamp(dbg, 7);
         float* mine = xch + (size_t)(quarter * 32 + lane) * 9;                   // what I give away
         const float* theirs = xch + (size_t)((quarter ^ 2) * 32 + lane) * 9;     // what my partner gives me
 #pragma unroll

@@ -12,7 +12,7 @@ del sd
 cond, neg = synthetic.layoutsam_prompts(dims, B, seed=1234)
 ids, mask = synthetic.collate_cfg_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
 emb = eng.language_model.get_input_embeddings()(ids.to(dev))
-names = ["entry", "X producer past wait", "first stage full", "last stage full", "accumulator done", "epilogue done", "exit"]
+names = ["entry", "X producer past wait", "first stage full", "last stage full", "accumulator done", "epilogue done", "exit", "first TMEM chunk read (SwiGLU)"]
 for n in [int(x) for x in os.environ.get("PG_N", "11264,6144,2048").split(",")]:
     dbg = torch.zeros(2048 * 8 + 512, dtype=torch.int64, device=dev)
     eng.set_option("gemm_dbg_n", n); eng.set_option("gemm_dbg_ptr", dbg.data_ptr())
@@ -25,7 +25,8 @@ for n in [int(x) for x in os.environ.get("PG_N", "11264,6144,2048").split(",")]:
     t = t[t[:, 0] > 0]
     t0 = t[:, 0].min()
     print(f"--- weight rows {n}: {t.shape[0]} CTAs")
-    for k in range(7):
+    for k in range(8):
+        if not (t[:, k] > 0).any(): continue
         v = (t[:, k] - t0) / 1e3
         print(f"  {names[k]:22s} min {v.min():6.2f}  p50 {np.median(v):6.2f}  p90 {np.percentile(v, 90):6.2f}  max {v.max():6.2f} us")
     for nm, o in (("MMA saw stage full", 0), ("W producer issued", 64), ("X producer issued", 128)):
