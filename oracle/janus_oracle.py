@@ -142,7 +142,58 @@ def _vq_decoder_shapes(d: JanusDims) -> List[Tuple[str, Tuple[int, ...], str]]:
     return out
 
 
-def tensor_specs(d: JanusDims, with_vq: bool = True, with_lm_head: bool = False) -> List[Tuple[str, Tuple[int, ...], str]]:
+def _vq_encoder_shapes(d: JanusDims) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(name, shape, kind) for VQModel's encode side (vq_model.py:46-106 Encoder.__init__, :493 quant_conv)."""
+    out: List[Tuple[str, Tuple[int, ...], str]] = []
+    p = "gen_vision_model."
+
+    def conv(name, cin, cout, k):
+        out.append((name + ".weight", (cout, cin, k, k), "conv"))
+        out.append((name + ".bias", (cout,), "bias:%d" % (cin * k * k)))
+
+    def norm(name, c):
+        out.append((name + ".weight", (c,), "norm_w"))
+        out.append((name + ".bias", (c,), "norm_b"))
+
+    def res(name, cin, cout):
+        norm(name + ".norm1", cin)
+        conv(name + ".conv1", cin, cout, 3)
+        norm(name + ".norm2", cout)
+        conv(name + ".conv2", cout, cout, 3)
+        if cin != cout:
+            conv(name + ".nin_shortcut", cin, cout, 1)
+
+    def attn(name, c):
+        norm(name + ".norm", c)
+        for n in ("q", "k", "v", "proj_out"):
+            conv(name + "." + n, c, c, 1)
+
+    ep = p + "encoder."
+    nres = len(d.vq_ch_mult)
+    conv(ep + "conv_in", 3, d.vq_ch, 3)
+    in_mult = (1,) + tuple(d.vq_ch_mult)
+    block_in = d.vq_ch
+    for i_level in range(nres):
+        block_in = d.vq_ch * in_mult[i_level]
+        block_out = d.vq_ch * d.vq_ch_mult[i_level]
+        for j in range(d.vq_res_blocks):
+            res(ep + f"conv_blocks.{i_level}.res.{j}", block_in, block_out)
+            block_in = block_out
+            if i_level == nres - 1:
+                attn(ep + f"conv_blocks.{i_level}.attn.{j}", block_in)
+        if i_level != nres - 1:
+            conv(ep + f"conv_blocks.{i_level}.downsample.conv", block_in, block_in, 3)
+    res(ep + "mid.0", block_in, block_in)
+    attn(ep + "mid.1", block_in)
+    res(ep + "mid.2", block_in, block_in)
+    norm(ep + "norm_out", block_in)
+    conv(ep + "conv_out", block_in, d.vq_z, 3)
+    conv(p + "quant_conv", d.vq_z, d.code_dim, 1)
+    return out
+
+
+def tensor_specs(d: JanusDims, with_vq: bool = True, with_lm_head: bool = False,
+                 with_vq_encoder: bool = False) -> List[Tuple[str, Tuple[int, ...], str]]:
     """All state-dict tensors the decode path touches, reference naming.  `with_lm_head` adds the
     untied text head used by the stage-1 layout-text decode (x2t, §8f rank 1)."""
     s: List[Tuple[str, Tuple[int, ...], str]] = []
@@ -174,11 +225,14 @@ def tensor_specs(d: JanusDims, with_vq: bool = True, with_lm_head: bool = False)
     s.append(("gen_aligner.layers.2.bias", (d.D,), "bias:%d" % d.D))
     if with_vq:
         s.extend(_vq_decoder_shapes(d))
+    if with_vq_encoder:
+        s.extend(_vq_encoder_shapes(d))
     return s
 
 
 def init_state_dict(d: JanusDims, seed: int = 0, with_vq: bool = True,
-                    lm_std: float = 0.02, only: Optional[str] = None, with_lm_head: bool = False) -> Dict[str, torch.Tensor]:
+                    lm_std: float = 0.02, only: Optional[str] = None, with_lm_head: bool = False,
+                    with_vq_encoder: bool = False) -> Dict[str, torch.Tensor]:
     """Deterministic random-init fp32 weights (CPU generator; identical on every
     box with the same torch build).  Every tensor has its own generator seeded
     from (seed, crc32(name)), so any subset (`only` = name prefix) reproduces the
@@ -189,7 +243,7 @@ def init_state_dict(d: JanusDims, seed: int = 0, with_vq: bool = True,
     them is caught."""
     import zlib
     sd: Dict[str, torch.Tensor] = {}
-    for name, shape, kind in tensor_specs(d, with_vq, with_lm_head):
+    for name, shape, kind in tensor_specs(d, with_vq, with_lm_head, with_vq_encoder):
         if only is not None and not name.startswith(only):
             continue
         g = torch.Generator(device="cpu").manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
@@ -467,6 +521,53 @@ def vq_decode(sd, d: JanusDims, quant: torch.Tensor) -> torch.Tensor:
             h = _upsample(h, sd, dp + f"conv_blocks.{idx}.upsample")
     h = _swish(_gn(h, sd, dp + "norm_out"))
     return _conv(h, sd, dp + "conv_out", 1)
+
+
+def _downsample(x, sd, name):
+    """Downsample.forward (vq_model.py:440-445): asymmetric zero pad (right, bottom), 3x3 stride-2 conv."""
+    x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
+    return F.conv2d(x, sd[name + ".conv.weight"], sd[name + ".conv.bias"], stride=2, padding=0)
+
+
+def vq_encoder_forward(sd, d: JanusDims, x: torch.Tensor) -> torch.Tensor:
+    """Encoder.forward (vq_model.py:108-124) + quant_conv (:495-496): (B,3,H,W) -> (B,code_dim,H/16,W/16)."""
+    p = "gen_vision_model."
+    ep = p + "encoder."
+    nres = len(d.vq_ch_mult)
+    h = _conv(x, sd, ep + "conv_in", 1)
+    for i_level in range(nres):
+        for j in range(d.vq_res_blocks):
+            h = _resblock(h, sd, ep + f"conv_blocks.{i_level}.res.{j}")
+            if i_level == nres - 1:
+                h = _attnblock(h, sd, ep + f"conv_blocks.{i_level}.attn.{j}")
+        if i_level != nres - 1:
+            h = _downsample(h, sd, ep + f"conv_blocks.{i_level}.downsample")
+    h = _resblock(h, sd, ep + "mid.0")
+    h = _attnblock(h, sd, ep + "mid.1")
+    h = _resblock(h, sd, ep + "mid.2")
+    h = _swish(_gn(h, sd, ep + "norm_out"))
+    h = _conv(h, sd, ep + "conv_out", 1)
+    return _conv(h, sd, p + "quant_conv", 0)
+
+
+def vq_quantize_indices(sd, z: torch.Tensor, return_distances: bool = False):
+    """VectorQuantizer.forward (vq_model.py:236-262), inference branch, l2_norm=True: nearest code of every
+    position.  z (B,C,H,W) -> flat int64 indices (B*H*W,) in (b, h, w) order."""
+    z = torch.einsum("b c h w -> b h w c", z).contiguous()
+    z_flattened = z.view(-1, z.shape[-1])
+    z_flattened = F.normalize(z_flattened, p=2, dim=-1)
+    embedding = F.normalize(sd["gen_vision_model.quantize.embedding.weight"], p=2, dim=-1)
+    dist = (torch.sum(z_flattened ** 2, dim=1, keepdim=True) + torch.sum(embedding ** 2, dim=1)
+            - 2 * torch.einsum("bd,dn->bn", z_flattened, torch.einsum("n d -> d n", embedding)))
+    idx = torch.argmin(dist, dim=1)
+    return (idx, dist) if return_distances else idx
+
+
+def vq_encode(sd, d: JanusDims, img: torch.Tensor, mode: str = "fp32") -> torch.Tensor:
+    """`vl_gpt.gen_vision_model.encode(img)[-1][-1]` (plangen_base.py:532; VQModel.encode vq_model.py:494-498):
+    (B,3,H,W) image in [-1,1] -> flat int64 code indices (B * H/16 * W/16,)."""
+    with torch.inference_mode(), _autocast_ctx(mode, img.device):
+        return vq_quantize_indices(sd, vq_encoder_forward(sd, d, img))
 
 
 def decode_code(sd, d: JanusDims, code_b: torch.Tensor, shape: Sequence[int]) -> torch.Tensor:

@@ -155,9 +155,39 @@ def golden_x2t(name: str, d: O.JanusDims, batch: int, max_new: int, lo: int, hi:
     print(name, "eos", eos, "tokens", out.sequences.tolist())
 
 
+def golden_vq_encode(name: str, d: O.JanusDims, batch: int, size: int):
+    """VQ encode side (editing path, plangen_base.py:528-532): the reference's own Encoder / quant_conv /
+    VectorQuantizer classes (imported by file path) at test-sized channel counts with the oracle's weights."""
+    ref = load_ref_vq()
+    sd = O.init_state_dict(d, seed=0, with_vq=True, with_vq_encoder=True, only="gen_vision_model.")
+    enc = ref.Encoder(ch=d.vq_ch, ch_mult=tuple(d.vq_ch_mult), num_res_blocks=d.vq_res_blocks, z_channels=d.vq_z).eval()
+    qc = torch.nn.Conv2d(d.vq_z, d.code_dim, 1).eval()
+    vq = ref.VectorQuantizer(d.img_vocab, d.code_dim, 0.25, 0.0, True, False).eval()
+    pre = "gen_vision_model."
+    missing, unexpected = enc.load_state_dict({k[len(pre + "encoder."):]: v for k, v in sd.items() if k.startswith(pre + "encoder.")}, strict=True)
+    assert not missing and not unexpected
+    qc.load_state_dict({"weight": sd[pre + "quant_conv.weight"], "bias": sd[pre + "quant_conv.bias"]})
+    vq.embedding.weight.data.copy_(sd[pre + "quantize.embedding.weight"])
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand(batch, 3, size, size, generator=g) * 2 - 1
+    with torch.inference_mode():
+        z = qc(enc(img))
+        _, _, info = vq(z)
+    idx = info[-1]
+    mine = O.vq_encode(sd, d, img)
+    assert torch.equal(mine, idx), "oracle restatement disagrees with the reference classes"
+    np.savez_compressed(os.path.join(OUT, name), dims=np.array(d.name), img=img.numpy(), z=z.numpy(), indices=idx.numpy(),
+                        versions=versions())
+    print(name, "indices", idx.tolist()[:12], "...")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(sys.argv) > 1 and sys.argv[1] == "vqenc":   # only the VQ encode-side vectors
+        golden_vq_encode("vqenc_tiny.npz", O.TINY, batch=2, size=32)
+        golden_vq_encode("vqenc_small.npz", O.SMALL, batch=1, size=48)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "x2t":     # only the stage-1 text-decode vectors
         golden_x2t("x2t_tiny_fp32.npz", O.TINY, batch=3, max_new=24, lo=5, hi=14)
         golden_x2t("x2t_small_fp32.npz", O.SMALL, batch=4, max_new=20, lo=9, hi=40, eos_from=(1, 5))
@@ -171,6 +201,8 @@ def main():
     golden_x2t("x2t_tiny_fp32.npz", O.TINY, batch=3, max_new=24, lo=5, hi=14)
     golden_x2t("x2t_small_fp32.npz", O.SMALL, batch=4, max_new=20, lo=9, hi=40, eos_from=(1, 5))
     golden_x2t("x2t_tiny_stop_fp32.npz", O.TINY, batch=1, max_new=24, lo=11, hi=11, eos_from=(0, 6))
+    golden_vq_encode("vqenc_tiny.npz", O.TINY, batch=2, size=32)
+    golden_vq_encode("vqenc_small.npz", O.SMALL, batch=1, size=48)
 
 
 if __name__ == "__main__":

@@ -207,3 +207,27 @@ def test_generate_greedy_positions_are_mask_aware():
     b = O.generate_greedy(sd, d, O.embed_tokens(sd, ids2), mask2, 6, d.vocab - 1, d.vocab - 1, return_logits=True)[1]
     for x, y in zip(a, b):
         assert torch.allclose(x[0], y[0], atol=2e-6)
+
+
+# ------------------------------------------------------------------ VQ encode side (editing path)
+@pytest.mark.parametrize("name,dims", [("vqenc_tiny.npz", O.TINY), ("vqenc_small.npz", O.SMALL)])
+def test_vq_encode_matches_reference_classes_golden(golden_dir, name, dims):
+    """`gen_vision_model.encode(img)[-1][-1]` (plangen_base.py:532): the restated Encoder / quant_conv / nearest-code
+    search against the committed output of the reference's own classes (oracle/make_golden.py::golden_vq_encode)."""
+    g = np.load(os.path.join(golden_dir, name))
+    sd = O.init_state_dict(dims, seed=0, with_vq=True, with_vq_encoder=True, only="gen_vision_model.")
+    img = torch.from_numpy(g["img"])
+    with torch.inference_mode():
+        z = O.vq_encoder_forward(sd, dims, img)
+    assert np.abs(z.numpy() - g["z"]).max() <= 1e-5 * max(1.0, np.abs(g["z"]).max())
+    assert O.vq_encode(sd, dims, img).tolist() == g["indices"].tolist()
+
+
+def test_vq_encode_decode_round_trip_codes():
+    """decode_code(encode(x)) re-encoded lands on codes whose embeddings are the nearest ones (idempotence of the
+    quantiser on its own code vectors): quantising the exact code embeddings returns the codes themselves."""
+    d = O.TINY
+    sd = O.init_state_dict(d, seed=0, with_vq=True, with_vq_encoder=True, only="gen_vision_model.")
+    codes = torch.arange(0, d.img_vocab, 97)[:16].reshape(1, 16)
+    zq = O.get_codebook_entry(sd, codes, [1, d.code_dim, 4, 4])
+    assert O.vq_quantize_indices(sd, zq).tolist() == codes.reshape(-1).tolist()
