@@ -120,6 +120,13 @@ int pg_generate_greedy(pg_engine* e, float* x_prompt, const int32_t* kv_start, i
 int pg_vq_decode_code(pg_engine* e, const int32_t* codes, int B, int gh, int gw,
                       float* image_out, void* stream);
 
+/* replaces: vl_gpt.gen_vision_model.encode(img)[-1][-1]   (plangen_base.py:532, editing path;
+ *           three_party/Janus/janus/models/vq_model.py:494-498 -> Encoder.forward :108-124, quant_conv,
+ *           VectorQuantizer.forward :236-262)
+ * image fp32 NCHW [B,3,H,W] in [-1,1] (H, W multiples of 16) -> codes int32 [B, (H/16)*(W/16)]: index of the nearest
+ * L2-normalised codebook entry per position (first index on ties).  Needs the optional encoder / quant_conv tensors. */
+int pg_vq_encode(pg_engine* e, const float* image, int B, int H, int W, int32_t* codes_out, void* stream);
+
 /* Bench / profiling helpers */
 int pg_engine_set_option(pg_engine* e, const char* key, int64_t value);
 int pg_engine_get_counter(const pg_engine* e, const char* key, int64_t* value);

@@ -185,8 +185,8 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
     if len(sys.argv) > 1 and sys.argv[1] == "vqenc":   # only the VQ encode-side vectors
-        golden_vq_encode("vqenc_tiny.npz", O.TINY, batch=2, size=32)
-        golden_vq_encode("vqenc_small.npz", O.SMALL, batch=1, size=48)
+        golden_vq_encode("vqenc_tiny.npz", O.TINY, batch=3, size=8)
+        golden_vq_encode("vqenc_small.npz", O.SMALL, batch=2, size=24)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "x2t":     # only the stage-1 text-decode vectors
         golden_x2t("x2t_tiny_fp32.npz", O.TINY, batch=3, max_new=24, lo=5, hi=14)
@@ -201,8 +201,8 @@ def main():
     golden_x2t("x2t_tiny_fp32.npz", O.TINY, batch=3, max_new=24, lo=5, hi=14)
     golden_x2t("x2t_small_fp32.npz", O.SMALL, batch=4, max_new=20, lo=9, hi=40, eos_from=(1, 5))
     golden_x2t("x2t_tiny_stop_fp32.npz", O.TINY, batch=1, max_new=24, lo=11, hi=11, eos_from=(0, 6))
-    golden_vq_encode("vqenc_tiny.npz", O.TINY, batch=2, size=32)
-    golden_vq_encode("vqenc_small.npz", O.SMALL, batch=1, size=48)
+    golden_vq_encode("vqenc_tiny.npz", O.TINY, batch=3, size=8)
+    golden_vq_encode("vqenc_small.npz", O.SMALL, batch=2, size=24)
 
 
 if __name__ == "__main__":

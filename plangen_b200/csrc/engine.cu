@@ -415,6 +415,7 @@ static void layout_workspace(pg_engine* e, Carve& c) {
     }
   }
   e->vq_act_elems = act * Bc; e->vq_col_elems = col * Bc; e->vq_part_elems = part * Bc;
+  e->vq_part_elems = std::max(e->vq_part_elems, (size_t)d.img_vocab * (d.code_dim + 1));   // normalised codebook + norms (pg_vq_encode)
   for (int i = 0; i < 3; ++i) e->vq_act[i] = c.take(e->vq_act_elems * es);
   e->vq_col = c.take(e->vq_col_elems * es);
   e->vq_part = (float*)c.take(e->vq_part_elems * 4);
@@ -1555,6 +1556,102 @@ extern "C" int pg_vq_decode_code(pg_engine* e, const int32_t* codes, int B, int 
   e->use_pdl = saved_pdl;
   return 0;
 }
+
+// ------------------------------------------------------------------------------ f3: VQ encode (editing path)
+// Downsample: asymmetric zero pad + 3x3 stride-2 conv (vq_model.py:440-445) as im2col + contraction
+static int vq_conv_down(VqCtx& c, const void* in, int Hi, int Wi, int C, const std::string& name, void* out) {
+  pg_engine* e = c.e;
+  const void* W = T_(e, "vq." + name + ".weight");
+  const float* bias = (const float*)T_(e, "vq." + name + ".bias");
+  if (!W || !bias) return fail("missing conv tensors for %s", name.c_str());
+  if (C % 4 || (Hi & 1) || (Wi & 1)) return fail("downsample needs C %% 4 == 0 and even H, W");
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  const size_t pixels = (size_t)c.Bc * Ho * Wo;
+  if (pixels * 9 * C > e->vq_col_elems || pixels * C > e->vq_part_elems) return fail("internal: vq scratch too small (downsample)");
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((pixels + 7) / 8, (size_t)e->num_sms * 32));
+  DISPATCH_T(e,
+             launch(e, im2col_down_kernel<bf16>, dim3(blocks), dim3(256), 0, c.st, (const bf16*)in, (bf16*)e->vq_col, Hi, Wi, C, pixels),
+             launch(e, im2col_down_kernel<float>, dim3(blocks), dim3(256), 0, c.st, (const float*)in, (float*)e->vq_col, Hi, Wi, C, pixels));
+  int S = 1;
+  TRY(run_gemm(e, e->vq_col, W, (int)pixels, C, 9 * C, e->vq_part, e->vq_part_elems * 4, &S, c.st, -1, 1));
+  TRY(vq_epilogue(c, e->vq_part, bias, nullptr, out, nullptr, C, Ho * Wo, pixels, 0));
+  return 0;
+}
+
+constexpr int VQ_IN_CPAD = 8;     // image channels padded 3 -> 8 (weights.py pads conv_in's taps with zeros)
+
+// replaces: vl_gpt.gen_vision_model.encode(img)[-1][-1]   (plangen_base.py:532; VQModel.encode vq_model.py:494-498)
+extern "C" int pg_vq_encode(pg_engine* e, const float* image, int B, int H, int W, int32_t* codes_out, void* stream) {
+  TRY(check_ready(e));
+  const pg_dims& d = e->d;
+  const int nres = d.vq_nres;
+  const int down = 1 << (nres - 1);
+  if (H < down || W < down || H % down || W % down || H / down > d.grid || W / down > d.grid)
+    return fail("image %dx%d: sides must be multiples of %d and at most %d", H, W, down, d.grid * down);
+  if (d.code_dim > VQ_CD_MAX) return fail("code_dim %d exceeds %d", d.code_dim, VQ_CD_MAX);
+  cudaStream_t st = (cudaStream_t)stream;
+  NEED(codebook, float, "vq.codebook");
+  if (!T_(e, "vq.encoder.conv_in.weight") || !T_(e, "vq.quant_conv.weight"))
+    return fail("VQ encoder tensors not set: the engine was built without gen_vision_model.encoder.* / quant_conv.*");
+  const int chunk = vq_chunk_of(e);
+  const int saved_pdl = e->use_pdl;
+  for (int b0 = 0; b0 < B; b0 += chunk) {
+    VqCtx c{e, st, std::min(chunk, B - b0)};
+    void *A = e->vq_act[0], *Bf = e->vq_act[1], *Cf = e->vq_act[2];
+    int Hc = H, Wc = W;
+    {
+      const size_t total = (size_t)c.Bc * H * W * VQ_IN_CPAD;
+      if (total > e->vq_act_elems) return fail("internal: vq activation buffer too small");
+      const float* img = image + (size_t)b0 * 3 * H * W;
+      DISPATCH_T(e,
+                 launch(e, nchw_to_nhwc_pad_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, img, (bf16*)A, 3, VQ_IN_CPAD, H * W, total),
+                 launch(e, nchw_to_nhwc_pad_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, img, (float*)A, 3, VQ_IN_CPAD, H * W, total));
+    }
+    int ch = d.vq_ch;
+    TRY(vq_conv(c, A, Hc, Wc, VQ_IN_CPAD, "encoder.conv_in", ch, 3, 1, nullptr, false, nullptr, Bf, nullptr));
+    void *cur = Bf, *t1 = A, *t2 = Cf;
+    auto rot = [&](void* newcur) {
+      void* old = cur;
+      if (newcur == t1) t1 = old; else t2 = old;
+      cur = newcur;
+    };
+    for (int lvl = 0; lvl < nres; ++lvl) {
+      const int cout = d.vq_ch * d.vq_ch_mult[lvl];
+      for (int j = 0; j < d.vq_res_blocks; ++j) {
+        const std::string rn = "encoder.conv_blocks." + std::to_string(lvl) + ".res." + std::to_string(j);
+        TRY(vq_resblock(c, rn, cur, t1, t2, Hc, Wc, ch, cout)); rot(t2);
+        ch = cout;
+        if (lvl == nres - 1) {
+          const std::string an = "encoder.conv_blocks." + std::to_string(lvl) + ".attn." + std::to_string(j);
+          TRY(vq_attnblock(c, an, cur, t1, Hc, Wc, ch)); rot(t1);
+        }
+      }
+      if (lvl != nres - 1) {
+        const std::string dn = "encoder.conv_blocks." + std::to_string(lvl) + ".downsample.conv";
+        TRY(vq_conv_down(c, cur, Hc, Wc, ch, dn, t1)); rot(t1);
+        Hc /= 2; Wc /= 2;
+      }
+    }
+    TRY(vq_resblock(c, "encoder.mid.0", cur, t1, t2, Hc, Wc, ch, ch)); rot(t2);
+    TRY(vq_attnblock(c, "encoder.mid.1", cur, t1, Hc, Wc, ch)); rot(t1);
+    TRY(vq_resblock(c, "encoder.mid.2", cur, t1, t2, Hc, Wc, ch, ch)); rot(t2);
+    TRY(vq_conv(c, cur, Hc, Wc, ch, "encoder.conv_out", d.vq_z, 3, 1, "encoder.norm_out", true, nullptr, t1, nullptr)); rot(t1);
+    TRY(vq_conv(c, cur, Hc, Wc, d.vq_z, "quant_conv", d.code_dim, 1, 1, nullptr, false, nullptr, t1, nullptr)); rot(t1);
+    // nearest code: normalised codebook + its squared norms in the (now idle) partial buffer
+    const size_t n_pix = (size_t)c.Bc * Hc * Wc;
+    float* en = e->vq_part;
+    float* e2 = e->vq_part + (size_t)d.img_vocab * d.code_dim;
+    if ((size_t)d.img_vocab * (d.code_dim + 1) > e->vq_part_elems) return fail("internal: vq partial buffer too small (codebook)");
+    TRY(launch(e, vq_codebook_norm_kernel, dim3((d.img_vocab + 255) / 256), dim3(256), 0, st, codebook, en, e2, d.img_vocab, d.code_dim));
+    int32_t* out = codes_out + (size_t)b0 * Hc * Wc;
+    DISPATCH_T(e,
+               launch(e, vq_quantize_kernel<bf16>, dim3((unsigned)n_pix), dim3(256), 0, st, (const bf16*)cur, (const float*)en, (const float*)e2, out, d.img_vocab, d.code_dim),
+               launch(e, vq_quantize_kernel<float>, dim3((unsigned)n_pix), dim3(256), 0, st, (const float*)cur, (const float*)en, (const float*)e2, out, d.img_vocab, d.code_dim));
+  }
+  e->use_pdl = saved_pdl;
+  return 0;
+}
+
 
 // ------------------------------------------------------------------------------ debug / test hooks
 // Launch the decode-attention kernel of one layer alone on the current KV cache (bench roofline leg).

@@ -246,6 +246,113 @@ im2col_kernel(const T* __restrict__ in, T* __restrict__ col, const float* __rest
   }
 }
 
+// ------------------------------------------------------------------ VQ encode side (editing path)
+// image fp32 NCHW [B][3][H][W] -> NHWC [B][H][W][Cp] in the activation type, channels 3..Cp-1 zero (the padded
+// conv_in weight has zero taps there), so conv_in runs on the same im2col + contraction path as every other conv
+template <typename T>
+__global__ void __launch_bounds__(256)
+nchw_to_nhwc_pad_kernel(const float* __restrict__ img, T* __restrict__ out, int C, int Cp, int HW, size_t total /* B*HW*Cp */) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cp);
+    const size_t pix = i / Cp, b = pix / HW, p = pix % HW;
+    Act<T>::st(out + i, c < C ? img[(b * C + c) * HW + p] : 0.f);
+  }
+}
+
+// Downsample (vq_model.py:440-445): F.pad(x, (0,1,0,1)) then 3x3 stride-2 conv without padding:
+// col[b, oy, ox][tap * C + c] = in[b, 2 oy + tap / 3, 2 ox + tap % 3, c]  (zero past the bottom / right edge)
+template <typename T>
+__global__ void __launch_bounds__(256)
+im2col_down_kernel(const T* __restrict__ in, T* __restrict__ col, int Hi, int Wi, int C, size_t n_pix /* B*Ho*Wo */) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  const size_t warp_id = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t n_warps = (size_t)gridDim.x * (blockDim.x >> 5);
+  for (size_t pix = warp_id; pix < n_pix; pix += n_warps) {
+    const int ox = (int)(pix % Wo);
+    const int oy = (int)((pix / Wo) % Ho);
+    const int b = (int)(pix / ((size_t)Wo * Ho));
+    T* dst_row = col + pix * (size_t)9 * C;
+    for (int c0 = lane * 4; c0 < C; c0 += 128) {
+      for (int tap = 0; tap < 9; ++tap) {
+        const int iy = 2 * oy + tap / 3, ix = 2 * ox + tap % 3;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (iy < Hi && ix < Wi) Ch4<T>::ld(in + (((size_t)b * Hi + iy) * Wi + ix) * C + c0, v);
+        Ch4<T>::st(dst_row + (size_t)tap * C + c0, v);
+      }
+    }
+  }
+}
+
+// VectorQuantizer.forward, inference branch with l2_norm (vq_model.py:236-262).
+// Pre-pass: en[v][:] = codebook[v] / max(||codebook[v]||, 1e-12), e2[v] = sum(en[v]^2)   (every call, as the reference)
+__global__ void vq_codebook_norm_kernel(const float* __restrict__ codebook, float* __restrict__ en, float* __restrict__ e2,
+                                        int V, int Cd) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  float ss = 0.f;
+  for (int k = 0; k < Cd; ++k) ss += codebook[(size_t)v * Cd + k] * codebook[(size_t)v * Cd + k];
+  const float den = fmaxf(sqrtf(ss), 1e-12f);
+  float s2 = 0.f;
+  for (int k = 0; k < Cd; ++k) {
+    const float x = codebook[(size_t)v * Cd + k] / den;
+    en[(size_t)v * Cd + k] = x;
+    s2 += x * x;
+  }
+  e2[v] = s2;
+}
+// One CTA per position: zn = z / max(||z||, 1e-12) (fp32), d[v] = (sum(zn^2) + e2[v]) - 2 * (zn . en[v]) with the
+// product evaluated as the reference's matmul is (bf16 operands / bf16 result under autocast, fp32 in check mode),
+// index of the smallest distance, FIRST index on ties (torch.argmin).
+constexpr int VQ_CD_MAX = 16;
+template <typename T>
+__global__ void __launch_bounds__(256)
+vq_quantize_kernel(const T* __restrict__ z, const float* __restrict__ en, const float* __restrict__ e2,
+                   int32_t* __restrict__ idx_out, int V, int Cd) {
+  __shared__ float bd[8];
+  __shared__ int bi[8];
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t pix = blockIdx.x;
+  float zn[VQ_CD_MAX];
+  float ss = 0.f;
+  for (int k = 0; k < Cd; ++k) { zn[k] = Act<T>::ld(z + pix * Cd + k); ss += zn[k] * zn[k]; }
+  const float den = fmaxf(sqrtf(ss), 1e-12f);
+  float z2 = 0.f;
+  for (int k = 0; k < Cd; ++k) { zn[k] = zn[k] / den; z2 += zn[k] * zn[k]; }
+  float zq[VQ_CD_MAX];
+  for (int k = 0; k < Cd; ++k) zq[k] = Act<T>::rnd(zn[k]);           // matmul operand cast (autocast) / identity (fp32)
+  float best = INFINITY;
+  int besti = 0x7fffffff;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    float dot = 0.f;
+    for (int k = 0; k < Cd; ++k) dot = fmaf(zq[k], Act<T>::rnd(en[(size_t)v * Cd + k]), dot);
+    dot = Act<T>::rnd(dot);
+    const float dist = (z2 + e2[v]) - 2.0f * dot;
+    if (dist < best) { best = dist; besti = v; }                     // ascending v per thread: first index kept on ties
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+    if (od < best || (od == best && oi < besti)) { best = od; besti = oi; }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { bd[warp] = best; bi[warp] = besti; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+      if (bd[w] < best || (bd[w] == best && bi[w] < besti)) { best = bd[w]; besti = bi[w]; }
+    idx_out[pix] = besti < V ? besti : 0;
+  }
+}
+
 // -------------------------------------------------------- conv epilogue: + bias (+ residual)
 // out[pix][co] = rnd(rnd(part + bias) + residual)   NHWC; or NCHW fp32 for the final conv_out.
 template <typename T>

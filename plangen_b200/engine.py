@@ -176,6 +176,21 @@ class _GenVisionModel:
         return out.to(e.out_dtype)
 
 
+    def encode(self, img: torch.Tensor):
+        """`VQModel.encode` as the editing path uses it (plangen_base.py:532: `encode(img)[-1][-1]`): returns
+        `(None, None, (None, None, indices))` with the flat int64 nearest-code indices (B * H/16 * W/16,);
+        the quantised tensor and the losses of the training branch are not produced."""
+        e = self._e
+        x = img.to(device=e.device, dtype=torch.float32).contiguous()
+        B, C, H, W = x.shape
+        if C != 3:
+            raise ValueError("encode expects (B, 3, H, W) images")
+        down = 2 ** (len(e.dims.vq_ch_mult) - 1)
+        codes = torch.empty(B, (H // down) * (W // down), dtype=torch.int32, device=e.device)
+        _lib.check(e._lib.pg_vq_encode(e._h, _ptr(x), B, H, W, _ptr(codes), _stream_ptr(e.device)))
+        return None, None, (None, None, codes.reshape(-1).to(torch.int64))
+
+
 class FastJanus:
     """B200 engine behind the `MultiModalityCausalLM` attribute surface."""
 

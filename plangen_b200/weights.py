@@ -19,6 +19,9 @@ import torch
 from .config import Dims
 
 
+VQ_IN_CPAD = 8      # csrc/engine.cu VQ_IN_CPAD
+
+
 def rope_tables(dims: Dims, tmax: int):
     """cos/sin of LlamaRotaryEmbedding (HF modeling_llama.py:124-136) for positions 0..tmax-1, fp32
     [tmax, head_dim/2] (the two halves of HF's `emb = cat(freqs, freqs)` are identical)."""
@@ -78,11 +81,16 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, mode: str, device, 
         out["vq.pqc.w"] = w(sd[g + "post_quant_conv.weight"].reshape(dims.vq_z, dims.code_dim))
         out["vq.pqc.b"] = f(sd[g + "post_quant_conv.bias"])
         for k, v in sd.items():
-            if not k.startswith(g + "decoder."):
+            # decoder always; encoder / quant_conv when present (editing path: gen_vision_model.encode)
+            if not (k.startswith(g + "decoder.") or k.startswith(g + "encoder.") or k.startswith(g + "quant_conv.")):
                 continue
             name = "vq." + k[len(g):]
             if v.dim() == 4:       # conv weight -> [Cout, kh*kw*Cin]
-                out[name] = w(v.permute(0, 2, 3, 1).reshape(v.shape[0], -1))
+                t = v.permute(0, 2, 3, 1)
+                if k == g + "encoder.conv_in.weight":
+                    # image channels padded 3 -> 8 with zero taps (pg_vq_encode pads the NHWC image the same way)
+                    t = torch.nn.functional.pad(t, (0, VQ_IN_CPAD - t.shape[-1]))
+                out[name] = w(t.reshape(v.shape[0], -1))
             else:                  # conv bias / GroupNorm scale+shift
                 out[name] = f(v)
     return out
