@@ -345,13 +345,19 @@ class FastJanus:
     def t2i(self, inputs_ids=None, parallel_size=1, image_token_num_per_image=None, cfg_weight=5.0, temperature=1.0,
             img_size=None, patch_size=None, gt_image=None, batch=None, mask=None, tokens=None, emb=None,
             gt_labels=None, greedy: bool = False):
-        """System.t2i (plangen_base.py:525-565), `tokens`/`emb` branches.  Returns (dec, mask_image);
-        gt_labels replaces the VQ-encoder call of the editing path (encoder is out of scope here)."""
+        """System.t2i (plangen_base.py:525-565), `tokens`/`emb` branches.  Returns (dec, mask_image).
+        Teacher forcing (layout-guided editing, `args.use_teacher_forcing`, :528-532, :593-598, :557-562) is on when
+        `batch` carries 'edit_region' and either `gt_image` (encoded here with the VQ encoder, as the reference does)
+        or ready-made `gt_labels` is given."""
         n = image_token_num_per_image or self.dims.n_img_tokens
         img_size = img_size or self.dims.img_size
         patch_size = patch_size or 2 ** (len(self.dims.vq_ch_mult) - 1)      # 16 for VQ-16
         if tokens is None and emb is None:
             raise NotImplementedError("pass `tokens` (2B, P) or `emb`; the un-batched branch is unused by PlanGen")
+        teacher = batch is not None and batch.get("edit_region") is not None
+        if teacher and gt_labels is None and gt_image is not None:
+            gt_images = gt_image.to(device=self.device, dtype=self.out_dtype)          # `gt_image.bfloat16()` (:530)
+            gt_labels = self.gen_vision_model.encode(gt_images)[-1][-1].reshape(gt_images.shape[0], -1)
         if tokens is not None:
             tokens = torch.cat([tokens.to(self.device)] * parallel_size)
             inputs_embeds = self.language_model.get_input_embeddings()(tokens)
@@ -363,7 +369,13 @@ class FastJanus:
         g = img_size // patch_size
         dec = self.gen_vision_model.decode_code(gen.to(dtype=torch.int), shape=[num_gen, self.dims.code_dim, g, g])
         self.last_tokens = gen
-        return dec, None
+        mask_image = None
+        if teacher and gt_labels is not None:
+            # resize_pt(edit_region.reshape(bs,1,g,g).repeat(1,3,1,1), janus_hw).to(dec)   (:559-560; torchvision Resize =
+            # bilinear interpolation, antialiasing is a no-op when upscaling)
+            er = batch["edit_region"].to(self.device).reshape(-1, 1, g, g).repeat(1, 3, 1, 1).float()
+            mask_image = torch.nn.functional.interpolate(er, size=(img_size, img_size), mode="bilinear", align_corners=False).to(dec)
+        return dec, mask_image
 
     # ------------------------------------------------------------------ host-buffer entry (end to end)
     @torch.inference_mode()

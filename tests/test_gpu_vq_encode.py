@@ -94,3 +94,66 @@ def test_encode_properties_and_errors():
     no_enc = FastJanus(O.init_state_dict(d, seed=0, with_vq=True), product_dims(d), mode="bf16", max_batch=2, max_prompt=64)
     with pytest.raises(_lib.PgError, match="encoder"):
         no_enc.gen_vision_model.encode(torch.zeros(1, 3, 24, 24, device="cuda"))
+
+
+def test_fullsize_vq16_encode_vs_autocast_reference():
+    """The real VQ-16 encoder shapes (ch 128, mult (1,1,2,2,4), z 256, codebook 16384 x 8) on 384 x 384 images - the
+    editing path's `encode(gt_image)` - vs the reference PyTorch path under autocast(bf16) on the same GPU; the LM
+    part of the engine is tiny (it plays no role here)."""
+    import dataclasses
+    import time
+    from plangen_b200.engine import FastJanus
+    d = dataclasses.replace(O.TINY, name="tiny-lm-vq16", img_vocab=16384, img_embed=256, grid=24, vq_ch=128,
+                            vq_ch_mult=(1, 1, 2, 2, 4), vq_z=256)
+    sd = O.init_state_dict(d, seed=0, with_vq=True, with_vq_encoder=True)
+    eng = FastJanus(sd, product_dims(d), mode="bf16", max_batch=2, max_prompt=64, max_steps=16, with_vq=True)
+    sdc = {k: v.cuda() for k, v in sd.items() if k.startswith("gen_vision_model.")}
+    g = torch.Generator().manual_seed(17)
+    # smooth images (random low-resolution pattern upsampled) in [-1, 1]
+    img = torch.nn.functional.interpolate(torch.rand(2, 3, 24, 24, generator=g) * 2 - 1, size=(384, 384), mode="bilinear").cuda()
+    with torch.inference_mode():
+        z32 = O.vq_encoder_forward(sdc, d, img)
+    ref16 = O.vq_encode(sdc, d, img, mode="autocast")
+    idx = eng.gen_vision_model.encode(img)[-1][-1]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.gen_vision_model.encode(img)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert idx.shape == (2 * 576,)
+    exc_mine = _excess_distance(sd, z32.cpu(), idx.cpu())
+    exc_ref = _excess_distance(sd, z32.cpu(), ref16.cpu())
+    agree = float((idx == ref16).float().mean())
+    print(f"VQ-16 encode 2 x 384^2: {dt * 1e3:.1f} ms; agree {agree:.3f}; excess mine mean {exc_mine.mean():.4g} max {exc_mine.max():.4g} | "
+          f"ref mean {exc_ref.mean():.4g} max {exc_ref.max():.4g}")
+    assert exc_mine.mean() <= 1.5 * exc_ref.mean() + 1e-3 and exc_mine.max() <= 1.5 * exc_ref.max() + 2e-2
+    assert agree >= 0.5
+    # round trip through the decoder: codes -> image -> codes is stable in shape / range (no identity for random weights)
+    dec = eng.gen_vision_model.decode_code(idx.reshape(2, 576).int(), shape=[2, d.code_dim, 24, 24])
+    again = eng.gen_vision_model.encode(dec.float())[-1][-1]
+    assert again.shape == idx.shape and int(again.min()) >= 0 and int(again.max()) < d.img_vocab
+
+
+def test_t2i_editing_branch_teacher_forcing_from_gt_image():
+    """System.t2i with use_teacher_forcing (plangen_base.py:528-532, :593-598, :557-562): gt_image is VQ-encoded on
+    the device, positions whose edit_region is 0 take the ground-truth code, the others are sampled; edit_region all 0
+    reproduces encode(gt_image), all 1 reproduces the free run; the returned mask image is the upscaled edit region."""
+    d = O.SMALL
+    eng, sd = _engine(d, "bf16")
+    B, n, side = 3, d.n_img_tokens, d.grid * 2 ** (len(d.vq_ch_mult) - 1)
+    cond, neg = O.synthetic_prompts(d, B, seed=5, lo=9, hi=40, neg_len=13)
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, d.pad_id, n)
+    g = torch.Generator().manual_seed(2)
+    gt_image = (torch.rand(B, 3, side, side, generator=g) * 2 - 1).cuda()
+    labels = eng.gen_vision_model.encode(gt_image.to(torch.bfloat16))[-1][-1].reshape(B, -1)
+    free, _ = eng.t2i(tokens=ids.cuda(), mask=mask.cuda()), None
+    free_tok = eng.last_tokens.clone()
+    dec0, m0 = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": torch.zeros(B, n, dtype=torch.int64)})
+    assert torch.equal(eng.last_tokens.long(), labels) and m0.shape == dec0.shape and float(m0.abs().max()) == 0.0
+    dec1, m1 = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": torch.ones(B, n, dtype=torch.int64)})
+    assert torch.equal(eng.last_tokens, free_tok) and float(m1.min()) == 1.0
+    er = (torch.rand(B, n, generator=g) > 0.5).long()
+    eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": er})
+    got = eng.last_tokens.long().cpu()
+    keep = er == 0
+    assert torch.equal(got[keep], labels.cpu()[keep])
