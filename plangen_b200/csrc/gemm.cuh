@@ -349,7 +349,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       // Each gate warp (quarters 0, 1) pairs with the up warp two quarters above it.  Per 16-column chunk the
       // gate warp hands g of columns 8..15 to the up warp and receives u of columns 0..7, so all four warps
       // compute (8 tokens each) and the 8 results of a thread are independent chains the scheduler can overlap.
-      float* xch = reinterpret_cast<float*>(smem);            // [128 lanes][9] fp32 per 16-column chunk
+      // exchange buffers in the (now idle) first pipeline stage, addressed in the shared window: two of
+      // [128 lanes][9] fp32, alternating per 16-column chunk so one named barrier per chunk is enough (a thread can
+      // only write buffer b again after the barrier of the chunk in between, which every reader of b has passed)
+      const uint32_t xch_s = smem_u32(smem);
       const int F = N / 2;
       const int pair = quarter & 1;                           // f-block within the tile
       const int f = blockIdx.x * 64 + pair * 32 + lane;
@@ -360,31 +363,36 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         uint32_t v[16];
         tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
         if (c0 == 0 && warp == 2 && lane == 0) gemm_stamp(dbg, 7);
-        float* mine = xch + (size_t)(quarter * 32 + lane) * 9;                   // what I give away
-        const float* theirs = xch + (size_t)((quarter ^ 2) * 32 + lane) * 9;     // what my partner gives me
+        const uint32_t buf = xch_s + (uint32_t)((c0 >> 4) & 1) * (128u * 9u * 4u);
+        const uint32_t mine = buf + (uint32_t)(quarter * 32 + lane) * 36u;           // what I give away
+        const uint32_t theirs = buf + (uint32_t)((quarter ^ 2) * 32 + lane) * 36u;   // what my partner gives me
 #pragma unroll
-        for (int j = 0; j < 8; ++j) mine[j] = __uint_as_float(v[(is_gate ? 8 : 0) + j]);
+        for (int j = 0; j < 8; ++j)
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(mine + 4u * j), "r"(v[(is_gate ? 8 : 0) + j]) : "memory");
         asm volatile("bar.sync 2, 128;" ::: "memory");
         float h[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float own = __uint_as_float(v[jbase + j]), other = theirs[j];
+          uint32_t ow;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(ow) : "r"(theirs + 4u * j) : "memory");
+          const float own = __uint_as_float(v[jbase + j]), other = __uint_as_float(ow);
           const float g = bf16_round(is_gate ? own : other);
           const float u = bf16_round(is_gate ? other : own);
-          // ex2.approx / rcp-based division: ~1e-6 relative error against a result kept to 8 mantissa bits;
-          // the exact expf + IEEE division cost ~100 dependent instructions per element on warps that have
-          // their scheduler to themselves (measured 1.4 us per 16-column chunk)
-          const float sg = bf16_round(__fdividef(g, 1.0f + __expf(-g)));
+          // silu(g) = g / (1 + 2^(-g log2 e)) with ex2.approx / rcp.approx (flush-to-zero forms: no denormal
+          // fix-up code): ~1e-6 relative error against a result kept to 8 mantissa bits; the exact expf + IEEE
+          // division cost ~100 dependent instructions per element on warps that have their scheduler to themselves
+          float ex, rc;
+          asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-g * 1.4426950408889634f));
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(1.0f + ex));
+          const float sg = bf16_round(g * rc);
           h[j] = sg * u;
         }
         if (f < F) {
+          bf16* dst = swiglu_out + (size_t)(m0 + c0 + jbase) * F + f;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int m = m0 + c0 + jbase + j;
-            if (m < M) swiglu_out[(size_t)m * F + f] = __float2bfloat16_rn(h[j]);
-          }
+          for (int j = 0; j < 8; ++j)
+            if (m0 + c0 + jbase + j < M) dst[(size_t)j * F] = __float2bfloat16_rn(h[j]);
         }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
       }
     } else if (nkb > 0) {
       mbar_wait(tmem_full_bar, 0, 3);
