@@ -352,7 +352,12 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
 }
 
 // ------------------------------------------------------------------------------ sizes
-static int vq_chunk_of(const pg_engine* e) { return e->vq_chunk > 0 ? e->vq_chunk : (e->bf16 ? 4 : 1); }
+// images per VQ pass: the whole batch up to 16 in the bf16 regime (16 x 530 MB of scratch; measured 46.2 / 41.1 / 38.8 ms
+// per 16 images at 4 / 8 / 16 - fewer, larger launches), one image at a time in fp32 check mode
+static int vq_chunk_of(const pg_engine* e) {
+  if (e->vq_chunk > 0) return e->vq_chunk;
+  return e->bf16 ? std::max(1, std::min(16, e->d.max_rows / 2)) : 1;
+}
 
 static void layout_workspace(pg_engine* e, Carve& c) {
   const pg_dims& d = e->d;
