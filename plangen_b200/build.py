@@ -26,19 +26,33 @@ def _stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
-    cmd[1:1] = os.environ.get("PG_NVCC_FLAGS", "").split()
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        sys.stderr.write(r.stdout + r.stderr)
-        raise RuntimeError("nvcc failed building libplangen_b200.so")
-    if verbose:
-        print(r.stderr)
+    # one builder at a time (torchrun starts N ranks that may all find the library stale): exclusive lock, re-check,
+    # compile into a private file and publish it with an atomic rename so no rank ever maps a half-written library
+    import fcntl
+    with open(LIB + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not _stale():
+                return LIB
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = f"{LIB}.tmp{os.getpid()}"
+            cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                   "-shared", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
+                   "-o", tmp] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lcudart"]
+            cmd[1:1] = os.environ.get("PG_NVCC_FLAGS", "").split()
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                sys.stderr.write(r.stdout + r.stderr)
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed building libplangen_b200.so")
+            os.replace(tmp, LIB)
+            if verbose:
+                print(r.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB
 
 
