@@ -243,3 +243,36 @@ def test_two_stage_flow_on_one_engine():
         i, img = stage2(both)
         assert torch.equal(t, t_ref), "stage-1 tokens changed after an image decode on the same engine"
         assert torch.equal(i, i_ref) and torch.equal(img, img_ref), "stage-2 result changed after a text decode"
+
+
+def test_uni_2stage_flow_through_the_prompt_pipeline():
+    """BASELINE configs[2] end to end through the public API with a toy tokenizer: stage-1 layout text (generate) ->
+    `<grounding>` parsing -> re-wrapped uni prompt -> CFG collate -> t2i.  Must equal the same steps driven by hand."""
+    from plangen_b200.engine import FastJanus
+    from plangen_b200.prompts import PromptPipeline
+
+    class Tok:
+        def encode(self, s):
+            return [ord(c) % 3000 + 10 for c in s]
+
+        def decode(self, ids):
+            return "".join(chr((int(t) - 10) % 3000) for t in ids)
+
+    d = O.SMALL
+    sd = O.init_state_dict(d, seed=0, with_vq=True, with_lm_head=True)
+    eng = FastJanus(sd, product_dims(d), mode="bf16", max_batch=4, max_prompt=512, max_steps=64, with_vq=True)
+    pp = PromptPipeline(Tok(), pad_id=d.pad_id, image_token_num=d.n_img_tokens, neg_prompt="low quality, blurry")
+    caps = ["a yellow car in front of the tree", "two cats", "a very long caption about a harbour at dusk with boats"]
+    eos = d.vocab - 1
+    dec, layouts = pp.plan_then_generate(eng, caps, eos_token_id=eos, max_new_tokens=24)
+    assert dec.shape == (3, 3, d.img_size, d.img_size) and torch.isfinite(dec.float()).all()
+    assert len(layouts) == 3 and all(t.startswith("<grounding>") and t.endswith("</grounding>") for t in layouts)
+    # by hand
+    s1_ids, s1_mask = pp.stage1_batch(caps)
+    emb = eng.language_model.get_input_embeddings()(s1_ids.cuda())
+    new = eng.language_model.generate(inputs_embeds=emb, attention_mask=s1_mask.cuda(), pad_token_id=eos, eos_token_id=eos, max_new_tokens=24)
+    assert pp.decode_plan_text_batch(new.cpu().tolist()) == layouts
+    uni_ids, uni_mask = pp.uni_batch(caps, layouts)
+    ids, mask = pp.t2i_infer_collate_batch(uni_ids, uni_mask)
+    dec2, _ = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), image_token_num_per_image=d.n_img_tokens)
+    assert torch.equal(dec, dec2)

@@ -118,3 +118,73 @@ def test_dp_gather_world_size_2_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=240)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "rank 0 batches [0, 2, 4]" in r.stdout and "rank 1 batches [1, 3]" in r.stdout, r.stdout
+
+
+# ------------------------------------------------------------------ host prompt pipeline
+class _CharTok:
+    """Toy tokenizer for host-logic tests: one id per character (no vocabulary files offline)."""
+
+    def encode(self, s):
+        return [ord(c) % 900 + 10 for c in s]
+
+    def decode(self, ids):
+        return "".join(chr((int(t) - 10) % 900) for t in ids)
+
+
+def test_sft_prompt_matches_reference_conversation_template():
+    from plangen_b200 import prompts as PR
+    convs = [
+        [{"role": PR.USER, "content": "a yellow car in front of the tree"}, {"role": PR.ASSISTANT, "content": ""}],
+        [{"role": PR.USER, "content": "  two cats "}, {"role": PR.ASSISTANT, "content": "<grounding><ref>cat</ref><box>[1, 2, 3, 4]</box></grounding>"}],
+        [{"role": PR.USER, "content": "x"}, {"role": PR.ASSISTANT, "content": "y"}, {"role": PR.USER, "content": "z"}, {"role": PR.ASSISTANT, "content": ""}],
+    ]
+    want = [
+        "<|User|>: a yellow car in front of the tree\n\n<|Assistant|>:",
+        "<|User|>: two cats\n\n<|Assistant|>: <grounding><ref>cat</ref><box>[1, 2, 3, 4]</box></grounding><｜end▁of▁sentence｜>",
+        "<|User|>: x\n\n<|Assistant|>: y<｜end▁of▁sentence｜><|User|>: z\n\n<|Assistant|>:",
+    ]
+    assert [PR.sft_prompt(c) for c in convs] == want
+    assert PR.sft_prompt(convs[0], system_prompt="be brief") == "be brief\n\n" + want[0]
+    ref_path = "/root/reference/three_party/Janus/janus/utils/conversation.py"
+    if os.path.exists(ref_path):          # the reference's own template code, when the tree is mounted (authoring container)
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_conversation", ref_path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        for c, w in zip(convs, want):
+            conv = mod.get_conv_template("deepseek")
+            conv.set_system_message("")
+            for m in c:
+                conv.append_message(m["role"], m["content"].strip())
+            assert conv.get_prompt().strip() == w
+
+
+def test_prompt_pipeline_wraps_pads_and_collates_like_the_reference():
+    from plangen_b200 import prompts as PR
+    from oracle import janus_oracle as O
+    tok = _CharTok()
+    pp = PR.PromptPipeline(tok, pad_id=5, image_token_num=16, neg_prompt="bad")
+    p_t2i, ids_t2i = pp.wrap_t2i_prompt("a dog")
+    assert p_t2i == "<|User|>: a dog\n\n<|Assistant|>:<begin_of_image>" and ids_t2i.tolist() == tok.encode(p_t2i)
+    p_uni, ids_uni = pp.wrap_uni_prompt("a dog", "<grounding>G</grounding>")
+    assert p_uni.endswith("<grounding>G</grounding><｜end▁of▁sentence｜><begin_of_image>")
+    p_s1, ids_s1 = pp.wrap_uni_prompt("a dog", "<grounding>", in_stage1=True)
+    assert p_s1 == "<|User|>: a dog\n\n<|Assistant|>: <grounding><｜end▁of▁sentence｜>" and ids_s1.tolist() == tok.encode(p_s1)[:-1]
+    caps, grs = ["a dog", "two red birds on a wire"], ["<grounding>A</grounding>", "<grounding>BB</grounding>"]
+    uni_ids, uni_mask = pp.uni_batch(caps, grs)
+    assert uni_mask.shape[1] == uni_ids.shape[1] + 16 and bool((uni_mask[:, -16:] == 1).all())
+    assert bool((uni_ids[0, :(uni_mask[0, :uni_ids.shape[1]] == 0).sum()] == 5).all())          # LEFT padding with pad_id
+    ids, mask = pp.t2i_infer_collate_batch(uni_ids, uni_mask)
+    cond = [pp.wrap_uni_prompt(c, g)[1].tolist() for c, g in zip(caps, grs)]
+    neg = [pp.wrap_uni_prompt("bad", "")[1].tolist()] * 2
+    want_ids, want_mask = O.t2i_infer_collate_batch(cond, neg, 5, 16)
+    assert ids.dtype == torch.int32 and torch.equal(ids, want_ids) and torch.equal(mask, want_mask)
+    # per-sample negatives longer than every cond prompt: the cond side is padded on the left (plangen_base.py:656-662)
+    long_neg = (["x" * 80, "y" * 90], ["<grounding></grounding>"] * 2)
+    ids2, mask2 = pp.t2i_infer_collate_batch(uni_ids, uni_mask, neg=long_neg)
+    negs = [pp.wrap_uni_prompt(c, g)[1].tolist() for c, g in zip(*long_neg)]
+    w2_ids, w2_mask = O.t2i_infer_collate_batch(cond, negs, 5, 16)
+    assert torch.equal(ids2, w2_ids) and torch.equal(mask2, w2_mask)
+    # stage-1 output parsing (plangen_base.py:296-306)
+    rows = [tok.encode("<ref>cat</ref></grounding> trailing"), tok.encode("no closing tag")]
+    assert pp.decode_plan_text_batch(rows) == ["<grounding><ref>cat</ref></grounding>", "<grounding></grounding>"]
