@@ -188,8 +188,9 @@ def run_reference_arm(args):
 
 # ----------------------------------------------------------------------------- B200 arm
 def kernel_roofline(eng, kv_start, lens, P: int, peaks: dict, iters: int = 6):
-    """Dominant kernel of the decode step timed alone (38 % of a mid-sequence step, profiles/): the KV-cache
-    decode attention `attn_decode_tma_kernel`, one launch per layer, rotating over all L layers so the K/V
+    """Dominant kernel of the decode step timed alone (29 % of a mid-sequence step in the ncu launch list, 44 % of the
+    in-graph critical path, profiles/): the KV-cache
+    decode attention `attn_decode_v5_kernel`, one launch per layer, rotating over all L layers so the K/V
     tiles come from HBM (L x ~130 MB >> 126 MB L2).  Position = the middle of the 576-token loop.
     achieved = algorithmic K+V bytes per launch / CUDA-event time per launch on the launching stream."""
     import ctypes as C

@@ -1,4 +1,5 @@
-/* plangen_b200 C-ABI — the drop-in boundary for PlanGen's CFG image-token decode path.
+/* plangen_b200 C-ABI — the drop-in boundary for PlanGen's CFG image-token decode path (and the rows next to it:
+ * stage-1 layout-text decode pg_generate_greedy, VQ encode of the editing path pg_vq_encode).
  *
  * The reference (360CVGroup/PlanGen) is pure Python: the seam is duck-typed attribute
  * access on `self.vl_gpt` from `System.t2i` / `System.sample_image`

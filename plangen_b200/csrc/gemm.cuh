@@ -8,8 +8,9 @@
 //                      operand (N = NT tokens, 16..256), so a decode step with R = 2..128 rows
 //                      streams weights at full TMA rate without padding rows to 128.
 //                      TMA (SWIZZLE_128B) -> smem ring -> tcgen05.mma (fp32 accum in TMEM) ->
-//                      tcgen05.ld epilogue.  Warp-specialised: warp0 TMA, warp1 MMA, warps2-5 epilogue
-//                      (warps 2 and 3 double as the second weight producer and the token-tile producer).
+//                      tcgen05.ld epilogue.  Warp-specialised, six warps: warp 0 weight producer (even
+//                      k-blocks), warp 1 MMA issuer, warps 2-5 epilogue - whose lane 0 first serves as second
+//                      weight producer (warp 2), token-tile producers (warps 3, 4) and second MMA issuer (warp 5).
 //                      With PDL the weight tiles of all stages are requested BEFORE
 //                      griddepcontrol.wait, so the HBM stream does not drain at kernel boundaries.
 //   gemm_simt_kernel : fp32 (check mode) / bf16 CUDA-core fallback used for parity tests and for
