@@ -188,3 +188,31 @@ def test_prompt_pipeline_wraps_pads_and_collates_like_the_reference():
     # stage-1 output parsing (plangen_base.py:296-306)
     rows = [tok.encode("<ref>cat</ref></grounding> trailing"), tok.encode("no closing tag")]
     assert pp.decode_plan_text_batch(rows) == ["<grounding><ref>cat</ref></grounding>", "<grounding></grounding>"]
+
+
+def test_bench_reference_arm_prints_the_contract_line(capsys):
+    """`bench.py --impl reference` (the reference's CPU path = oracle port on the host cores): one JSON line with the
+    keys the driver reads, on the B200 arm's metric / unit, `impl: reference`, a cpu_baseline describing the run and an
+    e2e block with zero copy bytes.  Run on the tiny preset so it takes seconds."""
+    import argparse
+    import json
+    import bench
+    args = argparse.Namespace(model="tiny", gpus=1, steps=1, warmup=1, impl="reference")
+    os.environ.pop("RANK", None)
+    bench.run_reference_arm(args)
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["vs_baseline"] is None
+    # ranks other than 0 do no work and print nothing
+    os.environ["RANK"] = "1"
+    try:
+        bench.run_reference_arm(args)
+        assert capsys.readouterr().out.strip() == ""
+    finally:
+        os.environ.pop("RANK", None)
