@@ -15,7 +15,7 @@ import torch
 from .config import Dims
 
 
-def state_dict_names(d: Dims, with_vq: bool = True) -> List[Tuple[str, Tuple[int, ...], str]]:
+def state_dict_names(d: Dims, with_vq: bool = True, with_vq_encoder: bool = False) -> List[Tuple[str, Tuple[int, ...], str]]:
     s: List[Tuple[str, Tuple[int, ...], str]] = []
     lm = "language_model.model."
     HD = d.H * d.head_dim
@@ -80,13 +80,32 @@ def state_dict_names(d: Dims, with_vq: bool = True) -> List[Tuple[str, Tuple[int
             conv(dp + f"conv_blocks.{idx}.upsample.conv", block_in, block_in, 3)
     norm(dp + "norm_out", block_in)
     conv(dp + "conv_out", block_in, 3, 3)
+    if with_vq_encoder:      # encode side of the editing path (gen_vision_model.encode): Encoder + quant_conv
+        ep = p + "encoder."
+        conv(ep + "conv_in", 3, d.vq_ch, 3)
+        in_mult = (1,) + tuple(d.vq_ch_mult)
+        cin = d.vq_ch
+        for lvl in range(nres):
+            cin, cout = d.vq_ch * in_mult[lvl], d.vq_ch * d.vq_ch_mult[lvl]
+            for j in range(d.vq_res_blocks):
+                res(ep + f"conv_blocks.{lvl}.res.{j}", cin, cout)
+                cin = cout
+                if lvl == nres - 1:
+                    attn(ep + f"conv_blocks.{lvl}.attn.{j}", cin)
+            if lvl != nres - 1:
+                conv(ep + f"conv_blocks.{lvl}.downsample.conv", cin, cin, 3)
+        res(ep + "mid.0", cin, cin); attn(ep + "mid.1", cin); res(ep + "mid.2", cin, cin)
+        norm(ep + "norm_out", cin)
+        conv(ep + "conv_out", cin, d.vq_z, 3)
+        conv(p + "quant_conv", d.vq_z, d.code_dim, 1)
     return s
 
 
-def random_state_dict(d: Dims, device, seed: int = 0, with_vq: bool = True, with_lm_head: bool = False) -> Dict[str, torch.Tensor]:
+def random_state_dict(d: Dims, device, seed: int = 0, with_vq: bool = True, with_lm_head: bool = False,
+                      with_vq_encoder: bool = False) -> Dict[str, torch.Tensor]:
     g = torch.Generator(device=device).manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
-    names = state_dict_names(d, with_vq)
+    names = state_dict_names(d, with_vq, with_vq and with_vq_encoder)
     if with_lm_head:       # untied text head, only needed by language_model.generate (stage-1 layout-text decode)
         names = names + [("language_model.lm_head.weight", (d.vocab, d.D), "lm")]
     for name, shape, kind in names:

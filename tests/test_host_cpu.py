@@ -74,6 +74,9 @@ def test_synthetic_state_dict_names_match_oracle_specs():
         a = [(n, s) for n, s, _ in synthetic.state_dict_names(Dims.from_any(d))]
         b = [(n, s) for n, s, _ in O.tensor_specs(d)]
         assert sorted(a) == sorted(b)
+        a = [(n, s) for n, s, _ in synthetic.state_dict_names(Dims.from_any(d), with_vq_encoder=True)]
+        b = [(n, s) for n, s, _ in O.tensor_specs(d, with_vq_encoder=True)]
+        assert sorted(a) == sorted(b)
 
 
 def test_weight_bytes_per_step_matches_baseline_md():
