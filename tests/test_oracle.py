@@ -231,3 +231,24 @@ def test_vq_encode_decode_round_trip_codes():
     codes = torch.arange(0, d.img_vocab, 97)[:16].reshape(1, 16)
     zq = O.get_codebook_entry(sd, codes, [1, d.code_dim, 4, 4])
     assert O.vq_quantize_indices(sd, zq).tolist() == codes.reshape(-1).tolist()
+
+
+@pytest.mark.parametrize("seed,batch,eos_step", [(11, 2, 2), (12, 4, 5), (13, 1, 9)])
+def test_generate_greedy_matches_live_hf_generate(seed, batch, eos_step):
+    """Beyond the committed goldens: the restated greedy search against the INSTALLED HF `generate` on fresh ragged
+    batches (left padding, eos chosen from a free run so rows stop at different steps / all rows stop early)."""
+    pytest.importorskip("transformers")
+    from oracle.make_golden import hf_llama_causal
+    d = O.TINY
+    sd = O.init_state_dict(d, seed=0, with_vq=False, with_lm_head=True)
+    hf = hf_llama_causal(d, sd)
+    cond, _ = O.synthetic_prompts(d, batch, seed=seed, lo=4, hi=19, neg_len=3)
+    ids, mask = O.pad_input_ids(cond, d.pad_id)
+    kw = dict(bos_token_id=1, max_new_tokens=14, do_sample=False, use_cache=True)
+    with torch.inference_mode():
+        emb = hf.get_input_embeddings()(ids.long())
+        free = hf.generate(inputs_embeds=emb, attention_mask=mask.long(), pad_token_id=d.vocab - 1, eos_token_id=d.vocab - 1, **kw)
+        eos = int(free[0, eos_step])
+        want = hf.generate(inputs_embeds=emb, attention_mask=mask.long(), pad_token_id=eos, eos_token_id=eos, **kw)
+    got = O.generate_greedy(sd, d, O.embed_tokens(sd, ids), mask, 14, eos, eos)
+    assert got.tolist() == want.tolist()
