@@ -277,6 +277,12 @@ class FastJanus:
         return d.L * per_layer + d.D * 4 + head
 
     # ------------------------------------------------------------------ duck-typed pieces
+    def prepare_inputs_embeds(self, *args, **kwargs):
+        """mmu front-end (`plangen_base.py:289,366,855`: SigLIP vision tower + aligner + embedding scatter): SURVEY.md §8f
+        rank 2, not built.  Fails loudly instead of serving the call with anything else."""
+        raise NotImplementedError("prepare_inputs_embeds (image understanding: SigLIP + aligner) is not part of plangen_b200 yet; "
+                                  "pass precomputed inputs_embeds to language_model.generate / language_model.model")
+
     def gen_head(self, h: torch.Tensor) -> torch.Tensor:
         R = h.shape[0]
         x = h.to(device=self.device, dtype=torch.float32).contiguous()
