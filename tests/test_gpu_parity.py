@@ -213,3 +213,21 @@ def test_bf16_long_ragged_context(path):
         eng.set_option("use_mega", 0)
         eng.set_option("fuse_norm", 0)
     assert_close(dbg.cpu().numpy(), ref_logits, 2e-2, 2e-2, f"bf16 long-context CFG logits ({path})")
+
+
+def test_fp32_t2i_parallel_size_two_matches_oracle():
+    """System.t2i with parallel_size = 2 (plangen_base.py:547-549: ids and mask tiled, num_gen = B * parallel_size
+    images sampled in one batch from one Philox stream): token ids identical to the oracle, images within fp32 noise."""
+    d = O.SMALL
+    sd = O.init_state_dict(d, seed=0, with_vq=True)
+    eng = get_engine(d, "fp32", with_vq=True)
+    cond, neg = O.synthetic_prompts(d, 2, seed=31, lo=9, hi=33, neg_len=11)
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, d.pad_id, d.n_img_tokens)
+    sms, mt = _num_sms()
+    want_tok, want_img = O.t2i(sd, d, ids, mask, parallel_size=2, sampler=PX.PhiloxSampler(0, sms, mt), mode="fp32")
+    dec, _ = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), parallel_size=2, cfg_weight=5.0, temperature=1.0)
+    assert eng.last_tokens.shape == (4, d.n_img_tokens)
+    assert eng.last_tokens.cpu().tolist() == want_tok.tolist()
+    assert not torch.equal(eng.last_tokens[:2], eng.last_tokens[2:])          # the two copies are different samples
+    err = (dec.float().cpu() - want_img).abs().max().item()
+    assert err < 1e-3 * want_img.abs().max().item() + 1e-4, err
