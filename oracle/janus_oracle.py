@@ -405,6 +405,123 @@ def embed_tokens(sd, ids: torch.Tensor) -> torch.Tensor:
     return F.embedding(ids.long(), sd["language_model.model.embed_tokens.weight"])
 
 
+# ------------------------------------------------------- mmu front-end - ORACLE ONLY
+# The CUDA path for this row is NOT built yet (plangen_b200.engine.FastJanus.prepare_inputs_embeds raises); the
+# restatement and its pin are here so the row can start from a checked oracle.
+@dataclass(frozen=True)
+class SigLIPDims:
+    """SigLIP_MODEL_CONFIG["siglip_large_patch16_384"] (siglip_vit.py:628-637): the vision tower of Janus-1.3B."""
+    name: str = "siglip_large_patch16_384"
+    width: int = 1024
+    layers: int = 24
+    heads: int = 16
+    patch: int = 16
+    image: int = 384
+    mlp_ratio: float = 4.0
+
+    @property
+    def n_patches(self) -> int:
+        return (self.image // self.patch) ** 2
+
+
+SIGLIP_L16_384 = SigLIPDims()
+SIGLIP_TINY = SigLIPDims(name="siglip-tiny", width=64, layers=2, heads=2, patch=16, image=32)
+
+
+def siglip_tensor_specs(v: SigLIPDims, d: JanusDims) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """State-dict names of `vision_model.vision_tower` (VisionTransformer, siglip_vit.py:262-440, class_token=False,
+    qkv_bias=True, no pre-norm, LayerNorm eps 1e-6) and of the understanding `aligner` (MlpProjector mlp_gelu depth 2,
+    projector.py:39-45)."""
+    p = "vision_model.vision_tower."
+    hid = int(v.width * v.mlp_ratio)
+    s: List[Tuple[str, Tuple[int, ...], str]] = [
+        (p + "pos_embed", (1, v.n_patches, v.width), "lm"),
+        (p + "patch_embed.proj.weight", (v.width, 3, v.patch, v.patch), "conv"),
+        (p + "patch_embed.proj.bias", (v.width,), "bias:%d" % (3 * v.patch * v.patch)),
+    ]
+    for i in range(v.layers):
+        b = p + f"blocks.{i}."
+        s += [(b + "norm1.weight", (v.width,), "norm_w"), (b + "norm1.bias", (v.width,), "norm_b"),
+              (b + "attn.qkv.weight", (3 * v.width, v.width), "lm"), (b + "attn.qkv.bias", (3 * v.width,), "norm_b"),
+              (b + "attn.proj.weight", (v.width, v.width), "lm"), (b + "attn.proj.bias", (v.width,), "norm_b"),
+              (b + "norm2.weight", (v.width,), "norm_w"), (b + "norm2.bias", (v.width,), "norm_b"),
+              (b + "mlp.fc1.weight", (hid, v.width), "lm"), (b + "mlp.fc1.bias", (hid,), "norm_b"),
+              (b + "mlp.fc2.weight", (v.width, hid), "lm"), (b + "mlp.fc2.bias", (v.width,), "norm_b")]
+    s += [(p + "norm.weight", (v.width,), "norm_w"), (p + "norm.bias", (v.width,), "norm_b")]
+    s += [("aligner.layers.0.weight", (d.D, v.width), "linear"), ("aligner.layers.0.bias", (d.D,), "bias:%d" % v.width),
+          ("aligner.layers.2.weight", (d.D, d.D), "linear"), ("aligner.layers.2.bias", (d.D,), "bias:%d" % d.D)]
+    return s
+
+
+def init_siglip_state_dict(v: SigLIPDims, d: JanusDims, seed: int = 0) -> Dict[str, torch.Tensor]:
+    import zlib
+    sd: Dict[str, torch.Tensor] = {}
+    for name, shape, kind in siglip_tensor_specs(v, d):
+        g = torch.Generator(device="cpu").manual_seed((seed * 1000003 + zlib.crc32(name.encode())) % (2 ** 63))
+        if kind == "lm":
+            t = torch.empty(shape).normal_(0.0, 0.02, generator=g)
+        elif kind == "norm_w":
+            t = 1.0 + 0.1 * torch.empty(shape).normal_(0.0, 1.0, generator=g)
+        elif kind == "norm_b":
+            t = 0.1 * torch.empty(shape).normal_(0.0, 1.0, generator=g)
+        else:
+            fan = int(math.prod(shape[1:])) if not kind.startswith("bias:") else int(kind.split(":")[1])
+            b = 1.0 / math.sqrt(fan)
+            t = torch.empty(shape).uniform_(-b, b, generator=g)
+        sd[name] = t
+    return sd
+
+
+def siglip_forward(sd, v: SigLIPDims, images: torch.Tensor) -> torch.Tensor:
+    """CLIPVisionTower.forward (clip_encoder.py:107-122; no image_norm in the Janus config, select_feature "same") ->
+    VisionTransformer.forward with ignore_head (siglip_vit.py:584-606): patch embedding (conv16/16), + learned position
+    embedding, `layers` x [x += proj(SDPA(qkv(LN1 x))); x += fc2(GELU(fc1(LN2 x)))], final LayerNorm.
+    (B,3,H,W) -> (B, n_patches, width)."""
+    p = "vision_model.vision_tower."
+    x = F.conv2d(images, sd[p + "patch_embed.proj.weight"], sd[p + "patch_embed.proj.bias"], stride=v.patch)
+    x = x.flatten(2).transpose(1, 2)
+    x = x + sd[p + "pos_embed"]
+    B, N, C = x.shape
+    hd = C // v.heads
+    for i in range(v.layers):
+        b = p + f"blocks.{i}."
+        h = F.layer_norm(x, (C,), sd[b + "norm1.weight"], sd[b + "norm1.bias"], eps=1e-6)
+        qkv = F.linear(h, sd[b + "attn.qkv.weight"], sd[b + "attn.qkv.bias"]).reshape(B, N, 3, v.heads, hd).permute(2, 0, 3, 1, 4)
+        q, k, vv = qkv.unbind(0)
+        a = F.scaled_dot_product_attention(q, k, vv).transpose(1, 2).reshape(B, N, C)
+        x = x + F.linear(a, sd[b + "attn.proj.weight"], sd[b + "attn.proj.bias"])
+        h = F.layer_norm(x, (C,), sd[b + "norm2.weight"], sd[b + "norm2.bias"], eps=1e-6)
+        h = F.linear(F.gelu(F.linear(h, sd[b + "mlp.fc1.weight"], sd[b + "mlp.fc1.bias"])), sd[b + "mlp.fc2.weight"], sd[b + "mlp.fc2.bias"])
+        x = x + h
+    return F.layer_norm(x, (C,), sd[p + "norm.weight"], sd[p + "norm.bias"], eps=1e-6)
+
+
+def understanding_aligner(sd, x: torch.Tensor) -> torch.Tensor:
+    """`aligner` = MlpProjector mlp_gelu depth 2 (projector.py:39-45): Linear(width, D) -> GELU -> Linear(D, D)."""
+    x = F.linear(x, sd["aligner.layers.0.weight"], sd["aligner.layers.0.bias"])
+    return F.linear(F.gelu(x), sd["aligner.layers.2.weight"], sd["aligner.layers.2.bias"])
+
+
+def prepare_inputs_embeds(sd, v: SigLIPDims, input_ids: torch.Tensor, pixel_values: torch.Tensor,
+                          images_seq_mask: torch.Tensor, images_emb_mask: torch.Tensor, mode: str = "fp32") -> torch.Tensor:
+    """MultiModalityCausalLM.prepare_inputs_embeds (modeling_vlm.py:221-268): image features of every image
+    (b, n, 3, h, w) through the vision tower and the aligner, scattered into the text embeddings at the
+    `<image_placeholder>` positions; negative ids (image slots) are embedded as id 0 first."""
+    bs, n = pixel_values.shape[:2]
+    images = pixel_values.reshape(bs * n, *pixel_values.shape[2:])
+    if mode == "autocast":
+        images = images.bfloat16()                                     # `images.bfloat16()` (:247)
+    with _autocast_ctx(mode, images.device):
+        emb = understanding_aligner(sd, siglip_forward(sd, v, images.float() if mode == "fp32" else images))
+    emb = emb.reshape(bs, n * emb.shape[1], emb.shape[2])
+    emb_mask = images_emb_mask.reshape(bs, -1).bool()
+    ids = input_ids.clone()
+    ids[ids < 0] = 0
+    out = embed_tokens(sd, ids).clone()
+    out[images_seq_mask.bool()] = emb[emb_mask].to(out.dtype)
+    return out
+
+
 # --------------------------------------------------- stage-1 layout-text decode (x2t)
 def generate_greedy(sd, d: JanusDims, inputs_embeds: torch.Tensor, attention_mask: torch.Tensor,
                     max_new_tokens: int, eos_token_id: int, pad_token_id: int, mode: str = "fp32",

@@ -181,9 +181,48 @@ def golden_vq_encode(name: str, d: O.JanusDims, batch: int, size: int):
     print(name, "indices", idx.tolist()[:12], "...")
 
 
+REF_SIGLIP = "/root/reference/three_party/Janus/janus/models/siglip_vit.py"
+
+
+def load_ref_siglip():
+    """The reference's own siglip_vit.py (its Attention / Block / VisionTransformer), executed with oracle/timm_stub.py
+    standing in for the few timm layers it imports when timm is not installed."""
+    from oracle import timm_stub
+    timm_stub.install()
+    spec = importlib.util.spec_from_file_location("ref_siglip_vit", REF_SIGLIP)
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["ref_siglip_vit"] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def golden_siglip(name: str, v: O.SigLIPDims, d: O.JanusDims, batch: int):
+    """mmu front-end (oracle only this round): the reference VisionTransformer (ignore_head) with the oracle's weights."""
+    ref = load_ref_siglip()
+    sd = O.init_siglip_state_dict(v, d, seed=0)
+    m = ref.VisionTransformer(img_size=v.image, patch_size=v.patch, embed_dim=v.width, depth=v.layers, num_heads=v.heads,
+                              mlp_ratio=v.mlp_ratio, class_token=False, global_pool="map", ignore_head=True,
+                              weight_init="skip", num_classes=0).eval()
+    pre = "vision_model.vision_tower."
+    missing, unexpected = m.load_state_dict({k[len(pre):]: t for k, t in sd.items() if k.startswith(pre)}, strict=False)
+    assert not unexpected and all(k.startswith("attn_pool") for k in missing), (missing, unexpected)
+    g = torch.Generator().manual_seed(8)
+    img = torch.rand(batch, 3, v.image, v.image, generator=g) * 2 - 1
+    with torch.inference_mode():
+        want = m(img)
+        mine = O.siglip_forward(sd, v, img)
+    err = (mine - want).abs().max().item()
+    assert err <= 1e-5 * max(1.0, want.abs().max().item()), err
+    np.savez_compressed(os.path.join(OUT, name), dims=np.array(v.name), img=img.numpy(), features=want.numpy(), versions=versions())
+    print(name, "features", tuple(want.shape), "max|restatement - reference| =", err)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count() or 1)
+    if len(sys.argv) > 1 and sys.argv[1] == "siglip":  # only the mmu front-end vectors
+        golden_siglip("siglip_tiny.npz", O.SIGLIP_TINY, O.TINY, batch=2)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "vqenc":   # only the VQ encode-side vectors
         golden_vq_encode("vqenc_tiny.npz", O.TINY, batch=3, size=8)
         golden_vq_encode("vqenc_small.npz", O.SMALL, batch=2, size=24)
@@ -203,6 +242,7 @@ def main():
     golden_x2t("x2t_tiny_stop_fp32.npz", O.TINY, batch=1, max_new=24, lo=11, hi=11, eos_from=(0, 6))
     golden_vq_encode("vqenc_tiny.npz", O.TINY, batch=3, size=8)
     golden_vq_encode("vqenc_small.npz", O.SMALL, batch=2, size=24)
+    golden_siglip("siglip_tiny.npz", O.SIGLIP_TINY, O.TINY, batch=2)
 
 
 if __name__ == "__main__":

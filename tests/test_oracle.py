@@ -252,3 +252,40 @@ def test_generate_greedy_matches_live_hf_generate(seed, batch, eos_step):
         want = hf.generate(inputs_embeds=emb, attention_mask=mask.long(), pad_token_id=eos, eos_token_id=eos, **kw)
     got = O.generate_greedy(sd, d, O.embed_tokens(sd, ids), mask, 14, eos, eos)
     assert got.tolist() == want.tolist()
+
+
+# ---------------------------------------------------------- mmu front-end (oracle only; CUDA path not built yet)
+def test_siglip_restatement_matches_reference_class_golden(golden_dir):
+    """SigLIP vision tower: the restated forward against the committed output of the reference's own
+    VisionTransformer (oracle/make_golden.py::golden_siglip; timm's PatchEmbed / Mlp come from oracle/timm_stub.py)."""
+    g = np.load(os.path.join(golden_dir, "siglip_tiny.npz"))
+    v, d = O.SIGLIP_TINY, O.TINY
+    sd = O.init_siglip_state_dict(v, d, seed=0)
+    with torch.inference_mode():
+        out = O.siglip_forward(sd, v, torch.from_numpy(g["img"]))
+    assert out.shape == (2, v.n_patches, v.width)
+    assert np.abs(out.numpy() - g["features"]).max() <= 1e-5 * max(1.0, np.abs(g["features"]).max())
+
+
+def test_prepare_inputs_embeds_scatters_image_features():
+    """modeling_vlm.py:221-268: aligned image features land exactly on the masked sequence slots, in order; text slots
+    keep their embed_tokens rows; negative (image) ids are embedded as id 0 before being overwritten."""
+    v, d = O.SIGLIP_TINY, O.TINY
+    sd = {**O.init_state_dict(d, seed=0, with_vq=False), **O.init_siglip_state_dict(v, d, seed=0)}
+    n = v.n_patches
+    g = torch.Generator().manual_seed(4)
+    pix = torch.rand(2, 1, 3, v.image, v.image, generator=g) * 2 - 1
+    T = n + 5
+    ids = torch.randint(1, 900, (2, T), generator=g)
+    seq_mask = torch.zeros(2, T, dtype=torch.bool)
+    seq_mask[0, 2:2 + n] = True
+    seq_mask[1, 4:4 + n] = True
+    ids[seq_mask] = -1
+    emb_mask = torch.ones(2, 1, n, dtype=torch.bool)
+    with torch.inference_mode():
+        out = O.prepare_inputs_embeds(sd, v, ids, pix, seq_mask, emb_mask)
+        feats = O.understanding_aligner(sd, O.siglip_forward(sd, v, pix.reshape(2, 3, v.image, v.image)))
+    assert out.shape == (2, T, d.D)
+    assert torch.allclose(out[0, 2:2 + n], feats[0]) and torch.allclose(out[1, 4:4 + n], feats[1])
+    keep = ~seq_mask
+    assert torch.equal(out[keep], O.embed_tokens(sd, ids.clamp_min(0))[keep])
