@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define PG_ABI_VERSION 1
+#define PG_ABI_VERSION 2
 
 /* arithmetic regimes */
 #define PG_MODE_BF16 0 /* the reference's regime: fp32 master weights under autocast(bf16), plangen_base.py:360 */
@@ -84,10 +84,13 @@ int pg_gen_head(pg_engine* e, const float* hidden, int R, float* logits_out, voi
  * torch.multinomial(1) (Philox4x32-10, bit-compatible with torch's CUDA generator at
  * (seed, philox_offset)), teacher-forcing override (:593-598), token duplication and
  * prepare_gen_img_embeds.  logits fp32 [2B, V] (rows interleaved cond/uncond).
- * edit_region / gt_labels: int32 [B, n_steps] or NULL.  greedy != 0 -> argmax.
+ * edit_region / gt_labels: int32 [B, n_steps], both or neither (NULL = no teacher forcing; the caller gates them on
+ * args.use_teacher_forcing as the reference does, :593).  greedy != 0 -> argmax.
+ * top_k > 0: only CFG logits >= the k-th largest survive (`logits[logits < topk(logits,k)[..., -1:]] = -inf`) before
+ * the softmax; 0 = off = the reference (it has no top-k; north_star names the option).
  * tokens_out int32 [B, n_steps] (column `step` written); x_next fp32 [2B, D]. */
 int pg_cfg_sample_embed(pg_engine* e, const float* logits, int B, float cfg_weight,
-                        float temperature, uint64_t seed, uint64_t philox_offset, int greedy,
+                        float temperature, uint64_t seed, uint64_t philox_offset, int greedy, int top_k,
                         const int32_t* edit_region, const int32_t* gt_labels, int step,
                         int n_steps, int32_t* tokens_out, float* x_next, void* stream);
 
@@ -97,9 +100,10 @@ int pg_prepare_gen_img_embeds(pg_engine* e, const int32_t* ids, int n, float* ou
 
 /* replaces: System.sample_image (plangen_base.py:567-607), whole loop on the device:
  * prefill + n_steps x (gen_head, CFG, sample, embed, decode step) with no host sync.
- * x_prompt fp32 [R,P,D] (consumed).  tokens_out int32 [R/2, n_steps]. */
+ * x_prompt fp32 [R,P,D] (consumed).  tokens_out int32 [R/2, n_steps].  kv_start / edit_region / gt_labels are copied
+ * into engine-owned buffers at entry (captured graphs are keyed on shapes and scalars, not on caller addresses). */
 int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_start, int R, int P,
-                    int n_steps, float cfg_weight, float temperature, uint64_t seed, int greedy,
+                    int n_steps, float cfg_weight, float temperature, uint64_t seed, int greedy, int top_k,
                     const int32_t* edit_region, const int32_t* gt_labels,
                     int32_t* tokens_out, void* stream);
 
@@ -127,6 +131,10 @@ int pg_vq_decode_code(pg_engine* e, const int32_t* codes, int B, int gh, int gw,
  * image fp32 NCHW [B,3,H,W] in [-1,1] (H, W multiples of 16) -> codes int32 [B, (H/16)*(W/16)]: index of the nearest
  * L2-normalised codebook entry per position (first index on ties).  Needs the optional encoder / quant_conv tensors. */
 int pg_vq_encode(pg_engine* e, const float* image, int B, int H, int W, int32_t* codes_out, void* stream);
+
+/* replaces: denorm_pt + `(x*255).astype(np.uint8)` of the image writers (src/utils/funcs.py:511-512, :497-498;
+ *           plangen_base.py:444, :1168-1181): image fp32 [n] in about [-1,1] -> uint8 [n] = trunc(((clamp(x,-1,1)+1)/2)*255) */
+int pg_images_to_u8(pg_engine* e, const float* image, size_t n, uint8_t* out, void* stream);
 
 /* Bench / profiling helpers */
 int pg_engine_set_option(pg_engine* e, const char* key, int64_t value);

@@ -1,14 +1,15 @@
-// Decode attention, generation 5: the group streams of attn_tma.cuh with the item-boundary round trips
-// taken off the stream.
+// Decode attention: the group streams described in attn_tma.cuh with the item-boundary round trips taken off the
+// stream.
 //
-// What the in-kernel timeline (tools/attn_timeline.py, %globaltimer stamps per group) showed for generation 3:
+// What the in-kernel timeline (tools/attn_timeline.py, %globaltimer stamps per group) showed for an earlier
+// generation that merged hand-offs through threadfence + counter (round 1, removed):
 // the kernel costs  t = ~15 us + bytes / 7.6 TB/s .  While the KV stream saturates the memory pipe (~20-28 MB
 // of tile requests queued chip-wide) one L2 round trip takes 4-5 us instead of ~1 us, and every item boundary
 // of a group paid several of them in sequence: the split-K QKV partials of the next item's q, then
 // threadfence -> atomic -> last-arriver loads for the hand-off.  Groups whose range began with a lone
 // new-token unit paid two boundaries before their first tile and finished last.
 //
-// Changes, all on the consumer side (same warp layout as generation 3):
+// Hence, on the consumer side:
 //   * the token being decoded rides on the item's last tile (no unit of its own): no empty segments;
 //   * the partials of the NEXT segment's q / k / v are loaded into registers before the current segment's
 //     tile loop and only consumed at the boundary: the round trip overlaps the stream;
@@ -19,7 +20,7 @@
 //     in the same load - merges in rank order and clears the words for the next launch;
 //   * 2 ring stages per group instead of 3: 19 MB in flight still covers bandwidth x latency and shortens
 //     every queue; warp-parallel row lookup in the prologue.
-// Arithmetic per tile and merge formulas are those of generation 3; results are deterministic.
+// Results are deterministic (fixed merge order).
 #pragma once
 #include "attn_tma.cuh"
 
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_decode_v5_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ cosT,
                       const float* __restrict__ sinT, bf16* __restrict__ kcache, bf16* __restrict__ vcache,
                       const int32_t* __restrict__ kv_start, bf16* __restrict__ out, float* __restrict__ ws_ll_f,
-                      int* __restrict__ /*unused*/, int R, int H, int Tmax, int pos_base,
+                      int R, int H, int Tmax, int pos_base,
                       const int* __restrict__ step_ptr, float scale, int bf16_trig, int early_trigger, Prof prof,
                       unsigned long long* dbg) {
   extern __shared__ uint8_t smem_raw[];
@@ -365,7 +366,10 @@ attn_decode_v5_kernel(const float* __restrict__ part, int S, size_t split_stride
   if (tid < AT_NG) at_stamp(dbg, tid, 0);
   if (early_trigger & 1) pdl_launch_dependents();
   prof_begin(prof);
-  const int pos = pos_base + (step_ptr ? *step_ptr : 0);    // see attn_decode_tma_kernel
+  // The step counter is only written by the last kernel of a decode step; graph replays are fully ordered, and
+  // with plain launches the host passes the position explicitly (step_ptr == nullptr), so reading it before the
+  // PDL wait is safe.
+  const int pos = pos_base + (step_ptr ? *step_ptr : 0);
 
   if (tid == 0) {
     for (int i = 0; i < A5_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], AT_GW); }

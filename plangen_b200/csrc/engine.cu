@@ -17,9 +17,7 @@
 #include "gemm.cuh"
 #include "lm_kernels.cuh"
 #include "attn_tma.cuh"
-#include "attn_v4.cuh"
 #include "attn_v5.cuh"
-#include "step_kernel.cuh"
 #include "sample.cuh"
 #include "text_decode.cuh"
 #include "attn_prefill_tc.cuh"
@@ -75,7 +73,7 @@ struct pg_engine {
   struct Tiled { const uint8_t* ptr; int N, K; };
   std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
   uint8_t* tiled_buf = nullptr;
-  int cluster_z = 0, rn_threads = 0;
+  int rn_threads = 0;
   // L2 prefetch of the next attention launch's KV tiles from the decode-step norm kernels (lm_kernels.cuh KvPrefetch):
   // tiles with (index mod kvpf_den) < kvpf1 by the post-attention norm, the next kvpf2 residues by the post-MLP norm
   int kvpf_den = 8, kvpf1 = 0, kvpf2 = 0;
@@ -86,20 +84,14 @@ struct pg_engine {
   void* vT = nullptr;                        // [R][H][128][Ppad] key-contiguous copy of V for the prefill attention
   int norm_tma = 3;      // bit 0: decode-step norms through the TMA-staged kernel, bit 1: prefill norms too
   int tc_prefetch = 0, tc_prefetch_gu = 0;   // weight tiles a decode contraction may request before its dependency wait (0 = ring depth)
-  // resid+RMSNorm folded into the contractions (gemm.cuh NormFuse): parity-green but measured slower (2.13 vs 1.62 ms per
-  // step): two converter warps cannot build the normalised token tile at the MMA cadence, and cluster launches lose the
-  // early residency / weight prefetch that PDL gives plain launches.  Off by default; kept for round 2.
-  int fuse_norm = 0;
-  float* ssq_o = nullptr; float* ssq_d = nullptr;
-  int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2, sample_cluster = 1, fuse_conv_epilogue = 0;   // fused conv epilogue measured slower (VQ 57 vs 42.5 ms): 2-byte scattered stores on the GEMM critical path
+  int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2, fuse_conv_epilogue = 0;   // fused conv epilogue measured slower (VQ 57 vs 42.5 ms): 2-byte scattered stores on the GEMM critical path
   EncodeTiledFn encode = nullptr;
   // options
   uint64_t attn_dbg_ptr = 0;
   int64_t attn_test_flags = 0;
-  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 3, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, use_mega = 0, mega_coop = 0, fuse_swiglu = 1, tc_stages = 0, tc_stages_gu = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
+  int use_tc = 1, use_pdl = 1, use_graph = 1, attn_impl = 3, attn_ctas = 0, attn_trigger = 1, attn_attr = 1, fuse_swiglu = 1, tc_stages = 0, tc_stages_gu = 0, vq_chunk = 0, attn_splits = 0, gemm_splits = 0;
   float* dbg_logits = nullptr;
   float* dbg_text_logits = nullptr;
-  unsigned long long* sk_prof = nullptr;
   unsigned long long* prof_buf = nullptr;   // per-kernel timeline of ONE decode step (plain-launch mode)
   int prof_step = -1, prof_slot = 0;
   bool prof_active = false;
@@ -111,26 +103,21 @@ struct pg_engine {
   // workspace carve-outs
   void *xn = nullptr, *qbuf = nullptr, *attn_out = nullptr, *hbuf = nullptr, *hidden_t = nullptr, *head_h = nullptr;
   float *part = nullptr, *x_dec = nullptr, *hidden_f = nullptr, *attn_ws = nullptr, *attn_ll = nullptr;
+  // engine-owned staging of the per-call inputs / outputs of the fused loops, so captured graphs depend on shapes
+  // and scalars only (the caller's tensors are fresh allocations on every call)
+  int32_t *st_kv_start = nullptr, *st_edit = nullptr, *st_gt = nullptr, *st_tokens = nullptr;
   size_t part_bytes = 0;
   int *attn_cnt = nullptr, *attn_flag = nullptr, *step_ctr = nullptr, *greedy_state = nullptr;
-  cudaGraphExec_t txt_graph_exec = nullptr;          // one text-decode step (pg_generate_greedy)
-  std::string txt_graph_key;
-  int64_t txt_graph_launches = 0;
   int* poll_host = nullptr;                          // pinned: early-exit poll of the greedy loop
   void *embed_table = nullptr, *align_tmp = nullptr;
-  // persistent step kernel state
-  CUtensorMap* wmaps_dev = nullptr; CUtensorMap* amaps_dev = nullptr; float* ln_dev = nullptr;
-  unsigned long long* sk_sync = nullptr;     // [0] grid barrier counter, [1] launch epoch
-  CUtensorMap amaps_host[3];
-  int amaps_R = -1;
   void *vq_act[3] = {nullptr, nullptr, nullptr};
   void* vq_col = nullptr; float* vq_part = nullptr; float *gn_partial = nullptr, *gn_stats = nullptr;
   size_t vq_act_elems = 0, vq_col_elems = 0, vq_part_elems = 0;
   int gn_chunks_max = 0;
-  // graph cache
-  cudaGraphExec_t graph_exec = nullptr;
-  std::string graph_key;
-  int64_t graph_launches = 0;     // kernels per replay, counted while capturing
+  // graph cache: one instantiated decode-step graph per (kind, shape, scalars) key; a handful of shapes alternate in
+  // practice (x2t and t2i of the two-stage flow, edit / non-edit calls), so a small map, flushed when it outgrows its cap
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int64_t launches = 0; };   // launches: kernels per replay
+  std::unordered_map<std::string, GraphEntry> graphs;
   // the decode loop runs on the engine's own stream (the caller's may be the legacy default stream,
   // which cannot be captured); ordered against the caller's stream with events
   cudaStream_t own_stream = nullptr;
@@ -160,19 +147,13 @@ static int launch(pg_engine* e, void (*kernel)(KArgs...), dim3 grid, dim3 block,
                   Args... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   int na = 0;
   if (e->use_pdl) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;
     ++na;
   }
-  if (e->cluster_z > 1) {                       // one-shot: thread-block cluster along z for the next launch
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 1; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = (unsigned)e->cluster_z;
-    ++na;
-  }
-  e->cluster_z = 0;
   cfg.attrs = attr;
   cfg.numAttrs = na;
   e->launches++;
@@ -197,30 +178,10 @@ static int make_map_2d(pg_engine* e, CUtensorMap* m, const void* ptr, uint64_t r
   return 0;
 }
 
-static GemmSched sched_for(int N, int K, int G, int max_splits = 16) {
-  GemmSched g;
-  g.n_tiles = (N + TC_BM - 1) / TC_BM;
-  g.num_kb = (K + TC_BK - 1) / TC_BK;
-  int best_s = 1;
-  double best_eff = -1.0;
-  for (int s = 1; s <= std::min(max_splits, g.num_kb); ++s) {
-    const int kb_per = (g.num_kb + s - 1) / s;
-    if ((s - 1) * kb_per >= g.num_kb) continue;            // an empty split
-    const long items = (long)g.n_tiles * s;
-    const long waves = (items + G - 1) / G;
-    // time ~ waves * kb_per (longest item) ; ideal ~ n_tiles * num_kb / G
-    const double eff = ((double)g.n_tiles * g.num_kb / G) / ((double)waves * kb_per);
-    if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
-  }
-  g.splits = best_s;
-  g.kb_per_split = (g.num_kb + best_s - 1) / best_s;
-  return g;
-}
-
 template <int NT>
 static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx, float* C, int M, int N, int K,
                      int splits, int kb_per_split, bool w_const, const void* w_tiled, void* swiglu_out, cudaStream_t st,
-                     const ConvGeom* conv = nullptr, int grid_y = 0, const NormFuse* nfp = nullptr) {
+                     const ConvGeom* conv = nullptr, int grid_y = 0) {
   using Cfg = TcCfg<NT>;
   // wide token tiles (prefill, VQ convolutions) are tensor-bound: a shallow ring leaves room for two CTAs per SM,
   // whose epilogues overlap each other's main loops (measured: prefill 75.6 -> 68 ms); the weight-streaming decode
@@ -232,16 +193,12 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   stages = std::max(2, std::min(stages, 12));
   stages = std::min(stages, std::max(2, kb_per_split));
   if (stages < kb_per_split && (stages & 1)) --stages;   // reused rings must be even (see the invariant in gemm_tc_kernel)
-  if (nfp && nfp->xsrc) stages = std::min(stages, 6);      // room for the fp32 staging rings of the normalising producers
-  const size_t smem = Cfg::smem_bytes(stages) + ((nfp && nfp->xsrc) ? NF_STAGING_BYTES : 0);
+  const size_t smem = Cfg::smem_bytes(stages);
   dim3 grid((N + TC_BM - 1) / TC_BM, conv ? grid_y : (M + NT - 1) / NT, splits);
   ConvGeom cg = {};
   if (conv) cg = *conv;
-  NormFuse nf = {};
-  if (nfp) nf = *nfp;
-  if (nf.xres) e->cluster_z = splits;            // the split-K CTAs of a tile reduce through distributed shared memory
   return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
-                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out, cg, nf,
+                e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out, cg,
                 NT <= 64 ? (swiglu_out ? e->tc_prefetch_gu : e->tc_prefetch) : 0);
 }
 
@@ -286,20 +243,18 @@ static int run_conv_gemm(pg_engine* e, const void* act, const void* Wc, int B, i
 // C[splits][M][N] fp32 = X[M][K] * W[N][K]^T.  Returns the number of splits used through *splits_out.
 static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, int K, float* C, size_t c_bytes,
                     int* splits_out, cudaStream_t st, int force_impl = -1, int force_splits = 0, bool w_const = true,
-                    const void* w_tiled = nullptr, void* swiglu_out = nullptr, const NormFuse* nf = nullptr) {
+                    const void* w_tiled = nullptr, void* swiglu_out = nullptr) {
   const bool tc = e->bf16 && ((force_impl == 1) || (force_impl < 0 && e->use_tc)) && (K % 8 == 0) &&
                   (((uintptr_t)X & 15) == 0) && (((uintptr_t)W & 15) == 0);
   if (force_impl == 1 && !tc) return fail("tcgen05 GEMM needs bf16 operands, K %% 8 == 0 and 16-byte aligned pointers");
   int splits = 1;
   if (tc) {
-    const int NT = (nf && M <= 32) ? 32 : M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
+    const int NT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     const int tiles = ((N + TC_BM - 1) / TC_BM) * ((M + NT - 1) / NT);
     const int num_kb = (K + TC_BK - 1) / TC_BK;
     int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : std::max(1, e->num_sms / tiles));
     if (swiglu_out) want = 1;                               // the SwiGLU epilogue is non-linear: whole K in one CTA
     want = std::min(std::min(want, 16), num_kb);
-    if (nf && nf->xres) want = std::min(want, 8);          // portable cluster size
-    if (nf && NT != 32) return fail("internal: fused norm needs the 32-token tile");
     while (want > 1 && (size_t)want * M * N * 4 > c_bytes) --want;
     const int kb_per_split = (num_kb + want - 1) / want;
     splits = (num_kb + kb_per_split - 1) / kb_per_split;
@@ -311,22 +266,9 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     CUtensorMap mw, mx;
     TRY(make_map_2d(e, &mw, W, (uint64_t)N, (uint64_t)K, TC_BM));
     TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
-    NormFuse nf_local;
-    if (nf && nf->xsrc) {
-      nf_local = *nf;
-      cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
-      cuuint64_t gstr[1] = {(cuuint64_t)K * 4};
-      cuuint32_t box[2] = {(cuuint32_t)TC_BK, 32};
-      cuuint32_t estr[2] = {1, 1};
-      CUresult r = e->encode(&nf_local.map_xf, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(nf->xsrc), gdim, gstr, box, estr,
-                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (residual stream) failed (%d)", (int)r);
-      nf = &nf_local;
-    }
     switch (NT) {
       case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
-      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st, nullptr, 0, nf)); break;
+      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
       case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
       case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
       default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
@@ -381,18 +323,19 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->attn_ws = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 4);
   e->attn_cnt = (int*)c.take(R * d.H * 4);
   e->attn_flag = (int*)c.take(R * d.H * 64 * 4);
-  e->ssq_o = (float*)c.take((size_t)((d.D + TC_BM - 1) / TC_BM) * 32 * 4);
-  e->ssq_d = (float*)c.take((size_t)((d.D + TC_BM - 1) / TC_BM) * 32 * 4);
   e->attn_ll = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 8);
   e->step_ctr = (int*)c.take(256);
   e->greedy_state = (int*)c.take(256 + R * 4);      // [0] rows unfinished, [1] steps generated, [64..] per-row flags
   e->vT = c.take(R * d.H * HEAD_DIM * align_up((size_t)std::max(d.max_prompt, 1), 64) * 2);
   e->embed_table = c.take((size_t)d.img_vocab * d.D * es);
   e->align_tmp = c.take((size_t)d.img_vocab * d.D * es);
-  e->wmaps_dev = (CUtensorMap*)c.take((size_t)d.L * 4 * sizeof(CUtensorMap));
-  e->amaps_dev = (CUtensorMap*)c.take(3 * sizeof(CUtensorMap));
-  e->ln_dev = (float*)c.take((size_t)d.L * 2 * d.D * 4);
-  e->sk_sync = (unsigned long long*)c.take(256);
+  {
+    const size_t B = (R + 1) / 2;
+    e->st_kv_start = (int32_t*)c.take(R * 4);
+    e->st_edit = (int32_t*)c.take(B * std::max(d.max_steps, 1) * 4);
+    e->st_gt = (int32_t*)c.take(B * std::max(d.max_steps, 1) * 4);
+    e->st_tokens = (int32_t*)c.take(R * (size_t)e->Tmax * 4);      // image loop: [B][n_steps]; text loop: [R][max_new]
+  }
   // VQ decoder scratch, per chunk of images
   const int Bc = vq_chunk_of(e);
   size_t act = 0, col = 0, part = 0;
@@ -427,6 +370,11 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->gn_chunks_max = 1024;
   e->gn_partial = (float*)c.take((size_t)Bc * e->gn_chunks_max * 32 * 2 * 4);
   e->gn_stats = (float*)c.take((size_t)Bc * 32 * 2 * 4);
+}
+
+static void drop_graphs(pg_engine* e) {
+  for (auto& kv : e->graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  e->graphs.clear();
 }
 
 // ------------------------------------------------------------------------------ C-ABI: lifetime
@@ -474,22 +422,16 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaFuncSetAttribute(resid_rmsnorm_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(resid_rmsnorm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PA_SMEM));
-  CK(cudaFuncSetAttribute(attn_decode_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM));
-  CK(cudaFuncSetAttribute(attn_decode_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A4_SMEM));
   CK(cudaFuncSetAttribute(attn_decode_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM));
-  CK(cudaFuncSetAttribute(decode_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
-  CK(cudaFuncSetAttribute(cfg_sample_embed_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, dims->img_vocab * 4));
-  CK(cudaFuncSetAttribute(cfg_sample_embed_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, dims->img_vocab * 4));
   *out = e;
   return 0;
 }
 
 extern "C" int pg_engine_destroy(pg_engine* e) {
   if (!e) return 0;
-  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
-  if (e->txt_graph_exec) cudaGraphExecDestroy(e->txt_graph_exec);
+  drop_graphs(e);
   if (e->poll_host) cudaFreeHost(e->poll_host);
   if (e->tiled_buf) cudaFree(e->tiled_buf);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
@@ -506,7 +448,7 @@ extern "C" int pg_engine_query_bytes(const pg_engine* e_, size_t* kv_bytes, size
   layout_workspace(&tmp, c);
   if (kv_bytes) *kv_bytes = (size_t)tmp.d.L * 2 * tmp.d.max_rows * tmp.d.H * tmp.Tmax * HEAD_DIM * tmp.esz;
   if (ws_bytes) *ws_bytes = align_up(c.off, 1024) + 1024;
-  tmp.graph_exec = nullptr;
+  tmp.graphs.clear();
   return 0;
 }
 
@@ -543,7 +485,6 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "use_tiled") e->use_tiled = (int)value;
-  else if (k == "fuse_norm") e->fuse_norm = (int)value;
   else if (k == "rn_threads") e->rn_threads = (int)value;
   else if (k == "norm_tma") e->norm_tma = (int)value;
   else if (k == "prefill_attn_tc") e->prefill_attn_tc = (int)value;
@@ -554,7 +495,6 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "kvpf_den") e->kvpf_den = std::max(1, (int)value);
   else if (k == "kvpf1") e->kvpf1 = (int)value;
   else if (k == "kvpf2") e->kvpf2 = (int)value;
-  else if (k == "sample_cluster") e->sample_cluster = (int)value;
   else if (k == "fuse_conv_epilogue") e->fuse_conv_epilogue = (int)value;
   else if (k == "tc_wide_stages") e->tc_wide_stages = std::max(2, (int)value);
   else if (k == "use_implicit_conv") e->use_implicit_conv = (int)value;
@@ -567,20 +507,16 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_test_flags") e->attn_test_flags = value;
   else if (k == "attn_ctas") e->attn_ctas = (int)value;
   else if (k == "attn_trigger") e->attn_trigger = (int)value;
-  else if (k == "use_mega") e->use_mega = (int)value;
   else if (k == "fuse_swiglu") e->fuse_swiglu = (int)value;
-  else if (k == "mega_coop") e->mega_coop = (int)value;
   else if (k == "attn_attr") e->attn_attr = (int)value;
   else if (k == "gemm_splits") e->gemm_splits = (int)value;
   else if (k == "dbg_logits_ptr") e->dbg_logits = (float*)(uintptr_t)value;
   else if (k == "dbg_text_logits_ptr") e->dbg_text_logits = (float*)(uintptr_t)value;   // [max_new][R][vocab] fp32
-  else if (k == "sk_prof_ptr") e->sk_prof = (unsigned long long*)(uintptr_t)value;
   else if (k == "prof_ptr") e->prof_buf = (unsigned long long*)(uintptr_t)value;
   else if (k == "prof_step") e->prof_step = (int)value;
   else if (k == "reset_launches") e->launches = 0;
   else return fail("unknown option '%s'", key);
-  if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; e->graph_key.clear(); }
-  if (e->txt_graph_exec) { cudaGraphExecDestroy(e->txt_graph_exec); e->txt_graph_exec = nullptr; e->txt_graph_key.clear(); }
+  drop_graphs(e);          // options are baked into captured launches
   return 0;
 }
 
@@ -691,23 +627,6 @@ extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
   CK(cudaMemsetAsync(e->attn_ll, 0, (size_t)d.max_rows * d.H * 64 * (HEAD_DIM + 2) * 8, st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 256, st));
   CK(cudaMemsetAsync(e->vT, 0, (size_t)d.max_rows * d.H * HEAD_DIM * align_up((size_t)std::max(d.max_prompt, 1), 64) * 2, st));   // must stay finite
-  CK(cudaMemsetAsync(e->sk_sync, 0, 256, st));
-  if (e->bf16) {
-    // per-layer weight tensor maps and norm scales for the persistent step kernel
-    std::vector<CUtensorMap> maps((size_t)d.L * 4);
-    for (int l = 0; l < d.L; ++l) {
-      LayerW w;
-      TRY(layer_weights(e, l, &w));
-      TRY(make_map_2d(e, &maps[(size_t)l * 4 + 0], w.wqkv, (uint64_t)3 * e->HD, (uint64_t)d.D, TC_BM));
-      TRY(make_map_2d(e, &maps[(size_t)l * 4 + 1], w.wo, (uint64_t)d.D, (uint64_t)e->HD, TC_BM));
-      TRY(make_map_2d(e, &maps[(size_t)l * 4 + 2], w.wgu, (uint64_t)2 * d.F, (uint64_t)d.D, TC_BM));
-      TRY(make_map_2d(e, &maps[(size_t)l * 4 + 3], w.wd, (uint64_t)d.D, (uint64_t)d.F, TC_BM));
-      CK(cudaMemcpyAsync(e->ln_dev + ((size_t)l * 2 + 0) * d.D, w.ln1, (size_t)d.D * 4, cudaMemcpyDeviceToDevice, st));
-      CK(cudaMemcpyAsync(e->ln_dev + ((size_t)l * 2 + 1) * d.D, w.ln2, (size_t)d.D * 4, cudaMemcpyDeviceToDevice, st));
-    }
-    CK(cudaMemcpyAsync(e->wmaps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st));
-    CK(cudaStreamSynchronize(st));
-  }
   if (e->bf16 && !e->tiled_buf) {
     // tile-major copies of the weights that are streamed once per step (see tile_weight_kernel)
     struct Item { const void* w; int N, K; };
@@ -760,12 +679,11 @@ static int elementwise_blocks(pg_engine* e, size_t total) {
 // otherwise the contraction followed by swiglu_kernel.
 // (decode-sized token counts only: with 256-token tiles the two gate warps' expf work would outlast the MMAs)
 static bool fused_swiglu_ok(const pg_engine* e, int tok) { return e->bf16 && e->use_tc && e->fuse_swiglu && e->d.F % 64 == 0 && tok <= 128; }
-static int k_gate_up(pg_engine* e, const LayerW& w, int tok, cudaStream_t st, const NormFuse* nf = nullptr) {
+static int k_gate_up(pg_engine* e, const LayerW& w, int tok, cudaStream_t st) {
   const pg_dims& d = e->d;
   const int F = d.F, D = d.D;
   int S = 1;
-  if (fused_swiglu_ok(e, tok)) return run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, e->hbuf, nf);
-  if (nf) return fail("internal: fused norm needs the fused SwiGLU epilogue");
+  if (fused_swiglu_ok(e, tok)) return run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, e->hbuf);
   TRY(run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st));
   const size_t total = (size_t)tok * F;
   const int il = (e->bf16 && F % 64 == 0) ? 1 : 0;         // bf16 weights are packed interleaved when F % 64 == 0 (weights.py)
@@ -857,93 +775,12 @@ static int attn_split_count(pg_engine* e, int R, int T) {
 }
 
 // one decode step over e->x_dec (fp32 [R, D]); xn for layer 0 already in e->xn when first_norm_done
-static bool mega_ok(const pg_engine* e, int R) {
-  const pg_dims& d = e->d;
-  return e->bf16 && e->use_mega && e->use_tc && R <= SK_NT && R <= AT_MAX_ROWS && d.D <= SK_RNK * SK_WTHREADS &&
-         d.D % 8 == 0 && d.F % 64 == 0;
-}
-
-// activation tensor maps of the step kernel depend on the row count of the batch; refreshed outside any
-// stream capture
-static int prepare_amaps(pg_engine* e, int R, cudaStream_t st) {
-  const pg_dims& d = e->d;
-  if (e->amaps_R == R) return 0;
-  TRY(make_map_2d(e, &e->amaps_host[0], e->xn, (uint64_t)R, (uint64_t)d.D, SK_NT));
-  TRY(make_map_2d(e, &e->amaps_host[1], e->attn_out, (uint64_t)R, (uint64_t)e->HD, SK_NT));
-  TRY(make_map_2d(e, &e->amaps_host[2], e->hbuf, (uint64_t)R, (uint64_t)d.F, SK_NT));
-  CK(cudaMemcpyAsync(e->amaps_dev, e->amaps_host, sizeof(e->amaps_host), cudaMemcpyHostToDevice, st));
-  CK(cudaStreamSynchronize(st));
-  e->amaps_R = R;
-  return 0;
-}
-
-// The TMA-staged decode-attention generations share one signature (attn_impl: 1 = generation 3 with a
-// last-arriver counter, 2 = helper-warp variant, 3 = generation 5, the default)
-using AttnKernel = decltype(&attn_decode_tma_kernel);
-struct AttnVariant { AttnKernel fn; int threads; int smem; int* sync; float* ws; };
-static AttnVariant attn_variant(const pg_engine* e) {
-  if (e->attn_impl >= 3) return {attn_decode_v5_kernel, AT_THREADS, A5_SMEM, e->attn_flag, e->attn_ll};
-  if (e->attn_impl == 2) return {attn_decode_v4_kernel, A4_THREADS, A4_SMEM, e->attn_flag, e->attn_ws};
-  return {attn_decode_tma_kernel, AT_THREADS, AT_SMEM, e->attn_cnt, e->attn_ws};
-}
-
-// all layers of one decode step in ONE persistent kernel (step_kernel.cuh); xn of layer 0 must be ready
-static int decode_layers_mega(pg_engine* e, const int32_t* kv_start, int R, int pos_base, int* step_ptr, bool inc_step,
-                              cudaStream_t st) {
-  const pg_dims& d = e->d;
-  NEED(cosT, float, "rope_cos");
-  NEED(sinT, float, "rope_sin");
-  NEED(normw, float, "norm");
-  const int G = e->num_sms;
-  StepParams p = {};
-  p.R = R; p.H = d.H; p.D = d.D; p.HD = e->HD; p.F = d.F; p.L = d.L; p.Tmax = e->Tmax;
-  p.eps = d.rms_eps; p.scale = 1.0f / sqrtf((float)HEAD_DIM);
-  p.wmaps = e->wmaps_dev; p.amaps = e->amaps_dev; p.ln = e->ln_dev; p.norm_w = normw;
-  p.x = e->x_dec; p.xn = (bf16*)e->xn; p.attn_out = (bf16*)e->attn_out; p.h = (bf16*)e->hbuf;
-  p.hidden_t = (bf16*)e->hidden_t; p.hidden_f = e->hidden_f;
-  p.g_qkv = sched_for(3 * e->HD, d.D, G, SK_MAXS); p.g_o = sched_for(d.D, e->HD, G, SK_MAXS);
-  p.g_gu = sched_for(2 * d.F, d.D, G, SK_MAXS); p.g_d = sched_for(d.D, d.F, G, SK_MAXS);
-  size_t off = 0;
-  auto carve = [&](size_t floats) { float* q = e->part + off; off += (floats + 255) / 256 * 256; return q; };
-  p.part_qkv = carve((size_t)p.g_qkv.splits * R * 3 * e->HD);
-  p.part_o = carve((size_t)p.g_o.splits * R * d.D);
-  p.part_gu = carve((size_t)p.g_gu.splits * R * 2 * d.F);
-  p.part_d = carve((size_t)p.g_d.splits * R * d.D);
-  if (off * 4 > e->part_bytes) return fail("internal: split-K scratch too small for the step kernel");
-  p.kv = (bf16*)e->kv; p.kv_start = kv_start; p.cosT = cosT; p.sinT = sinT;
-  p.attn_ws = e->attn_ws; p.attn_cnt = e->attn_cnt;
-  p.grid_bar = e->sk_sync; p.epoch = e->sk_sync + 1;
-  p.pos_base = pos_base; p.step_ptr = step_ptr; p.inc_step = inc_step ? 1 : 0;
-  p.prof = e->sk_prof;
-  if (e->amaps_R != R) return fail("internal: activation tensor maps were not prepared for R=%d", R);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(G); cfg.blockDim = dim3(SK_THREADS); cfg.dynamicSmemBytes = SK_SMEM; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeCooperative;
-  attr[0].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = e->mega_coop ? 1 : 0;
-  e->launches++;
-  cudaError_t le = cudaLaunchKernelEx(&cfg, decode_step_kernel, p);
-  if (le != cudaSuccess) return fail("decode_step_kernel launch failed: %s", cudaGetErrorString(le));
-  return 0;
-}
-
 // regime 0: image-token decode (inputs_embeds = bf16 gen_aligner output => bf16 residual stream, bf16 trig, absolute
 // positions); regime 1: text decode inside generate() (fp32 embed_tokens rows => fp32 residual stream, fp32 trig,
 // mask-aware positions) - the rounding points HF's autocast produces for each input dtype
 static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_base, const int* step_ptr,
                          bool first_norm_done, bool inc_step, int T_hint, cudaStream_t st, int regime = 0) {
   const pg_dims& d = e->d;
-  if (regime == 0 && mega_ok(e, R)) {
-    TRY(prepare_amaps(e, R, st));          // no-op when already prepared (must be, inside a capture)
-    if (!first_norm_done) {
-      LayerW w0;
-      TRY(layer_weights(e, 0, &w0));
-      TRY(k_resid_norm(e, e->x_dec, nullptr, 0, 0, w0.ln1, e->xn, nullptr, R, 1, 0, RN_ROUND_RESID, st));
-    }
-    return decode_layers_mega(e, kv_start, R, pos_base, const_cast<int*>(step_ptr), inc_step, st);
-  }
   NEED(cosT, float, "rope_cos");
   NEED(sinT, float, "rope_sin");
   NEED(normw, float, "norm");
@@ -953,7 +790,6 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
   const int trig = regime == 0 ? (e->bf16 ? 1 : 0) : ROPE_REL;
   const int nsp = attn_split_count(e, R, T_hint);
   int S = 1;
-  bool fused_tail = false;
   // KV tiles of attention launch (layer tl) prefetched into L2 by the norm kernels in front of it; tl == L means layer 0
   // of the NEXT step (one more token in the cache)
   const bool kvpf_on = e->bf16 && e->attn_impl >= 1 && R <= AT_MAX_ROWS && (e->kvpf1 > 0 || e->kvpf2 > 0);
@@ -971,26 +807,13 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     LayerW w;
     TRY(layer_weights(e, l, &w));
     if (l == 0 && !first_norm_done) TRY(k_resid_norm(e, e->x_dec, nullptr, 0, 0, w.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
-    // fused path: resid + RMSNorm live inside the contractions around them (gemm.cuh NormFuse), 5 kernels per layer
-    const bool fuse = regime == 0 && e->bf16 && e->use_tc && e->fuse_norm && R <= 32 && fused_swiglu_ok(e, R) && D % 8 == 0 && HD % 8 == 0 &&
-                      F % 8 == 0 && D <= 32 * TC_BM * 8;
-    NormFuse nf_qkv = {}, nf_o = {}, nf_gu = {}, nf_d = {};
-    if (fuse) {
-      const int nt = (D + TC_BM - 1) / TC_BM;
-      nf_qkv.xsrc = e->x_dec; nf_qkv.ssq = e->ssq_d; nf_qkv.normw = w.ln1; nf_qkv.n_ssq_tiles = nt; nf_qkv.eps = d.rms_eps;
-      nf_gu.xsrc = e->x_dec; nf_gu.ssq = e->ssq_o; nf_gu.normw = w.ln2; nf_gu.n_ssq_tiles = nt; nf_gu.eps = d.rms_eps;
-      nf_o.xres = e->x_dec; nf_o.ssq_out = e->ssq_o;
-      nf_d.xres = e->x_dec; nf_d.ssq_out = e->ssq_d;
-    }
-    TRY(run_gemm(e, e->xn, w.wqkv, R, 3 * HD, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr,
-                 (fuse && l > 0) ? &nf_qkv : nullptr));
-    if (e->bf16 && e->attn_impl >= 1 && R <= AT_MAX_ROWS && (regime == 0 || e->attn_impl >= 3)) {
+    TRY(run_gemm(e, e->xn, w.wqkv, R, 3 * HD, D, e->part, e->part_bytes, &S, st));
+    if (e->bf16 && e->attn_impl >= 1 && R <= AT_MAX_ROWS) {
       const int ctas = e->attn_ctas > 0 ? e->attn_ctas : e->num_sms;
       const int saved = e->use_pdl;
       if (!e->attn_attr) e->use_pdl = 0;
-      const AttnVariant av = attn_variant(e);
-      int rc = launch(e, av.fn, dim3(ctas), dim3(av.threads), av.smem, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
-                      (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, av.ws, av.sync,
+      int rc = launch(e, attn_decode_v5_kernel, dim3(ctas), dim3(AT_THREADS), A5_SMEM, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
+                      (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ll,
                       R, d.H, e->Tmax, pos_base, step_ptr, scale, trig, e->attn_trigger, next_prof(e), (unsigned long long*)nullptr);
       e->use_pdl = saved;
       TRY(rc);
@@ -1003,15 +826,6 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
                         (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), kv_start, (float*)e->attn_out, e->attn_ws,
                         e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, trig));
     }
-    if (fuse) {
-      int So = 1;
-      TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &So, st, -1, 0, true, nullptr, nullptr, &nf_o));
-      TRY(k_gate_up(e, w, R, st, &nf_gu));
-      TRY(run_gemm(e, e->hbuf, w.wd, R, D, F, e->part, e->part_bytes, &So, st, -1, 0, true, nullptr, nullptr, &nf_d));
-      fused_tail = true;
-      continue;
-    }
-    fused_tail = false;
     TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &S, st));
     const KvPrefetch pf1 = kv_prefetch(l + 1, 0, e->kvpf1);
     TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st, &pf1,
@@ -1027,8 +841,7 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     }
   }
   const KvPrefetch pf_last = kv_prefetch(d.L, e->kvpf1, e->kvpf1 + e->kvpf2);
-  // final norm: the fused path has already folded the last down projection into the residual stream
-  TRY(k_resid_norm(e, e->x_dec, fused_tail ? nullptr : e->part, S, (size_t)R * D, normw, e->hidden_t, e->hidden_f, R, 1, 0,
+  TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, normw, e->hidden_t, e->hidden_f, R, 1, 0,
                    rflag | (inc_step ? RN_INC_STEP : 0), st, &pf_last));
   return 0;
 }
@@ -1094,33 +907,20 @@ static void philox_policy(pg_engine* e, size_t numel, uint64_t* counter_offset, 
 }
 
 static int k_sample(pg_engine* e, const float* part, int S, size_t sstride, const float* bias, int B, float cfg_weight,
-                    float temperature, uint64_t seed, uint64_t offset_base, int greedy, const int32_t* edit_region,
+                    float temperature, uint64_t seed, uint64_t offset_base, int greedy, int top_k, const int32_t* edit_region,
                     const int32_t* gt_labels, int step_base, const int* step_ptr, int n_steps, int32_t* tokens_out,
                     float* x_next, const float* next_norm_w, void* xn_next, cudaStream_t st) {
   const pg_dims& d = e->d;
   uint64_t per_step, stride;
   philox_policy(e, (size_t)B * d.img_vocab, &per_step, &stride);
-  const size_t smem = (size_t)d.img_vocab * 4;
-  if (e->sample_cluster) {
-    const size_t csm = (size_t)((d.img_vocab + SAMPLE_CLUSTER - 1) / SAMPLE_CLUSTER) * 4;
-    DISPATCH_T(e,
-               launch(e, cfg_sample_embed_cluster_kernel<bf16>, dim3(B * SAMPLE_CLUSTER), dim3(SAMPLE_CL_THREADS), csm, st, part, S, sstride, bias, B, d.img_vocab,
-                      cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, edit_region, gt_labels, step_base,
-                      step_ptr, n_steps, tokens_out, (const bf16*)e->embed_table, d.D, x_next, next_norm_w, (bf16*)xn_next,
-                      d.rms_eps, 1, e->dbg_logits),
-               launch(e, cfg_sample_embed_cluster_kernel<float>, dim3(B * SAMPLE_CLUSTER), dim3(SAMPLE_CL_THREADS), csm, st, part, S, sstride, bias, B, d.img_vocab,
-                      cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, edit_region, gt_labels, step_base,
-                      step_ptr, n_steps, tokens_out, (const float*)e->embed_table, d.D, x_next, next_norm_w, (float*)xn_next,
-                      d.rms_eps, 0, e->dbg_logits));
-    return 0;
-  }
+  const size_t csm = (size_t)((d.img_vocab + SAMPLE_CLUSTER - 1) / SAMPLE_CLUSTER) * 4;
   DISPATCH_T(e,
-             launch(e, cfg_sample_embed_kernel<bf16>, dim3(B), dim3(SAMPLE_THREADS), smem, st, part, S, sstride, bias, B, d.img_vocab,
-                    cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, edit_region, gt_labels, step_base,
+             launch(e, cfg_sample_embed_cluster_kernel<bf16>, dim3(B * SAMPLE_CLUSTER), dim3(SAMPLE_CL_THREADS), csm, st, part, S, sstride, bias, B, d.img_vocab,
+                    cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, top_k, edit_region, gt_labels, step_base,
                     step_ptr, n_steps, tokens_out, (const bf16*)e->embed_table, d.D, x_next, next_norm_w, (bf16*)xn_next,
                     d.rms_eps, 1, e->dbg_logits),
-             launch(e, cfg_sample_embed_kernel<float>, dim3(B), dim3(SAMPLE_THREADS), smem, st, part, S, sstride, bias, B, d.img_vocab,
-                    cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, edit_region, gt_labels, step_base,
+             launch(e, cfg_sample_embed_cluster_kernel<float>, dim3(B * SAMPLE_CLUSTER), dim3(SAMPLE_CL_THREADS), csm, st, part, S, sstride, bias, B, d.img_vocab,
+                    cfg_weight, temperature, seed, offset_base, per_step, stride, greedy, top_k, edit_region, gt_labels, step_base,
                     step_ptr, n_steps, tokens_out, (const float*)e->embed_table, d.D, x_next, next_norm_w, (float*)xn_next,
                     d.rms_eps, 0, e->dbg_logits));
   return 0;
@@ -1128,13 +928,15 @@ static int k_sample(pg_engine* e, const float* part, int S, size_t sstride, cons
 
 // a6-a8
 extern "C" int pg_cfg_sample_embed(pg_engine* e, const float* logits, int B, float cfg_weight, float temperature,
-                                   uint64_t seed, uint64_t philox_offset, int greedy, const int32_t* edit_region,
-                                   const int32_t* gt_labels, int step, int n_steps, int32_t* tokens_out, float* x_next,
-                                   void* stream) {
+                                   uint64_t seed, uint64_t philox_offset, int greedy, int top_k,
+                                   const int32_t* edit_region, const int32_t* gt_labels, int step, int n_steps,
+                                   int32_t* tokens_out, float* x_next, void* stream) {
   TRY(check_ready(e));
   if (B < 1 || 2 * B > e->d.max_rows) return fail("sample B=%d exceeds engine limits", B);
   if (step < 0 || step >= n_steps) return fail("step %d out of range", step);
-  return k_sample(e, logits, 1, 0, nullptr, B, cfg_weight, temperature, seed, philox_offset, greedy, edit_region,
+  if (top_k < 0) return fail("top_k must be >= 0");
+  if ((edit_region == nullptr) != (gt_labels == nullptr)) return fail("edit_region and gt_labels go together");
+  return k_sample(e, logits, 1, 0, nullptr, B, cfg_weight, temperature, seed, philox_offset, greedy, top_k, edit_region,
                   gt_labels, step, nullptr, n_steps, tokens_out, x_next, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -1152,8 +954,8 @@ extern "C" int pg_prepare_gen_img_embeds(pg_engine* e, const int32_t* ids, int n
 // (graph replays; consecutive graph launches are fully ordered, so kernels may read it before their
 // PDL wait).
 static int one_step(pg_engine* e, const int32_t* kv_start, int R, int P, int n_steps, float cfg_weight, float temperature,
-                    uint64_t seed, int greedy, const int32_t* edit_region, const int32_t* gt_labels, int32_t* tokens_out,
-                    bool with_lm, int step_host, cudaStream_t st) {
+                    uint64_t seed, int greedy, int top_k, const int32_t* edit_region, const int32_t* gt_labels,
+                    int32_t* tokens_out, bool with_lm, int step_host, cudaStream_t st) {
   NEED(b1, float, "head.b1");
   LayerW w0;
   TRY(layer_weights(e, 0, &w0));
@@ -1163,7 +965,7 @@ static int one_step(pg_engine* e, const int32_t* kv_start, int R, int P, int n_s
   uint64_t per_step, stride;
   philox_policy(e, (size_t)(R / 2) * e->d.img_vocab, &per_step, &stride);
   TRY(k_sample(e, e->part, S, (size_t)R * e->d.img_vocab, b1, R / 2, cfg_weight, temperature, seed,
-               host ? per_step * (uint64_t)step_host : 0, greedy, edit_region, gt_labels, host ? step_host : 0,
+               host ? per_step * (uint64_t)step_host : 0, greedy, top_k, edit_region, gt_labels, host ? step_host : 0,
                host ? nullptr : e->step_ctr, n_steps, tokens_out, with_lm ? e->x_dec : nullptr, w0.ln1,
                with_lm ? e->xn : nullptr, st));
   if (with_lm)
@@ -1172,56 +974,84 @@ static int one_step(pg_engine* e, const int32_t* kv_start, int R, int P, int n_s
   return 0;
 }
 
+// Captured decode-step graphs, keyed by shape and scalars only: the per-call tensors live in engine-owned staging
+// buffers (pg_engine::st_*), so a second call with the same shape replays the instantiated graph whatever addresses
+// the caller's allocator hands out.  `capture` records one step on `st`.
+template <typename F>
+static int graph_for(pg_engine* e, const std::string& key, cudaStream_t st, F&& capture, pg_engine::GraphEntry** out) {
+  auto it = e->graphs.find(key);
+  if (it != e->graphs.end()) { *out = &it->second; return 0; }
+  if (e->graphs.size() >= 8) drop_graphs(e);
+  cudaGraph_t graph = nullptr;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  const int64_t before = e->launches;
+  int rc = capture();
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  const int64_t per_replay = e->launches - before;
+  e->launches = before;
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (ce != cudaSuccess) return fail("stream capture failed: %s", cudaGetErrorString(ce));
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
+  pg_engine::GraphEntry& ge = e->graphs[key];
+  ge.exec = exec; ge.launches = per_replay;
+  *out = &ge;
+  return 0;
+}
+
 extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_start, int R, int P, int n_steps,
-                               float cfg_weight, float temperature, uint64_t seed, int greedy,
+                               float cfg_weight, float temperature, uint64_t seed, int greedy, int top_k,
                                const int32_t* edit_region, const int32_t* gt_labels, int32_t* tokens_out, void* stream) {
   TRY(check_ready(e));
   if (R % 2) return fail("R must be even (interleaved cond/uncond rows)");
+  if (R < 2 || R > e->d.max_rows) return fail("sample_image R=%d exceeds engine limits", R);
   if (n_steps < 1 || n_steps > e->d.max_steps) return fail("n_steps %d exceeds engine limit %d", n_steps, e->d.max_steps);
+  if (top_k < 0) return fail("top_k must be >= 0");
+  if ((edit_region == nullptr) != (gt_labels == nullptr)) return fail("edit_region and gt_labels go together ([R/2][n_steps] each)");
+  if (!kv_start || !tokens_out) return fail("null argument");
   cudaStream_t user = (cudaStream_t)stream;
   cudaStream_t st = e->own_stream;
+  const int B = R / 2;
+  const size_t tok_bytes = (size_t)B * n_steps * 4;
   CK(cudaEventRecord(e->ev_in, user));
   CK(cudaStreamWaitEvent(st, e->ev_in, 0));
-  TRY(pg_prefill(e, x_prompt, kv_start, R, P, nullptr, 0, (void*)st));
-  if (mega_ok(e, R)) TRY(prepare_amaps(e, R, st));
+  CK(cudaMemcpyAsync(e->st_kv_start, kv_start, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+  if (edit_region) {
+    CK(cudaMemcpyAsync(e->st_edit, edit_region, tok_bytes, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(e->st_gt, gt_labels, tok_bytes, cudaMemcpyDeviceToDevice, st));
+  }
+  const int32_t* kvs = e->st_kv_start;
+  const int32_t* er = edit_region ? e->st_edit : nullptr;
+  const int32_t* gl = edit_region ? e->st_gt : nullptr;
+  int32_t* toks = e->st_tokens;
+  TRY(pg_prefill(e, x_prompt, kvs, R, P, nullptr, 0, (void*)st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 4, st));
   if (n_steps > 1) {
     if (e->use_graph) {
-      char key[512];
-      snprintf(key, sizeof(key), "%d/%d/%d/%a/%a/%llu/%d/%p/%p/%p/%p/%d/%d/%d/%d", R, P, n_steps, cfg_weight, temperature,
-               (unsigned long long)seed, greedy, (const void*)kv_start, (const void*)edit_region, (const void*)gt_labels,
-               (void*)tokens_out, e->use_pdl, e->use_tc, e->bf16 ? 1 : 0, e->use_mega + 2 * (e->prof_buf && e->prof_step >= 0 ? 1 : 0));
-      if (!e->graph_exec || e->graph_key != key) {
-        if (e->graph_exec) { cudaGraphExecDestroy(e->graph_exec); e->graph_exec = nullptr; }
-        cudaGraph_t graph = nullptr;
-        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        const int64_t before = e->launches;
+      char key[256];
+      snprintf(key, sizeof(key), "img/%d/%d/%d/%a/%a/%llu/%d/%d/%d/%d", R, P, n_steps, cfg_weight, temperature,
+               (unsigned long long)seed, greedy, top_k, edit_region ? 1 : 0, (e->prof_buf && e->prof_step >= 0) ? 1 : 0);
+      pg_engine::GraphEntry* ge = nullptr;
+      TRY(graph_for(e, key, st, [&]() {
         e->prof_active = (e->prof_buf != nullptr && e->prof_step >= 0);
         e->prof_slot = 0;
-        int rc = one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels,
-                          tokens_out, true, -1, st);
+        int rc = one_step(e, kvs, R, P, n_steps, cfg_weight, temperature, seed, greedy, top_k, er, gl, toks, true, -1, st);
         e->prof_active = false;
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        e->graph_launches = e->launches - before;
-        e->launches = before;
-        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-        if (ce != cudaSuccess) return fail("stream capture failed: %s", cudaGetErrorString(ce));
-        ce = cudaGraphInstantiate(&e->graph_exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) { e->graph_exec = nullptr; return fail("graph instantiate failed: %s", cudaGetErrorString(ce)); }
-        e->graph_key = key;
-      }
+        return rc;
+      }, &ge));
       for (int i = 0; i < n_steps - 1; ++i) {
         const bool prof_now = e->prof_buf && i == e->prof_step;
         if (prof_now) {
           CK(cudaMemsetAsync(e->prof_buf, 0xFF, PROF_SLOTS * 8, st));
           CK(cudaMemsetAsync(e->prof_buf + PROF_SLOTS, 0, PROF_SLOTS * 8, st));
         }
-        CK(cudaGraphLaunch(e->graph_exec, st));
+        CK(cudaGraphLaunch(ge->exec, st));
         if (prof_now)
           CK(cudaMemcpyAsync(e->prof_buf + 2 * PROF_SLOTS, e->prof_buf, 2 * PROF_SLOTS * 8, cudaMemcpyDeviceToDevice, st));
       }
-      e->launches += e->graph_launches * (n_steps - 1);
+      e->launches += ge->launches * (n_steps - 1);
     } else {
       for (int i = 0; i < n_steps - 1; ++i) {
         e->prof_active = (e->prof_buf && i == e->prof_step);
@@ -1230,7 +1060,7 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
           CK(cudaMemsetAsync(e->prof_buf, 0xFF, PROF_SLOTS * 8, st));
           CK(cudaMemsetAsync(e->prof_buf + PROF_SLOTS, 0, PROF_SLOTS * 8, st));
         }
-        int rc = one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, true, i, st);
+        int rc = one_step(e, kvs, R, P, n_steps, cfg_weight, temperature, seed, greedy, top_k, er, gl, toks, true, i, st);
         if (e->prof_active)
           CK(cudaMemcpyAsync(e->prof_buf + 2 * PROF_SLOTS, e->prof_buf, 2 * PROF_SLOTS * 8, cudaMemcpyDeviceToDevice, st));
         e->prof_active = false;
@@ -1239,8 +1069,8 @@ extern "C" int pg_sample_image(pg_engine* e, float* x_prompt, const int32_t* kv_
     }
   }
   // last token: head + sample only (the reference computes and drops one more embed)
-  TRY(one_step(e, kv_start, R, P, n_steps, cfg_weight, temperature, seed, greedy, edit_region, gt_labels, tokens_out, false,
-               n_steps - 1, st));
+  TRY(one_step(e, kvs, R, P, n_steps, cfg_weight, temperature, seed, greedy, top_k, er, gl, toks, false, n_steps - 1, st));
+  CK(cudaMemcpyAsync(tokens_out, toks, tok_bytes, cudaMemcpyDeviceToDevice, st));
   CK(cudaEventRecord(e->ev_out, st));
   CK(cudaStreamWaitEvent(user, e->ev_out, 0));
   return 0;
@@ -1289,49 +1119,68 @@ extern "C" int pg_generate_greedy(pg_engine* e, float* x_prompt, const int32_t* 
   cudaStream_t st = e->own_stream;
   CK(cudaEventRecord(e->ev_in, user));
   CK(cudaStreamWaitEvent(st, e->ev_in, 0));
-  TRY(prefill_impl(e, x_prompt, kv_start, R, P, nullptr, 0, true, (void*)st));
+  CK(cudaMemcpyAsync(e->st_kv_start, kv_start, (size_t)R * 4, cudaMemcpyDeviceToDevice, st));
+  const int32_t* kvs = e->st_kv_start;
+  int32_t* toks = e->st_tokens;                      // [R][max_new_tokens]
+  TRY(prefill_impl(e, x_prompt, kvs, R, P, nullptr, 0, true, (void*)st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 4, st));
   GreedyState gs = {e->greedy_state + 64, e->greedy_state, e->greedy_state + 1};
   greedy_state_init_kernel<<<(R + 127) / 128, 128, 0, st>>>(gs, R, max_new_tokens);
   CK(cudaGetLastError());
   const int poll_every = 16;
   bool stopped = false;
+  pg_engine::GraphEntry* ge = nullptr;
   if (max_new_tokens > 1 && e->use_graph) {
-    char key[384];
-    snprintf(key, sizeof(key), "%d/%d/%d/%d/%d/%p/%p/%d/%d/%d", R, P, max_new_tokens, eos_id, pad_id, (const void*)kv_start,
-             (void*)tokens_out, e->use_pdl, e->use_tc, e->bf16 ? 1 : 0);
-    if (!e->txt_graph_exec || e->txt_graph_key != key) {
-      if (e->txt_graph_exec) { cudaGraphExecDestroy(e->txt_graph_exec); e->txt_graph_exec = nullptr; }
-      cudaGraph_t graph = nullptr;
-      CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-      const int64_t before = e->launches;
-      int rc = text_step(e, kv_start, R, P, max_new_tokens, eos_id, pad_id, tokens_out, true, -1, st);
-      cudaError_t ce = cudaStreamEndCapture(st, &graph);
-      e->txt_graph_launches = e->launches - before;
-      e->launches = before;
-      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-      if (ce != cudaSuccess) return fail("stream capture failed: %s", cudaGetErrorString(ce));
-      ce = cudaGraphInstantiate(&e->txt_graph_exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (ce != cudaSuccess) { e->txt_graph_exec = nullptr; return fail("graph instantiate failed: %s", cudaGetErrorString(ce)); }
-      e->txt_graph_key = key;
-    }
+    char key[256];
+    snprintf(key, sizeof(key), "txt/%d/%d/%d/%d/%d/%d", R, P, max_new_tokens, eos_id, pad_id, e->dbg_text_logits ? 1 : 0);
+    TRY(graph_for(e, key, st, [&]() { return text_step(e, kvs, R, P, max_new_tokens, eos_id, pad_id, toks, true, -1, st); }, &ge));
   }
   for (int i = 0; i < max_new_tokens - 1 && !stopped; ++i) {
-    if (e->use_graph) { CK(cudaGraphLaunch(e->txt_graph_exec, st)); e->launches += e->txt_graph_launches; }
-    else TRY(text_step(e, kv_start, R, P, max_new_tokens, eos_id, pad_id, tokens_out, true, i, st));
+    if (ge) { CK(cudaGraphLaunch(ge->exec, st)); e->launches += ge->launches; }
+    else TRY(text_step(e, kvs, R, P, max_new_tokens, eos_id, pad_id, toks, true, i, st));
     if ((i + 1) % poll_every == 0) {            // every row done?  (HF checks after every token, with a host sync each)
       CK(cudaMemcpyAsync(e->poll_host, e->greedy_state, 8, cudaMemcpyDeviceToHost, st));
       CK(cudaStreamSynchronize(st));
       if (e->poll_host[0] == 0) stopped = true;
     }
   }
-  if (!stopped) TRY(text_step(e, kv_start, R, P, max_new_tokens, eos_id, pad_id, tokens_out, false, max_new_tokens - 1, st));
+  if (!stopped) TRY(text_step(e, kvs, R, P, max_new_tokens, eos_id, pad_id, toks, false, max_new_tokens - 1, st));
+  CK(cudaMemcpyAsync(tokens_out, toks, (size_t)R * max_new_tokens * 4, cudaMemcpyDeviceToDevice, st));
   CK(cudaMemcpyAsync(e->poll_host, e->greedy_state, 8, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   *n_generated = e->poll_host[1];
   CK(cudaEventRecord(e->ev_out, st));
   CK(cudaStreamWaitEvent(user, e->ev_out, 0));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ images -> uint8
+// replaces: denorm_pt (src/utils/funcs.py:511-512: (x.clamp(-1,1)+1)/2) followed by `(x*255).astype(np.uint8)`
+// (funcs.py:497-498 / pt2pil :507; truncation toward zero)
+__global__ void __launch_bounds__(256) images_to_u8_kernel(const float* __restrict__ x, uint8_t* __restrict__ out, size_t n) {
+  for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (size_t)gridDim.x * blockDim.x * 4) {
+    if (i + 4 <= n) {
+      const float4 v = *reinterpret_cast<const float4*>(x + i);
+      const float f[4] = {v.x, v.y, v.z, v.w};
+      uint32_t pk = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float t = ((fminf(fmaxf(f[j], -1.f), 1.f) + 1.f) / 2.f) * 255.f;
+        pk |= (uint32_t)(uint8_t)(int)t << (8 * j);
+      }
+      *reinterpret_cast<uint32_t*>(out + i) = pk;
+    } else {
+      for (size_t j = i; j < n; ++j) out[j] = (uint8_t)(int)(((fminf(fmaxf(x[j], -1.f), 1.f) + 1.f) / 2.f) * 255.f);
+    }
+  }
+}
+extern "C" int pg_images_to_u8(pg_engine* e, const float* image, size_t n, uint8_t* out, void* stream) {
+  if (!e || !image || !out) return fail("null argument");
+  if (((uintptr_t)image & 15) || ((uintptr_t)out & 3)) return fail("pg_images_to_u8: image must be 16-byte and out 4-byte aligned");
+  const int blocks = (int)std::max<size_t>(1, std::min<size_t>((n / 4 + 255) / 256, (size_t)e->num_sms * 16));
+  images_to_u8_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(image, out, n);
+  CK(cudaGetLastError());
+  e->launches++;
   return 0;
 }
 
@@ -1674,10 +1523,9 @@ extern "C" int pg_test_attn_decode(pg_engine* e, const int32_t* kv_start, int R,
   const int ctas = e->attn_ctas > 0 ? e->attn_ctas : e->num_sms;
   const int saved = e->use_pdl;
   e->use_pdl = 0;
-  const AttnVariant av = attn_variant(e);
-  int rc = launch(e, av.fn, dim3(ctas), dim3(av.threads), av.smem, st, (const float*)e->part, 1, (size_t)R * 3 * HD,
+  int rc = launch(e, attn_decode_v5_kernel, dim3(ctas), dim3(AT_THREADS), A5_SMEM, st, (const float*)e->part, 1, (size_t)R * 3 * HD,
                   cosT, sinT, (bf16*)kv_ptr(e, layer, 0, R), (bf16*)kv_ptr(e, layer, 1, R), kv_start, (bf16*)e->attn_out,
-                  av.ws, av.sync, R, e->d.H, e->Tmax, pos, (const int*)nullptr, 1.0f / sqrtf((float)HEAD_DIM), 1,
+                  e->attn_ll, R, e->d.H, e->Tmax, pos, (const int*)nullptr, 1.0f / sqrtf((float)HEAD_DIM), 1,
                   (int)e->attn_test_flags, next_prof(e), (unsigned long long*)e->attn_dbg_ptr);
   e->use_pdl = saved;
   return rc;

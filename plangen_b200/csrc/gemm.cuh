@@ -104,36 +104,11 @@ struct ConvGeom {
   bf16* out_bf16;
 };
 
-// Decode-step fusion of the residual + RMSNorm kernels into the contractions around them (NT = 32, bf16 regime):
-//  * producer side (O / down projection, `xres` set): the split-K CTAs of one weight tile form a thread-block
-//    CLUSTER along z; every CTA parks its fp32 accumulator tile in its own shared memory, then rank r sums
-//    tokens [r*tpr, (r+1)*tpr) over all ranks through distributed shared memory (rank order = split order,
-//    deterministic), applies  x = rnd(x + rnd(sum))  to the residual stream in place and writes the tile's
-//    per-token sum of squares to ssq_out[tile][token].  No fp32 partial slabs, no reduction kernel.
-//  * consumer side (QKV / gate|up, `xsrc` set): instead of a TMA load of a pre-normalised bf16 activation,
-//    two warps build the token tile of every k-block themselves:  rnd(w[k] * rnd(x[t][k] * rstd[t]))  with
-//    rstd[t] from the producer's per-tile sums of squares, written in the SWIZZLE_128B image the MMA expects
-//    (HF LlamaRMSNorm :60-65 rounding points, as resid_rmsnorm_kernel).
-constexpr int NF_DEPTH = 3;                                  // fp32 staging slots per converter warp
-constexpr int NF_SLOT_BYTES = 32 * TC_BK * 4;               // 32 tokens x 64 k fp32 = 8 KB
-constexpr int NF_STAGING_BYTES = 2 * NF_DEPTH * NF_SLOT_BYTES;
-struct NormFuse {
-  alignas(64) CUtensorMap map_xf;   // consumer: 2-D map over xsrc, box {64 k, 32 tokens}, no swizzle
-  const float* xsrc;      // consumer: residual stream [M][K] fp32
-  const float* ssq;       // consumer: [n_ssq_tiles][32] partial sums of squares
-  const float* normw;     // consumer: [K]
-  int n_ssq_tiles;
-  float eps;
-  float* xres;            // producer: residual stream [M][N] fp32, updated in place
-  float* ssq_out;         // producer: [N / 128][32]
-};
-
 template <int NT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                float* __restrict__ C, int M, int N, int K, int kb_per_split, int num_stages, int use_pdl,
-               const uint8_t* __restrict__ w_tiled, Prof prof, bf16* __restrict__ swiglu_out, ConvGeom cg, const __grid_constant__ NormFuse nf,
-               int w_prefetch) {
+               const uint8_t* __restrict__ w_tiled, Prof prof, bf16* __restrict__ swiglu_out, ConvGeom cg, int w_prefetch) {
   using Cfg = TcCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -257,68 +232,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     }
     umma_commit(tmem_full_bar);                // this issuer's accumulators complete -> epilogue
   };
-  // consumer side of NormFuse: a whole warp builds the normalised token tile of k-blocks first, first + 2, ...
-  auto produce_x_norm = [&](int first) {
-    if constexpr (NT == 32) {
-      // private fp32 staging ring of this warp: TMA brings the raw residual tile (8 KB) of its k-blocks
-      // NF_DEPTH ahead, so the L2 round trip is off the conversion loop
-      uint64_t* stg_bar = bars + 2 * num_stages + 2 + first * NF_DEPTH;
-      uint8_t* stg = smem + num_stages * Cfg::STAGE_BYTES + 256 + first * NF_DEPTH * NF_SLOT_BYTES;
-      if (lane == 0) {
-        for (int d = 0; d < NF_DEPTH; ++d) mbar_init(&stg_bar[d], 1);
-        mbar_fence_init();
-      }
-      __syncwarp();
-      if (use_pdl & 1) pdl_wait();
-      if (first == 0 && lane == 0) gemm_stamp(dbg, 1);
-      const uint64_t pol_x = policy_evict_last();
-      auto fetch = [&](int j) {                             // j-th k-block of this warp (k-block first + 2 j)
-        const int i = first + 2 * j;
-        if (i < nkb && lane == 0) {
-          mbar_expect_tx(&stg_bar[j % NF_DEPTH], NF_SLOT_BYTES);
-          tma_load_2d(stg + (j % NF_DEPTH) * NF_SLOT_BYTES, &nf.map_xf, &stg_bar[j % NF_DEPTH], (kb_begin + i) * TC_BK, 0, pol_x);
-        }
-      };
-      for (int j = 0; j < NF_DEPTH; ++j) fetch(j);
-      float ssum = 0.f;                                     // lane = token row
-      if (lane < M) for (int j = 0; j < nf.n_ssq_tiles; ++j) ssum += nf.ssq[j * 32 + lane];
-      const float rstd = rsqrtf(ssum / (float)K + nf.eps);
-      const int c = lane & 7;
-      int j = 0;
-      for (int i = first; i < nkb; i += 2, ++j) {
-        const int s = i % num_stages;
-        const int k = (kb_begin + i) * TC_BK + c * 8;
-        float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
-        if (k < K) { w0 = *reinterpret_cast<const float4*>(nf.normw + k); w1 = *reinterpret_cast<const float4*>(nf.normw + k + 4); }
-        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        mbar_wait(&stg_bar[j % NF_DEPTH], ((uint32_t)(j / NF_DEPTH)) & 1u, 5, i);
-        mbar_wait(&empty_bar[s], (((uint32_t)(i / num_stages)) & 1u) ^ 1u, 1);
-        const float* src = reinterpret_cast<const float*>(stg + (j % NF_DEPTH) * NF_SLOT_BYTES);
-        const uint32_t tile = smem_u32(smem + s * Cfg::STAGE_BYTES + TC_A_BYTES);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int r = q * 4 + (lane >> 3);
-          const float rr = __shfl_sync(0xffffffffu, rstd, r);
-          const float4 xa = *reinterpret_cast<const float4*>(src + r * TC_BK + c * 8);
-          const float4 xb = *reinterpret_cast<const float4*>(src + r * TC_BK + c * 8 + 4);
-          const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-          uint32_t pk[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const float y0 = wv[2 * u] * bf16_round(xv[2 * u] * rr), y1 = wv[2 * u + 1] * bf16_round(xv[2 * u + 1] * rr);
-            const __nv_bfloat162 o = __floats2bfloat162_rn(y0, y1);
-            pk[u] = *reinterpret_cast<const uint32_t*>(&o);
-          }
-          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4))),
-                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-        }
-        fence_proxy_async();                                // generic-proxy stores -> visible to tcgen05.mma (async proxy)
-        __syncwarp();                                       // also: every lane is done with the staging slot
-        if (lane == 0) mbar_arrive(&full_bar[s]);
-        fetch(j + NF_DEPTH);
-      }
-    }
-  };
   if (warp == 0) {
     if (lane == 0) produce_w(0);
   } else if (warp == 1) {
@@ -329,9 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const int n = n0 + quarter * 32 + lane;
     float* out = C + (size_t)split * M * N;
     const int acc_used = (DUAL && nkb < 2) ? Cfg::NACC / 2 : Cfg::NACC;   // the second issuer's blocks stay unwritten
-    if (nf.xsrc != nullptr && (warp == 3 || warp == 4)) {
-      produce_x_norm(warp - 3);                 // whole warp
-    } else if (lane == 0) {                     // producer / second issuer duty first (see above), then the epilogue
+    if (lane == 0) {                            // producer / second issuer duty first (see above), then the epilogue
       if (warp == 2) produce_w(1);
       else if (warp == 5) { if (DUAL) issue_mma(1, 2, Cfg::NACC / 2, Cfg::NACC / 2); }
       else produce_x(warp - 3);
@@ -399,17 +310,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       mbar_wait(tmem_full_bar, 0, 3);
       if (warp == 2 && lane == 0) gemm_stamp(dbg, 4);
       tc_fence_after();
-      if (nf.xres != nullptr) {
-        // NormFuse producer: park the accumulator tile [token][128 rows] in this CTA's (now idle) first stage
-        float* red = reinterpret_cast<float*>(smem);
-#pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) red[(c0 + j) * TC_BM + quarter * 32 + lane] = __uint_as_float(v[j]);
-        }
-      } else if (!cg.enabled) {
+      if (!cg.enabled) {
         // plain split-K partial store (the decode step's hot epilogue: keep it branch-free)
 #pragma unroll 1
         for (int c0 = 0; c0 < NT; c0 += 16) {
@@ -454,56 +355,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         if (m < M) out[(size_t)m * N + n] = 0.f;
       }
     }
-  }
-  if (nf.xres != nullptr) {
-    // ---- cluster split-K reduction + residual update (see NormFuse); every thread of every CTA takes the barriers
-    __shared__ float ssq_s[4][NT];
-    cluster_sync_all();
-    if (warp >= 2) {
-      const int quarter = warp & 3, nl = quarter * 32 + lane, n = n0 + nl;
-      const uint32_t S = gridDim.z, rank = blockIdx.z;
-      const int tpr = (NT + (int)S - 1) / (int)S;          // tokens per rank
-      const float* red = reinterpret_cast<const float*>(smem);
-      for (int t0 = 0; t0 < tpr; t0 += 4) {
-        float part[4][8];
-#pragma unroll
-        for (int tt = 0; tt < 4; ++tt) {
-          const int tok = (int)rank * tpr + t0 + tt;
-#pragma unroll
-          for (uint32_t sp = 0; sp < 8; ++sp)
-            part[tt][sp] = (t0 + tt < tpr && tok < NT && sp < S) ? __uint_as_float(dsmem_ld_u32(red + tok * TC_BM + nl, sp)) : 0.f;
-        }
-#pragma unroll
-        for (int tt = 0; tt < 4; ++tt) {
-          const int tok = (int)rank * tpr + t0 + tt;
-          if (t0 + tt < tpr && tok < NT) {
-            float a = part[tt][0];
-#pragma unroll
-            for (uint32_t sp = 1; sp < 8; ++sp) if (sp < S) a += part[tt][sp];
-            for (uint32_t sp = 8; sp < S; ++sp) a += __uint_as_float(dsmem_ld_u32(red + tok * TC_BM + nl, sp));
-            float sq = 0.f;
-            if (tok < M && n < N) {
-              float* xp = nf.xres + (size_t)tok * N + n;
-              const float xn = bf16_round(*xp + bf16_round(a));   // residual add in the bf16-rounded stream
-              *xp = xn;
-              sq = xn * xn;
-            }
-            sq = warp_sum(sq);
-            if (lane == 0) ssq_s[quarter][tok] = sq;
-          }
-        }
-      }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      const int tid4 = threadIdx.x - 64;                     // 0..127 over the four epilogue warps (warps 2..5)
-      if (tid4 < tpr) {
-        const int tok = (int)rank * tpr + tid4;
-        if (tok < NT && tok < M) {
-          // quarters in tile-row order: warps 4, 5, 2, 3 hold rows 0-31, 32-63, 64-95, 96-127
-          nf.ssq_out[blockIdx.x * 32 + tok] = ((ssq_s[0][tok] + ssq_s[1][tok]) + ssq_s[2][tok]) + ssq_s[3][tok];
-        }
-      }
-    }
-    cluster_sync_all();                                       // nobody leaves while its tile can still be read
   }
   if (warp == 2 && lane == 0) gemm_stamp(dbg, 5);
   tc_fence_before();

@@ -44,153 +44,30 @@ PG_DEVINL float torch_exponential_at(uint64_t li, uint64_t stride, uint64_t seed
   return -lg;
 }
 
-constexpr int SAMPLE_THREADS = 1024;
-
 // logits: fp32 split partials [S][2B][V] of gen_head's second Linear (+ bias added here), or, when
 // bias == nullptr and S == 1, final logits handed in through the drop-in API.
 __device__ unsigned long long* g_sample_dbg = nullptr;   // debug timeline (tools/sample_timeline.py); nullptr in production
 #define SAMPLE_STAMP(k) do { if (g_sample_dbg && threadIdx.x == 0) g_sample_dbg[blockIdx.x * 16 + (k)] = global_timer_ns(); } while (0)
 
-template <typename T>
-__global__ void __launch_bounds__(SAMPLE_THREADS)
-cfg_sample_embed_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ bias,
-                        int B, int V, float cfg_weight, float temperature, uint64_t seed, uint64_t offset_base,
-                        uint64_t offset_per_step, uint64_t philox_stride, int greedy,
-                        const int32_t* __restrict__ edit_region, const int32_t* __restrict__ gt_labels,
-                        int step_base, const int* __restrict__ step_ptr, int n_steps,
-                        int32_t* __restrict__ tokens_out, const T* __restrict__ embed_table, int D,
-                        float* __restrict__ x_next, const float* __restrict__ next_norm_w, T* __restrict__ xn_next,
-                        float eps, int round_resid, float* __restrict__ dbg_logits) {
-  extern __shared__ float sh[];      // [V] CFG logits -> probabilities
-  __shared__ float red[32];
-  __shared__ float bestv[32];
-  __shared__ int besti[32];
-  __shared__ int tok_s;
-  pdl_launch_dependents();
-  SAMPLE_STAMP(0);
-  pdl_wait();
-  SAMPLE_STAMP(1);
-  const int b = blockIdx.x, tid = threadIdx.x;
-  const int step = step_base + (step_ptr ? *step_ptr : 0);
-  const uint64_t offset = offset_base + offset_per_step * (uint64_t)(step - step_base);
-  const size_t rc = (size_t)(2 * b) * V, ru = (size_t)(2 * b + 1) * V;
-  float mx = -INFINITY;
-  // eight elements (16 independent loads) in flight per thread: one element per iteration cost a full L2
-  // round trip each (measured 22 us for this loop at V = 16384)
-  for (int v0 = tid; v0 < V; v0 += 8 * SAMPLE_THREADS) {
-    float cs[8], us[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int v = v0 + j * SAMPLE_THREADS;
-      cs[j] = us[j] = 0.f;
-      if (v < V) {
-        if (S == 1) { cs[j] = __ldcg(part + rc + v); us[j] = __ldcg(part + ru + v); }
-        else { cs[j] = reduce_splits(part, S, split_stride, rc + v); us[j] = reduce_splits(part, S, split_stride, ru + v); }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int v = v0 + j * SAMPLE_THREADS;
-      if (v < V) {
-        float c = cs[j], u = us[j];
-        if (bias) { const float bb = bias[v]; c += bb; u += bb; }
-        c = Act<T>::rnd(c); u = Act<T>::rnd(u);
-        // logits = uncond + w * (cond - uncond); / temperature     (plangen_base.py:587-588); each op
-        // is a separate rounded elementwise kernel in the reference (bf16 under autocast)
-        float t = Act<T>::rnd(__fsub_rn(c, u));
-        t = Act<T>::rnd(__fmul_rn(cfg_weight, t));
-        t = Act<T>::rnd(__fadd_rn(u, t));
-        t = Act<T>::rnd(__fdiv_rn(t, temperature));
-        sh[v] = t;
-        if (dbg_logits) dbg_logits[((size_t)step * B + b) * V + v] = t;
-        mx = fmaxf(mx, t);
-      }
-    }
-  }
-  SAMPLE_STAMP(2);
-  mx = block_max(mx, red);
-  float sum = 0.f;
-  for (int v = tid; v < V; v += SAMPLE_THREADS) {
-    const float e = expf(sh[v] - mx);
-    sh[v] = e;
-    sum += e;
-  }
-  SAMPLE_STAMP(3);
-  sum = block_sum(sum, red);
-  // argmax over p/q (first index wins ties, like torch.argmax)
-  float bv = -INFINITY;
-  int bi = 0x7fffffff;
-  for (int v = tid; v < V; v += SAMPLE_THREADS) {
-    const float p = __fdiv_rn(sh[v], sum);
-    float score = p;
-    if (!greedy) {
-      const float q = torch_exponential_at((uint64_t)b * V + v, philox_stride, seed, offset);
-      score = __fdiv_rn(p, q);
-    }
-    if (score > bv || (score == bv && v < bi)) { bv = score; bi = v; }
-  }
-  SAMPLE_STAMP(4);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-  }
-  if ((tid & 31) == 0) { bestv[tid >> 5] = bv; besti[tid >> 5] = bi; }
-  __syncthreads();
-  if (tid < 32) {
-    bv = bestv[tid]; bi = besti[tid];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
-    }
-    if (tid == 0) {
-      int tok = bi;
-      // teacher forcing (plangen_base.py:593-598): outside the edit region keep the ground truth
-      if (edit_region != nullptr && edit_region[(size_t)b * n_steps + step] == 0) tok = gt_labels[(size_t)b * n_steps + step];
-      tok = min(max(tok, 0), V - 1);
-      tok_s = tok;
-      tokens_out[(size_t)b * n_steps + step] = tok;
-    }
-  }
-  __syncthreads();
-  SAMPLE_STAMP(5);
-  if (x_next == nullptr) return;
-  // next input = gen_aligner(gen_embed(tok)) duplicated to the cond and uncond rows (:602-604),
-  // plus (optionally) the first decoder layer's input RMSNorm of those rows
-  const T* erow = embed_table + (size_t)tok_s * D;
-  float ss = 0.f;
-  for (int d = tid; d < D; d += SAMPLE_THREADS) {
-    const float v = Act<T>::ld(erow + d);
-    x_next[(size_t)(2 * b) * D + d] = v;
-    x_next[(size_t)(2 * b + 1) * D + d] = v;
-    ss += v * v;
-  }
-  if (xn_next == nullptr) return;
-  SAMPLE_STAMP(6);
-  ss = block_sum(ss, red);
-  const float r = rsqrtf(ss / (float)D + eps);
-  for (int d = tid; d < D; d += SAMPLE_THREADS) {
-    float hn = Act<T>::ld(erow + d) * r;
-    if (round_resid) hn = Act<T>::rnd(hn);
-    const float y = next_norm_w[d] * hn;
-    Act<T>::st(xn_next + (size_t)(2 * b) * D + d, y);
-    Act<T>::st(xn_next + (size_t)(2 * b + 1) * D + d, y);
-  }
-  SAMPLE_STAMP(7);
-}
-
 // ---------------------------------------------------------------------------------------------------
-// Same operation on a thread-block CLUSTER: 8 CTAs per image, each owning an eighth of the vocabulary (and
-// of the embedding row).  One CTA per image kept a single SM busy for ~40 us per decode step (16 Philox
-// evaluations + logf + two IEEE divisions per thread, behind 16 dependent logit loads); the cluster spreads
-// the arithmetic over 128 SMs and combines max / sum / arg-max / sum of squares through distributed shared
-// memory in rank order (deterministic).  Per-element arithmetic is that of cfg_sample_embed_kernel; the
-// arg-max is order independent (value, then lowest index), so tokens only differ where the softmax
-// denominator's last bit decides.
+// A thread-block CLUSTER per image: 8 CTAs, each owning an eighth of the vocabulary (and of the embedding row).
+// One CTA per image kept a single SM busy for ~40 us per decode step (16 Philox evaluations + logf + two IEEE
+// divisions per thread, behind 16 dependent logit loads); the cluster spreads the arithmetic over 128 SMs and
+// combines max / sum / arg-max / sum of squares through distributed shared memory in rank order (deterministic).
+// The arg-max is order independent (value, then lowest index).
+//
+// top_k > 0 (north_star (4); the reference has none, so 0 = off is the default): only logits >= the k-th largest
+// CFG logit of the image survive (`logits[logits < topk(logits, k).values[..., -1:]] = -inf`, ties at the threshold
+// kept), the rest get probability 0; softmax and the Philox draw still run over the full (B, V) tensor, so the
+// result equals torch.multinomial on the masked distribution with the same generator.  The threshold is found by
+// a 4-pass radix select (8 bits per pass) over an order-preserving integer key, histograms summed across the
+// cluster through distributed shared memory.
 constexpr int SAMPLE_CLUSTER = 8;
+// order-preserving map float -> uint32 (larger value, larger key; -0 < +0 is harmless here)
+PG_DEVINL uint32_t sample_order_key(float t) {
+  const uint32_t u = __float_as_uint(t);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
 #ifndef PG_SAMPLE_CL_THREADS
 #define PG_SAMPLE_CL_THREADS 256
 #endif
@@ -205,13 +82,16 @@ template <typename T>
 __global__ void __cluster_dims__(SAMPLE_CLUSTER, 1, 1) __launch_bounds__(SAMPLE_CL_THREADS)
 cfg_sample_embed_cluster_kernel(const float* __restrict__ part, int S, size_t split_stride, const float* __restrict__ bias,
                                 int B, int V, float cfg_weight, float temperature, uint64_t seed, uint64_t offset_base,
-                                uint64_t offset_per_step, uint64_t philox_stride, int greedy,
+                                uint64_t offset_per_step, uint64_t philox_stride, int greedy, int top_k,
                                 const int32_t* __restrict__ edit_region, const int32_t* __restrict__ gt_labels,
                                 int step_base, const int* __restrict__ step_ptr, int n_steps,
                                 int32_t* __restrict__ tokens_out, const T* __restrict__ embed_table, int D,
                                 float* __restrict__ x_next, const float* __restrict__ next_norm_w, T* __restrict__ xn_next,
                                 float eps, int round_resid, float* __restrict__ dbg_logits) {
   extern __shared__ float sh[];      // this CTA's slice of the CFG logits -> unnormalised probabilities
+  __shared__ int hist[4][256];       // top-k radix select: one histogram per pass (read by the other CTAs)
+  __shared__ int hsum[256];
+  __shared__ uint32_t sel_s[2];      // {digit, remaining k} of the current pass
   __shared__ float red[32];
   __shared__ float bestv[32];
   __shared__ int besti[32];
@@ -258,6 +138,62 @@ cfg_sample_embed_cluster_kernel(const float* __restrict__ part, int S, size_t sp
     }
   }
   SAMPLE_STAMP(2);
+  if (top_k > 0 && top_k < V) {
+    // k-th largest CFG logit of the image: radix select on key(t) (monotone in t), most significant byte first
+    for (int i = tid; i < 4 * 256; i += SAMPLE_CL_THREADS) (&hist[0][0])[i] = 0;
+    __syncthreads();
+    uint32_t prefix = 0, krem = (uint32_t)top_k;
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      const uint32_t himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int v = v_lo + tid; v < v_hi; v += SAMPLE_CL_THREADS) {
+        const uint32_t key = sample_order_key(sh[v - v_lo]);
+        if ((key & himask) == prefix) atomicAdd(&hist[pass][(key >> shift) & 255u], 1);
+      }
+      cluster_sync_all();                                  // every CTA's histogram of this pass is complete
+      for (int d = tid; d < 256; d += SAMPLE_CL_THREADS) {
+        int c = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < SAMPLE_CLUSTER; ++r) c += (int)dsmem_ld_u32(&hist[pass][d], r);
+        hsum[d] = c;
+      }
+      __syncthreads();
+      if (tid < 32) {
+        // lane l owns digits 8l .. 8l+7; suffix counts from the top digit down
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mine += hsum[tid * 8 + j];
+        // suffix scan over the 32 lanes: above = elements in digits owned by higher lanes
+        int run = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_down_sync(0xffffffffu, run, o);
+          if (tid + o < 32) run += t;
+        }
+        const int above = run - mine;
+        const bool here = (uint32_t)above < krem && (uint32_t)(above + mine) >= krem;   // exactly one lane
+        if (here) {
+          int cum = above;
+          for (int j = 7; j >= 0; --j) {
+            const int c = hsum[tid * 8 + j];
+            if ((uint32_t)(cum + c) >= krem) { sel_s[0] = (uint32_t)(tid * 8 + j); sel_s[1] = krem - (uint32_t)cum; break; }
+            cum += c;
+          }
+        }
+      }
+      __syncthreads();
+      prefix |= sel_s[0] << shift;
+      krem = sel_s[1];
+      __syncthreads();
+    }
+    // prefix = key of the k-th largest logit: everything below it leaves the distribution
+    mx = -INFINITY;
+    for (int v = v_lo + tid; v < v_hi; v += SAMPLE_CL_THREADS) {
+      float t = sh[v - v_lo];
+      if (sample_order_key(t) < prefix) { t = -INFINITY; sh[v - v_lo] = t; }
+      mx = fmaxf(mx, t);
+    }
+  }
   mx = block_max(mx, red);
   if (tid == 0) xc.mx = mx;
   cluster_sync_all();

@@ -42,11 +42,14 @@ def kv_start_from_mask(mask: torch.Tensor, P: int) -> torch.Tensor:
     plangen_base.py:708-712,668,686): number of leading pad columns per row.  Any other mask shape is
     rejected - the reference never produces one on this path."""
     m = (mask[:, :P] != 0)
-    if mask.shape[1] > P and not bool((mask[:, P:] != 0).all()):
-        raise ValueError("attention_mask must be all ones on the image-token part")
     first = torch.where(m.any(1), m.int().argmax(1), torch.full((m.shape[0],), P, device=m.device))
     ar = torch.arange(P, device=m.device)[None, :]
-    if not bool((m == (ar >= first[:, None])).all()):
+    tail_ok = (mask[:, P:] != 0).all() if mask.shape[1] > P else torch.ones((), dtype=torch.bool, device=m.device)
+    left_ok = (m == (ar >= first[:, None])).all()
+    ok = int(tail_ok) + 2 * int(left_ok) if mask.device.type == "cpu" else int((tail_ok.int() + 2 * left_ok.int()).item())  # one sync
+    if not ok & 1:
+        raise ValueError("attention_mask must be all ones on the image-token part")
+    if not ok & 2:
         raise ValueError("attention_mask must be LEFT padded (zeros then ones)")
     return first.to(torch.int32).contiguous()
 
@@ -196,12 +199,15 @@ class FastJanus:
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], dims: Dims, mode: str = "bf16",
                  max_batch: int = 16, max_prompt: int = 512, max_steps: Optional[int] = None,
-                 device: str = "cuda:0", seed: int = 0, with_vq: bool = True, options: Optional[dict] = None):
+                 device: str = "cuda:0", seed: int = 0, with_vq: bool = True, options: Optional[dict] = None,
+                 use_teacher_forcing: bool = False, top_k: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("plangen_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if mode not in MODE_IDS:
             raise ValueError(mode)
         self.dims, self.mode, self.seed = dims, mode, seed
+        self.use_teacher_forcing = bool(use_teacher_forcing)      # args.use_teacher_forcing (plangen_base.py:528,556,593)
+        self.top_k = int(top_k)                                   # 0 = off (the reference has no top-k)
         self.device = torch.device(device)
         self.out_dtype = torch.bfloat16 if mode == "bf16" else torch.float32
         self.max_rows = 2 * max_batch
@@ -298,12 +304,13 @@ class FastJanus:
 
     def cfg_sample_embed(self, logits: torch.Tensor, cfg_weight: float, temperature: float, seed: int, offset: int,
                          step: int, n_steps: int, tokens_out: torch.Tensor, greedy: bool = False,
-                         edit_region: Optional[torch.Tensor] = None, gt_labels: Optional[torch.Tensor] = None):
+                         edit_region: Optional[torch.Tensor] = None, gt_labels: Optional[torch.Tensor] = None,
+                         top_k: int = 0):
         """plangen_base.py:580-604 in one launch; returns the next inputs_embeds (2B, D) fp32."""
         B = logits.shape[0] // 2
         lg = logits.to(device=self.device, dtype=torch.float32).contiguous()
         x_next = torch.empty(2 * B, self.dims.D, device=self.device, dtype=torch.float32)
-        _lib.check(self._lib.pg_cfg_sample_embed(self._h, _ptr(lg), B, cfg_weight, temperature, seed, offset, int(greedy),
+        _lib.check(self._lib.pg_cfg_sample_embed(self._h, _ptr(lg), B, cfg_weight, temperature, seed, offset, int(greedy), int(top_k),
                                                  _ptr(edit_region), _ptr(gt_labels), step, n_steps, _ptr(tokens_out),
                                                  _ptr(x_next), _stream_ptr(self.device)))
         return x_next
@@ -314,12 +321,39 @@ class FastJanus:
         return ((numel - 1) // (256 * grid * 4) + 1) * 4
 
     # ------------------------------------------------------------------ fused fast path
+    def _teacher_inputs(self, batch, gt_labels, num_gen: int, n: int):
+        """`edit_region` / `gt_labels` of the reference's override loop (plangen_base.py:593-598) as (num_gen, n) int32.
+        The reference overrides rows `bid in range(len(edit_region))` only: with parallel_size > 1 the extra copies are
+        sampled freely, so rows >= bs get edit_region = 1 (no override)."""
+        if batch is None or batch.get("edit_region") is None:
+            raise ValueError("use_teacher_forcing needs batch['edit_region'] (plangen_base.py:594)")
+        if gt_labels is None:
+            raise ValueError("use_teacher_forcing needs gt_labels (or gt_image for t2i to encode, plangen_base.py:528-532)")
+        er = batch["edit_region"].to(device=self.device, dtype=torch.int32)
+        bs = er.shape[0]
+        er = er.reshape(bs, -1)
+        gl = gt_labels.to(device=self.device, dtype=torch.int32).reshape(gt_labels.shape[0], -1)
+        if gl.shape[0] != bs:
+            raise ValueError(f"gt_labels has {gl.shape[0]} rows, edit_region {bs}")
+        if bs > num_gen:
+            raise ValueError(f"edit_region has {bs} rows but only {num_gen} images are generated")
+        if er.shape[1] < n or gl.shape[1] < n:
+            raise ValueError(f"edit_region / gt_labels need at least {n} columns (got {er.shape[1]}, {gl.shape[1]})")
+        er, gl = er[:, :n], gl[:, :n]
+        if bs < num_gen:
+            er = torch.cat([er, torch.ones(num_gen - bs, n, dtype=torch.int32, device=self.device)])
+            gl = torch.cat([gl, torch.zeros(num_gen - bs, n, dtype=torch.int32, device=self.device)])
+        return er.contiguous(), gl.contiguous()
+
     @torch.inference_mode()
     def sample_image(self, inputs_embeds, num_gen, image_token_num_per_image, mask, cfg_weight, temperature,
-                     generator=None, batch=None, gt_labels=None, greedy: bool = False):
+                     generator=None, batch=None, gt_labels=None, greedy: bool = False,
+                     use_teacher_forcing: Optional[bool] = None, top_k: Optional[int] = None):
         """System.sample_image (plangen_base.py:567-607).  `generator`: torch CUDA generator (its seed and
-        philox offset are honoured and advanced) or an int seed.  Teacher forcing when `batch` carries
-        'edit_region' and gt_labels is given (:593-598)."""
+        philox offset are honoured and advanced) or an int seed.  Teacher forcing (:593-598) is gated on
+        `use_teacher_forcing` (default: the engine's flag = `args.use_teacher_forcing`), never on the mere presence
+        of batch['edit_region'] - the reference's datasets emit an all-zero edit_region for non-edit samples.
+        `top_k` > 0 keeps the k largest CFG logits before the softmax (north_star (4); 0 = off = the reference)."""
         R, P, D = inputs_embeds.shape
         if R != 2 * num_gen:
             raise ValueError("inputs_embeds rows must be 2 * num_gen (interleaved cond/uncond)")
@@ -334,13 +368,14 @@ class FastJanus:
                     else torch.zeros(R, dtype=torch.int32, device=self.device))
         x = inputs_embeds.to(device=self.device, dtype=torch.float32).contiguous().clone()
         tokens = torch.zeros(num_gen, n, dtype=torch.int32, device=self.device)
+        teacher = self.use_teacher_forcing if use_teacher_forcing is None else bool(use_teacher_forcing)
         er = gl = None
-        if gt_labels is not None and batch is not None and batch.get("edit_region") is not None:
-            er = batch["edit_region"].to(device=self.device, dtype=torch.int32).reshape(num_gen, -1)[:, :n].contiguous()
-            gl = gt_labels.to(device=self.device, dtype=torch.int32).reshape(num_gen, -1)[:, :n].contiguous()
+        if teacher:
+            er, gl = self._teacher_inputs(batch, gt_labels, num_gen, n)
+        k = int(self.top_k if top_k is None else top_k)
         self._keep = (kv_start, x, er, gl)        # keep alive until the stream has consumed them
         _lib.check(self._lib.pg_sample_image(self._h, _ptr(x), _ptr(kv_start), R, P, n, float(cfg_weight),
-                                             float(temperature), seed, int(greedy), _ptr(er), _ptr(gl), _ptr(tokens),
+                                             float(temperature), seed, int(greedy), k, _ptr(er), _ptr(gl), _ptr(tokens),
                                              _stream_ptr(self.device)))
         self._serial += 1
         if isinstance(generator, torch.Generator):
@@ -350,17 +385,18 @@ class FastJanus:
     @torch.inference_mode()
     def t2i(self, inputs_ids=None, parallel_size=1, image_token_num_per_image=None, cfg_weight=5.0, temperature=1.0,
             img_size=None, patch_size=None, gt_image=None, batch=None, mask=None, tokens=None, emb=None,
-            gt_labels=None, greedy: bool = False):
+            gt_labels=None, greedy: bool = False, use_teacher_forcing: Optional[bool] = None, top_k: Optional[int] = None):
         """System.t2i (plangen_base.py:525-565), `tokens`/`emb` branches.  Returns (dec, mask_image).
-        Teacher forcing (layout-guided editing, `args.use_teacher_forcing`, :528-532, :593-598, :557-562) is on when
-        `batch` carries 'edit_region' and either `gt_image` (encoded here with the VQ encoder, as the reference does)
-        or ready-made `gt_labels` is given."""
+        Teacher forcing (layout-guided editing, :528-532, :593-598, :557-562) follows `use_teacher_forcing` (default: the
+        engine's flag, the counterpart of `args.use_teacher_forcing`): `gt_image` is encoded with the VQ encoder as the
+        reference does (or ready-made `gt_labels` are used), and `mask_image` is returned.  With the flag off `gt_image` and
+        batch['edit_region'] are ignored, exactly as in the reference."""
         n = image_token_num_per_image or self.dims.n_img_tokens
         img_size = img_size or self.dims.img_size
         patch_size = patch_size or 2 ** (len(self.dims.vq_ch_mult) - 1)      # 16 for VQ-16
         if tokens is None and emb is None:
             raise NotImplementedError("pass `tokens` (2B, P) or `emb`; the un-batched branch is unused by PlanGen")
-        teacher = batch is not None and batch.get("edit_region") is not None
+        teacher = self.use_teacher_forcing if use_teacher_forcing is None else bool(use_teacher_forcing)
         if teacher and gt_labels is None and gt_image is not None:
             gt_images = gt_image.to(device=self.device, dtype=self.out_dtype)          # `gt_image.bfloat16()` (:530)
             gt_labels = self.gen_vision_model.encode(gt_images)[-1][-1].reshape(gt_images.shape[0], -1)
@@ -371,17 +407,28 @@ class FastJanus:
             inputs_embeds = emb
         mask = torch.cat([mask.to(self.device)] * parallel_size)
         num_gen = inputs_embeds.shape[0] // 2
-        gen = self.sample_image(inputs_embeds, num_gen, n, mask, cfg_weight, temperature, None, batch, gt_labels, greedy)
+        gen = self.sample_image(inputs_embeds, num_gen, n, mask, cfg_weight, temperature, None, batch, gt_labels, greedy,
+                                use_teacher_forcing=teacher, top_k=top_k)
         g = img_size // patch_size
         dec = self.gen_vision_model.decode_code(gen.to(dtype=torch.int), shape=[num_gen, self.dims.code_dim, g, g])
         self.last_tokens = gen
         mask_image = None
-        if teacher and gt_labels is not None:
-            # resize_pt(edit_region.reshape(bs,1,g,g).repeat(1,3,1,1), janus_hw).to(dec)   (:559-560; torchvision Resize =
-            # bilinear interpolation, antialiasing is a no-op when upscaling)
+        if teacher:
+            # resize_pt(edit_region.reshape(bs,1,g,g).repeat(1,3,1,1), janus_hw).to(dec)   (:559-560).  resize_pt is a
+            # torchvision Resize on the LONG tensor: bilinear interpolation in float, then round and cast back to int64,
+            # so the reference's mask is binary before `.to(dec)`
             er = batch["edit_region"].to(self.device).reshape(-1, 1, g, g).repeat(1, 3, 1, 1).float()
-            mask_image = torch.nn.functional.interpolate(er, size=(img_size, img_size), mode="bilinear", align_corners=False).to(dec)
+            mask_image = torch.nn.functional.interpolate(er, size=(img_size, img_size), mode="bilinear",
+                                                         align_corners=False).round().to(dec)
         return dec, mask_image
+
+    def images_to_uint8(self, dec: torch.Tensor) -> torch.Tensor:
+        """denorm_pt (src/utils/funcs.py:511-512) then `(x*255).astype(np.uint8)` (funcs.py:497-498, truncation) on the
+        device: (B,3,H,W) float -> uint8, one kernel (pg_images_to_u8)."""
+        x = dec.to(device=self.device, dtype=torch.float32).contiguous()
+        out = torch.empty(x.shape, dtype=torch.uint8, device=self.device)
+        _lib.check(self._lib.pg_images_to_u8(self._h, _ptr(x), x.numel(), _ptr(out), _stream_ptr(self.device)))
+        return out
 
     # ------------------------------------------------------------------ host-buffer entry (end to end)
     @torch.inference_mode()
@@ -391,8 +438,7 @@ class FastJanus:
         ids = ids_host.to(self.device, non_blocking=True)
         mask = mask_host.to(self.device, non_blocking=True)
         dec, _ = self.t2i(tokens=ids, mask=mask, cfg_weight=cfg_weight, temperature=temperature)
-        # denorm_pt (src/utils/funcs.py:511-512) then `(x*255).astype(np.uint8)` (funcs.py:508): truncation
-        img = (((dec.float().clamp(-1, 1) + 1) / 2) * 255).to(torch.uint8)
+        img = self.images_to_uint8(dec)
         if out_host is None:
             out_host = torch.empty(img.shape, dtype=torch.uint8, pin_memory=True)
         out_host.copy_(img, non_blocking=True)

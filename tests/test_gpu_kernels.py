@@ -83,6 +83,42 @@ def test_sampler_is_bit_exact_with_torch_multinomial(B, V):
         assert off2 == off and eng.philox_offset_per_step(B) == off2 // (step + 1)
 
 
+@pytest.mark.parametrize("B,V,k", [(3, 16384, 50), (2, 16384, 1), (4, 2048, 2047), (16, 16384, 1000)])
+def test_sampler_top_k_matches_torch_topk_masked_multinomial(B, V, k):
+    """north_star (4) top-k: `logits[logits < topk(logits, k).values[..., -1:]] = -inf` before the softmax, then the same
+    Philox draw: tokens equal torch.multinomial on the masked distribution for the same (seed, offset); every sampled
+    token lies inside the top-k set; top_k = 0 and top_k >= V reproduce the unmasked sampler bit for bit."""
+    d = O.JanusDims(**{**O.TINY.__dict__, "name": f"tiny-v{V}", "img_vocab": V})
+    eng = get_engine(d, "fp32", max_batch=max(B, 4), with_vq=False)
+    gen = torch.Generator(device="cuda").manual_seed(77)
+    tg = torch.Generator(device="cuda").manual_seed(5 + k)
+    n_steps = 4
+    toks = torch.zeros(B, n_steps, dtype=torch.int32, device="cuda")
+    off = 0
+    for step in range(n_steps):
+        logits = torch.randn(2 * B, V, device="cuda", generator=tg) * 2.0
+        if step == 1:                                       # ties at the threshold are kept (like the torch idiom)
+            logits[:, : V // 2] = logits[:, V // 2: 2 * (V // 2)]
+        cfg = logits[1::2] + 5.0 * (logits[0::2] - logits[1::2])
+        kth = torch.topk(cfg, k, dim=-1).values[:, -1:]
+        masked = cfg.masked_fill(cfg < kth, float("-inf"))
+        probs = torch.softmax(masked / 1.0, dim=-1)
+        want = torch.multinomial(probs, 1, generator=gen).squeeze(-1)
+        eng.cfg_sample_embed(logits, 5.0, 1.0, 77, off, step, n_steps, toks, top_k=k)
+        torch.cuda.synchronize()
+        assert toks[:, step].tolist() == want.tolist(), f"step {step}"
+        assert bool((cfg.gather(1, toks[:, step:step + 1].long()) >= kth).all())
+        off = gen.get_offset()
+    # off / degenerate settings are the plain sampler
+    logits = torch.randn(2 * B, V, device="cuda", generator=tg)
+    outs = []
+    for kk in (0, V, V + 5):
+        t = torch.zeros(B, 1, dtype=torch.int32, device="cuda")
+        eng.cfg_sample_embed(logits, 5.0, 1.0, 3, 0, 0, 1, t, top_k=kk)
+        outs.append(t.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
 def test_sampler_teacher_forcing_and_greedy():
     eng = get_engine(O.TINY, "fp32")
     B, V, n = 2, O.TINY.img_vocab, 3

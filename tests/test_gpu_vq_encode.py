@@ -148,12 +148,43 @@ def test_t2i_editing_branch_teacher_forcing_from_gt_image():
     labels = eng.gen_vision_model.encode(gt_image.to(torch.bfloat16))[-1][-1].reshape(B, -1)
     free, _ = eng.t2i(tokens=ids.cuda(), mask=mask.cuda()), None
     free_tok = eng.last_tokens.clone()
-    dec0, m0 = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": torch.zeros(B, n, dtype=torch.int64)})
+    dec0, m0 = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": torch.zeros(B, n, dtype=torch.int64)},
+                      use_teacher_forcing=True)
     assert torch.equal(eng.last_tokens.long(), labels) and m0.shape == dec0.shape and float(m0.abs().max()) == 0.0
-    dec1, m1 = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": torch.ones(B, n, dtype=torch.int64)})
+    dec1, m1 = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": torch.ones(B, n, dtype=torch.int64)},
+                      use_teacher_forcing=True)
     assert torch.equal(eng.last_tokens, free_tok) and float(m1.min()) == 1.0
     er = (torch.rand(B, n, generator=g) > 0.5).long()
-    eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": er})
+    eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": er}, use_teacher_forcing=True)
     got = eng.last_tokens.long().cpu()
     keep = er == 0
     assert torch.equal(got[keep], labels.cpu()[keep])
+
+
+def test_t2i_ignores_edit_region_when_teacher_forcing_is_off():
+    """the reference gates teacher forcing on args.use_teacher_forcing (plangen_base.py:528,556,593),
+    and its datasets emit an all-zero edit_region for plain layout-to-image samples (data_hico.py:355,367) while
+    uni_generate always passes gt_image.  With the flag off the call must be a free generation: same tokens as without
+    gt_image / batch, no mask image.  With the flag on and parallel_size = 2, only the first bs rows are overridden."""
+    d = O.SMALL
+    eng, sd = _engine(d, "bf16")
+    B, n, side = 2, d.n_img_tokens, d.grid * 2 ** (len(d.vq_ch_mult) - 1)
+    cond, neg = O.synthetic_prompts(d, B, seed=6, lo=9, hi=40, neg_len=13)
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, d.pad_id, n)
+    g = torch.Generator().manual_seed(3)
+    gt_image = (torch.rand(B, 3, side, side, generator=g) * 2 - 1).cuda()
+    batch = {"edit_region": torch.zeros(B, n, dtype=torch.int64)}
+    eng.t2i(tokens=ids.cuda(), mask=mask.cuda())
+    free_tok = eng.last_tokens.clone()
+    dec, mask_image = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch=batch)
+    assert mask_image is None and torch.equal(eng.last_tokens, free_tok)
+    labels = eng.gen_vision_model.encode(gt_image.to(torch.bfloat16))[-1][-1].reshape(B, -1)
+    assert not torch.equal(free_tok.long(), labels)
+    # flag on, two parallel copies: rows 0..B-1 reproduce the labels, rows B..2B-1 are sampled freely
+    eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), parallel_size=2, gt_image=gt_image, batch=batch, use_teacher_forcing=True)
+    tok = eng.last_tokens.long()
+    assert tok.shape == (2 * B, n) and torch.equal(tok[:B], labels) and not torch.equal(tok[B:], labels)
+    # mask image is binary (resize_pt rounds back to integers, plangen_base.py:560)
+    er = (torch.rand(B, n, generator=g) > 0.5).long()
+    _, m = eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=gt_image, batch={"edit_region": er}, use_teacher_forcing=True)
+    assert set(m.float().unique().tolist()) <= {0.0, 1.0}

@@ -23,7 +23,8 @@ def test_library_builds_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(cdll, name), f"{name} declared in include/plangen_b200.h but not exported"
     assert declared == set(_lib.EXPORTS), "ctypes table and header disagree"
-    assert cdll.pg_abi_version() == 1
+    m = re.search(r"#define PG_ABI_VERSION (\d+)", header)
+    assert cdll.pg_abi_version() == int(m.group(1))
 
 
 def test_engine_fails_loudly_without_gpu():
@@ -105,6 +106,11 @@ mine = dp.shard_batches(5, rank, world)
 local = torch.full((2, 3, 4, 4), rank, dtype=torch.uint8)
 allimg = dp.gather_images(local, world)
 assert allimg.shape == (2 * world, 3, 4, 4) and allimg[2 * rank].eq(rank).all() and allimg[2 * (1 - rank)].eq(1 - rank).all()
+# unequal shares (5 batches over 2 ranks): rank 0 holds 3 images, rank 1 holds 2; nobody hangs, order is rank-major
+uneven = dp.gather_images(torch.full((len(mine), 3, 4, 4), 10 + rank, dtype=torch.uint8), world)
+assert uneven.shape == (5, 3, 4, 4) and uneven[:3].eq(10).all() and uneven[3:].eq(11).all()
+only0 = dp.gather_images(torch.full((1 if rank == 0 else 0, 3, 4, 4), 7, dtype=torch.uint8), world)
+assert only0.shape == (1, 3, 4, 4) and only0.eq(7).all()
 t = dp.max_over_ranks(1.0 + rank, torch.device("cpu"))
 assert t == float(world)
 sys.stdout.write("rank %d batches %s\n" % (rank, mine)); sys.stdout.flush()
@@ -212,6 +218,10 @@ def test_bench_reference_arm_prints_the_contract_line(capsys):
     assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": bench.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["vs_baseline"] is None
+    # nothing is extrapolated: the line's time is the wall time of the one image that was run, value = 1 / that time
+    assert abs(d["ms_per_step"] * d["steps"] - 1e3 * d["timed"]["wall_s"]) < 1e-6 * d["timed"]["wall_s"] * 1e3 + 1e-9
+    assert abs(d["value"] * d["timed"]["wall_s"] - 1.0) < 1e-9 and d["timed"]["decode_steps"] == O.TINY.n_img_tokens - 1
+    assert d["cpu_baseline_b16"]["images_per_s_estimate"] > 0
     # ranks other than 0 do no work and print nothing
     os.environ["RANK"] = "1"
     try:
@@ -219,3 +229,38 @@ def test_bench_reference_arm_prints_the_contract_line(capsys):
         assert capsys.readouterr().out.strip() == ""
     finally:
         os.environ.pop("RANK", None)
+
+
+# ------------------------------------------------------------------ teacher-forcing gate (plangen_base.py:528,593)
+def test_teacher_inputs_validation_and_padding():
+    """`_teacher_inputs` mirrors the reference's override loop: exactly `len(edit_region)` rows are overridden, rows of
+    further parallel copies are sampled freely (edit_region = 1), malformed shapes are rejected."""
+    import types
+    import torch
+    from plangen_b200.engine import FastJanus
+    stub = types.SimpleNamespace(device=torch.device("cpu"))
+    f = FastJanus._teacher_inputs
+    er = torch.zeros(2, 6, dtype=torch.int64)
+    gt = torch.arange(12).reshape(2, 6)
+    e, g = f(stub, {"edit_region": er}, gt, 2, 6)
+    assert e.dtype == torch.int32 and e.shape == (2, 6) and g.tolist() == gt.tolist()
+    e, g = f(stub, {"edit_region": er}, gt, 4, 6)                     # parallel_size = 2: rows 2, 3 are free
+    assert e.shape == (4, 6) and e[:2].eq(0).all() and e[2:].eq(1).all() and g[:2].tolist() == gt.tolist()
+    e, g = f(stub, {"edit_region": er}, gt, 2, 4)                     # fewer steps than columns: leading columns
+    assert e.shape == (2, 4) and g.tolist() == gt[:, :4].tolist()
+    for bad in (lambda: f(stub, None, gt, 2, 6), lambda: f(stub, {"edit_region": er}, None, 2, 6),
+                lambda: f(stub, {"edit_region": er}, gt[:1], 2, 6), lambda: f(stub, {"edit_region": er}, gt, 1, 6),
+                lambda: f(stub, {"edit_region": er}, gt, 2, 7)):
+        with pytest.raises(ValueError):
+            bad()
+
+
+def test_kv_start_from_mask_contract():
+    import torch
+    from plangen_b200.engine import kv_start_from_mask
+    m = torch.tensor([[0, 0, 1, 1, 1, 1], [1, 1, 1, 1, 1, 1], [0, 0, 0, 0, 1, 1]])
+    assert kv_start_from_mask(m, 4).tolist() == [2, 0, 4]
+    with pytest.raises(ValueError):
+        kv_start_from_mask(torch.tensor([[1, 0, 1, 1, 1, 1]]), 4)
+    with pytest.raises(ValueError):
+        kv_start_from_mask(torch.tensor([[0, 1, 1, 1, 0, 1]]), 4)

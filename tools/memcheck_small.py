@@ -20,6 +20,6 @@ emb = eng.language_model.get_input_embeddings()(tids.cuda())
 txt = eng.language_model.generate(inputs_embeds=emb, attention_mask=tmask.cuda(), pad_token_id=d.vocab - 1, eos_token_id=d.vocab - 1, max_new_tokens=20)
 side = d.grid * 2 ** (len(d.vq_ch_mult) - 1)
 img = torch.rand(3, 3, side, side, generator=g).cuda() * 2 - 1
-eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=img, batch={"edit_region": torch.zeros(3, d.n_img_tokens, dtype=torch.int64)})
+eng.t2i(tokens=ids.cuda(), mask=mask.cuda(), gt_image=img, batch={"edit_region": torch.zeros(3, d.n_img_tokens, dtype=torch.int64)}, use_teacher_forcing=True)
 torch.cuda.synchronize()
 print("ok", tuple(dec.shape), tuple(txt.shape), eng.last_tokens[0, :4].tolist())

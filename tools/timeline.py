@@ -6,7 +6,7 @@ from plangen_b200 import JANUS_1P3B, synthetic
 from plangen_b200.engine import FastJanus
 B = int(os.environ.get("PG_B", "16")); dims = JANUS_1P3B; dev = torch.device("cuda", 0)
 sd = synthetic.random_state_dict(dims, dev, seed=0, with_vq=False)
-eng = FastJanus(sd, dims, mode="bf16", max_batch=B, max_prompt=512, with_vq=False, options={"use_graph": int(os.environ.get("PG_GRAPH", "1")), "fuse_swiglu": int(os.environ.get("PG_FUSE", "1")), "fuse_norm": int(os.environ.get("PG_FUSE_NORM", "0"))})
+eng = FastJanus(sd, dims, mode="bf16", max_batch=B, max_prompt=512, with_vq=False, options={"use_graph": int(os.environ.get("PG_GRAPH", "1")), "fuse_swiglu": int(os.environ.get("PG_FUSE", "1"))})
 del sd
 cond, neg = synthetic.layoutsam_prompts(dims, B, seed=1234)
 ids, mask = synthetic.collate_cfg_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
