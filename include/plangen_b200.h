@@ -37,6 +37,9 @@ typedef struct pg_dims {
   int32_t max_rows;                  /* R = 2 * B * parallel_size upper bound */
   int32_t max_prompt;                /* padded prompt length P upper bound */
   int32_t max_steps;                 /* image tokens per image (576) upper bound */
+  /* mmu front-end (SigLIP vision tower, siglip_vit.py:628-637 SigLIP_MODEL_CONFIG); sig_layers = 0 or max_images = 0: not built */
+  int32_t sig_width, sig_layers, sig_heads, sig_patch, sig_image, sig_mlp;
+  int32_t max_images;                /* images per prepare_inputs_embeds call upper bound */
 } pg_dims;
 
 const char* pg_last_error(void);
@@ -131,6 +134,22 @@ int pg_vq_decode_code(pg_engine* e, const int32_t* codes, int B, int gh, int gw,
  * image fp32 NCHW [B,3,H,W] in [-1,1] (H, W multiples of 16) -> codes int32 [B, (H/16)*(W/16)]: index of the nearest
  * L2-normalised codebook entry per position (first index on ties).  Needs the optional encoder / quant_conv tensors. */
 int pg_vq_encode(pg_engine* e, const float* image, int B, int H, int W, int32_t* codes_out, void* stream);
+
+/* replaces: vl_gpt.prepare_inputs_embeds(input_ids, pixel_values, images_seq_mask, images_emb_mask)
+ *           (plangen_base.py:289,366,855 -> three_party/Janus/janus/models/modeling_vlm.py:221-268): every image through the
+ *           SigLIP vision tower (clip_encoder.py:107-122, siglip_vit.py:562-591) and the `aligner` MLP (projector.py:39-45),
+ *           scattered into the text embeddings at the positions images_seq_mask selects; ids < 0 are embedded as id 0.
+ * mmu front-end.  pixel_values fp32 [n_images,3,S,S] ("b n c h w" flattened over (b n)); input_ids
+ * int32 [B*T]; images_seq_mask uint8 [B*T]; images_emb_mask uint8 [n_images * n_patches]; embeds_out fp32 [B,T,D].
+ * Fails if the two masks select different counts (the reference asserts it).  Synchronises `stream` once (that check).
+ * Needs the optional tensors sig.* / ualign.* and pg_dims.sig_layers > 0, max_images > 0. */
+int pg_prepare_inputs_embeds(pg_engine* e, const float* pixel_values, int n_images, const int32_t* input_ids,
+                             const uint8_t* images_seq_mask, const uint8_t* images_emb_mask, int B, int T,
+                             float* embeds_out, void* stream);
+
+/* Vision tower + aligner alone: aligner(vision_model(images)) (modeling_vlm.py:250), pixel fp32 [n,3,S,S] ->
+ * feat_out fp32 [n * n_patches, D] (NULL: features stay in the engine; bench). */
+int pg_vision_features(pg_engine* e, const float* pixel_values, int n_images, float* feat_out, void* stream);
 
 /* replaces: denorm_pt + `(x*255).astype(np.uint8)` of the image writers (src/utils/funcs.py:511-512, :497-498;
  *           plangen_base.py:444, :1168-1181): image fp32 [n] in about [-1,1] -> uint8 [n] = trunc(((clamp(x,-1,1)+1)/2)*255) */

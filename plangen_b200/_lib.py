@@ -20,6 +20,8 @@ class PgDims(C.Structure):
         ("vq_ch", C.c_int32), ("vq_nres", C.c_int32), ("vq_ch_mult", C.c_int32 * 8), ("vq_z", C.c_int32),
         ("vq_res_blocks", C.c_int32), ("mode", C.c_int32), ("max_rows", C.c_int32), ("max_prompt", C.c_int32),
         ("max_steps", C.c_int32),
+        ("sig_width", C.c_int32), ("sig_layers", C.c_int32), ("sig_heads", C.c_int32), ("sig_patch", C.c_int32),
+        ("sig_image", C.c_int32), ("sig_mlp", C.c_int32), ("max_images", C.c_int32),
     ]
 
 
@@ -50,6 +52,9 @@ EXPORTS = {
                                      C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "pg_vq_decode_code": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "pg_vq_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "pg_prepare_inputs_embeds": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                           C.c_void_p, C.c_void_p]),
+    "pg_vision_features": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "pg_images_to_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "pg_engine_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "pg_engine_get_counter": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),

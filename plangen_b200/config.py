@@ -26,6 +26,14 @@ class Dims:
     vq_z: int = 256
     vq_res_blocks: int = 2
     pad_id: int = 100002
+    # understanding-side vision tower: SigLIP_MODEL_CONFIG["siglip_large_patch16_384"] (siglip_vit.py:628-637), the tower
+    # of both Janus-1.3B and Janus-Pro-7B; `sig_mlp` = width * mlp_ratio
+    sig_width: int = 1024
+    sig_layers: int = 24
+    sig_heads: int = 16
+    sig_patch: int = 16
+    sig_image: int = 384
+    sig_mlp: int = 4096
 
     @property
     def n_img_tokens(self) -> int:
@@ -35,11 +43,20 @@ class Dims:
     def img_size(self) -> int:
         return self.grid * 2 ** (len(self.vq_ch_mult) - 1)
 
+    @property
+    def sig_patches(self) -> int:
+        return (self.sig_image // self.sig_patch) ** 2
+
     @classmethod
-    def from_any(cls, other) -> "Dims":
-        """Build from any object carrying the same attribute names."""
-        return cls(**{f.name: (tuple(getattr(other, f.name)) if f.name == "vq_ch_mult" else getattr(other, f.name))
-                      for f in fields(cls)})
+    def from_any(cls, other, vision=None) -> "Dims":
+        """Build from any object carrying the same attribute names (fields it lacks keep their defaults); `vision`:
+        an object with width / layers / heads / patch / image / mlp_ratio (the oracle's SigLIPDims)."""
+        kw = {f.name: (tuple(getattr(other, f.name)) if f.name == "vq_ch_mult" else getattr(other, f.name))
+              for f in fields(cls) if hasattr(other, f.name)}
+        if vision is not None:
+            kw.update(sig_width=vision.width, sig_layers=vision.layers, sig_heads=vision.heads, sig_patch=vision.patch,
+                      sig_image=vision.image, sig_mlp=int(vision.width * vision.mlp_ratio))
+        return cls(**kw)
 
 
 JANUS_1P3B = Dims()

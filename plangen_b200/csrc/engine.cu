@@ -22,6 +22,7 @@
 #include "text_decode.cuh"
 #include "attn_prefill_tc.cuh"
 #include "vq_kernels.cuh"
+#include "vit_kernels.cuh"
 
 using namespace pg;
 
@@ -106,6 +107,13 @@ struct pg_engine {
   // engine-owned staging of the per-call inputs / outputs of the fused loops, so captured graphs depend on shapes
   // and scalars only (the caller's tensors are fresh allocations on every call)
   int32_t *st_kv_start = nullptr, *st_edit = nullptr, *st_gt = nullptr, *st_tokens = nullptr;
+  // mmu front-end (SigLIP tower + aligner + scatter, vit_kernels.cuh); carved only when dims.sig_layers > 0
+  int sig_chunk = 0, sig_np = 0;                      // images per pass, patches per image
+  float *sig_x = nullptr, *sig_part = nullptr;
+  void *sig_xn = nullptr, *sig_qkv = nullptr, *sig_vT = nullptr, *sig_attn = nullptr, *sig_h = nullptr, *sig_feat = nullptr;
+  size_t sig_part_bytes = 0;
+  int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
+  int sig_attn_tc = 1;                                // tcgen05 attention (bf16, head_dim 64); 0 = CUDA-core kernel
   size_t part_bytes = 0;
   int *attn_cnt = nullptr, *attn_flag = nullptr, *step_ctr = nullptr, *greedy_state = nullptr;
   int* poll_host = nullptr;                          // pinned: early-exit poll of the greedy loop
@@ -336,6 +344,25 @@ static void layout_workspace(pg_engine* e, Carve& c) {
     e->st_gt = (int32_t*)c.take(B * std::max(d.max_steps, 1) * 4);
     e->st_tokens = (int32_t*)c.take(R * (size_t)e->Tmax * 4);      // image loop: [B][n_steps]; text loop: [R][max_new]
   }
+  if (d.sig_layers > 0 && d.max_images > 0) {
+    // SigLIP tower scratch for one pass of sig_chunk images; features of ALL images stay (the scatter needs them)
+    e->sig_np = (d.sig_image / d.sig_patch) * (d.sig_image / d.sig_patch);
+    e->sig_chunk = std::min(d.max_images, 32);
+    const size_t Mc = (size_t)e->sig_chunk * e->sig_np, W = d.sig_width, Kp = (size_t)3 * d.sig_patch * d.sig_patch;
+    const size_t widest = std::max<size_t>(std::max<size_t>(3 * W, d.sig_mlp), d.D);
+    e->sig_x = (float*)c.take(Mc * W * 4);
+    e->sig_xn = c.take(Mc * std::max(W, Kp) * es);
+    e->sig_qkv = c.take(Mc * 3 * W * es);
+    e->sig_vT = c.take((size_t)e->sig_chunk * W * align_up((size_t)e->sig_np, 8) * 2);
+    e->sig_attn = c.take(Mc * W * es);
+    e->sig_h = c.take(Mc * std::max<size_t>(d.sig_mlp, d.D) * es);
+    e->sig_part_bytes = Mc * widest * 4;
+    e->sig_part = (float*)c.take(e->sig_part_bytes);
+    e->sig_feat = c.take((size_t)d.max_images * e->sig_np * d.D * es);
+    e->sig_rank_dst = (int32_t*)c.take(max_tok * 4);
+    e->sig_inv_src = (int32_t*)c.take((size_t)d.max_images * e->sig_np * 4);
+    e->sig_counts = (int32_t*)c.take(256);
+  }
   // VQ decoder scratch, per chunk of images
   const int Bc = vq_chunk_of(e);
   size_t act = 0, col = 0, part = 0;
@@ -422,6 +449,15 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaFuncSetAttribute(resid_rmsnorm_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(resid_rmsnorm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PA_SMEM));
+  CK(cudaFuncSetAttribute(vit_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM));
+  if (dims->sig_layers > 0) {
+    if (dims->sig_width % 8 || dims->sig_mlp % 8 || dims->sig_patch % 4 || dims->sig_heads < 1 || dims->sig_width % dims->sig_heads ||
+        dims->sig_image % dims->sig_patch || dims->sig_width > 4 * LN_MAXQ * LN_THREADS)
+      return fail("unsupported SigLIP dims (width %d, heads %d, patch %d, image %d, mlp %d)", dims->sig_width, dims->sig_heads,
+                  dims->sig_patch, dims->sig_image, dims->sig_mlp);
+    const int np = (dims->sig_image / dims->sig_patch) * (dims->sig_image / dims->sig_patch);
+    if (np > 32 * VA_MAXI || (np & 1) || dims->sig_width / dims->sig_heads > 128) return fail("unsupported SigLIP patch count %d / head_dim", np);
+  }
   CK(cudaFuncSetAttribute(attn_decode_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A5_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
   CK(cudaFuncSetAttribute(attn_prefill_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_PREFILL_SMEM));
@@ -488,6 +524,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "rn_threads") e->rn_threads = (int)value;
   else if (k == "norm_tma") e->norm_tma = (int)value;
   else if (k == "prefill_attn_tc") e->prefill_attn_tc = (int)value;
+  else if (k == "sig_attn_tc") e->sig_attn_tc = (int)value;
   else if (k == "tc_prefetch") e->tc_prefetch = (int)value;
   else if (k == "tc_prefetch_gu") e->tc_prefetch_gu = (int)value;
   else if (k == "norm_smem_kb") e->norm_smem_kb = (int)value;
@@ -1151,6 +1188,156 @@ extern "C" int pg_generate_greedy(pg_engine* e, float* x_prompt, const int32_t* 
   *n_generated = e->poll_host[1];
   CK(cudaEventRecord(e->ev_out, st));
   CK(cudaStreamWaitEvent(user, e->ev_out, 0));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ f2: mmu front-end
+// replaces: vl_gpt.prepare_inputs_embeds(input_ids, pixel_values, images_seq_mask, images_emb_mask)
+//           (plangen_base.py:289,366,855; modeling_vlm.py:221-268)
+static int sig_tensor(pg_engine* e, const std::string& name, const void** out) {
+  *out = T_(e, name);
+  if (!*out) return fail("tensor '%s' was not registered (the engine was built without the vision tower / aligner)", name.c_str());
+  return 0;
+}
+#define SIGT(var, type, name) const type* var = nullptr; TRY(sig_tensor(e, (name), (const void**)&var))
+
+// vision tower + aligner for images [i0, i0 + n): pixel fp32 [n][3][S][S] -> feat T [n * NP][D]
+static int sig_tower(pg_engine* e, const float* pixel, int n, void* feat, cudaStream_t st) {
+  const pg_dims& d = e->d;
+  const int W = d.sig_width, NP = e->sig_np, heads = d.sig_heads, hd = W / heads, Kp = 3 * d.sig_patch * d.sig_patch;
+  const int M = n * NP;
+  const float eps = 1e-6f;
+  int S = 1;
+  SIGT(pw, void, "sig.patch.w"); SIGT(pb, float, "sig.patch.b"); SIGT(pos, float, "sig.pos");
+  {
+    const size_t total4 = (size_t)M * Kp / 4;
+    DISPATCH_T(e,
+               launch(e, vit_patchify_kernel<bf16>, dim3(elementwise_blocks(e, total4)), dim3(256), 0, st, pixel, (bf16*)e->sig_xn, d.sig_image, d.sig_patch, total4),
+               launch(e, vit_patchify_kernel<float>, dim3(elementwise_blocks(e, total4)), dim3(256), 0, st, pixel, (float*)e->sig_xn, d.sig_image, d.sig_patch, total4));
+    TRY(run_gemm(e, e->sig_xn, pw, M, W, Kp, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+    const size_t total = (size_t)M * W;
+    DISPATCH_T(e,
+               launch(e, vit_patch_epilogue_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->sig_part, S, total, pb, pos, e->sig_x, W, NP, total),
+               launch(e, vit_patch_epilogue_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->sig_part, S, total, pb, pos, e->sig_x, W, NP, total));
+  }
+  auto resid_ln = [&](const float* part, const float* bias, const float* w, const float* b) {
+    const size_t stride = (size_t)M * W;
+    DISPATCH_T(e,
+               launch(e, vit_resid_ln_kernel<bf16>, dim3(M), dim3(LN_THREADS), 0, st, e->sig_x, part, S, stride, bias, w, b, (bf16*)e->sig_xn, W, eps),
+               launch(e, vit_resid_ln_kernel<float>, dim3(M), dim3(LN_THREADS), 0, st, e->sig_x, part, S, stride, bias, w, b, (float*)e->sig_xn, W, eps));
+    return 0;
+  };
+  auto bias_act = [&](const float* bias, void* out, int N, int gelu) {
+    const size_t total = (size_t)M * N;
+    DISPATCH_T(e,
+               launch(e, bias_act_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->sig_part, S, total, bias, (bf16*)out, (float*)nullptr, N, total, gelu),
+               launch(e, bias_act_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, e->sig_part, S, total, bias, (float*)out, (float*)nullptr, N, total, gelu));
+    return 0;
+  };
+  const bool tc_attn = e->bf16 && e->use_tc && e->sig_attn_tc && hd == VT_HD;
+  for (int l = 0; l < d.sig_layers; ++l) {
+    const std::string p = "sig." + std::to_string(l) + ".";
+    SIGT(ln1w, float, p + "ln1.w"); SIGT(ln1b, float, p + "ln1.b"); SIGT(ln2w, float, p + "ln2.w"); SIGT(ln2b, float, p + "ln2.b");
+    SIGT(wqkv, void, p + "qkv.w"); SIGT(bqkv, float, p + "qkv.b"); SIGT(wproj, void, p + "proj.w"); SIGT(bproj, float, p + "proj.b");
+    SIGT(wfc1, void, p + "fc1.w"); SIGT(bfc1, float, p + "fc1.b"); SIGT(wfc2, void, p + "fc2.w"); SIGT(bfc2, float, p + "fc2.b");
+    if (l == 0) TRY(resid_ln(nullptr, nullptr, ln1w, ln1b));
+    TRY(run_gemm(e, e->sig_xn, wqkv, M, 3 * W, W, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+    TRY(bias_act(bqkv, e->sig_qkv, 3 * W, 0));
+    if (tc_attn) {
+      const int NPpad = (int)align_up((size_t)NP, 8);
+      TRY(launch(e, vit_v_transpose_kernel, dim3((NPpad + 63) / 64, heads, n), dim3(256), 0, st, (const bf16*)e->sig_qkv, (bf16*)e->sig_vT, NP, NPpad, W, heads, hd));
+      CUtensorMap mq, mk, mv;
+      TRY(make_map_2d(e, &mq, e->sig_qkv, (uint64_t)M, (uint64_t)3 * W, VT_BQ));
+      TRY(make_map_2d(e, &mk, e->sig_qkv, (uint64_t)M, (uint64_t)3 * W, VT_BK));
+      TRY(make_map_2d(e, &mv, e->sig_vT, (uint64_t)n * heads * hd, (uint64_t)NPpad, 64));
+      TRY(launch(e, vit_attn_tc_kernel, dim3((NP + VT_BQ - 1) / VT_BQ, heads, n), dim3(128), VT_SMEM, st, mq, mk, mv, (bf16*)e->sig_attn, NP, W,
+                 heads, 1.0f / sqrtf((float)hd)));
+    } else {
+      DISPATCH_T(e,
+                 launch(e, vit_attn_kernel<bf16>, dim3((NP + 3) / 4, heads, n), dim3(128), 0, st, (const bf16*)e->sig_qkv, (bf16*)e->sig_attn, NP, W, heads, hd, 1.0f / sqrtf((float)hd)),
+                 launch(e, vit_attn_kernel<float>, dim3((NP + 3) / 4, heads, n), dim3(128), 0, st, (const float*)e->sig_qkv, (float*)e->sig_attn, NP, W, heads, hd, 1.0f / sqrtf((float)hd)));
+    }
+    TRY(run_gemm(e, e->sig_attn, wproj, M, W, W, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+    TRY(resid_ln(e->sig_part, bproj, ln2w, ln2b));
+    TRY(run_gemm(e, e->sig_xn, wfc1, M, d.sig_mlp, W, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+    TRY(bias_act(bfc1, e->sig_h, d.sig_mlp, 1));
+    TRY(run_gemm(e, e->sig_h, wfc2, M, W, d.sig_mlp, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+    if (l + 1 < d.sig_layers) {
+      const std::string pn = "sig." + std::to_string(l + 1) + ".";
+      SIGT(nw, float, pn + "ln1.w"); SIGT(nb, float, pn + "ln1.b");
+      TRY(resid_ln(e->sig_part, bfc2, nw, nb));
+    } else {
+      SIGT(nw, float, "sig.norm.w"); SIGT(nb, float, "sig.norm.b");
+      TRY(resid_ln(e->sig_part, bfc2, nw, nb));
+    }
+  }
+  // aligner: Linear(W, D) -> GELU -> Linear(D, D)   (projector.py:39-45)
+  SIGT(aw0, void, "ualign.w0"); SIGT(ab0, float, "ualign.b0"); SIGT(aw1, void, "ualign.w1"); SIGT(ab1, float, "ualign.b1");
+  TRY(run_gemm(e, e->sig_xn, aw0, M, d.D, W, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+  TRY(bias_act(ab0, e->sig_h, d.D, 1));
+  TRY(run_gemm(e, e->sig_h, aw1, M, d.D, d.D, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+  TRY(bias_act(ab1, feat, d.D, 0));
+  return 0;
+}
+
+extern "C" int pg_prepare_inputs_embeds(pg_engine* e, const float* pixel_values, int n_images, const int32_t* input_ids,
+                                        const uint8_t* images_seq_mask, const uint8_t* images_emb_mask, int B, int T,
+                                        float* embeds_out, void* stream) {
+  TRY(check_ready(e));
+  const pg_dims& d = e->d;
+  if (d.sig_layers <= 0 || !e->sig_x) return fail("the engine was created without the vision tower (pg_dims.sig_layers / max_images = 0)");
+  if (!input_ids || !images_seq_mask || !embeds_out || B < 1 || T < 1) return fail("bad argument");
+  if ((size_t)B * T > (size_t)d.max_rows * std::max(d.max_prompt, 1)) return fail("B*T = %d x %d exceeds max_rows x max_prompt", B, T);
+  if (n_images < 0 || n_images > d.max_images) return fail("n_images %d exceeds max_images %d", n_images, d.max_images);
+  if (n_images > 0 && (!pixel_values || !images_emb_mask)) return fail("pixel_values / images_emb_mask missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  NEED(table, float, "embed_tokens");
+  if (!e->poll_host) CK(cudaMallocHost(&e->poll_host, 64));
+  const int NP = e->sig_np;
+  const int saved_pdl = e->use_pdl;
+  for (int i0 = 0; i0 < n_images; i0 += e->sig_chunk) {
+    const int n = std::min(e->sig_chunk, n_images - i0);
+    const size_t img_elems = (size_t)3 * d.sig_image * d.sig_image;
+    TRY(sig_tower(e, pixel_values + (size_t)i0 * img_elems, n, (uint8_t*)e->sig_feat + (size_t)i0 * NP * d.D * e->esz, st));
+  }
+  e->use_pdl = saved_pdl;
+  // scatter: k-th set position of images_seq_mask <- k-th selected image token
+  CK(cudaMemsetAsync(e->sig_counts, 0, 8, st));
+  if (n_images > 0) mask_rank_kernel<<<1, 1024, 0, st>>>(images_emb_mask, n_images * NP, (int32_t*)nullptr, e->sig_inv_src, e->sig_counts + 1);
+  mask_rank_kernel<<<1, 1024, 0, st>>>(images_seq_mask, B * T, e->sig_rank_dst, (int32_t*)nullptr, e->sig_counts);
+  CK(cudaGetLastError());
+  e->launches += 2;
+  CK(cudaMemcpyAsync(e->poll_host, e->sig_counts, 8, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  if (e->poll_host[0] != e->poll_host[1])
+    return fail("images_seq_mask selects %d positions but images_emb_mask selects %d image tokens (modeling_vlm.py:236 asserts they are equal)",
+                e->poll_host[0], e->poll_host[1]);
+  DISPATCH_T(e,
+             launch(e, embed_scatter_kernel<bf16>, dim3(B * T), dim3(256), 0, st, input_ids, (const int32_t*)e->sig_rank_dst, (const int32_t*)e->sig_inv_src,
+                    (const int32_t*)(e->sig_counts + 1), (const bf16*)e->sig_feat, table, embeds_out, d.D, d.vocab),
+             launch(e, embed_scatter_kernel<float>, dim3(B * T), dim3(256), 0, st, input_ids, (const int32_t*)e->sig_rank_dst, (const int32_t*)e->sig_inv_src,
+                    (const int32_t*)(e->sig_counts + 1), (const float*)e->sig_feat, table, embeds_out, d.D, d.vocab));
+  return 0;
+}
+
+// Vision tower + aligner alone (bench / tests): pixel fp32 [n][3][S][S] -> features fp32 [n * NP][D]
+extern "C" int pg_vision_features(pg_engine* e, const float* pixel_values, int n_images, float* feat_out, void* stream) {
+  TRY(check_ready(e));
+  const pg_dims& d = e->d;
+  if (d.sig_layers <= 0 || !e->sig_x) return fail("the engine was created without the vision tower");
+  if (n_images < 1 || n_images > d.max_images || !pixel_values) return fail("bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int NP = e->sig_np;
+  for (int i0 = 0; i0 < n_images; i0 += e->sig_chunk) {
+    const int n = std::min(e->sig_chunk, n_images - i0);
+    TRY(sig_tower(e, pixel_values + (size_t)i0 * 3 * d.sig_image * d.sig_image, n, (uint8_t*)e->sig_feat + (size_t)i0 * NP * d.D * e->esz, st));
+  }
+  if (feat_out) {
+    const size_t total = (size_t)n_images * NP * d.D;
+    DISPATCH_T(e,
+               launch(e, to_f32_kernel<bf16>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, (const bf16*)e->sig_feat, feat_out, total),
+               launch(e, to_f32_kernel<float>, dim3(elementwise_blocks(e, total)), dim3(256), 0, st, (const float*)e->sig_feat, feat_out, total));
+  }
   return 0;
 }
 

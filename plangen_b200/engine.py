@@ -200,7 +200,7 @@ class FastJanus:
     def __init__(self, state_dict: Dict[str, torch.Tensor], dims: Dims, mode: str = "bf16",
                  max_batch: int = 16, max_prompt: int = 512, max_steps: Optional[int] = None,
                  device: str = "cuda:0", seed: int = 0, with_vq: bool = True, options: Optional[dict] = None,
-                 use_teacher_forcing: bool = False, top_k: int = 0):
+                 use_teacher_forcing: bool = False, top_k: int = 0, max_images: int = 0):
         if not torch.cuda.is_available():
             raise RuntimeError("plangen_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         if mode not in MODE_IDS:
@@ -224,6 +224,13 @@ class FastJanus:
         for i, m in enumerate(dims.vq_ch_mult):
             pd.vq_ch_mult[i] = m
         pd.mode, pd.max_rows, pd.max_prompt, pd.max_steps = MODE_IDS[mode], self.max_rows, max_prompt, self.max_steps
+        # mmu front-end: built when the state dict carries the vision tower and max_images > 0
+        self.with_vision = max_images > 0 and "vision_model.vision_tower.pos_embed" in state_dict
+        self.max_images = int(max_images) if self.with_vision else 0
+        if self.with_vision:
+            for k in ("sig_width", "sig_layers", "sig_heads", "sig_patch", "sig_image", "sig_mlp"):
+                setattr(pd, k, getattr(dims, k))
+            pd.max_images = self.max_images
         h = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(self._lib.pg_engine_create(C.byref(pd), self.device.index or 0, C.byref(h)))
@@ -236,7 +243,8 @@ class FastJanus:
             self._ws = torch.empty(wsb.value, dtype=torch.uint8, device=self.device)
             _lib.check(self._lib.pg_engine_bind_buffers(h, _ptr(self._kv), kvb.value, _ptr(self._ws), wsb.value))
             tmax = self.counter("tmax")
-            self._weights = pack_state_dict(state_dict, dims, mode, self.device, tmax, with_vq=with_vq)
+            self._weights = pack_state_dict(state_dict, dims, mode, self.device, tmax, with_vq=with_vq,
+                                            with_vision=self.with_vision)
             for name, t in self._weights.items():
                 _lib.check(self._lib.pg_engine_set_tensor(h, name.encode(), _ptr(t), t.numel() * t.element_size()))
             _lib.check(self._lib.pg_engine_finalize(h, _stream_ptr(self.device)))
@@ -283,11 +291,49 @@ class FastJanus:
         return d.L * per_layer + d.D * 4 + head
 
     # ------------------------------------------------------------------ duck-typed pieces
-    def prepare_inputs_embeds(self, *args, **kwargs):
-        """mmu front-end (`plangen_base.py:289,366,855`: SigLIP vision tower + aligner + embedding scatter): SURVEY.md §8f
-        rank 2, not built.  Fails loudly instead of serving the call with anything else."""
-        raise NotImplementedError("prepare_inputs_embeds (image understanding: SigLIP + aligner) is not part of plangen_b200 yet; "
-                                  "pass precomputed inputs_embeds to language_model.generate / language_model.model")
+    @torch.inference_mode()
+    def prepare_inputs_embeds(self, input_ids, pixel_values, images_seq_mask, images_emb_mask, **kwargs):
+        """`MultiModalityCausalLM.prepare_inputs_embeds` (modeling_vlm.py:221-268; called at plangen_base.py:289,366,855):
+        input_ids (b, T), pixel_values (b, n, 3, h, w), images_seq_mask (b, T), images_emb_mask (b, n, n_image_tokens)
+        -> inputs_embeds (b, T, D) fp32 (the text embedding's dtype).  SigLIP tower + aligner + scatter on the device
+        (pg_prepare_inputs_embeds); raises if the two masks select different counts, as the reference asserts."""
+        if not self.with_vision:
+            raise RuntimeError("this engine was built without the vision tower: pass a state_dict with "
+                               "vision_model.vision_tower.* / aligner.* and max_images > 0")
+        ids = input_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        b, T = ids.shape
+        pv = pixel_values.to(device=self.device)
+        if pv.dim() != 5 or pv.shape[0] != b or pv.shape[2] != 3:
+            raise ValueError("pixel_values must be (b, n_images, 3, h, w)")
+        n_img = pv.shape[0] * pv.shape[1]
+        S = self.dims.sig_image
+        if pv.shape[3] != S or pv.shape[4] != S:
+            raise ValueError(f"the vision tower takes {S}x{S} images")
+        if self.mode == "bf16":
+            pv = pv.to(torch.bfloat16)                    # `images.bfloat16()` (:249) - also when the caller passes fp32
+        pv = pv.to(torch.float32).reshape(n_img, 3, S, S).contiguous()
+        seq = images_seq_mask.to(self.device).reshape(b, T).ne(0).to(torch.uint8).contiguous()
+        emb = images_emb_mask.to(self.device).reshape(n_img, -1).ne(0).to(torch.uint8).contiguous()
+        if emb.shape[1] != self.dims.sig_patches:
+            raise ValueError(f"images_emb_mask must have {self.dims.sig_patches} entries per image")
+        out = torch.empty(b, T, self.dims.D, device=self.device, dtype=torch.float32)
+        _lib.check(self._lib.pg_prepare_inputs_embeds(self._h, _ptr(pv), n_img, _ptr(ids), _ptr(seq), _ptr(emb), b, T, _ptr(out),
+                                                      _stream_ptr(self.device)))
+        return out
+
+    @torch.inference_mode()
+    def vision_features(self, images: torch.Tensor) -> torch.Tensor:
+        """`aligner(vision_model(images))` (modeling_vlm.py:250): (n, 3, S, S) -> (n, n_patches, D) in the engine's dtype."""
+        if not self.with_vision:
+            raise RuntimeError("this engine was built without the vision tower")
+        pv = images.to(device=self.device)
+        if self.mode == "bf16":
+            pv = pv.to(torch.bfloat16)
+        pv = pv.to(torch.float32).contiguous()
+        n = pv.shape[0]
+        out = torch.empty(n, self.dims.sig_patches, self.dims.D, device=self.device, dtype=torch.float32)
+        _lib.check(self._lib.pg_vision_features(self._h, _ptr(pv), n, _ptr(out), _stream_ptr(self.device)))
+        return out.to(self.out_dtype)
 
     def gen_head(self, h: torch.Tensor) -> torch.Tensor:
         R = h.shape[0]

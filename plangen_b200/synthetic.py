@@ -101,11 +101,36 @@ def state_dict_names(d: Dims, with_vq: bool = True, with_vq_encoder: bool = Fals
     return s
 
 
+def vision_state_dict_names(d: Dims) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """vision_model.vision_tower.* (VisionTransformer, siglip_vit.py:262-440: no class token, qkv bias, LayerNorm affine)
+    and the understanding `aligner` (projector.py:39-45)."""
+    p = "vision_model.vision_tower."
+    W, hid, pp = d.sig_width, d.sig_mlp, d.sig_patch
+    s: List[Tuple[str, Tuple[int, ...], str]] = [
+        (p + "pos_embed", (1, d.sig_patches, W), "lm"),
+        (p + "patch_embed.proj.weight", (W, 3, pp, pp), "fan"),
+        (p + "patch_embed.proj.bias", (W,), "bias:%d" % (3 * pp * pp))]
+    for i in range(d.sig_layers):
+        b = p + f"blocks.{i}."
+        s += [(b + "norm1.weight", (W,), "norm_w"), (b + "norm1.bias", (W,), "norm_b"),
+              (b + "attn.qkv.weight", (3 * W, W), "lm"), (b + "attn.qkv.bias", (3 * W,), "norm_b"),
+              (b + "attn.proj.weight", (W, W), "lm"), (b + "attn.proj.bias", (W,), "norm_b"),
+              (b + "norm2.weight", (W,), "norm_w"), (b + "norm2.bias", (W,), "norm_b"),
+              (b + "mlp.fc1.weight", (hid, W), "lm"), (b + "mlp.fc1.bias", (hid,), "norm_b"),
+              (b + "mlp.fc2.weight", (W, hid), "lm"), (b + "mlp.fc2.bias", (W,), "norm_b")]
+    s += [(p + "norm.weight", (W,), "norm_w"), (p + "norm.bias", (W,), "norm_b"),
+          ("aligner.layers.0.weight", (d.D, W), "fan"), ("aligner.layers.0.bias", (d.D,), "bias:%d" % W),
+          ("aligner.layers.2.weight", (d.D, d.D), "fan"), ("aligner.layers.2.bias", (d.D,), "bias:%d" % d.D)]
+    return s
+
+
 def random_state_dict(d: Dims, device, seed: int = 0, with_vq: bool = True, with_lm_head: bool = False,
-                      with_vq_encoder: bool = False) -> Dict[str, torch.Tensor]:
+                      with_vq_encoder: bool = False, with_vision: bool = False) -> Dict[str, torch.Tensor]:
     g = torch.Generator(device=device).manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
     names = state_dict_names(d, with_vq, with_vq and with_vq_encoder)
+    if with_vision:
+        names = names + vision_state_dict_names(d)
     if with_lm_head:       # untied text head, only needed by language_model.generate (stage-1 layout-text decode)
         names = names + [("language_model.lm_head.weight", (d.vocab, d.D), "lm")]
     for name, shape, kind in names:

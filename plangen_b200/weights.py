@@ -5,6 +5,7 @@ registers through `pg_engine_set_tensor`.
   ...mlp.{gate,up}_proj.weight                                   -> l{i}.wgu   [2*F, D]      (fp32: rows gate | up;
                                                                     bf16: interleaved in blocks of 64 rows)
   conv weights [Cout, Cin, kh, kw]                               -> [Cout, kh*kw*Cin]        (channels-last taps)
+  vision_model.vision_tower.* / aligner.* (mmu front-end)        -> sig.* / ualign.*          (nn.Linear layout kept)
 
 Weights are stored in the engine's operand type: bf16 (round-to-nearest-even of the fp32 master
 weights - exactly the cast torch.autocast performs at every Linear/conv call, plangen_base.py:360)
@@ -32,7 +33,7 @@ def rope_tables(dims: Dims, tmax: int):
 
 
 def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, mode: str, device, tmax: int,
-                    with_vq: bool = True) -> Dict[str, torch.Tensor]:
+                    with_vq: bool = True, with_vision: bool = False) -> Dict[str, torch.Tensor]:
     wt = torch.bfloat16 if mode == "bf16" else torch.float32
     out: Dict[str, torch.Tensor] = {}
 
@@ -75,6 +76,23 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], dims: Dims, mode: str, device, 
     cos, sin = rope_tables(dims, tmax)
     out["rope_cos"] = cos.to(device)
     out["rope_sin"] = sin.to(device)
+    if with_vision:
+        # understanding side: SigLIP tower (vision_model.vision_tower.*, siglip_vit.py) + `aligner` (projector.py:39-45)
+        p = "vision_model.vision_tower."
+        out["sig.pos"] = f(sd[p + "pos_embed"]).reshape(dims.sig_patches, dims.sig_width).contiguous()
+        out["sig.patch.w"] = w(sd[p + "patch_embed.proj.weight"].reshape(dims.sig_width, -1))      # k = c*p*p + ky*p + kx
+        out["sig.patch.b"] = f(sd[p + "patch_embed.proj.bias"])
+        for i in range(dims.sig_layers):
+            b = p + f"blocks.{i}."
+            out[f"sig.{i}.ln1.w"], out[f"sig.{i}.ln1.b"] = f(sd[b + "norm1.weight"]), f(sd[b + "norm1.bias"])
+            out[f"sig.{i}.ln2.w"], out[f"sig.{i}.ln2.b"] = f(sd[b + "norm2.weight"]), f(sd[b + "norm2.bias"])
+            out[f"sig.{i}.qkv.w"], out[f"sig.{i}.qkv.b"] = w(sd[b + "attn.qkv.weight"]), f(sd[b + "attn.qkv.bias"])
+            out[f"sig.{i}.proj.w"], out[f"sig.{i}.proj.b"] = w(sd[b + "attn.proj.weight"]), f(sd[b + "attn.proj.bias"])
+            out[f"sig.{i}.fc1.w"], out[f"sig.{i}.fc1.b"] = w(sd[b + "mlp.fc1.weight"]), f(sd[b + "mlp.fc1.bias"])
+            out[f"sig.{i}.fc2.w"], out[f"sig.{i}.fc2.b"] = w(sd[b + "mlp.fc2.weight"]), f(sd[b + "mlp.fc2.bias"])
+        out["sig.norm.w"], out["sig.norm.b"] = f(sd[p + "norm.weight"]), f(sd[p + "norm.bias"])
+        out["ualign.w0"], out["ualign.b0"] = w(sd["aligner.layers.0.weight"]), f(sd["aligner.layers.0.bias"])
+        out["ualign.w1"], out["ualign.b1"] = w(sd["aligner.layers.2.weight"]), f(sd["aligner.layers.2.bias"])
     if with_vq:
         g = "gen_vision_model."
         out["vq.codebook"] = f(sd[g + "quantize.embedding.weight"])
