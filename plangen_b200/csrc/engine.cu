@@ -114,6 +114,7 @@ struct pg_engine {
   size_t sig_part_bytes = 0;
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
   int sig_attn_tc = 1;                                // tcgen05 attention (bf16, head_dim 64); 0 = CUDA-core kernel
+  int sig_fuse = 1;                                   // bias / GELU / residual in the contraction epilogues (gemm.cuh EpiFuse)
   size_t part_bytes = 0;
   int *attn_cnt = nullptr, *attn_flag = nullptr, *step_ctr = nullptr, *greedy_state = nullptr;
   int* poll_host = nullptr;                          // pinned: early-exit poll of the greedy loop
@@ -189,7 +190,7 @@ static int make_map_2d(pg_engine* e, CUtensorMap* m, const void* ptr, uint64_t r
 template <int NT>
 static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx, float* C, int M, int N, int K,
                      int splits, int kb_per_split, bool w_const, const void* w_tiled, void* swiglu_out, cudaStream_t st,
-                     const ConvGeom* conv = nullptr, int grid_y = 0) {
+                     const ConvGeom* conv = nullptr, int grid_y = 0, const EpiFuse* epi = nullptr) {
   using Cfg = TcCfg<NT>;
   // wide token tiles (prefill, VQ convolutions) are tensor-bound: a shallow ring leaves room for two CTAs per SM,
   // whose epilogues overlap each other's main loops (measured: prefill 75.6 -> 68 ms); the weight-streaming decode
@@ -205,9 +206,12 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   dim3 grid((N + TC_BM - 1) / TC_BM, conv ? grid_y : (M + NT - 1) / NT, splits);
   ConvGeom cg = {};
   if (conv) cg = *conv;
+  EpiFuse ep = {};
+  if (epi) ep = *epi;
+  if (ep.out && (size_t)stages * Cfg::STAGE_BYTES < (size_t)NT * 256) return fail("internal: operand ring too small to stage the output tile");
   return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
                 e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out, cg,
-                NT <= 64 ? (swiglu_out ? e->tc_prefetch_gu : e->tc_prefetch) : 0);
+                NT <= 64 ? (swiglu_out ? e->tc_prefetch_gu : e->tc_prefetch) : 0, ep);
 }
 
 // 3x3 convolution (pad 1) as an implicit GEMM on the tcgen05 path: act bf16 NHWC [B][H][W][Cin], Wc bf16
@@ -251,7 +255,7 @@ static int run_conv_gemm(pg_engine* e, const void* act, const void* Wc, int B, i
 // C[splits][M][N] fp32 = X[M][K] * W[N][K]^T.  Returns the number of splits used through *splits_out.
 static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, int K, float* C, size_t c_bytes,
                     int* splits_out, cudaStream_t st, int force_impl = -1, int force_splits = 0, bool w_const = true,
-                    const void* w_tiled = nullptr, void* swiglu_out = nullptr) {
+                    const void* w_tiled = nullptr, void* swiglu_out = nullptr, const EpiFuse* epi = nullptr) {
   const bool tc = e->bf16 && ((force_impl == 1) || (force_impl < 0 && e->use_tc)) && (K % 8 == 0) &&
                   (((uintptr_t)X & 15) == 0) && (((uintptr_t)W & 15) == 0);
   if (force_impl == 1 && !tc) return fail("tcgen05 GEMM needs bf16 operands, K %% 8 == 0 and 16-byte aligned pointers");
@@ -261,7 +265,8 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     const int tiles = ((N + TC_BM - 1) / TC_BM) * ((M + NT - 1) / NT);
     const int num_kb = (K + TC_BK - 1) / TC_BK;
     int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : std::max(1, e->num_sms / tiles));
-    if (swiglu_out) want = 1;                               // the SwiGLU epilogue is non-linear: whole K in one CTA
+    if (swiglu_out || epi) want = 1;                        // fused epilogues need the whole K in one CTA
+    if (epi && (N % 8 != 0)) return fail("fused epilogue needs N %% 8 == 0 (N=%d)", N);
     want = std::min(std::min(want, 16), num_kb);
     while (want > 1 && (size_t)want * M * N * 4 > c_bytes) --want;
     const int kb_per_split = (num_kb + want - 1) / want;
@@ -275,14 +280,14 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     TRY(make_map_2d(e, &mw, W, (uint64_t)N, (uint64_t)K, TC_BM));
     TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
     switch (NT) {
-      case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
-      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
-      case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
-      case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
-      default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st)); break;
+      case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st, nullptr, 0, epi)); break;
+      case 32: TRY(launch_tc<32>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st, nullptr, 0, epi)); break;
+      case 64: TRY(launch_tc<64>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st, nullptr, 0, epi)); break;
+      case 128: TRY(launch_tc<128>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st, nullptr, 0, epi)); break;
+      default: TRY(launch_tc<256>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st, nullptr, 0, epi)); break;
     }
   } else {
-    if (swiglu_out) return fail("internal: fused SwiGLU epilogue needs the tcgen05 path");
+    if (swiglu_out || epi) return fail("internal: fused epilogues need the tcgen05 path");
     if (K % 4 != 0) return fail("SIMT GEMM needs K %% 4 == 0 (K=%d)", K);
     const int tiles = ((N + 63) / 64) * ((M + 63) / 64);
     int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : std::max(1, (2 * e->num_sms) / tiles));
@@ -525,6 +530,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "norm_tma") e->norm_tma = (int)value;
   else if (k == "prefill_attn_tc") e->prefill_attn_tc = (int)value;
   else if (k == "sig_attn_tc") e->sig_attn_tc = (int)value;
+  else if (k == "sig_fuse") e->sig_fuse = (int)value;
   else if (k == "tc_prefetch") e->tc_prefetch = (int)value;
   else if (k == "tc_prefetch_gu") e->tc_prefetch_gu = (int)value;
   else if (k == "norm_smem_kb") e->norm_smem_kb = (int)value;
@@ -1235,14 +1241,32 @@ static int sig_tower(pg_engine* e, const float* pixel, int n, void* feat, cudaSt
     return 0;
   };
   const bool tc_attn = e->bf16 && e->use_tc && e->sig_attn_tc && hd == VT_HD;
+  const bool fuse = e->bf16 && e->use_tc && e->sig_fuse;
+  // contraction + bias (+ GELU) -> T, or contraction + bias + residual add; fused into the tcgen05 epilogue when possible
+  auto linear_out = [&](const void* X, const void* Wt, const float* bias, void* out, int N, int K, int gelu) {
+    if (fuse) {
+      EpiFuse ep = {bias, (bf16*)out, nullptr, gelu};
+      return run_gemm(e, X, Wt, M, N, K, e->sig_part, e->sig_part_bytes, &S, st, -1, 1, true, nullptr, nullptr, &ep);
+    }
+    TRY(run_gemm(e, X, Wt, M, N, K, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+    return bias_act(bias, out, N, gelu);
+  };
+  auto linear_resid_ln = [&](const void* X, const void* Wt, const float* bias, int K, const float* lw, const float* lb) {
+    if (fuse) {
+      EpiFuse ep = {bias, nullptr, e->sig_x, 0};
+      TRY(run_gemm(e, X, Wt, M, W, K, e->sig_part, e->sig_part_bytes, &S, st, -1, 1, true, nullptr, nullptr, &ep));
+      return resid_ln(nullptr, nullptr, lw, lb);
+    }
+    TRY(run_gemm(e, X, Wt, M, W, K, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+    return resid_ln(e->sig_part, bias, lw, lb);
+  };
   for (int l = 0; l < d.sig_layers; ++l) {
     const std::string p = "sig." + std::to_string(l) + ".";
     SIGT(ln1w, float, p + "ln1.w"); SIGT(ln1b, float, p + "ln1.b"); SIGT(ln2w, float, p + "ln2.w"); SIGT(ln2b, float, p + "ln2.b");
     SIGT(wqkv, void, p + "qkv.w"); SIGT(bqkv, float, p + "qkv.b"); SIGT(wproj, void, p + "proj.w"); SIGT(bproj, float, p + "proj.b");
     SIGT(wfc1, void, p + "fc1.w"); SIGT(bfc1, float, p + "fc1.b"); SIGT(wfc2, void, p + "fc2.w"); SIGT(bfc2, float, p + "fc2.b");
     if (l == 0) TRY(resid_ln(nullptr, nullptr, ln1w, ln1b));
-    TRY(run_gemm(e, e->sig_xn, wqkv, M, 3 * W, W, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
-    TRY(bias_act(bqkv, e->sig_qkv, 3 * W, 0));
+    TRY(linear_out(e->sig_xn, wqkv, bqkv, e->sig_qkv, 3 * W, W, 0));
     if (tc_attn) {
       const int NPpad = (int)align_up((size_t)NP, 8);
       TRY(launch(e, vit_v_transpose_kernel, dim3((NPpad + 63) / 64, heads, n), dim3(256), 0, st, (const bf16*)e->sig_qkv, (bf16*)e->sig_vT, NP, NPpad, W, heads, hd));
@@ -1257,26 +1281,21 @@ static int sig_tower(pg_engine* e, const float* pixel, int n, void* feat, cudaSt
                  launch(e, vit_attn_kernel<bf16>, dim3((NP + 3) / 4, heads, n), dim3(128), 0, st, (const bf16*)e->sig_qkv, (bf16*)e->sig_attn, NP, W, heads, hd, 1.0f / sqrtf((float)hd)),
                  launch(e, vit_attn_kernel<float>, dim3((NP + 3) / 4, heads, n), dim3(128), 0, st, (const float*)e->sig_qkv, (float*)e->sig_attn, NP, W, heads, hd, 1.0f / sqrtf((float)hd)));
     }
-    TRY(run_gemm(e, e->sig_attn, wproj, M, W, W, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
-    TRY(resid_ln(e->sig_part, bproj, ln2w, ln2b));
-    TRY(run_gemm(e, e->sig_xn, wfc1, M, d.sig_mlp, W, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
-    TRY(bias_act(bfc1, e->sig_h, d.sig_mlp, 1));
-    TRY(run_gemm(e, e->sig_h, wfc2, M, W, d.sig_mlp, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
+    TRY(linear_resid_ln(e->sig_attn, wproj, bproj, W, ln2w, ln2b));
+    TRY(linear_out(e->sig_xn, wfc1, bfc1, e->sig_h, d.sig_mlp, W, 1));
     if (l + 1 < d.sig_layers) {
       const std::string pn = "sig." + std::to_string(l + 1) + ".";
       SIGT(nw, float, pn + "ln1.w"); SIGT(nb, float, pn + "ln1.b");
-      TRY(resid_ln(e->sig_part, bfc2, nw, nb));
+      TRY(linear_resid_ln(e->sig_h, wfc2, bfc2, d.sig_mlp, nw, nb));
     } else {
       SIGT(nw, float, "sig.norm.w"); SIGT(nb, float, "sig.norm.b");
-      TRY(resid_ln(e->sig_part, bfc2, nw, nb));
+      TRY(linear_resid_ln(e->sig_h, wfc2, bfc2, d.sig_mlp, nw, nb));
     }
   }
   // aligner: Linear(W, D) -> GELU -> Linear(D, D)   (projector.py:39-45)
   SIGT(aw0, void, "ualign.w0"); SIGT(ab0, float, "ualign.b0"); SIGT(aw1, void, "ualign.w1"); SIGT(ab1, float, "ualign.b1");
-  TRY(run_gemm(e, e->sig_xn, aw0, M, d.D, W, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
-  TRY(bias_act(ab0, e->sig_h, d.D, 1));
-  TRY(run_gemm(e, e->sig_h, aw1, M, d.D, d.D, e->sig_part, e->sig_part_bytes, &S, st, -1, 1));
-  TRY(bias_act(ab1, feat, d.D, 0));
+  TRY(linear_out(e->sig_xn, aw0, ab0, e->sig_h, d.D, W, 1));
+  TRY(linear_out(e->sig_h, aw1, ab1, feat, d.D, d.D, 0));
   return 0;
 }
 

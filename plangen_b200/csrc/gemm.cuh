@@ -104,11 +104,27 @@ struct ConvGeom {
   bf16* out_bf16;
 };
 
+// Fused row epilogue (no split-K) for the wide-tile contractions of the vision tower / aligner (and any other
+// Linear with a bias): instead of fp32 partials for a row kernel to re-read,
+//   out  : out[m][n]   = bf16( act( bf16(acc + bias[n]) ) )         act = identity | exact-erf GELU
+//          the 128 x NT tile is staged in the (idle) operand ring as [m][128 n] bf16 and written with 16-byte stores,
+//          256 contiguous bytes per token row;
+//   resid: resid[m][n] += bf16(acc + bias[n])                        fp32 residual stream updated in place
+//          (128 contiguous bytes per warp access, the pattern of the partial store).
+// Rounding points are those of bias_act_kernel / vit_resid_ln_kernel (autocast: Linear output in bf16).
+struct EpiFuse {
+  const float* bias;   // [N] or nullptr
+  bf16* out;           // [M][N] row-major, or nullptr
+  float* resid;        // [M][N] fp32, or nullptr
+  int gelu;
+};
+
 template <int NT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                float* __restrict__ C, int M, int N, int K, int kb_per_split, int num_stages, int use_pdl,
-               const uint8_t* __restrict__ w_tiled, Prof prof, bf16* __restrict__ swiglu_out, ConvGeom cg, int w_prefetch) {
+               const uint8_t* __restrict__ w_tiled, Prof prof, bf16* __restrict__ swiglu_out, ConvGeom cg, int w_prefetch,
+               EpiFuse ep) {
   using Cfg = TcCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -310,7 +326,60 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
       mbar_wait(tmem_full_bar, 0, 3);
       if (warp == 2 && lane == 0) gemm_stamp(dbg, 4);
       tc_fence_after();
-      if (!cg.enabled) {
+      if (ep.out != nullptr) {
+        // ---- fused bias (+ GELU) -> bf16 row-major, staged through the idle operand ring
+        const float bias_n = (ep.bias && n < N) ? ep.bias[n] : 0.f;
+        const uint32_t stg = smem_u32(smem);                   // [NT][128] bf16 = NT * 256 bytes
+        const int nl = quarter * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float t = bf16_round(__uint_as_float(v[j]) + bias_n);
+            if (ep.gelu) t = t * 0.5f * (1.0f + erff(t * 0.70710678118654752440f));
+            const unsigned short hb = __bfloat16_as_ushort(__float2bfloat16_rn(t));
+            asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)((c0 + j) * 256 + nl * 2)), "h"(hb) : "memory");
+          }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        const int t128 = threadIdx.x - 64;                      // 0..127 over the epilogue warps 2..5
+        const int ch = t128 & 15, r0 = t128 >> 4;              // 16-byte chunk of the 256-byte row, first row
+        if (n0 + ch * 8 < N) {
+#pragma unroll 4
+          for (int r = r0; r < NT; r += 8) {
+            const int m = m0 + r;
+            if (m < M) {
+              uint4 q;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                           : "r"(stg + (uint32_t)(r * 256 + ch * 16)));
+              *reinterpret_cast<uint4*>(ep.out + (size_t)m * N + n0 + ch * 8) = q;
+            }
+          }
+        }
+      } else if (ep.resid != nullptr) {
+        // ---- fused bias + residual add into the fp32 stream
+        const float bias_n = (ep.bias && n < N) ? ep.bias[n] : 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_acc_sum<Cfg::NACC, NT>(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)c0, v, acc_used);
+          if (n < N) {
+            float xo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int m = m0 + c0 + j;
+              xo[j] = (m < M) ? ep.resid[(size_t)m * N + n] : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int m = m0 + c0 + j;
+              if (m < M) ep.resid[(size_t)m * N + n] = xo[j] + bf16_round(__uint_as_float(v[j]) + bias_n);
+            }
+          }
+        }
+      } else if (!cg.enabled) {
         // plain split-K partial store (the decode step's hot epilogue: keep it branch-free)
 #pragma unroll 1
         for (int c0 = 0; c0 < NT; c0 += 16) {
