@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--model", default="janus-1.3b", choices=["janus-1.3b", "janus-pro-7b"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the bounded configs[2]/[3]/[4] measurements after the timed region")
     ap.add_argument("--option", action="append", default=[], help="engine option key=value")
     return ap.parse_args()
 
@@ -319,6 +320,134 @@ def _ncu_traffic_bytes():
     return int(total) if seen == 2 else None
 
 
+def _timed(st, fn):
+    import torch
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    out = fn()
+    e1.record(st)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1), out
+
+
+def extra_configs(dev, peaks):
+    """The other BASELINE.json configurations, measured AFTER the timed region of the headline config (rank 0, one GPU,
+    bounded: one warm + one timed pass each, CUDA events on the launching stream).  Not part of `value`.
+      configs[2]  uni_2stage per-GPU share: stage-1 greedy layout-text decode of 64 rows (prompts 80-160 tokens, 200 new
+                  tokens, eos never hit) + stage-2 CFG image decode at B=64 (R=128 rows)
+      configs[3]  mmu per-GPU share: SigLIP-L tower + aligner on 128 images, scatter into 620-token prompts, prefill +
+                  64 greedy tokens for 128 rows
+      configs[4]  Janus-Pro-7B architecture, layout2image B=32 per GPU (R=64 rows)"""
+    import gc
+    import torch
+    from plangen_b200 import JANUS_1P3B, JANUS_7B, synthetic
+    from plangen_b200.engine import FastJanus
+    peak = peaks.get("hbm_gbs") or 6650.0
+    tpeak = peaks.get("bf16_tflops_sustained") or 1369.6
+    st = torch.cuda.current_stream(dev)
+    out = {}
+
+    def loop_bytes(eng, dims, lens, n_new, head_bytes):
+        kvb = 2 * dims.L * dims.D * 2
+        return eng.weight_bytes_per_step + head_bytes + len(lens) * (sum(lens) / len(lens) + n_new / 2) * kvb + len(lens) * kvb
+
+    def text_batch(dims, rows, P, seed):
+        g = torch.Generator().manual_seed(seed)
+        lens = torch.randint(P // 2, P + 1, (rows,), generator=g).tolist()
+        lens[0] = P
+        ids = torch.full((rows, P), dims.pad_id, dtype=torch.int32)
+        mask = torch.zeros(rows, P, dtype=torch.int32)
+        for r, n in enumerate(lens):
+            ids[r, P - n:] = torch.randint(0, dims.pad_id, (n,), generator=g, dtype=torch.int32)
+            mask[r, P - n:] = 1
+        return ids.to(dev), mask.to(dev), lens
+
+    # ---- configs[2] and configs[3] on one Janus-1.3B engine (64 images / 128 text rows per GPU, vision tower built)
+    dims = JANUS_1P3B
+    sd = synthetic.random_state_dict(dims, dev, seed=0, with_vq=True, with_lm_head=True, with_vision=True)
+    eng = FastJanus(sd, dims, mode="bf16", max_batch=64, max_prompt=640, device=str(dev), max_images=128)
+    del sd
+    ids, mask, lens = text_batch(dims, 64, 160, 5)
+    emb = eng.language_model.get_input_embeddings()(ids)
+    eos, N = dims.vocab - 1, 200
+    gen = lambda n: eng.language_model.generate(inputs_embeds=emb, attention_mask=mask, pad_token_id=eos, eos_token_id=eos, max_new_tokens=n)
+    gen(N)
+    t1, _ = _timed(st, lambda: gen(1))
+    tn, _ = _timed(st, lambda: gen(N))
+    step1 = (tn - t1) / (N - 1)
+    lm_head_extra = dims.vocab * dims.D * 2 - (dims.img_embed * dims.D + dims.img_vocab * dims.img_embed) * 2
+    cond, neg = synthetic.layoutsam_prompts(dims, 64, seed=77)
+    ids2, mask2 = synthetic.collate_cfg_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
+    ids2, mask2 = ids2.to(dev), mask2.to(dev)
+    P2 = ids2.shape[1]
+    lens2 = (mask2[:, :P2] != 0).sum(1).tolist()
+    run2 = lambda: eng.images_to_uint8(eng.t2i(tokens=ids2, mask=mask2, cfg_weight=5.0, temperature=1.0)[0])
+    run2()
+    t2, _ = _timed(st, run2)
+    e2 = eng.language_model.get_input_embeddings()(ids2)
+    tp, _ = _timed(st, lambda: eng.sample_image(e2, 64, 1, mask2, 5.0, 1.0, generator=0))
+    tl, _ = _timed(st, lambda: eng.sample_image(e2, 64, dims.n_img_tokens, mask2, 5.0, 1.0, generator=0))
+    step2 = (tl - tp) / (dims.n_img_tokens - 1)
+    out["configs[2] uni_2stage, 64 prompts per GPU"] = {
+        "images_per_s": 64 / ((tn + t2) / 1e3), "stage1_ms": tn, "stage1_ms_per_greedy_step": step1, "stage1_tokens_per_s": 64 / step1 * 1e3,
+        "stage1_step_frac_of_hbm_peak": loop_bytes(eng, dims, lens, N, lm_head_extra) / (step1 / 1e3) / 1e9 / peak,
+        "stage2_ms": t2, "stage2_images_per_s": 64 / (t2 / 1e3), "stage2_ms_per_decode_step": step2,
+        "stage2_step_frac_of_hbm_peak": loop_bytes(eng, dims, lens2, dims.n_img_tokens, 0) / (step2 / 1e3) / 1e9 / peak,
+        "shape": f"stage 1: 64 rows, prompts 80-160 tokens, {N} greedy tokens (lm_head 102400); stage 2: B=64 (R=128 rows), P={P2}, 576 tokens + VQ decode"}
+    # mmu: 128 rows, one image each: tower + aligner + scatter, then prefill + greedy tokens
+    nI, T, n_new = 128, 620, 64
+    g = torch.Generator().manual_seed(9)
+    pix = (torch.rand(nI, 1, 3, dims.sig_image, dims.sig_image, generator=g) * 2 - 1).to(dev)
+    idm = torch.randint(1, dims.pad_id, (nI, T), generator=g, dtype=torch.int32).to(dev)
+    seq = torch.zeros(nI, T, dtype=torch.bool, device=dev)
+    seq[:, 8:8 + dims.sig_patches] = True
+    embm = torch.ones(nI, 1, dims.sig_patches, dtype=torch.bool, device=dev)
+    am = torch.ones(nI, T, dtype=torch.int32, device=dev)
+    front = lambda: eng.prepare_inputs_embeds(idm, pix, seq, embm)
+    front()
+    tf, xm = _timed(st, front)
+    genm = lambda n: eng.language_model.generate(inputs_embeds=xm, attention_mask=am, pad_token_id=eos, eos_token_id=eos, max_new_tokens=n)
+    genm(2)
+    tg1, _ = _timed(st, lambda: genm(1))
+    tgn, _ = _timed(st, lambda: genm(n_new))
+    W, L, NP, F = dims.sig_width, dims.sig_layers, dims.sig_patches, dims.sig_mlp
+    flop_img = 2 * (L * (4 * W * W + 2 * W * F) + 3 * dims.sig_patch ** 2 * W + W * dims.D + dims.D * dims.D) * NP + L * 4 * NP * NP * W
+    out["configs[3] mmu, 128 images per GPU"] = {
+        "images_per_s": nI / ((tf + tgn) / 1e3), "front_end_ms": tf, "front_end_images_per_s": nI / (tf / 1e3),
+        "front_end_tflops": flop_img * nI / (tf / 1e3) / 1e12, "front_end_frac_of_sustained_bf16_peak": flop_img * nI / (tf / 1e3) / 1e12 / tpeak,
+        "prefill_plus_first_token_ms": tg1, "ms_per_greedy_step": (tgn - tg1) / (n_new - 1),
+        "shape": f"128 x (3,384,384) images -> SigLIP-L/16 + aligner + scatter into T={T} prompts; prefill + {n_new} greedy tokens, 128 rows"}
+    del eng, emb, e2, xm, pix
+    gc.collect()
+    torch.cuda.empty_cache()
+    # ---- configs[4]: Janus-Pro-7B architecture, B=32 per GPU
+    dims = JANUS_7B
+    sd = synthetic.random_state_dict(dims, dev, seed=0, with_vq=True)
+    eng = FastJanus(sd, dims, mode="bf16", max_batch=32, max_prompt=512, device=str(dev))
+    del sd
+    torch.cuda.empty_cache()
+    cond, neg = synthetic.layoutsam_prompts(dims, 32, seed=1234)
+    ids7, mask7 = synthetic.collate_cfg_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
+    ids7, mask7 = ids7.to(dev), mask7.to(dev)
+    P7 = ids7.shape[1]
+    lens7 = (mask7[:, :P7] != 0).sum(1).tolist()
+    run7 = lambda: eng.images_to_uint8(eng.t2i(tokens=ids7, mask=mask7, cfg_weight=5.0, temperature=1.0)[0])
+    e7 = eng.language_model.get_input_embeddings()(ids7)
+    eng.sample_image(e7, 32, 8, mask7, 5.0, 1.0, generator=0)                                  # warm (graph capture)
+    tp7, _ = _timed(st, lambda: eng.sample_image(e7, 32, 1, mask7, 5.0, 1.0, generator=0))
+    t7, _ = _timed(st, run7)
+    tl7, _ = _timed(st, lambda: eng.sample_image(e7, 32, dims.n_img_tokens, mask7, 5.0, 1.0, generator=0))
+    step7 = (tl7 - tp7) / (dims.n_img_tokens - 1)
+    out["configs[4] Janus-Pro-7B-arch layout2image, B=32 per GPU"] = {
+        "images_per_s": 32 / (t7 / 1e3), "ms_per_batch": t7, "prefill_ms": tp7, "ms_per_decode_step": step7,
+        "decode_step_frac_of_hbm_peak": loop_bytes(eng, dims, lens7, dims.n_img_tokens, 0) / (step7 / 1e3) / 1e9 / peak,
+        "shape": f"R=64 rows, P={P7}, 576 tokens, CFG 5 + VQ decode"}
+    del eng
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -465,6 +594,14 @@ def run_b200_arm(args):
     if not args.no_roofline:
         kvs = (dev_batches[args.warmup][1][:, :P] == 0).sum(1).to(torch.int32).contiguous()
         line["roofline"] = kernel_roofline(eng, kvs, lens, P, peaks)
+    if world == 1 and not args.no_extra and args.model == "janus-1.3b" and args.batch == 16:
+        del eng
+        eng = None
+        torch.cuda.empty_cache()
+        try:
+            line["extra"] = extra_configs(dev, peaks)
+        except Exception as ex:                      # the headline line must still be printed
+            line["extra"] = {"error": repr(ex)[:400]}
     if world == 1 and not args.no_cpu_baseline:
         del eng
         torch.cuda.empty_cache()

@@ -264,7 +264,20 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     const int NT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     const int tiles = ((N + TC_BM - 1) / TC_BM) * ((M + NT - 1) / NT);
     const int num_kb = (K + TC_BK - 1) / TC_BK;
-    int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : std::max(1, e->num_sms / tiles));
+    int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : 0);
+    if (want == 0) {
+      // split-K count: every CTA pays a fixed fill / drain cost (~3 us, about 9 k-blocks of streaming) on top of its
+      // k-blocks, CTAs run one per SM in waves.  Minimise waves x (9 + k-blocks per split); e.g. the 7B QKV projection
+      // (96 tiles x 64 k-blocks) takes 3 splits = 288 CTAs = two full waves of 22 k-blocks instead of one wave of 64
+      // on 96 of the 148 SMs.
+      long best = -1;
+      for (int sp = 1; sp <= std::min(16, num_kb); ++sp) {
+        const int kbp = (num_kb + sp - 1) / sp, real = (num_kb + kbp - 1) / kbp;
+        const long waves = ((long)tiles * real + e->num_sms - 1) / e->num_sms;
+        const long cost = waves * (9 + kbp);
+        if (best < 0 || cost < best) { best = cost; want = real; }
+      }
+    }
     if (swiglu_out || epi) want = 1;                        // fused epilogues need the whole K in one CTA
     if (epi && (N % 8 != 0)) return fail("fused epilogue needs N %% 8 == 0 (N=%d)", N);
     want = std::min(std::min(want, 16), num_kb);
