@@ -15,6 +15,7 @@
 #include "../../include/plangen_b200.h"
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm_sk.cuh"
 #include "lm_kernels.cuh"
 #include "attn_tma.cuh"
 #include "attn_v5.cuh"
@@ -113,6 +114,8 @@ struct pg_engine {
   void *sig_xn = nullptr, *sig_qkv = nullptr, *sig_vT = nullptr, *sig_attn = nullptr, *sig_h = nullptr, *sig_feat = nullptr;
   size_t sig_part_bytes = 0;
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
+  int gu_streamk = 1;                                 // decode gate|up + SwiGLU as a stream-K launch over all SMs (gemm_sk.cuh)
+  int* sk_counters = nullptr;
   int sig_attn_tc = 1;                                // tcgen05 attention (bf16, head_dim 64); 0 = CUDA-core kernel
   int sig_fuse = 1;                                   // bias / GELU / residual in the contraction epilogues (gemm.cuh EpiFuse)
   size_t part_bytes = 0;
@@ -351,6 +354,7 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->attn_flag = (int*)c.take(R * d.H * 64 * 4);
   e->attn_ll = (float*)c.take(R * d.H * 64 * (HEAD_DIM + 2) * 8);
   e->step_ctr = (int*)c.take(256);
+  e->sk_counters = (int*)c.take((size_t)((2 * d.F + TC_BM - 1) / TC_BM) * 4);
   e->greedy_state = (int*)c.take(256 + R * 4);      // [0] rows unfinished, [1] steps generated, [64..] per-row flags
   e->vT = c.take(R * d.H * HEAD_DIM * align_up((size_t)std::max(d.max_prompt, 1), 64) * 2);
   e->embed_table = c.take((size_t)d.img_vocab * d.D * es);
@@ -468,6 +472,9 @@ extern "C" int pg_engine_create(const pg_dims* dims, int device, pg_engine** out
   CK(cudaFuncSetAttribute(resid_rmsnorm_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CK(cudaFuncSetAttribute(attn_prefill_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PA_SMEM));
   CK(cudaFuncSetAttribute(vit_attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VT_SMEM));
+  CK(cudaFuncSetAttribute(gemm_swiglu_sk_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+  CK(cudaFuncSetAttribute(gemm_swiglu_sk_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
+  CK(cudaFuncSetAttribute(gemm_swiglu_sk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 216 * 1024));
   if (dims->sig_layers > 0) {
     if (dims->sig_width % 8 || dims->sig_mlp % 8 || dims->sig_patch % 4 || dims->sig_heads < 1 || dims->sig_width % dims->sig_heads ||
         dims->sig_image % dims->sig_patch || dims->sig_width > 4 * LN_MAXQ * LN_THREADS)
@@ -543,6 +550,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "norm_tma") e->norm_tma = (int)value;
   else if (k == "prefill_attn_tc") e->prefill_attn_tc = (int)value;
   else if (k == "sig_attn_tc") e->sig_attn_tc = (int)value;
+  else if (k == "gu_streamk") e->gu_streamk = (int)value;
   else if (k == "sig_fuse") e->sig_fuse = (int)value;
   else if (k == "tc_prefetch") e->tc_prefetch = (int)value;
   else if (k == "tc_prefetch_gu") e->tc_prefetch_gu = (int)value;
@@ -682,6 +690,7 @@ extern "C" int pg_engine_finalize(pg_engine* e, void* stream) {
   CK(cudaMemsetAsync(e->attn_flag, 0, (size_t)d.max_rows * d.H * 64 * 4, st));
   CK(cudaMemsetAsync(e->attn_ll, 0, (size_t)d.max_rows * d.H * 64 * (HEAD_DIM + 2) * 8, st));
   CK(cudaMemsetAsync(e->step_ctr, 0, 256, st));
+  CK(cudaMemsetAsync(e->sk_counters, 0, (size_t)((2 * d.F + TC_BM - 1) / TC_BM) * 4, st));
   CK(cudaMemsetAsync(e->vT, 0, (size_t)d.max_rows * d.H * HEAD_DIM * align_up((size_t)std::max(d.max_prompt, 1), 64) * 2, st));   // must stay finite
   if (e->bf16 && !e->tiled_buf) {
     // tile-major copies of the weights that are streamed once per step (see tile_weight_kernel)
@@ -739,6 +748,36 @@ static int k_gate_up(pg_engine* e, const LayerW& w, int tok, cudaStream_t st) {
   const pg_dims& d = e->d;
   const int F = d.F, D = d.D;
   int S = 1;
+  // Stream-K over all SMs (gemm_sk.cuh) when the one-CTA-per-tile launch would need more than one wave (Janus-Pro-7B:
+  // 172 tiles on 148 SMs; measured 4.17 -> 3.98 ms per step at B=16).  With fewer tiles than SMs (Janus-1.3B: 88) the
+  // plain launch is faster (1.49 vs 1.58 ms per step): the SMs it leaves free are not idle, they host the early-launched
+  // CTAs of the down projection prefetching their weights.  gu_streamk = 2 forces it.
+  if (fused_swiglu_ok(e, tok) && tok <= 64 && D % TC_BK == 0 && e->use_tiled &&
+      (e->gu_streamk == 2 || (e->gu_streamk == 1 && 2 * F / TC_BM > e->num_sms))) {
+    auto it = e->tiled.find(w.wgu);
+    if (it != e->tiled.end() && it->second.N == 2 * F && it->second.K == D) {
+      const int NT = tok <= 16 ? 16 : tok <= 32 ? 32 : 64;
+      const int n_tiles = 2 * F / TC_BM, num_kb = D / TC_BK;
+      const long U = (long)n_tiles * num_kb;
+      const int G = (int)std::min<long>(e->num_sms, U);
+      const int per_min = (int)std::max<long>(1, U / G);
+      const int max_contrib = (num_kb + per_min - 1) / per_min + 1;
+      if ((size_t)n_tiles * max_contrib * NT * TC_BM * 4 > e->part_bytes) return fail("internal: stream-K scratch does not fit the partial buffer");
+      CUtensorMap mx;
+      TRY(make_map_2d(e, &mx, e->xn, (uint64_t)tok, (uint64_t)D, (uint32_t)NT));
+      const int stage_bytes = TC_A_BYTES + NT * TC_BK * 2;
+      int stages = std::min(12, (200 * 1024) / stage_bytes) & ~1;
+      const size_t smem = (size_t)stages * stage_bytes + SKG_XCH_BYTES + 1024 + 512;
+      if (NT == 64)
+        return launch(e, gemm_swiglu_sk_kernel<64>, dim3(G), dim3(SKG_THREADS), smem, st, mx, it->second.ptr, tok, F, n_tiles, num_kb, stages,
+                      e->use_pdl, e->part, max_contrib, e->sk_counters, (bf16*)e->hbuf, next_prof(e));
+      if (NT == 16)
+        return launch(e, gemm_swiglu_sk_kernel<16>, dim3(G), dim3(SKG_THREADS), smem, st, mx, it->second.ptr, tok, F, n_tiles, num_kb, stages,
+                      e->use_pdl, e->part, max_contrib, e->sk_counters, (bf16*)e->hbuf, next_prof(e));
+      return launch(e, gemm_swiglu_sk_kernel<32>, dim3(G), dim3(SKG_THREADS), smem, st, mx, it->second.ptr, tok, F, n_tiles, num_kb, stages,
+                    e->use_pdl, e->part, max_contrib, e->sk_counters, (bf16*)e->hbuf, next_prof(e));
+    }
+  }
   if (fused_swiglu_ok(e, tok)) return run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, e->hbuf);
   TRY(run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st));
   const size_t total = (size_t)tok * F;

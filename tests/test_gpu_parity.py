@@ -210,6 +210,45 @@ def test_bf16_long_ragged_context(path):
     assert_close(dbg.cpu().numpy(), ref_logits, 2e-2, 2e-2, f"bf16 long-context CFG logits ({path})")
 
 
+@pytest.mark.parametrize("B", [5, 16, 32])
+def test_bf16_streamk_gate_up_matches_reference(B):
+    """Stream-K gate|up + SwiGLU (gemm_sk.cuh; the default for Janus-Pro-7B, forced here): token tiles of 16 / 32 / 64
+    rows, unit ranges of one or two k-blocks (176 units over 148 CTAs: up to eight partial contributors per tile,
+    fragments whose only k-block falls to one MMA issuer): CFG logits vs the autocast reference on the same GPU,
+    teacher-forced, and deterministic across runs."""
+    dims = O.SMALL
+    steps = 6
+    sd = O.init_state_dict(dims, seed=0, with_vq=False)
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    g = torch.Generator().manual_seed(40 + B)
+    lens = torch.randint(5, 120, (B,), generator=g).tolist()
+    cond = [torch.randint(0, dims.vocab - 2, (n,), generator=g).tolist() for n in lens]
+    neg = [torch.randint(0, dims.vocab - 2, (17,), generator=g).tolist()] * B
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
+    trace = {}
+    ref_tok, _ = O.t2i(sdc, dims, ids.cuda(), mask.cuda(), sampler=O.greedy_sampler, mode="autocast",
+                       image_token_num_per_image=steps, decode=False, trace=trace)
+    ref_logits = torch.stack(trace["logits"]).numpy()
+    eng = get_engine(dims, "bf16", with_vq=False, max_batch=32, max_prompt=128)
+    eng.set_option("gu_streamk", 2)
+    try:
+        outs = []
+        for _ in range(2):
+            dbg = torch.zeros(steps, B, dims.img_vocab, device="cuda")
+            eng.set_option("dbg_logits_ptr", dbg.data_ptr())
+            emb = eng.language_model.get_input_embeddings()(ids.cuda())
+            forced = {"edit_region": torch.zeros(B, steps, dtype=torch.int32)}
+            eng.sample_image(emb, B, steps, mask.cuda(), 5.0, 1.0, generator=0, batch=forced, gt_labels=ref_tok, greedy=True,
+                             use_teacher_forcing=True)
+            torch.cuda.synchronize()
+            outs.append(dbg.cpu().numpy())
+    finally:
+        eng.set_option("dbg_logits_ptr", 0)
+        eng.set_option("gu_streamk", 1)
+    assert np.array_equal(outs[0], outs[1]), "stream-K gate|up is not deterministic"
+    assert_close(outs[0], ref_logits, 2e-2, 2e-2, f"bf16 CFG logits, stream-K gate|up, B={B}")
+
+
 def test_fp32_t2i_parallel_size_two_matches_oracle():
     """System.t2i with parallel_size = 2 (plangen_base.py:547-549: ids and mask tiled, num_gen = B * parallel_size
     images sampled in one batch from one Philox stream): token ids identical to the oracle, images within fp32 noise."""
