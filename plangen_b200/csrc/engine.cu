@@ -114,6 +114,7 @@ struct pg_engine {
   void *sig_xn = nullptr, *sig_qkv = nullptr, *sig_vT = nullptr, *sig_attn = nullptr, *sig_h = nullptr, *sig_feat = nullptr;
   size_t sig_part_bytes = 0;
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
+  int prefill_fuse = 1;                               // prefill contractions with bf16 / residual epilogues (gemm.cuh EpiFuse) instead of fp32 partials
   int gu_streamk = 1;                                 // decode gate|up + SwiGLU as a stream-K launch over all SMs (gemm_sk.cuh)
   int* sk_counters = nullptr;
   int sig_attn_tc = 1;                                // tcgen05 attention (bf16, head_dim 64); 0 = CUDA-core kernel
@@ -551,6 +552,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "prefill_attn_tc") e->prefill_attn_tc = (int)value;
   else if (k == "sig_attn_tc") e->sig_attn_tc = (int)value;
   else if (k == "gu_streamk") e->gu_streamk = (int)value;
+  else if (k == "prefill_fuse") e->prefill_fuse = (int)value;
   else if (k == "sig_fuse") e->sig_fuse = (int)value;
   else if (k == "tc_prefetch") e->tc_prefetch = (int)value;
   else if (k == "tc_prefetch_gu") e->tc_prefetch_gu = (int)value;
@@ -809,10 +811,21 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
   const int tok = R * P, D = d.D, HD = e->HD, F = d.F;
   const float scale = 1.0f / sqrtf((float)HEAD_DIM);
   int S = 1;
+  // fused epilogues (bf16 regime on tcgen05): QKV and gate|up leave the contraction as bf16 rows, O and down add straight
+  // into the fp32 residual stream - no fp32 partial round trip (same values: the row kernels rounded the partials first)
+  const bool fuse = e->bf16 && e->use_tc && e->prefill_fuse && D % 8 == 0 && HD % 8 == 0 && F % 64 == 0 &&
+                    (size_t)tok * std::max(3 * HD, 2 * F) * 2 <= e->part_bytes;
+  bf16* stage16 = (bf16*)e->part;
   for (int l = 0; l < d.L; ++l) {
     LayerW w;
     TRY(layer_weights(e, l, &w));
     if (l == 0) TRY(k_resid_norm(e, x, nullptr, 0, 0, w.ln1, e->xn, nullptr, tok, 1, 0, 0, st));
+    if (fuse) {
+      EpiFuse ep = {nullptr, stage16, nullptr, 0};
+      TRY(run_gemm(e, e->xn, w.wqkv, tok, 3 * HD, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &ep));
+      TRY(launch(e, qkv_rope_store_bf16_kernel, dim3(tok), dim3(256), 0, st, (const bf16*)stage16, cosT, sinT, (bf16*)e->qbuf,
+                 (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax, rope_rel ? kv_start : (const int32_t*)nullptr));
+    } else {
     TRY(run_gemm(e, e->xn, w.wqkv, tok, 3 * HD, D, e->part, e->part_bytes, &S, st));
     DISPATCH_T(e,
                launch(e, qkv_rope_store_kernel<bf16>, dim3(tok), dim3(256), 0, st, e->part, S, (size_t)tok * 3 * HD, cosT, sinT,
@@ -821,6 +834,7 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
                launch(e, qkv_rope_store_kernel<float>, dim3(tok), dim3(256), 0, st, e->part, S, (size_t)tok * 3 * HD, cosT, sinT,
                       (float*)e->qbuf, (float*)kv_ptr(e, l, 0, R), (float*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax,
                       rope_rel ? kv_start : (const int32_t*)nullptr));
+    }
     if (e->bf16 && e->use_tc && e->prefill_attn_tc) {
       // tensor-core path: key-contiguous V copy, then one CTA per (row, head, 128-query tile)
       const int Ppad = (int)align_up((size_t)P, 64);
@@ -840,6 +854,26 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
                launch(e, attn_prefill_kernel<float>, dim3((P + 63) / 64, d.H, R), dim3(256), ATTN_PREFILL_SMEM, st,
                       (const float*)e->qbuf, (const float*)kv_ptr(e, l, 0, R), (const float*)kv_ptr(e, l, 1, R), kv_start,
                       (float*)e->attn_out, P, d.H, e->Tmax, scale));
+    if (fuse) {
+      EpiFuse er = {nullptr, nullptr, x, 0};
+      TRY(run_gemm(e, e->attn_out, w.wo, tok, D, HD, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &er));
+      TRY(k_resid_norm(e, x, nullptr, 0, 0, w.ln2, e->xn, nullptr, tok, 1, 0, 0, st));
+      if (fused_swiglu_ok(e, tok)) {
+        TRY(k_gate_up(e, w, tok, st));
+      } else {
+        EpiFuse eg = {nullptr, stage16, nullptr, 0};
+        TRY(run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &eg));
+        const size_t total8 = (size_t)tok * F / 8;
+        TRY(launch(e, swiglu_bf16_kernel, dim3(elementwise_blocks(e, total8)), dim3(256), 0, st, (const bf16*)stage16, (bf16*)e->hbuf, F, total8));
+      }
+      TRY(run_gemm(e, e->hbuf, w.wd, tok, D, F, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &er));
+      if (l + 1 < d.L) {
+        LayerW wn;
+        TRY(layer_weights(e, l + 1, &wn));
+        TRY(k_resid_norm(e, x, nullptr, 0, 0, wn.ln1, e->xn, nullptr, tok, 1, 0, 0, st));
+      }
+      continue;
+    }
     TRY(run_gemm(e, e->attn_out, w.wo, tok, D, HD, e->part, e->part_bytes, &S, st));
     TRY(k_resid_norm(e, x, e->part, S, (size_t)tok * D, w.ln2, e->xn, nullptr, tok, 1, 0, 0, st));
     TRY(k_gate_up(e, w, tok, st));
@@ -851,11 +885,12 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
     }
   }
   // final norm: all positions -> caller's buffer; last position of every row -> hidden_t for gen_head
+  const float* last_part = fuse ? nullptr : e->part;      // fused: the last down projection is already in the stream
   if (all_positions) {
-    TRY(k_resid_norm(e, x, e->part, S, (size_t)tok * D, normw, nullptr, hidden_out, tok, 1, 0, 0, st));
+    TRY(k_resid_norm(e, x, last_part, S, (size_t)tok * D, normw, nullptr, hidden_out, tok, 1, 0, 0, st));
     TRY(k_resid_norm(e, x, nullptr, 0, 0, normw, e->hidden_t, e->hidden_f, R, P, P - 1, 0, st));
   } else {
-    TRY(k_resid_norm(e, x, e->part, S, (size_t)tok * D, normw, e->hidden_t, e->hidden_f, R, P, P - 1, 0, st));
+    TRY(k_resid_norm(e, x, last_part, S, (size_t)tok * D, normw, e->hidden_t, e->hidden_f, R, P, P - 1, 0, st));
     if (hidden_out) CK(cudaMemcpyAsync(hidden_out, e->hidden_f, (size_t)R * D * 4, cudaMemcpyDeviceToDevice, st));
   }
   return 0;

@@ -395,6 +395,74 @@ qkv_rope_store_kernel(const float* __restrict__ part, int S, size_t split_stride
   }
 }
 
+// Prefill variant behind the contraction's fused bf16 epilogue (gemm.cuh EpiFuse): the projections arrive already
+// rounded to bf16 ([tok][3*H*128], q | k | v), so this kernel only rotates and scatters - same values as
+// qkv_rope_store_kernel<bf16> on the fp32 partials (it rounds them first), half the bytes.
+__global__ void __launch_bounds__(256)
+qkv_rope_store_bf16_kernel(const bf16* __restrict__ qkv, const float* __restrict__ cosT, const float* __restrict__ sinT,
+                           bf16* __restrict__ q_out, bf16* __restrict__ kcache, bf16* __restrict__ vcache, int P, int H, int Tmax,
+                           const int32_t* __restrict__ rope_start) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int tok = blockIdx.x;
+  const int r = tok / P, p = tok % P;
+  const int HD = H * HEAD_DIM;
+  const bf16* row = qkv + (size_t)tok * 3 * HD;
+  const int pr = rope_start ? max(p - rope_start[r], 0) : p;
+  for (int i = threadIdx.x; i < H * 16; i += blockDim.x) {
+    const int h = i >> 4, j = (i & 15) * 4;
+    const float4 c4 = *reinterpret_cast<const float4*>(cosT + pr * 64 + j), s4 = *reinterpret_cast<const float4*>(sinT + pr * 64 + j);
+    const float cs[4] = {c4.x, c4.y, c4.z, c4.w}, sn[4] = {s4.x, s4.y, s4.z, s4.w};
+    const size_t o1 = (size_t)h * HEAD_DIM + j, o2 = o1 + 64;
+    const size_t cidx = (((size_t)r * H + h) * Tmax + p) * HEAD_DIM + j;
+    auto ld4 = [&](size_t off, float (&dst)[4]) {
+      const uint2 t = *reinterpret_cast<const uint2*>(row + off);
+      dst[0] = bf16lo(t.x); dst[1] = bf16hi(t.x); dst[2] = bf16lo(t.y); dst[3] = bf16hi(t.y);
+    };
+    auto st4 = [&](bf16* dst, const float (&src)[4]) {
+      const __nv_bfloat162 x0 = __floats2bfloat162_rn(src[0], src[1]), x1 = __floats2bfloat162_rn(src[2], src[3]);
+      uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&x0); pk.y = *reinterpret_cast<const uint32_t*>(&x1);
+      *reinterpret_cast<uint2*>(dst) = pk;
+    };
+    float lo[4], hi[4], a[4], b[4];
+    ld4(o1, lo); ld4(o2, hi);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rope_pair<bf16>(lo[u], hi[u], cs[u], sn[u], false, a[u], b[u]);
+    st4(q_out + (size_t)tok * HD + o1, a); st4(q_out + (size_t)tok * HD + o2, b);
+    ld4(HD + o1, lo); ld4(HD + o2, hi);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rope_pair<bf16>(lo[u], hi[u], cs[u], sn[u], false, a[u], b[u]);
+    st4(kcache + cidx, a); st4(kcache + cidx + 64, b);
+    *reinterpret_cast<uint2*>(vcache + cidx) = *reinterpret_cast<const uint2*>(row + 2 * HD + o1);
+    *reinterpret_cast<uint2*>(vcache + cidx + 64) = *reinterpret_cast<const uint2*>(row + 2 * HD + o2);
+  }
+}
+
+// h = rnd(silu(g)) * u on bf16 gate | up projections ([tok][2F], interleaved in blocks of 64 as the weight rows are
+// packed): the prefill's SwiGLU behind the fused bf16 epilogue; values identical to swiglu_kernel<bf16>.
+__global__ void __launch_bounds__(256)
+swiglu_bf16_kernel(const bf16* __restrict__ gu, bf16* __restrict__ h, int F, size_t total8) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int F8 = F / 8;
+  for (size_t i8 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i8 < total8; i8 += (size_t)gridDim.x * blockDim.x) {
+    const size_t tok = i8 / F8;
+    const int f = (int)(i8 - tok * F8) * 8;
+    const bf16* row = gu + tok * 2 * F + (size_t)(f >> 6) * 128 + (f & 63);
+    const uint4 g4 = *reinterpret_cast<const uint4*>(row), u4 = *reinterpret_cast<const uint4*>(row + 64);
+    const uint32_t gw[4] = {g4.x, g4.y, g4.z, g4.w}, uw[4] = {u4.x, u4.y, u4.z, u4.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float g0 = bf16lo(gw[j]), g1 = bf16hi(gw[j]), u0 = bf16lo(uw[j]), u1 = bf16hi(uw[j]);
+      const float h0 = bf16_round(g0 / (1.0f + expf(-g0))) * u0, h1 = bf16_round(g1 / (1.0f + expf(-g1))) * u1;
+      const __nv_bfloat162 o = __floats2bfloat162_rn(h0, h1);
+      ow[j] = *reinterpret_cast<const uint32_t*>(&o);
+    }
+    *reinterpret_cast<uint4*>(h + tok * F + f) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
 // ---------------------------------------------------------------- a4.3: SwiGLU
 // h = silu(gate) * up   (HF LlamaMLP :182-184); partial layout [S][tok][2F]: [gate | up], or - when the
 // weight rows were packed for the fused tcgen05 epilogue - interleaved in blocks of 64 (g0-63, u0-63, g64-127, ...)
