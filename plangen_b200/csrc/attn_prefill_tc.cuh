@@ -51,7 +51,7 @@ v_transpose_kernel(const bf16* __restrict__ vcache, bf16* __restrict__ vT, int P
 __global__ void __launch_bounds__(128, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_vt, const int32_t* __restrict__ kv_start,
-                       bf16* __restrict__ out, int P, int H, int Tmax, float scale) {
+                       bf16* __restrict__ out, int P, int H, int Tmax, float scale, const int32_t* __restrict__ row_off) {
   extern __shared__ uint8_t pa_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)pa_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                      // 2 tiles: dims 0-63 | 64-127 of the 128 queries
@@ -83,7 +83,11 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   const int row = warp * 32 + lane;                 // query row within the tile = TMEM lane
   const int q = q0 + row;
   const int q_hi = min(q0 + PA_BQ - 1, P - 1);
-  bf16* orow = out + ((size_t)r * P + q) * HD + h * HEAD_DIM;
+  // row_off != nullptr: q and out hold the real tokens only, packed row after row (lm_kernels.cuh packed_row_of): column
+  // q of row r is packed row row_off[r] + q - start; the (pad) columns before `start` do not exist - a tile that
+  // straddles `start` loads whatever precedes the row (finite, or zeros below row 0) for them and never stores them
+  const int qbase = row_off != nullptr ? row_off[r] - start : r * P;
+  bf16* orow = out + (ptrdiff_t)(qbase + q) * HD + h * HEAD_DIM;
   float o[HEAD_DIM];
 #pragma unroll
   for (int j = 0; j < HEAD_DIM; ++j) o[j] = 0.f;
@@ -101,8 +105,8 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const uint64_t pol = policy_evict_first();
         mbar_expect_tx(bar_load, (it == 0 ? 2 * PA_TILE : 0) + 4 * PA_TILE);
         if (it == 0) {
-          tma_load_2d(sQ, &map_q, bar_load, h * HEAD_DIM, r * P + q0, pol);
-          tma_load_2d(sQ + PA_TILE, &map_q, bar_load, h * HEAD_DIM + 64, r * P + q0, pol);
+          tma_load_2d(sQ, &map_q, bar_load, h * HEAD_DIM, qbase + q0, pol);
+          tma_load_2d(sQ + PA_TILE, &map_q, bar_load, h * HEAD_DIM + 64, qbase + q0, pol);
         }
         const int krow = (r * H + h) * Tmax + key0;
         tma_load_2d(sK, &map_k, bar_load, 0, krow, pol);
@@ -200,7 +204,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       __syncthreads();          // next block: TMA overwrites K / V^T, the first MMA overwrites S
     }
   }
-  if (q < P) {
+  if (q < P && (row_off == nullptr || q >= start)) {
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;      // pad queries (nothing visible) produce zeros
 #pragma unroll
     for (int j = 0; j < HEAD_DIM; j += 8) {

@@ -86,7 +86,7 @@ struct pg_engine {
   void* vT = nullptr;                        // [R][H][128][Ppad] key-contiguous copy of V for the prefill attention
   int norm_tma = 3;      // bit 0: decode-step norms through the TMA-staged kernel, bit 1: prefill norms too
   int tc_prefetch = 0, tc_prefetch_gu = 0;   // weight tiles a decode contraction may request before its dependency wait (0 = ring depth)
-  int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2, fuse_conv_epilogue = 0;   // fused conv epilogue measured slower (VQ 57 vs 42.5 ms): 2-byte scattered stores on the GEMM critical path
+  int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2, fuse_conv_epilogue = 1;   // conv bias / residual / bf16 store in the contraction epilogue
   EncodeTiledFn encode = nullptr;
   // options
   uint64_t attn_dbg_ptr = 0;
@@ -114,6 +114,8 @@ struct pg_engine {
   void *sig_xn = nullptr, *sig_qkv = nullptr, *sig_vT = nullptr, *sig_attn = nullptr, *sig_h = nullptr, *sig_feat = nullptr;
   size_t sig_part_bytes = 0;
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
+  int prefill_pack = 1;                               // fused loops prefill the real tokens only (lm_kernels.cuh packed_row_of)
+  float* xpack = nullptr; float* x_last = nullptr; int32_t* row_off = nullptr; int32_t* row_off_host = nullptr;
   int prefill_fuse = 1;                               // prefill contractions with bf16 / residual epilogues (gemm.cuh EpiFuse) instead of fp32 partials
   int gu_streamk = 1;                                 // decode gate|up + SwiGLU as a stream-K launch over all SMs (gemm_sk.cuh)
   int* sk_counters = nullptr;
@@ -223,8 +225,7 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
 // (bf16, Cin % 64 == 0, W or a 192-pixel part of it tiles a 192-pixel block), 0 -> caller uses im2col.
 constexpr int CONV_NT = 192;
 static int run_conv_gemm(pg_engine* e, const void* act, const void* Wc, int B, int H, int W, int Cin, int Cout, float* C,
-                         size_t c_bytes, cudaStream_t st, int* taken, const float* bias = nullptr,
-                         const void* residual = nullptr, void* out_bf16 = nullptr) {
+                         size_t c_bytes, cudaStream_t st, int* taken, const EpiFuse* epi = nullptr) {
   *taken = 0;
   if (!e->bf16 || !e->use_tc || !e->use_implicit_conv || Cin % TC_BK != 0) return 0;
   if ((((uintptr_t)act) & 15) || (((uintptr_t)Wc) & 15)) return 0;
@@ -238,7 +239,6 @@ static int run_conv_gemm(pg_engine* e, const void* act, const void* Wc, int B, i
   ConvGeom cg;
   cg.enabled = 1; cg.H = H; cg.W = W; cg.Cin = Cin; cg.bw = bw; cg.bh = bh;
   cg.tiles_x = W / bw; cg.tiles_y = (H + bh - 1) / bh;
-  cg.bias = bias; cg.residual = (const bf16*)residual; cg.out_bf16 = (bf16*)out_bf16;
   CUtensorMap mw, mx;
   TRY(make_map_2d(e, &mw, Wc, (uint64_t)Cout, (uint64_t)9 * Cin, TC_BM));
   cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -251,7 +251,7 @@ static int run_conv_gemm(pg_engine* e, const void* act, const void* Wc, int B, i
   if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (conv activation) failed (%d) B=%d H=%d W=%d C=%d", (int)r, B, H, W, Cin);
   const int num_kb = 9 * Cin / TC_BK;
   TRY(launch_tc<CONV_NT>(e, mw, mx, C, (int)pixels, Cout, 9 * Cin, 1, num_kb, true, nullptr, nullptr, st, &cg,
-                         B * cg.tiles_x * cg.tiles_y));
+                         B * cg.tiles_x * cg.tiles_y, epi));
   *taken = 1;
   return 0;
 }
@@ -337,6 +337,9 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   const size_t max_tok = (size_t)d.max_rows * std::max(d.max_prompt, 1);
   const size_t R = d.max_rows;
   const size_t wide = std::max<size_t>(std::max(3 * e->HD, 2 * d.F), std::max(d.D, d.img_embed));
+  e->xpack = (float*)c.take(max_tok * d.D * 4);
+  e->x_last = (float*)c.take(R * d.D * 4);
+  e->row_off = (int32_t*)c.take((R + 1) * 4);
   e->xn = c.take(max_tok * d.D * es);
   e->qbuf = c.take(max_tok * e->HD * es);
   e->attn_out = c.take(max_tok * e->HD * es);
@@ -495,6 +498,7 @@ extern "C" int pg_engine_destroy(pg_engine* e) {
   if (!e) return 0;
   drop_graphs(e);
   if (e->poll_host) cudaFreeHost(e->poll_host);
+  if (e->row_off_host) cudaFreeHost(e->row_off_host);
   if (e->tiled_buf) cudaFree(e->tiled_buf);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -553,6 +557,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "sig_attn_tc") e->sig_attn_tc = (int)value;
   else if (k == "gu_streamk") e->gu_streamk = (int)value;
   else if (k == "prefill_fuse") e->prefill_fuse = (int)value;
+  else if (k == "prefill_pack") e->prefill_pack = (int)value;
   else if (k == "sig_fuse") e->sig_fuse = (int)value;
   else if (k == "tc_prefetch") e->tc_prefetch = (int)value;
   else if (k == "tc_prefetch_gu") e->tc_prefetch_gu = (int)value;
@@ -808,9 +813,33 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
   NEED(cosT, float, "rope_cos");
   NEED(sinT, float, "rope_sin");
   NEED(normw, float, "norm");
-  const int tok = R * P, D = d.D, HD = e->HD, F = d.F;
+  const int D = d.D, HD = e->HD, F = d.F;
+  int tok = R * P;
   const float scale = 1.0f / sqrtf((float)HEAD_DIM);
   int S = 1;
+  // ---- packed prefill (fused loops only: the drop-in call returns every position, pads included)
+  const int32_t* row_off = nullptr;
+  if (!all_positions && e->bf16 && e->use_tc && e->prefill_attn_tc && e->prefill_fuse && e->prefill_pack && D % 8 == 0 && HD % 8 == 0 &&
+      F % 64 == 0) {
+    if (!e->row_off_host) CK(cudaMallocHost(&e->row_off_host, (size_t)(d.max_rows + 1) * 4));
+    CK(cudaMemcpyAsync(e->row_off_host, kv_start, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::vector<int32_t> off((size_t)R + 1, 0);
+    bool ok = true;
+    for (int r = 0; r < R; ++r) {
+      const int len = P - e->row_off_host[r];
+      if (len < 1 || len > P) ok = false;                  // an empty row: leave it to the padded path
+      off[r + 1] = off[r] + std::max(len, 0);
+    }
+    if (ok && off[R] < R * P) {
+      memcpy(e->row_off_host, off.data(), (size_t)(R + 1) * 4);
+      CK(cudaMemcpyAsync(e->row_off, e->row_off_host, (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, st));
+      TRY(launch(e, prefill_pack_kernel, dim3(P, R), dim3(256), 0, st, (const float*)x, e->xpack, kv_start, (const int32_t*)e->row_off, P, D));
+      x = e->xpack;
+      tok = off[R];
+      row_off = e->row_off;
+    }
+  }
   // fused epilogues (bf16 regime on tcgen05): QKV and gate|up leave the contraction as bf16 rows, O and down add straight
   // into the fp32 residual stream - no fp32 partial round trip (same values: the row kernels rounded the partials first)
   const bool fuse = e->bf16 && e->use_tc && e->prefill_fuse && D % 8 == 0 && HD % 8 == 0 && F % 64 == 0 &&
@@ -824,7 +853,8 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
       EpiFuse ep = {nullptr, stage16, nullptr, 0};
       TRY(run_gemm(e, e->xn, w.wqkv, tok, 3 * HD, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &ep));
       TRY(launch(e, qkv_rope_store_bf16_kernel, dim3(tok), dim3(256), 0, st, (const bf16*)stage16, cosT, sinT, (bf16*)e->qbuf,
-                 (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax, rope_rel ? kv_start : (const int32_t*)nullptr));
+                 (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), P, d.H, e->Tmax, rope_rel ? kv_start : (const int32_t*)nullptr,
+                 row_off, kv_start, R));
     } else {
     TRY(run_gemm(e, e->xn, w.wqkv, tok, 3 * HD, D, e->part, e->part_bytes, &S, st));
     DISPATCH_T(e,
@@ -845,7 +875,7 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
       TRY(make_map_2d(e, &mk, kv_ptr(e, l, 0, R), (uint64_t)R * d.H * e->Tmax, (uint64_t)HEAD_DIM, PA_BK));
       TRY(make_map_2d(e, &mv, e->vT, (uint64_t)R * d.H * HEAD_DIM, (uint64_t)Ppad, HEAD_DIM));
       TRY(launch(e, attn_prefill_tc_kernel, dim3((P + PA_BQ - 1) / PA_BQ, d.H, R), dim3(128), PA_SMEM, st, mq, mk, mv, kv_start,
-                 (bf16*)e->attn_out, P, d.H, e->Tmax, scale));
+                 (bf16*)e->attn_out, P, d.H, e->Tmax, scale, row_off));
     } else
     DISPATCH_T(e,
                launch(e, attn_prefill_kernel<bf16>, dim3((P + 63) / 64, d.H, R), dim3(256), ATTN_PREFILL_SMEM, st,
@@ -886,7 +916,12 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
   }
   // final norm: all positions -> caller's buffer; last position of every row -> hidden_t for gen_head
   const float* last_part = fuse ? nullptr : e->part;      // fused: the last down projection is already in the stream
-  if (all_positions) {
+  if (row_off != nullptr) {
+    // packed: the last real token of every row
+    TRY(launch(e, gather_last_rows_kernel, dim3(R), dim3(256), 0, st, (const float*)x, e->x_last, row_off, D));
+    TRY(k_resid_norm(e, e->x_last, nullptr, 0, 0, normw, e->hidden_t, e->hidden_f, R, 1, 0, 0, st));
+    if (hidden_out) CK(cudaMemcpyAsync(hidden_out, e->hidden_f, (size_t)R * D * 4, cudaMemcpyDeviceToDevice, st));
+  } else if (all_positions) {
     TRY(k_resid_norm(e, x, last_part, S, (size_t)tok * D, normw, nullptr, hidden_out, tok, 1, 0, 0, st));
     TRY(k_resid_norm(e, x, nullptr, 0, 0, normw, e->hidden_t, e->hidden_f, R, P, P - 1, 0, st));
   } else {
@@ -1561,9 +1596,11 @@ static int vq_conv(VqCtx& c, const void* in, int Hi, int Wi, int Cin, const std:
       }
       if (pixels * Cout > e->vq_part_elems) return fail("internal: vq partial buffer too small");
       int taken = 0;
-      const bool fuse = out != nullptr && out_nchw == nullptr && e->fuse_conv_epilogue;   // bias (+ residual) -> bf16 in the GEMM epilogue
-      TRY(run_conv_gemm(e, act, W, c.Bc, Ho, Wo, Cin, Cout, e->vq_part, e->vq_part_elems * 4, c.st, &taken,
-                        fuse ? bias : nullptr, fuse ? residual : nullptr, fuse ? out : nullptr));
+      // bias (+ residual) -> bf16 NHWC rows in the contraction's epilogue (gemm.cuh EpiFuse); the final conv_out (3 channels,
+      // fp32 NCHW) keeps the row kernel
+      const bool fuse = out != nullptr && out_nchw == nullptr && e->fuse_conv_epilogue && Cout % 8 == 0;
+      EpiFuse ep = {bias, (bf16*)out, nullptr, 0, (const bf16*)residual};
+      TRY(run_conv_gemm(e, act, W, c.Bc, Ho, Wo, Cin, Cout, e->vq_part, e->vq_part_elems * 4, c.st, &taken, fuse ? &ep : nullptr));
       if (taken) {
         if (!fuse) TRY(vq_epilogue(c, e->vq_part, bias, residual, out, out_nchw, Cout, Ho * Wo, pixels, 0));
         return 0;

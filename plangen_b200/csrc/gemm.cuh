@@ -97,11 +97,6 @@ PG_DEVINL void gemm_stamp(unsigned long long* dbg, int k) {
 // out-of-bounds rows/columns are zero-filled by the hardware (the conv padding).  No im2col matrix exists.
 struct ConvGeom {
   int enabled, H, W, Cin, bw, bh, tiles_x, tiles_y;
-  // optional fused epilogue (no split-K): out[m][n] = rnd(rnd(acc + bias[n]) + residual[m][n]) as bf16, the
-  // rounding points of conv_epilogue_kernel; saves the fp32 partial round trip and a launch per convolution
-  const float* bias;
-  const bf16* residual;
-  bf16* out_bf16;
 };
 
 // Fused row epilogue (no split-K) for the wide-tile contractions of the vision tower / aligner (and any other
@@ -109,14 +104,20 @@ struct ConvGeom {
 //   out  : out[m][n]   = bf16( act( bf16(acc + bias[n]) ) )         act = identity | exact-erf GELU
 //          the 128 x NT tile is staged in the (idle) operand ring as [m][128 n] bf16 and written with 16-byte stores,
 //          256 contiguous bytes per token row;
+//          with add16: out[m][n] = bf16( bf16(acc + bias[n]) + add16[m][n] )  (VQ ResnetBlock / AttnBlock skip connection,
+//          vq_model.py:352,390; add16 may alias out: a thread reads its 16 bytes before it writes them).  In the
+//          implicit-GEMM convolution the tile's pixel block is a contiguous run of rows of the NHWC output (bw == W or
+//          bh == 1), so the same staged store serves it;
 //   resid: resid[m][n] += bf16(acc + bias[n])                        fp32 residual stream updated in place
 //          (128 contiguous bytes per warp access, the pattern of the partial store).
-// Rounding points are those of bias_act_kernel / vit_resid_ln_kernel (autocast: Linear output in bf16).
+// Rounding points are those of bias_act_kernel / vit_resid_ln_kernel / conv_epilogue_kernel (autocast: Linear and conv
+// outputs in bf16).
 struct EpiFuse {
   const float* bias;   // [N] or nullptr
   bf16* out;           // [M][N] row-major, or nullptr
   float* resid;        // [M][N] fp32, or nullptr
   int gelu;
+  const bf16* add16;   // [M][N] bf16 added after the first rounding (out mode), or nullptr
 };
 
 template <int NT>
@@ -346,15 +347,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
         asm volatile("bar.sync 2, 128;" ::: "memory");
         const int t128 = threadIdx.x - 64;                      // 0..127 over the epilogue warps 2..5
         const int ch = t128 & 15, r0 = t128 >> 4;              // 16-byte chunk of the 256-byte row, first row
+        // rows of the output this tile covers: token rows m0.., or (convolution) the pixel block's run of NHWC rows, which
+        // must not run past the end of its image (a partial block at the bottom edge)
+        const size_t row0 = cg.enabled ? ((size_t)cv_b * cg.H + cv_y0) * cg.W + cv_x0 : (size_t)m0;
+        const size_t row_end = cg.enabled ? (size_t)(cv_b + 1) * cg.H * cg.W : (size_t)M;
         if (n0 + ch * 8 < N) {
 #pragma unroll 4
           for (int r = r0; r < NT; r += 8) {
-            const int m = m0 + r;
-            if (m < M) {
+            const size_t m = row0 + r;
+            if (m < row_end) {
               uint4 q;
               asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
                            : "r"(stg + (uint32_t)(r * 256 + ch * 16)));
-              *reinterpret_cast<uint4*>(ep.out + (size_t)m * N + n0 + ch * 8) = q;
+              bf16* dst = ep.out + m * N + n0 + ch * 8;
+              if (ep.add16 != nullptr) {
+                const uint4 a = *reinterpret_cast<const uint4*>(ep.add16 + m * N + n0 + ch * 8);
+                uint32_t qs[4] = {q.x, q.y, q.z, q.w};
+                const uint32_t as[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const __nv_bfloat162 o = __floats2bfloat162_rn(bf16lo(qs[u]) + bf16lo(as[u]), bf16hi(qs[u]) + bf16hi(as[u]));
+                  qs[u] = *reinterpret_cast<const uint32_t*>(&o);
+                }
+                q = make_uint4(qs[0], qs[1], qs[2], qs[3]);
+              }
+              *reinterpret_cast<uint4*>(dst) = q;
             }
           }
         }
@@ -394,8 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
           }
         }
       } else {
-        // convolution: pixel (c0 + j) of the bw x bh block -> flat NHWC pixel index; optional fused bias/residual
-        const float bias_n = (cg.out_bf16 && n < N) ? cg.bias[n] : 0.f;
+        // convolution: pixel (c0 + j) of the bw x bh block -> flat NHWC pixel index
 #pragma unroll 1
         for (int c0 = 0; c0 < NT; c0 += 16) {
           uint32_t v[16];
@@ -406,13 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
               const int yy = (c0 + j) / cg.bw, y = cv_y0 + yy;
               if (y < cg.H) {
                 const size_t o = (size_t)((cv_b * cg.H + y) * cg.W + cv_x0 + (c0 + j) - yy * cg.bw) * N + n;
-                if (cg.out_bf16) {
-                  float r = bf16_round(__uint_as_float(v[j]) + bias_n);
-                  if (cg.residual) r = bf16_round(r + __bfloat162float(cg.residual[o]));
-                  cg.out_bf16[o] = __float2bfloat16_rn(r);
-                } else {
-                  out[o] = __uint_as_float(v[j]);
-                }
+                out[o] = __uint_as_float(v[j]);
               }
             }
           }

@@ -395,17 +395,62 @@ qkv_rope_store_kernel(const float* __restrict__ part, int S, size_t split_stride
   }
 }
 
+// ---------------------------------------------------------------- packed (ragged) prefill
+// The reference pads every prompt row on the LEFT to the batch maximum P and runs the padded (R, P) block through the
+// model (the 16 unconditional rows of configs[1] are ~110 tokens padded to ~350: 40 % of the positions are pads).  Pad
+// positions never influence a real position (they are masked as keys and their own outputs are discarded), so the
+// fused loops run the prefill on the REAL tokens only, packed row after row: token t of the packed stream belongs to
+// row r with row_off[r] <= t < row_off[r+1] and sits at column kv_start[r] + (t - row_off[r]).
+PG_DEVINL int packed_row_of(const int32_t* __restrict__ row_off, int R, int t) {
+  int lo = 0, hi = R - 1;                       // largest r with row_off[r] <= t
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (row_off[mid] <= t) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+// x [R][P][D] -> xp [sum len][D]: grid (P, R)
+__global__ void __launch_bounds__(256)
+prefill_pack_kernel(const float* __restrict__ x, float* __restrict__ xp, const int32_t* __restrict__ kv_start,
+                    const int32_t* __restrict__ row_off, int P, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int p = blockIdx.x, r = blockIdx.y;
+  const int start = kv_start[r];
+  if (p < start) return;
+  const float4* src = reinterpret_cast<const float4*>(x + ((size_t)r * P + p) * D);
+  float4* dst = reinterpret_cast<float4*>(xp + (size_t)(row_off[r] + p - start) * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = src[i];
+}
+// last real token of every row: xp[row_off[r+1] - 1] -> out[r]
+__global__ void __launch_bounds__(256)
+gather_last_rows_kernel(const float* __restrict__ xp, float* __restrict__ out, const int32_t* __restrict__ row_off, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r = blockIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(xp + (size_t)(row_off[r + 1] - 1) * D);
+  float4* dst = reinterpret_cast<float4*>(out + (size_t)r * D);
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = src[i];
+}
+
 // Prefill variant behind the contraction's fused bf16 epilogue (gemm.cuh EpiFuse): the projections arrive already
 // rounded to bf16 ([tok][3*H*128], q | k | v), so this kernel only rotates and scatters - same values as
 // qkv_rope_store_kernel<bf16> on the fp32 partials (it rounds them first), half the bytes.
 __global__ void __launch_bounds__(256)
 qkv_rope_store_bf16_kernel(const bf16* __restrict__ qkv, const float* __restrict__ cosT, const float* __restrict__ sinT,
                            bf16* __restrict__ q_out, bf16* __restrict__ kcache, bf16* __restrict__ vcache, int P, int H, int Tmax,
-                           const int32_t* __restrict__ rope_start) {
+                           const int32_t* __restrict__ rope_start, const int32_t* __restrict__ row_off,
+                           const int32_t* __restrict__ kv_start, int R) {
   pdl_launch_dependents();
   pdl_wait();
   const int tok = blockIdx.x;
-  const int r = tok / P, p = tok % P;
+  int r, p;
+  if (row_off != nullptr) {                      // packed stream (see packed_row_of)
+    r = packed_row_of(row_off, R, tok);
+    p = kv_start[r] + (tok - row_off[r]);
+  } else {
+    r = tok / P; p = tok % P;
+  }
   const int HD = H * HEAD_DIM;
   const bf16* row = qkv + (size_t)tok * 3 * HD;
   const int pr = rope_start ? max(p - rope_start[r], 0) : p;

@@ -210,6 +210,48 @@ def test_bf16_long_ragged_context(path):
     assert_close(dbg.cpu().numpy(), ref_logits, 2e-2, 2e-2, f"bf16 long-context CFG logits ({path})")
 
 
+def test_packed_prefill_is_bit_identical_to_padded_prefill():
+    """The fused loops prefill the real tokens only (packed row after row, lm_kernels.cuh packed_row_of); the reference runs
+    the LEFT-padded (R, P) block.  Pad positions never reach a real position, and every real position goes through the same
+    arithmetic in the same order, so the CFG logits of the following steps are bit-identical with packing on and off (rows
+    with 1 token, rows without padding, tiles straddling the first real column)."""
+    dims = O.SMALL
+    steps = 4
+    g = torch.Generator().manual_seed(12)
+    lens = [200, 1, 129, 128, 77, 255, 256, 3]
+    cond = [torch.randint(0, dims.vocab - 2, (n,), generator=g).tolist() for n in lens]
+    neg = [torch.randint(0, dims.vocab - 2, (31,), generator=g).tolist()] * len(lens)
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
+    eng = get_engine(dims, "bf16", with_vq=False, max_batch=8, max_prompt=256)
+    outs, toks = [], []
+    for pack in (1, 0):
+        eng.set_option("prefill_pack", pack)
+        dbg = torch.zeros(steps, len(lens), dims.img_vocab, device="cuda")
+        eng.set_option("dbg_logits_ptr", dbg.data_ptr())
+        try:
+            emb = eng.language_model.get_input_embeddings()(ids.cuda())
+            toks.append(eng.sample_image(emb, len(lens), steps, mask.cuda(), 5.0, 1.0, generator=0).cpu())
+            torch.cuda.synchronize()
+        finally:
+            eng.set_option("dbg_logits_ptr", 0)
+            eng.set_option("prefill_pack", 1)
+        outs.append(dbg.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(toks[0], toks[1])
+    # and for the text prefill of language_model.generate (mask-aware RoPE positions)
+    sd = O.init_state_dict(dims, seed=0, with_vq=False, with_lm_head=True)
+    from plangen_b200.engine import FastJanus
+    from tests.gpu_util import product_dims
+    te = FastJanus(sd, product_dims(dims), mode="bf16", max_batch=4, max_prompt=256, max_steps=32, with_vq=False)
+    tid, tmask = O.pad_input_ids([c[:n] for c, n in zip(cond, (200, 1, 64, 130, 9, 255, 256, 3))], dims.pad_id)
+    got = []
+    for pack in (1, 0):
+        te.set_option("prefill_pack", pack)
+        emb = te.language_model.get_input_embeddings()(tid.cuda())
+        got.append(te.language_model.generate(inputs_embeds=emb, attention_mask=tmask.cuda(), pad_token_id=7, eos_token_id=7,
+                                              max_new_tokens=8).cpu())
+    assert torch.equal(got[0], got[1])
+
+
 @pytest.mark.parametrize("B", [5, 16, 32])
 def test_bf16_streamk_gate_up_matches_reference(B):
     """Stream-K gate|up + SwiGLU (gemm_sk.cuh; the default for Janus-Pro-7B, forced here): token tiles of 16 / 32 / 64
