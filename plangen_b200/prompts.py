@@ -12,6 +12,14 @@ functions with a pluggable tokenizer (no vocabulary files are available offline;
   decode_plan_text_batch   System.decode_plan_text_batch  (plangen_base.py:296-306)
   plan_then_generate       the `uni_2stage` flow of System.test_step (plangen_base.py:369-400): stage-1 layout text
                            (x2t) -> re-wrapped prompt -> CFG image decode (t2i)
+  mmu_process_one / mmu_batchify / mmu_infer_batch
+                           the `mmu` / `mmu_infer` parts of System.mmu_collate (plangen_base.py:807-841) on top of
+                           VLChatProcessor.process_one / add_image_token / batchify (processing_vlm.py:215-258, :260-324,
+                           :361-423): `<image_placeholder>` expanded to boi + 576 image slots + eoi, LEFT padding,
+                           images_seq_mask / images_emb_mask - the inputs of vl_gpt.prepare_inputs_embeds
+  describe_then_ground     the `mmu` flow (plangen_base.py:851-881): prepare_inputs_embeds -> language_model.generate
+  write_png / save_images  the PNG side of the result writers (plangen_base.py:444-453, :1162-1181): denorm_pt +
+                           to_pil(...).save(...) without PIL (zlib + struct)
 
 Pure host code (lists, strings, small int tensors): it defines the row order and mask contract the device path
 consumes; no arithmetic lives here."""
@@ -21,7 +29,13 @@ from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
+import struct
+import zlib
+
 USER, ASSISTANT = "<|User|>", "<|Assistant|>"
+IMAGE_PLACEHOLDER = "<image_placeholder>"       # processing_vlm.py:88 (image_tag)
+# plangen_base.py:811, :828
+MMU_QUESTION = "Please describe this image and then give the description and bounding box of each object in the image."
 SEP, SEP2 = "\n\n", "<｜end▁of▁sentence｜>"
 IMAGE_START_TAG = "<begin_of_image>"            # processing_vlm.py:89
 # cfg/base.py:129
@@ -45,8 +59,13 @@ def sft_prompt(conversation: Sequence[Dict[str, str]], system_prompt: str = "") 
 
 
 class PromptPipeline:
-    def __init__(self, tokenizer, pad_id: int, image_token_num: int = 576, neg_prompt: str = DEFAULT_NEG_PROMPT):
+    def __init__(self, tokenizer, pad_id: int, image_token_num: int = 576, neg_prompt: str = DEFAULT_NEG_PROMPT,
+                 image_id: Optional[int] = None, image_start_id: Optional[int] = None, image_end_id: Optional[int] = None):
+        """`image_id` / `image_start_id` / `image_end_id`: vocabulary ids of `<image_placeholder>`, `<begin_of_image>`,
+        `<end_of_image>` (VLChatProcessor.image_id / image_start_id / image_end_id, processing_vlm.py:179-197); only the
+        mmu functions need them."""
         self.tok, self.pad_id, self.n_img, self.neg_prompt = tokenizer, int(pad_id), int(image_token_num), neg_prompt
+        self.image_id, self.image_start_id, self.image_end_id = image_id, image_start_id, image_end_id
 
     # ------------------------------------------------------------------ single prompts
     def wrap_t2i_prompt(self, caption: str) -> Tuple[str, torch.Tensor]:
@@ -131,3 +150,91 @@ class PromptPipeline:
         dec, _ = engine.t2i(tokens=ids.to(engine.device), mask=mask.to(engine.device), cfg_weight=cfg_weight, temperature=temperature,
                             image_token_num_per_image=self.n_img)
         return dec, layouts
+
+
+    # ------------------------------------------------------------------ mmu (image understanding)
+    def mmu_process_one(self, images: torch.Tensor, answer: str = "", question: str = MMU_QUESTION) -> Dict[str, object]:
+        """VLChatProcessor.process_one on the conversation System.mmu_collate builds (plangen_base.py:812-822, :829-839):
+        user turn `<image_placeholder>\n{question}`, assistant turn `answer` (empty for inference).  `images`:
+        (n, 3, H, W) pixel tensors already in the vision tower's input range.  Every placeholder token becomes
+        [boi, image_id x n_img, eoi] (add_image_token, processing_vlm.py:215-258, add_special_token = False)."""
+        if self.image_id is None or self.image_start_id is None or self.image_end_id is None:
+            raise ValueError("mmu prompts need image_id / image_start_id / image_end_id")
+        text = sft_prompt([{"role": USER, "content": f"{IMAGE_PLACEHOLDER}\n{question}"}, {"role": ASSISTANT, "content": f"{answer}"}])
+        ids = torch.LongTensor(self.tok.encode(text))
+        where = (ids == self.image_id).nonzero().flatten().tolist()
+        pieces, start = [], 0
+        for idx in where:
+            pieces += [ids[start:idx], torch.tensor([self.image_start_id]), torch.full((self.n_img,), self.image_id, dtype=torch.long),
+                       torch.tensor([self.image_end_id])]
+            start = idx + 1
+        pieces.append(ids[start:])
+        return {"sft_format": text, "input_ids": torch.cat(pieces), "pixel_values": images, "num_image_tokens": [self.n_img] * len(where)}
+
+    def mmu_batchify(self, prepares: Sequence[Dict[str, object]]) -> Dict[str, torch.Tensor]:
+        """VLChatProcessor.batchify (processing_vlm.py:361-423): LEFT padding with pad_id, attention mask, pixel values
+        stacked to (b, max_n_images, 3, H, W), images_seq_mask (b, T) = image slots, images_emb_mask (b, max_n, n_img)."""
+        bs = len(prepares)
+        T = max(len(p["input_ids"]) for p in prepares)
+        max_n = max(1, max(len(p["num_image_tokens"]) for p in prepares))
+        shape = next((tuple(p["pixel_values"].shape[1:]) for p in prepares if len(p["num_image_tokens"])), (3, 384, 384))
+        out = {"input_ids": torch.full((bs, T), self.pad_id, dtype=torch.long), "attention_mask": torch.zeros((bs, T), dtype=torch.long),
+               "pixel_values": torch.zeros((bs, max_n) + shape), "images_seq_mask": torch.zeros((bs, T), dtype=torch.bool),
+               "images_emb_mask": torch.zeros((bs, max_n, self.n_img), dtype=torch.bool), "sft_format": [p["sft_format"] for p in prepares]}
+        for i, p in enumerate(prepares):
+            ids, n = p["input_ids"], len(p["input_ids"])
+            out["attention_mask"][i, T - n:] = 1
+            out["input_ids"][i, T - n:] = ids
+            out["images_seq_mask"][i, T - n:] = ids == self.image_id
+            k = len(p["num_image_tokens"])
+            if k:
+                out["pixel_values"][i, :k] = p["pixel_values"]
+                for j, cnt in enumerate(p["num_image_tokens"]):
+                    out["images_emb_mask"][i, j, :cnt] = True
+        return out
+
+    def mmu_infer_batch(self, images: torch.Tensor, answers: Optional[Sequence[str]] = None) -> Dict[str, torch.Tensor]:
+        """`prepare_inputs_infer` (answers None: empty assistant turn) / `prepare_inputs` of System.mmu_collate for a batch of
+        images (b, 3, H, W), one image per sample."""
+        return self.mmu_batchify([self.mmu_process_one(images[i:i + 1], "" if answers is None else answers[i]) for i in range(len(images))])
+
+    def describe_then_ground(self, engine, images: torch.Tensor, eos_token_id: int, bos_token_id: Optional[int] = None,
+                             max_new_tokens: int = 512) -> List[str]:
+        """Image layout understanding (`mmu`, plangen_base.py:851-881): SigLIP + aligner + scatter (prepare_inputs_embeds),
+        then greedy decode of the description / boxes text."""
+        b = self.mmu_infer_batch(images)
+        x = engine.prepare_inputs_embeds(input_ids=b["input_ids"], pixel_values=b["pixel_values"], images_seq_mask=b["images_seq_mask"],
+                                         images_emb_mask=b["images_emb_mask"])
+        new = engine.language_model.generate(inputs_embeds=x, attention_mask=b["attention_mask"].to(engine.device), pad_token_id=eos_token_id,
+                                             bos_token_id=bos_token_id, eos_token_id=eos_token_id, max_new_tokens=max_new_tokens,
+                                             do_sample=False, use_cache=True)
+        return [self.tok.decode([int(t) for t in row if int(t) != eos_token_id]) for row in new.cpu().tolist()]
+
+
+# ---------------------------------------------------------------------- image writer (no PIL needed)
+def write_png(path: str, img) -> None:
+    """8-bit RGB (H, W, 3) or grey (H, W) array / tensor -> PNG file (zlib-compressed, filter 0 on every scanline)."""
+    a = img.detach().cpu().numpy() if isinstance(img, torch.Tensor) else img
+    if a.dtype.name != "uint8" or a.ndim not in (2, 3) or (a.ndim == 3 and a.shape[2] != 3):
+        raise ValueError("write_png takes uint8 (H, W, 3) or (H, W)")
+    h, w = a.shape[:2]
+    raw = b"".join(b"\x00" + a[y].tobytes() for y in range(h))
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2 if a.ndim == 3 else 0, 0, 0, 0)) +
+                chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))
+
+
+def save_images(engine, dec: torch.Tensor, path_format: str, start_index: int = 0) -> List[str]:
+    """`to_pil(denorm_pt(pr_image[i])).save(f"{path}/pr_image/{idx}.png")` (plangen_base.py:1174-1177): (B, 3, H, W) decoder
+    output -> one PNG per image; denorm + uint8 conversion on the device (engine.images_to_uint8), files named
+    path_format.format(index)."""
+    u8 = engine.images_to_uint8(dec).permute(0, 2, 3, 1).contiguous().cpu()
+    paths = []
+    for i in range(u8.shape[0]):
+        paths.append(path_format.format(start_index + i))
+        write_png(paths[-1], u8[i])
+    return paths

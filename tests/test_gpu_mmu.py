@@ -187,3 +187,34 @@ def test_mmu_flow_prepare_inputs_embeds_then_generate_fp32_tokens_match_oracle()
     got = eng.language_model.generate(inputs_embeds=xe, attention_mask=mask.cuda(), pad_token_id=eos, bos_token_id=1,
                                       eos_token_id=eos, max_new_tokens=12, do_sample=False, use_cache=True)
     assert got.cpu().tolist() == want.tolist()
+
+
+def test_describe_then_ground_host_flow_runs_the_mmu_stack():
+    """prompts.PromptPipeline.describe_then_ground (the `mmu` mode, plangen_base.py:851-881): mmu_collate-shaped batch ->
+    prepare_inputs_embeds -> generate; same token ids as the two engine calls made by hand."""
+    from plangen_b200.prompts import PromptPipeline, IMAGE_PLACEHOLDER
+    v, d = O.SIGLIP_TINY, O.TINY
+
+    class Tok:
+        def encode(self, s):
+            out = []
+            for part in s.split(IMAGE_PLACEHOLDER):
+                out += [ord(c) % 800 + 10 for c in part] + [900]
+            return out[:-1]
+
+        def decode(self, ids):
+            return " ".join(str(int(t)) for t in ids)
+
+    eng, _ = _engine(d, v, "fp32", with_lm_head=True)
+    pp = PromptPipeline(Tok(), pad_id=d.pad_id, image_token_num=v.n_patches, image_id=900, image_start_id=901, image_end_id=902)
+    g = torch.Generator().manual_seed(2)
+    images = torch.rand(2, 3, v.image, v.image, generator=g) * 2 - 1
+    b = pp.mmu_infer_batch(images)
+    b["input_ids"] = b["input_ids"][:, -56:]; b["attention_mask"] = b["attention_mask"][:, -56:]; b["images_seq_mask"] = b["images_seq_mask"][:, -56:]
+    assert int(b["images_seq_mask"].sum()) == 2 * v.n_patches
+    x = eng.prepare_inputs_embeds(b["input_ids"], b["pixel_values"], b["images_seq_mask"], b["images_emb_mask"])
+    want = eng.language_model.generate(inputs_embeds=x, attention_mask=b["attention_mask"].cuda(), pad_token_id=7, eos_token_id=7,
+                                       max_new_tokens=6)
+    pp.mmu_infer_batch = lambda images, answers=None: b              # same (truncated) batch through the one-call flow
+    texts = pp.describe_then_ground(eng, images, eos_token_id=7, max_new_tokens=6)
+    assert texts == [" ".join(str(int(t)) for t in row if int(t) != 7) for row in want.cpu().tolist()]

@@ -173,6 +173,29 @@ def test_t2i_end_to_end_small():
     assert torch.isfinite(dec.float()).all()
     img = eng.generate_from_host(ids.pin_memory(), mask.pin_memory())
     assert img.dtype == torch.uint8 and img.shape == (2, 3, d.img_size, d.img_size) and not img.is_cuda
+    # pg_images_to_u8 = denorm_pt + `(x*255).astype(np.uint8)` (src/utils/funcs.py:511-512, :497-498)
+    want = (((dec.float().clamp(-1, 1) + 1) / 2) * 255).to(torch.uint8)
+    assert torch.equal(eng.images_to_uint8(dec), want)
+    edge = torch.tensor([-3.0, -1.0, -0.999, 0.0, 0.5, 0.9999, 1.0, 7.0, 0.25, -0.25, 0.1, 0.7], device="cuda").reshape(1, 3, 2, 2)
+    assert torch.equal(eng.images_to_uint8(edge), (((edge.clamp(-1, 1) + 1) / 2) * 255).to(torch.uint8))
+
+
+def test_save_images_writes_the_decoded_pixels(tmp_path):
+    """PNG side of the result writers (plangen_base.py:1174-1177): files hold exactly denorm_pt(dec) * 255 truncated."""
+    from plangen_b200.prompts import save_images
+    d = O.SMALL
+    eng = get_engine(d, "bf16", with_vq=True)
+    codes = torch.randint(0, d.img_vocab, (2, d.n_img_tokens), dtype=torch.int32, device="cuda")
+    dec = eng.gen_vision_model.decode_code(codes, shape=[2, d.code_dim, d.grid, d.grid])
+    paths = save_images(eng, dec, str(tmp_path / "pr_{}.png"), start_index=5)
+    assert [os.path.basename(p) for p in paths] == ["pr_5.png", "pr_6.png"]
+    try:
+        from PIL import Image
+    except ImportError:
+        pytest.skip("PIL not installed")
+    want = eng.images_to_uint8(dec).permute(0, 2, 3, 1).cpu().numpy()
+    for i, p in enumerate(paths):
+        assert np.array_equal(np.asarray(Image.open(p)), want[i])
 
 
 @pytest.mark.parametrize("path", ["perop_v5", "perop_plain"])

@@ -264,3 +264,54 @@ def test_kv_start_from_mask_contract():
         kv_start_from_mask(torch.tensor([[1, 0, 1, 1, 1, 1]]), 4)
     with pytest.raises(ValueError):
         kv_start_from_mask(torch.tensor([[0, 1, 1, 1, 0, 1]]), 4)
+
+
+# ------------------------------------------------------------------ mmu host pipeline + PNG writer (SURVEY 8f rank 4 remainder)
+def test_mmu_batchify_layout_matches_the_reference_processor_contract():
+    """plangen_base.py:807-841 / processing_vlm.py:215-258, :361-423: each `<image_placeholder>` becomes boi + n image slots + eoi,
+    rows are LEFT padded, images_seq_mask marks exactly the image slots and selects as many positions as images_emb_mask."""
+    import torch
+    from plangen_b200.prompts import PromptPipeline, MMU_QUESTION, IMAGE_PLACEHOLDER
+
+    class Tok(_CharTok):
+        def encode(self, s):
+            out = []
+            for part in s.split(IMAGE_PLACEHOLDER):
+                out += super().encode(part) + [5000]
+            return out[:-1]
+
+    n_img = 6
+    pp = PromptPipeline(Tok(), pad_id=3, image_token_num=n_img, image_id=5000, image_start_id=5001, image_end_id=5002)
+    one = pp.mmu_process_one(torch.zeros(1, 3, 8, 8), answer="")
+    ids = one["input_ids"].tolist()
+    k = ids.index(5001)
+    assert ids[k:k + n_img + 2] == [5001] + [5000] * n_img + [5002] and ids.count(5000) == n_img
+    assert one["sft_format"].startswith("<|User|>: " + IMAGE_PLACEHOLDER + "\n" + MMU_QUESTION) and one["sft_format"].endswith("<|Assistant|>:")
+    imgs = torch.arange(2 * 3 * 8 * 8, dtype=torch.float32).reshape(2, 3, 8, 8)
+    b = pp.mmu_infer_batch(imgs, answers=["a cat", "a much longer answer about a dog"])
+    T = b["input_ids"].shape[1]
+    assert b["pixel_values"].shape == (2, 1, 3, 8, 8) and torch.equal(b["pixel_values"][:, 0], imgs)
+    assert b["images_emb_mask"].shape == (2, 1, n_img) and bool(b["images_emb_mask"].all())
+    assert int(b["images_seq_mask"].sum()) == int(b["images_emb_mask"].sum()) == 2 * n_img
+    assert torch.equal(b["images_seq_mask"], b["input_ids"] == 5000)
+    pad0 = int((b["attention_mask"][0] == 0).sum())
+    assert pad0 > 0 and bool((b["input_ids"][0, :pad0] == 3).all()) and bool((b["attention_mask"][0, pad0:] == 1).all())
+    assert int(b["attention_mask"][1].sum()) == T                      # the longest row has no padding
+
+
+def test_write_png_round_trips_through_pil(tmp_path):
+    import numpy as np
+    from plangen_b200.prompts import write_png
+    rng = np.random.default_rng(0)
+    rgb = rng.integers(0, 256, (13, 7, 3), dtype=np.uint8)
+    grey = rng.integers(0, 256, (5, 9), dtype=np.uint8)
+    write_png(str(tmp_path / "a.png"), rgb)
+    write_png(str(tmp_path / "g.png"), torch.from_numpy(grey))
+    try:
+        from PIL import Image
+    except ImportError:
+        pytest.skip("PIL not installed")
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "a.png")), rgb)
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "g.png")), grey)
+    with pytest.raises(ValueError):
+        write_png(str(tmp_path / "bad.png"), rgb.astype(np.float32))
