@@ -209,12 +209,11 @@ def test_describe_then_ground_host_flow_runs_the_mmu_stack():
     pp = PromptPipeline(Tok(), pad_id=d.pad_id, image_token_num=v.n_patches, image_id=900, image_start_id=901, image_end_id=902)
     g = torch.Generator().manual_seed(2)
     images = torch.rand(2, 3, v.image, v.image, generator=g) * 2 - 1
-    b = pp.mmu_infer_batch(images)
-    b["input_ids"] = b["input_ids"][:, -56:]; b["attention_mask"] = b["attention_mask"][:, -56:]; b["images_seq_mask"] = b["images_seq_mask"][:, -56:]
-    assert int(b["images_seq_mask"].sum()) == 2 * v.n_patches
+    b = pp.mmu_batchify([pp.mmu_process_one(images[i:i + 1], "", question=q) for i, q in enumerate(["hi", "what is it?"])])   # short: T <= 64
+    assert int(b["images_seq_mask"].sum()) == 2 * v.n_patches and b["input_ids"].shape[1] <= 64
     x = eng.prepare_inputs_embeds(b["input_ids"], b["pixel_values"], b["images_seq_mask"], b["images_emb_mask"])
     want = eng.language_model.generate(inputs_embeds=x, attention_mask=b["attention_mask"].cuda(), pad_token_id=7, eos_token_id=7,
                                        max_new_tokens=6)
-    pp.mmu_infer_batch = lambda images, answers=None: b              # same (truncated) batch through the one-call flow
+    pp.mmu_infer_batch = lambda images, answers=None: b              # same batch through the one-call flow
     texts = pp.describe_then_ground(eng, images, eos_token_id=7, max_new_tokens=6)
     assert texts == [" ".join(str(int(t)) for t in row if int(t) != 7) for row in want.cpu().tolist()]
