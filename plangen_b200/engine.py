@@ -12,7 +12,8 @@
 plus the fused fast path with the reference's own signatures, `sample_image(...)` / `t2i(...)`,
 which runs the whole 576-step loop on the device (CUDA graph, no host sync, no logits round trip).
 PyTorch is used only for device memory, streams and host<->device copies; all arithmetic happens in
-the sm_100a kernels behind the C-ABI (include/plangen_b200.h).  There is no CPU path.
+the sm_100a kernels behind the C-ABI (include/plangen_b200.h), reached through the torch custom-op layer
+`torch.ops.plangen_b200.*` (plangen_b200/ops.py).  There is no CPU path.
 """
 from __future__ import annotations
 
@@ -23,6 +24,7 @@ from typing import Dict, Optional, Sequence
 import torch
 
 from . import _lib
+from . import ops as _ops          # registers torch.ops.plangen_b200.* (the custom-op layer over the C-ABI)
 from .config import Dims
 from .weights import pack_state_dict
 
@@ -35,6 +37,15 @@ def _ptr(t: Optional[torch.Tensor]):
 
 def _stream_ptr(device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+OPS = torch.ops.plangen_b200
+
+
+def _i64(v: int) -> int:
+    """uint64 seeds through an int64 schema slot (two's complement)."""
+    v = int(v) & 0xFFFFFFFFFFFFFFFF
+    return v - (1 << 64) if v >= (1 << 63) else v
 
 
 def kv_start_from_mask(mask: torch.Tensor, P: int) -> torch.Tensor:
@@ -79,7 +90,7 @@ class _Embedding:
         e = self._e
         ids32 = ids.to(device=e.device, dtype=torch.int32).contiguous()
         out = torch.empty(*ids32.shape, e.dims.D, device=e.device, dtype=torch.float32)
-        _lib.check(e._lib.pg_embed_tokens(e._h, _ptr(ids32), ids32.numel(), _ptr(out), _stream_ptr(e.device)))
+        OPS.embed_tokens(e.handle, ids32, out)
         return out
 
 
@@ -101,7 +112,7 @@ class _LlamaModel:
                 kv_start = kv_start_from_mask(attention_mask.to(e.device), P)
             x = inputs_embeds.to(device=e.device, dtype=torch.float32).contiguous().clone()
             hidden = torch.empty(R, P, D, device=e.device, dtype=torch.float32)
-            _lib.check(e._lib.pg_prefill(e._h, _ptr(x), _ptr(kv_start), R, P, _ptr(hidden), 1, st))
+            OPS.prefill(e.handle, x, kv_start, hidden, True)
             e._serial += 1
             return ModelOutput(hidden, KVHandle(R, P, kv_start, e._serial))
         h = past_key_values
@@ -109,7 +120,7 @@ class _LlamaModel:
             raise ValueError("past_key_values does not belong to the engine's live cache")
         x = inputs_embeds.to(device=e.device, dtype=torch.float32).contiguous().view(R, D)
         hidden = torch.empty(R, 1, D, device=e.device, dtype=torch.float32)
-        _lib.check(e._lib.pg_decode_step(e._h, _ptr(x), _ptr(h.kv_start), R, h.length, _ptr(hidden), st))
+        OPS.decode_step(e.handle, x, h.kv_start, h.length, hidden.view(R, D))
         h.length += 1
         return ModelOutput(hidden, h)
 
@@ -175,7 +186,7 @@ class _GenVisionModel:
         codes = codes.reshape(B, gh * gw)
         up = 2 ** (len(e.dims.vq_ch_mult) - 1)
         out = torch.empty(B, 3, gh * up, gw * up, device=e.device, dtype=torch.float32)
-        _lib.check(e._lib.pg_vq_decode_code(e._h, _ptr(codes), B, gh, gw, _ptr(out), _stream_ptr(e.device)))
+        OPS.vq_decode_code(e.handle, codes, gh, gw, out)
         return out.to(e.out_dtype)
 
 
@@ -190,7 +201,7 @@ class _GenVisionModel:
             raise ValueError("encode expects (B, 3, H, W) images")
         down = 2 ** (len(e.dims.vq_ch_mult) - 1)
         codes = torch.empty(B, (H // down) * (W // down), dtype=torch.int32, device=e.device)
-        _lib.check(e._lib.pg_vq_encode(e._h, _ptr(x), B, H, W, _ptr(codes), _stream_ptr(e.device)))
+        OPS.vq_encode(e.handle, x, codes)
         return None, None, (None, None, codes.reshape(-1).to(torch.int64))
 
 
@@ -248,6 +259,7 @@ class FastJanus:
             for name, t in self._weights.items():
                 _lib.check(self._lib.pg_engine_set_tensor(h, name.encode(), _ptr(t), t.numel() * t.element_size()))
             _lib.check(self._lib.pg_engine_finalize(h, _stream_ptr(self.device)))
+        self.handle = _ops.register_engine(self)      # the integer the torch.ops.plangen_b200.* operators take
         self.language_model = _LanguageModel(self)
         self.gen_vision_model = _GenVisionModel(self)
         self.weight_bytes_per_step = self._weight_bytes_per_step()
@@ -317,8 +329,7 @@ class FastJanus:
         if emb.shape[1] != self.dims.sig_patches:
             raise ValueError(f"images_emb_mask must have {self.dims.sig_patches} entries per image")
         out = torch.empty(b, T, self.dims.D, device=self.device, dtype=torch.float32)
-        _lib.check(self._lib.pg_prepare_inputs_embeds(self._h, _ptr(pv), n_img, _ptr(ids), _ptr(seq), _ptr(emb), b, T, _ptr(out),
-                                                      _stream_ptr(self.device)))
+        OPS.prepare_inputs_embeds(self.handle, pv, ids, seq, emb, out)
         return out
 
     @torch.inference_mode()
@@ -339,13 +350,13 @@ class FastJanus:
         R = h.shape[0]
         x = h.to(device=self.device, dtype=torch.float32).contiguous()
         out = torch.empty(R, self.dims.img_vocab, device=self.device, dtype=torch.float32)
-        _lib.check(self._lib.pg_gen_head(self._h, _ptr(x), R, _ptr(out), _stream_ptr(self.device)))
+        OPS.gen_head(self.handle, x, out)
         return out.to(self.out_dtype)
 
     def prepare_gen_img_embeds(self, image_ids: torch.Tensor) -> torch.Tensor:
         ids = image_ids.to(device=self.device, dtype=torch.int32).contiguous()
         out = torch.empty(*ids.shape, self.dims.D, device=self.device, dtype=torch.float32)
-        _lib.check(self._lib.pg_prepare_gen_img_embeds(self._h, _ptr(ids), ids.numel(), _ptr(out), _stream_ptr(self.device)))
+        OPS.prepare_gen_img_embeds(self.handle, ids, out)
         return out.to(self.out_dtype)
 
     def cfg_sample_embed(self, logits: torch.Tensor, cfg_weight: float, temperature: float, seed: int, offset: int,
@@ -356,9 +367,8 @@ class FastJanus:
         B = logits.shape[0] // 2
         lg = logits.to(device=self.device, dtype=torch.float32).contiguous()
         x_next = torch.empty(2 * B, self.dims.D, device=self.device, dtype=torch.float32)
-        _lib.check(self._lib.pg_cfg_sample_embed(self._h, _ptr(lg), B, cfg_weight, temperature, seed, offset, int(greedy), int(top_k),
-                                                 _ptr(edit_region), _ptr(gt_labels), step, n_steps, _ptr(tokens_out),
-                                                 _ptr(x_next), _stream_ptr(self.device)))
+        OPS.cfg_sample_embed(self.handle, lg, float(cfg_weight), float(temperature), _i64(seed), int(offset), bool(greedy), int(top_k),
+                             edit_region, gt_labels, int(step), int(n_steps), tokens_out, x_next)
         return x_next
 
     def philox_offset_per_step(self, B: int) -> int:
@@ -420,9 +430,7 @@ class FastJanus:
             er, gl = self._teacher_inputs(batch, gt_labels, num_gen, n)
         k = int(self.top_k if top_k is None else top_k)
         self._keep = (kv_start, x, er, gl)        # keep alive until the stream has consumed them
-        _lib.check(self._lib.pg_sample_image(self._h, _ptr(x), _ptr(kv_start), R, P, n, float(cfg_weight),
-                                             float(temperature), seed, int(greedy), k, _ptr(er), _ptr(gl), _ptr(tokens),
-                                             _stream_ptr(self.device)))
+        OPS.sample_image(self.handle, x, kv_start, n, float(cfg_weight), float(temperature), _i64(seed), bool(greedy), k, er, gl, tokens)
         self._serial += 1
         if isinstance(generator, torch.Generator):
             generator.set_offset(off + n * self.philox_offset_per_step(num_gen))
@@ -473,7 +481,7 @@ class FastJanus:
         device: (B,3,H,W) float -> uint8, one kernel (pg_images_to_u8)."""
         x = dec.to(device=self.device, dtype=torch.float32).contiguous()
         out = torch.empty(x.shape, dtype=torch.uint8, device=self.device)
-        _lib.check(self._lib.pg_images_to_u8(self._h, _ptr(x), x.numel(), _ptr(out), _stream_ptr(self.device)))
+        OPS.images_to_u8(self.handle, x, out)
         return out
 
     # ------------------------------------------------------------------ host-buffer entry (end to end)

@@ -315,3 +315,17 @@ def test_write_png_round_trips_through_pil(tmp_path):
     assert np.array_equal(np.asarray(Image.open(tmp_path / "g.png")), grey)
     with pytest.raises(ValueError):
         write_png(str(tmp_path / "bad.png"), rgb.astype(np.float32))
+
+
+# ------------------------------------------------------------------ torch custom-op layer (north_star: "thin C-ABI torch custom-op layer")
+def test_custom_ops_are_registered_and_have_no_cpu_kernel():
+    """Every hot-path C-ABI entry point is a torch.library operator in the `plangen_b200` namespace with a schema that
+    names its mutated outputs; there is no CPU implementation to fall back to."""
+    import plangen_b200.ops as ops
+    from plangen_b200 import _lib
+    for name in ops.OP_NAMES:
+        op = getattr(torch.ops.plangen_b200, name)
+        assert "!" in str(op.default._schema), name                      # declares what it writes
+        assert "pg_" + name in _lib.EXPORTS, name                          # one C-ABI entry per operator
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.plangen_b200.images_to_u8(0, torch.zeros(4), torch.zeros(4, dtype=torch.uint8))
