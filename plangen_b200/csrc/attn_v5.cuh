@@ -376,6 +376,11 @@ attn_decode_v5_kernel(const float* __restrict__ part, int S, size_t split_stride
     mbar_fence_init();
   }
   if (tid < A5_STAGES) stage_tab[(tid % AT_NG) * A5_SPG + tid / AT_NG] = tid;   // group g owns stages g, g+4, ..
+  // the producers copy only the valid tokens of a tile (attn_produce_group): every slot must hold a finite value before
+  // the first copy lands, because a masked slot still enters o += 0 * v
+  for (int i = tid; i < A5_STAGES * 2 * AT_TILE_BYTES / 16; i += AT_THREADS)
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(smem_u32(ring) + (uint32_t)i * 16u), "r"(0u) : "memory");
+  fence_proxy_async();
   if (warp == 0) build_row_units(row_units, kv_start, R, pos, lane, row_start, 0);
   __syncthreads();
   if (tid < AT_NG) at_stamp(dbg, tid, 1);
@@ -393,9 +398,8 @@ attn_decode_v5_kernel(const float* __restrict__ part, int S, size_t split_stride
     // ============================== producers: one warp (lane 0) per group stream ==============================
     if (lane == 0) {
       int kload = 0;
-      attn_produce_group<A5_SPG, false>(gb, ge, row_units, R, H, Tmax, row_start, kcache, vcache, ring, 2 * AT_TILE_BYTES,
-                                        stage_tab + g * A5_SPG, full_bar, empty_bar, kload, 2 * AT_TILE_BYTES,
-                                        policy_evict_first(), r0);
+      attn_produce_group<A5_SPG>(gb, ge, row_units, R, H, Tmax, pos, row_start, kcache, vcache, ring, 2 * AT_TILE_BYTES,
+                                 stage_tab + g * A5_SPG, full_bar, empty_bar, kload, policy_evict_first(), r0);
       at_stamp(dbg, g, 7);
     }
     pdl_wait();
