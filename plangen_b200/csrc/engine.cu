@@ -1350,6 +1350,12 @@ static int sig_tower(pg_engine* e, const float* pixel, int n, void* feat, cudaSt
   }
   auto resid_ln = [&](const float* part, const float* bias, const float* w, const float* b) {
     const size_t stride = (size_t)M * W;
+    if (W <= 4 * 32 * LNW_MAXQ) {          // a warp per row
+      DISPATCH_T(e,
+                 launch(e, vit_resid_ln_warp_kernel<bf16>, dim3((M + 7) / 8), dim3(256), 0, st, e->sig_x, part, S, stride, bias, w, b, (bf16*)e->sig_xn, W, eps, M),
+                 launch(e, vit_resid_ln_warp_kernel<float>, dim3((M + 7) / 8), dim3(256), 0, st, e->sig_x, part, S, stride, bias, w, b, (float*)e->sig_xn, W, eps, M));
+      return 0;
+    }
     DISPATCH_T(e,
                launch(e, vit_resid_ln_kernel<bf16>, dim3(M), dim3(LN_THREADS), 0, st, e->sig_x, part, S, stride, bias, w, b, (bf16*)e->sig_xn, W, eps),
                launch(e, vit_resid_ln_kernel<float>, dim3(M), dim3(LN_THREADS), 0, st, e->sig_x, part, S, stride, bias, w, b, (float*)e->sig_xn, W, eps));

@@ -112,6 +112,20 @@ struct ConvGeom {
 //          (128 contiguous bytes per warp access, the pattern of the partial store).
 // Rounding points are those of bias_act_kernel / vit_resid_ln_kernel / conv_epilogue_kernel (autocast: Linear and conv
 // outputs in bf16).
+// erf for the fused GELU epilogue: Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7) with ex2.approx / rcp.approx, a dozen
+// instructions instead of erff's ~40 - the epilogue of the 4096-wide fc1 contraction of the vision tower was bound by
+// erff (tensor pipe 26 %).  The value is rounded to bf16 (8 mantissa bits) right after; the row kernels and the fp32 check
+// mode keep erff.  A deliberate approximation, like the SwiGLU epilogue's silu.
+PG_DEVINL float erf_fast(float x) {
+  const float ax = fabsf(x);
+  float t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, ax, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-ax * ax * 1.4426950408889634f));
+  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
+  const float r = fmaf(-poly, ex, 1.0f);
+  return copysignf(r, x);
+}
+
 struct EpiFuse {
   const float* bias;   // [N] or nullptr
   bf16* out;           // [M][N] row-major, or nullptr
@@ -339,7 +353,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float t = bf16_round(__uint_as_float(v[j]) + bias_n);
-            if (ep.gelu) t = t * 0.5f * (1.0f + erff(t * 0.70710678118654752440f));
+            if (ep.gelu) t = t * 0.5f * (1.0f + erf_fast(t * 0.70710678118654752440f));
             const unsigned short hb = __bfloat16_as_ushort(__float2bfloat16_rn(t));
             asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)((c0 + j) * 256 + nl * 2)), "h"(hb) : "memory");
           }
