@@ -14,6 +14,7 @@ cond/uncond pair, synthetic LayoutSAM-shaped prompts with 4-8 boxes).  Prints ON
             host memory; H2D and D2H inside the timed region)
   roofline  the dominant kernel (TMA-staged KV-cache decode attention) timed alone with CUDA events
   cpu_baseline  the oracle port of the reference PyTorch path on the box's host cores (bounded sample)
+  extra     the other BASELINE.json configurations (uni_2stage, mmu, Janus-Pro-7B), measured after the timed region
 
 `--impl reference` times the reference's own CPU implementation of the path: the oracle restatement
 of System.t2i / sample_image (oracle/janus_oracle.py; the reference itself cannot be imported here,
@@ -298,14 +299,14 @@ def kernel_roofline(eng, kv_start, lens, P: int, peaks: dict, iters: int = 6):
     return {"bound": "hbm", "kernel": "attn_decode_v5_kernel (KV-cache decode attention, paired CFG batch, 1 launch/layer)",
             "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak,
             "traffic": _ncu_traffic_bytes(), "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-            "at step ~290 of the same workload (profiles/r01_attn_decode.full.txt); algorithmic K+V bytes there ~128 MB, the excess "
-            "is the 32-token tile granularity (rows start mid-tile)",
+            "at step ~290 of the same workload (profiles/r02_attn_decode.full.txt); algorithmic K+V bytes there ~129 MB (the first / "
+            "last tile of a row copy only their valid tokens since round 2: 1.03x, was 1.14x)",
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "position": pos}
 
 
 def _ncu_traffic_bytes():
     """DRAM bytes of one attention launch from the committed ncu extract (None if the file is missing)."""
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_attn_decode.full.txt")
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_attn_decode.full.txt")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     total, seen = 0.0, 0
     try:
