@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libplangen_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "gemm.cuh", "gemm_sk.cuh", "lm_kernels.cuh", "attn_tma.cuh", "attn_v5.cuh", "sample.cuh", "text_decode.cuh", "attn_prefill_tc.cuh", "vq_kernels.cuh", "vit_kernels.cuh",
+HEADERS = ["common.cuh", "gemm.cuh", "gemm_sk.cuh", "gemm_tc2.cuh", "lm_kernels.cuh", "attn_tma.cuh", "attn_v5.cuh", "sample.cuh", "text_decode.cuh", "attn_prefill_tc.cuh", "vq_kernels.cuh", "vit_kernels.cuh",
            os.path.join("..", "..", "include", "plangen_b200.h")]
 
 

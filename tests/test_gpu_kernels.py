@@ -30,6 +30,8 @@ def _gemm(eng, impl, X, W, splits):
     (32, 6144, 2048, 3), (32, 2048, 5632, 9),
     # ring reuse with every token-tile width (the ring depth must stay even, see gemm_tc_kernel's invariant)
     (8, 256, 4096, 1), (16, 384, 5632, 1), (48, 256, 4096, 1), (100, 256, 2048, 1), (192, 256, 2304, 1), (300, 128, 4096, 1),
+    # CTA-pair kernel (gemm_tc2.cuh: M > 128, N > 128, no split): odd weight-tile counts, ragged M / N / K, ring reuse
+    (200, 256, 320, 1), (576, 576, 512, 1), (257, 384, 1024, 1), (1000, 1024, 4096, 1), (513, 200, 72, 1), (2048, 3072, 1024, 1),
 ])
 def test_gemm_tcgen05_matches_torch(M, N, K, splits):
     eng = get_engine(O.TINY, "bf16")
