@@ -115,7 +115,7 @@ struct pg_engine {
   void *sig_xn = nullptr, *sig_qkv = nullptr, *sig_vT = nullptr, *sig_attn = nullptr, *sig_h = nullptr, *sig_feat = nullptr;
   size_t sig_part_bytes = 0;
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
-  int use_tc2 = 1, tc2_stages = 3;                    // wide-tile contractions on CTA pairs (gemm_tc2.cuh, tcgen05 cta_group::2)
+  int use_tc2 = 1, tc2_stages = 4;                    // wide-tile contractions on CTA pairs (gemm_tc2.cuh, tcgen05 cta_group::2)
   int prefill_pack = 1;                               // fused loops prefill the real tokens only (lm_kernels.cuh packed_row_of)
   float* xpack = nullptr; float* x_last = nullptr; int32_t* row_off = nullptr; int32_t* row_off_host = nullptr;
   int prefill_fuse = 1;                               // prefill contractions with bf16 / residual epilogues (gemm.cuh EpiFuse) instead of fp32 partials
@@ -297,13 +297,14 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     }
     CUtensorMap mw, mx;
     TRY(make_map_2d(e, &mw, W, (uint64_t)N, (uint64_t)K, TC_BM));
-    if (e->use_tc2 && NT == 256 && splits == 1 && !swiglu_out && N > TC_BM && (!epi || !epi->out || e->tc2_stages * TC2_STAGE_BYTES >= TC2_NT * 256)) {
+    if (e->use_tc2 && NT == 256 && splits == 1 && !swiglu_out && N > TC_BM) {
       // tensor-bound shape: CTA pairs, one 256 x 256 x 16 MMA per pair and k-step (gemm_tc2.cuh)
       TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)(TC2_NT / 2)));
       EpiFuse ep2 = {};
       if (epi) ep2 = *epi;
-      const int pairs = ((N + TC_BM - 1) / TC_BM + 1) / 2;
-      TRY(launch(e, gemm_tc2_kernel, dim3(2 * pairs, (M + TC2_NT - 1) / TC2_NT, 1), dim3(192), (size_t)tc2_smem_bytes(e->tc2_stages), st, mw, mx, C, M,
+      const int n_tiles = (((N + TC_BM - 1) / TC_BM + 1) / 2) * ((M + TC2_NT - 1) / TC2_NT);
+      const int pairs = std::max(1, std::min(n_tiles, e->num_sms / 2));       // persistent: one CTA per SM
+      TRY(launch(e, gemm_tc2_kernel, dim3(2 * pairs, 1, 1), dim3(TC2_THREADS), (size_t)tc2p_smem_bytes(e->tc2_stages), st, mw, mx, C, M,
                  N, K, e->tc2_stages, e->use_pdl, next_prof(e), ep2));
       *splits_out = 1;
       return 0;
@@ -573,7 +574,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "prefill_fuse") e->prefill_fuse = (int)value;
   else if (k == "prefill_pack") e->prefill_pack = (int)value;
   else if (k == "use_tc2") e->use_tc2 = (int)value;
-  else if (k == "tc2_stages") e->tc2_stages = std::max(2, std::min(6, (int)value));
+  else if (k == "tc2_stages") e->tc2_stages = std::max(2, std::min(4, (int)value));
   else if (k == "sig_fuse") e->sig_fuse = (int)value;
   else if (k == "tc_prefetch") e->tc_prefetch = (int)value;
   else if (k == "tc_prefetch_gu") e->tc_prefetch_gu = (int)value;

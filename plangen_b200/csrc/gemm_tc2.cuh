@@ -14,7 +14,8 @@
 //   warp 1 (one thread)  leader only: tcgen05.mma.cta_group::2, commits multicast to both CTAs' empty / accumulator
 //                        barriers; both CTAs: cta_group::2 TMEM allocation;
 //   warps 2-5            epilogue of the CTA's own 128 weight rows x 256 tokens (accumulator in its own TMEM): fp32
-//                        partial store, or the fused row epilogues of gemm.cuh (EpiFuse).
+//                        partial store, or the fused row epilogues of gemm.cuh (EpiFuse); after draining a TMEM set
+//                        they arrive (remotely, for the peer) on the leader's accumulator-empty barrier.
 #pragma once
 #include "gemm.cuh"
 
@@ -55,23 +56,41 @@ PG_DEVINL void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+// remote arrive on the barrier at this offset in the LEADER CTA (rank 0) of the pair
+PG_DEVINL void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & TC2_PEER_MASK) : "memory");
+}
+
+// Persistent: one CTA per SM, 74 pairs walk the (token tile, weight-tile pair) space; TWO accumulator sets in TMEM (2 x 256
+// columns) so the epilogue of tile i (TMEM -> bias / GELU -> bf16 staging -> 256-byte row stores) overlaps the main loop of
+// tile i+1, and the operand ring never drains between tiles.
+constexpr int TC2_STG_BYTES = TC2_NT * 256;        // bf16 staging tile [256 tokens][128 n]
+static constexpr int tc2p_smem_bytes(int stages) { return stages * TC2_STAGE_BYTES + TC2_STG_BYTES + 1024 + 256; }
+
+constexpr int TC2_THREADS = 320;                   // producer warp, MMA warp, eight epilogue warps
+constexpr int TC2_EPI = 256;                       // epilogue threads: two warps per TMEM lane quarter, 128 columns each
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ C, int M, int N,
                 int K, int num_stages, int use_pdl, Prof prof, EpiFuse ep) {
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw2 + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + num_stages * TC2_STAGE_BYTES);
+  uint8_t* stg_buf = smem + num_stages * TC2_STAGE_BYTES;
+  uint64_t* bars = (uint64_t*)(stg_buf + TC2_STG_BYTES);
   uint64_t* full_bar = bars;                       // used in the leader only
   uint64_t* empty_bar = bars + num_stages;
-  uint64_t* tmem_full_bar = bars + 2 * num_stages;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * num_stages + 1);
+  uint64_t* acc_full = bars + 2 * num_stages;      // [2] both CTAs (multicast commit)
+  uint64_t* acc_empty = bars + 2 * num_stages + 2; // [2] leader only: 16 arrivals (8 epilogue warps x 2 CTAs)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * num_stages + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int n0 = blockIdx.x * TC_BM;               // this CTA's weight rows
-  const int m0 = blockIdx.y * TC2_NT;              // the pair's token tile
   const int nkb = (K + TC_BK - 1) / TC_BK;
+  // tile space: weight-tile pairs vary fastest, so the pairs running at the same time share their token tile in L2
+  const int pairs_x = ((N + TC_BM - 1) / TC_BM + 1) / 2, tiles_m = (M + TC2_NT - 1) / TC2_NT;
+  const int n_tiles = pairs_x * tiles_m;
+  const int pair_id = (int)blockIdx.x >> 1, n_pairs = (int)gridDim.x >> 1;
 
   if (use_pdl) pdl_launch_dependents();
   prof_begin(prof);
@@ -79,11 +98,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
     tma_prefetch_desc(&map_w);
     tma_prefetch_desc(&map_x);
     for (int i = 0; i < num_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-    mbar_init(tmem_full_bar, 1);
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_empty[0], 16); mbar_init(&acc_empty[1], 16);
     mbar_fence_init();
   }
   if (warp == 1) {
-    tmem2_alloc(tmem_slot, 256);
+    tmem2_alloc(tmem_slot, 512);
     tmem2_relinquish();
   }
   tc_fence_before();
@@ -94,118 +114,140 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   if (warp == 0) {
     // ===================== TMA producer (one thread per CTA) =====================
     if (lane == 0) {
-      const uint64_t pol_w = policy_evict_last(), pol_x = policy_evict_last();   // both operands are re-read by other tiles
+      const uint64_t pol = policy_evict_last();      // both operands are re-read by other tiles
       if (use_pdl) pdl_wait();
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % num_stages;
-        mbar_wait(&empty_bar[s], (((uint32_t)(i / num_stages)) & 1u) ^ 1u, 81);
-        // the leader posts the bytes of BOTH CTAs' loads of this stage; the peer's loads count on the same barrier
-        if (leader) mbar_expect_tx(&full_bar[s], 2 * TC2_STAGE_BYTES);
-        tma2_load_2d(smem + s * TC2_STAGE_BYTES, &map_w, &full_bar[s], i * TC_BK, n0, pol_w);
-        tma2_load_2d(smem + s * TC2_STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[s], i * TC_BK, m0 + (int)rank * (TC2_NT / 2), pol_x);
+      int it = 0;                                    // k-blocks issued so far (ring position)
+      for (int t = pair_id; t < n_tiles; t += n_pairs) {
+        const int n0 = ((t % pairs_x) * 2 + (int)rank) * TC_BM, m0 = (t / pairs_x) * TC2_NT + (int)rank * (TC2_NT / 2);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % num_stages;
+          mbar_wait(&empty_bar[s], (((uint32_t)(it / num_stages)) & 1u) ^ 1u, 81);
+          // the leader posts the bytes of BOTH CTAs' loads of this stage; the peer's loads count on the same barrier
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * TC2_STAGE_BYTES);
+          tma2_load_2d(smem + s * TC2_STAGE_BYTES, &map_w, &full_bar[s], i * TC_BK, n0, pol);
+          tma2_load_2d(smem + s * TC2_STAGE_BYTES + TC_A_BYTES, &map_x, &full_bar[s], i * TC_BK, m0, pol);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader only, one thread) =====================
     if (leader && lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(2 * TC_BM, TC2_NT);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % num_stages;
-        mbar_wait(&full_bar[s], ((uint32_t)(i / num_stages)) & 1u, 82);
+      int it = 0, j = 0;
+      for (int t = pair_id; t < n_tiles; t += n_pairs, ++j) {
+        const int set = j & 1;
+        mbar_wait(&acc_empty[set], (((uint32_t)(j >> 1)) & 1u) ^ 1u, 84);   // both CTAs' epilogues drained this set (tile j - 2)
         tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + s * TC2_STAGE_BYTES);
-        const uint64_t da = umma_desc_k_sw128(a_addr);
-        const uint64_t db = umma_desc_k_sw128(a_addr + TC_A_BYTES);
+        for (int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % num_stages;
+          mbar_wait(&full_bar[s], ((uint32_t)(it / num_stages)) & 1u, 82);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + s * TC2_STAGE_BYTES);
+          const uint64_t da = umma_desc_k_sw128(a_addr);
+          const uint64_t db = umma_desc_k_sw128(a_addr + TC_A_BYTES);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)
-          umma2_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
-        umma2_commit_mc(&empty_bar[s]);             // frees the stage in both CTAs once these MMAs retire
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma2_bf16(tmem_base + (uint32_t)(set * TC2_NT), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((i | k) != 0));
+          umma2_commit_mc(&empty_bar[s]);           // frees the stage in both CTAs once these MMAs retire
+        }
+        umma2_commit_mc(&acc_full[set]);            // this tile's accumulators (both CTAs) complete
       }
-      umma2_commit_mc(tmem_full_bar);               // accumulators of both CTAs complete
     }
   } else {
-    // ===================== epilogue: own 128 weight rows x 256 tokens =====================
-    const int quarter = warp & 3;
-    const int n = n0 + quarter * 32 + lane;
+    // ===================== epilogue: own 128 weight rows x 256 tokens per tile =====================
+    const int quarter = warp & 3;                     // TMEM lanes 32 * quarter ..
+    const int chalf = (warp - 2) >> 2;                // columns chalf * 128 .. + 127 of the tile
+    const int tE = threadIdx.x - 64;                  // 0 .. 255 over the epilogue warps
     if (use_pdl) pdl_wait();
-    mbar_wait(tmem_full_bar, 0, 83);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    if (ep.out != nullptr) {
-      const float bias_n = (ep.bias && n < N) ? ep.bias[n] : 0.f;
-      const uint32_t stg = smem_u32(smem);                   // [256][128] bf16 = 64 KB over the (now idle) ring
-      const int nl = quarter * 32 + lane;
+    int j = 0;
+    for (int t = pair_id; t < n_tiles; t += n_pairs, ++j) {
+      const int set = j & 1;
+      const int n0 = ((t % pairs_x) * 2 + (int)rank) * TC_BM, m0 = (t / pairs_x) * TC2_NT;
+      const int n = n0 + quarter * 32 + lane;
+      mbar_wait(&acc_full[set], ((uint32_t)(j >> 1)) & 1u, 83);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(set * TC2_NT);
+      if (ep.out != nullptr) {
+        const float bias_n = (ep.bias && n < N) ? ep.bias[n] : 0.f;
+        const uint32_t stg = smem_u32(stg_buf);
+        const int nl = quarter * 32 + lane;
+        asm volatile("bar.sync 2, 256;" ::: "memory");       // the previous tile's row stores have read the staging tile
 #pragma unroll 1
-      for (int c0 = 0; c0 < TC2_NT; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
+        for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+          uint32_t v[2][16];
+          tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v[0]);
+          tmem_ld_32x32b_x16(taddr + (uint32_t)c0 + 16u, v[1]);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float t = bf16_round(__uint_as_float(v[j]) + bias_n);
-          if (ep.gelu) t = t * 0.5f * (1.0f + erf_fast(t * 0.70710678118654752440f));
-          const unsigned short hb = __bfloat16_as_ushort(__float2bfloat16_rn(t));
-          asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)((c0 + j) * 256 + nl * 2)), "h"(hb) : "memory");
-        }
-      }
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      const int t128 = threadIdx.x - 64;
-      const int ch = t128 & 15, r0 = t128 >> 4;
-      if (n0 + ch * 8 < N) {
-#pragma unroll 4
-        for (int r = r0; r < TC2_NT; r += 8) {
-          const size_t m = (size_t)m0 + r;
-          if (m < (size_t)M) {
-            uint4 q;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
-                         : "r"(stg + (uint32_t)(r * 256 + ch * 16)));
-            if (ep.add16 != nullptr) {
-              const uint4 a = *reinterpret_cast<const uint4*>(ep.add16 + m * N + n0 + ch * 8);
-              uint32_t qs[4] = {q.x, q.y, q.z, q.w};
-              const uint32_t as[4] = {a.x, a.y, a.z, a.w};
+          for (int h2 = 0; h2 < 2; ++h2)
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const __nv_bfloat162 o = __floats2bfloat162_rn(bf16lo(qs[u]) + bf16lo(as[u]), bf16hi(qs[u]) + bf16hi(as[u]));
-                qs[u] = *reinterpret_cast<const uint32_t*>(&o);
-              }
-              q = make_uint4(qs[0], qs[1], qs[2], qs[3]);
+            for (int q = 0; q < 16; ++q) {
+              float x = bf16_round(__uint_as_float(v[h2][q]) + bias_n);
+              if (ep.gelu) x = x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
+              const unsigned short hb = __bfloat16_as_ushort(__float2bfloat16_rn(x));
+              asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)((c0 + h2 * 16 + q) * 256 + nl * 2)), "h"(hb) : "memory");
             }
-            *reinterpret_cast<uint4*>(ep.out + m * N + n0 + ch * 8) = q;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(&acc_empty[set]);   // TMEM set drained: the issuer may start tile j + 2 into it
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        const int ch = tE & 15, r0 = tE >> 4;
+        if (n0 + ch * 8 < N) {
+#pragma unroll 4
+          for (int r = r0; r < TC2_NT; r += 16) {
+            const size_t m = (size_t)m0 + r;
+            if (m < (size_t)M) {
+              uint4 q;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w)
+                           : "r"(stg + (uint32_t)(r * 256 + ch * 16)));
+              if (ep.add16 != nullptr) {
+                const uint4 a = *reinterpret_cast<const uint4*>(ep.add16 + m * N + n0 + ch * 8);
+                uint32_t qs[4] = {q.x, q.y, q.z, q.w};
+                const uint32_t as[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const __nv_bfloat162 o = __floats2bfloat162_rn(bf16lo(qs[u]) + bf16lo(as[u]), bf16hi(qs[u]) + bf16hi(as[u]));
+                  qs[u] = *reinterpret_cast<const uint32_t*>(&o);
+                }
+                q = make_uint4(qs[0], qs[1], qs[2], qs[3]);
+              }
+              *reinterpret_cast<uint4*>(ep.out + m * N + n0 + ch * 8) = q;
+            }
           }
         }
-      }
-    } else if (ep.resid != nullptr) {
-      const float bias_n = (ep.bias && n < N) ? ep.bias[n] : 0.f;
+      } else {
+        const float bias_n = (ep.bias && n < N) ? ep.bias[n] : 0.f;
 #pragma unroll 1
-      for (int c0 = 0; c0 < TC2_NT; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (n < N) {
-          float xo[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m0 + c0 + j;
-            xo[j] = (m < M) ? ep.resid[(size_t)m * N + n] : 0.f;
+        for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (c0 + 16 >= chalf * 128 + 128) {                    // this warp's last TMEM read of the tile
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_leader(&acc_empty[set]);
           }
+          if (n < N) {
+            if (ep.resid != nullptr) {
+              float xo[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m0 + c0 + j;
-            if (m < M) ep.resid[(size_t)m * N + n] = xo[j] + bf16_round(__uint_as_float(v[j]) + bias_n);
-          }
-        }
-      }
-    } else {
-#pragma unroll 1
-      for (int c0 = 0; c0 < TC2_NT; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (n < N) {
+              for (int q = 0; q < 16; ++q) {
+                const int m = m0 + c0 + q;
+                xo[q] = (m < M) ? ep.resid[(size_t)m * N + n] : 0.f;
+              }
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int m = m0 + c0 + j;
-            if (m < M) C[(size_t)m * N + n] = __uint_as_float(v[j]);
+              for (int q = 0; q < 16; ++q) {
+                const int m = m0 + c0 + q;
+                if (m < M) ep.resid[(size_t)m * N + n] = xo[q] + bf16_round(__uint_as_float(v[q]) + bias_n);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const int m = m0 + c0 + q;
+                if (m < M) C[(size_t)m * N + n] = __uint_as_float(v[q]);
+              }
+            }
           }
         }
       }
@@ -214,7 +256,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
   tc_fence_before();
   cluster_sync_all();                               // nobody leaves (or frees TMEM) while the pair can still touch it
   prof_end(prof);
-  if (warp == 1) tmem2_dealloc(tmem_base, 256);
+  if (warp == 1) tmem2_dealloc(tmem_base, 512);
 }
 
 }  // namespace pg
