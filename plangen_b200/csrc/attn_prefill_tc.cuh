@@ -130,12 +130,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       // ---- pass 1: masked row maximum (scores as the bf16 matmul output, scaled in bf16)
       float bm = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < PA_BK; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_lane + (uint32_t)c0, v);
+      for (int c0 = 0; c0 < PA_BK; c0 += 64) {            // 64 columns per TMEM round trip (common.cuh tmem_ld_32x32b_x64)
+        uint32_t v[64];
+        tmem_ld_32x32b_x64(t_lane + (uint32_t)c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
+        for (int j = 0; j < 64; ++j) {
           const int key = key0 + c0 + j;
           const bool vis = key >= start && key <= q && q < P;
           const float s = bf16_round(bf16_round(__uint_as_float(v[j])) * scale);
@@ -148,31 +148,31 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       float psum = 0.f;
       const uint32_t p_row = smem_u32(sP) + (uint32_t)row * 128;
 #pragma unroll 1
-      for (int c0 = 0; c0 < PA_BK; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_lane + (uint32_t)c0, v);
+      for (int c0 = 0; c0 < PA_BK; c0 += 64) {            // one P tile ([128][64 keys]) per TMEM round trip
+        uint32_t v[64];
+        tmem_ld_32x32b_x64(t_lane + (uint32_t)c0, v);
         tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float p2[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int key = key0 + c0 + j + u;
-            const bool vis = key >= start && key <= q && q < P;
-            const float s = bf16_round(bf16_round(__uint_as_float(v[j + u])) * scale);
-            p2[u] = vis ? exp2f((s - m_new) * LOG2E) : 0.f;
-            psum += p2[u];
-          }
-          const __nv_bfloat162 b = __floats2bfloat162_rn(p2[0], p2[1]);
-          pk[j >> 1] = *reinterpret_cast<const uint32_t*>(&b);
-        }
         const uint32_t tile = p_row + (uint32_t)(c0 >> 6) * PA_TILE;
-        const int cc = (c0 & 63) >> 3;                       // 16-byte chunk index within the 128-byte row
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (uint32_t)(((cc) ^ (row & 7)) << 4)),
-                     "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (uint32_t)(((cc + 1) ^ (row & 7)) << 4)),
-                     "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]) : "memory");
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {                     // 16-byte chunk (8 keys) of the 128-byte row
+          uint32_t pk[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            float p2[2];
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+              const int j = cc * 8 + 2 * u + w, key = key0 + c0 + j;
+              const bool vis = key >= start && key <= q && q < P;
+              const float s = bf16_round(bf16_round(__uint_as_float(v[j])) * scale);
+              p2[w] = vis ? exp2f((s - m_new) * LOG2E) : 0.f;
+              psum += p2[w];
+            }
+            const __nv_bfloat162 b = __floats2bfloat162_rn(p2[0], p2[1]);
+            pk[u] = *reinterpret_cast<const uint32_t*>(&b);
+          }
+          asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(tile + (uint32_t)((cc ^ (row & 7)) << 4)),
+                       "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+        }
       }
       l_run = l_run * alpha + psum;
       m_run = m_new;
@@ -193,12 +193,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       mbar_wait(bar_mma, 1u, 52);
       tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < HEAD_DIM; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(t_lane + 128u + (uint32_t)c0, v);
+      for (int c0 = 0; c0 < HEAD_DIM; c0 += 64) {
+        uint32_t v[64];
+        tmem_ld_32x32b_x64(t_lane + 128u + (uint32_t)c0, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[c0 + j] = o[c0 + j] * alpha + __uint_as_float(v[j]);
+        for (int j = 0; j < 64; ++j) o[c0 + j] = o[c0 + j] * alpha + __uint_as_float(v[j]);
       }
       tc_fence_before();
       __syncthreads();          // next block: TMA overwrites K / V^T, the first MMA overwrites S
