@@ -76,17 +76,9 @@ struct pg_engine {
   struct Tiled { const uint8_t* ptr; int N, K; };
   std::unordered_map<const void*, Tiled> tiled;      // row-major weight -> engine-owned tile-major copy (bf16 mode)
   uint8_t* tiled_buf = nullptr;
-  int rn_threads = 0;
-  // L2 prefetch of the next attention launch's KV tiles from the decode-step norm kernels (lm_kernels.cuh KvPrefetch):
-  // tiles with (index mod kvpf_den) < kvpf1 by the post-attention norm, the next kvpf2 residues by the post-MLP norm
-  int kvpf_den = 8, kvpf1 = 0, kvpf2 = 0;
-  // dynamic shared memory requested by the decode-step norm kernels (they use none): keeps a 200 KB contraction CTA
-  // from becoming co-resident on a norm CTA's SM, where its queued weight-tile requests delay the norm's loads
-  int norm_smem_kb = 0, norm_smem_mask = 3;
   int prefill_attn_tc = 1;                   // prompt-prefill attention on tcgen05 (attn_prefill_tc.cuh); 0 = CUDA-core kernel
   void* vT = nullptr;                        // [R][H][128][Ppad] key-contiguous copy of V for the prefill attention
   int norm_tma = 3;      // bit 0: decode-step norms through the TMA-staged kernel, bit 1: prefill norms too
-  int tc_prefetch = 0, tc_prefetch_gu = 0;   // weight tiles a decode contraction may request before its dependency wait (0 = ring depth)
   int use_tiled = 1, use_implicit_conv = 1, tc_wide_stages = 2, fuse_conv_epilogue = 1;   // conv bias / residual / bf16 store in the contraction epilogue
   EncodeTiledFn encode = nullptr;
   // options
@@ -219,7 +211,7 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   if (ep.out && (size_t)stages * Cfg::STAGE_BYTES < (size_t)NT * 256) return fail("internal: operand ring too small to stage the output tile");
   return launch(e, gemm_tc_kernel<NT>, grid, dim3(192), smem, st, mw, mx, C, M, N, K, kb_per_split, stages,
                 e->use_pdl ? (w_const ? 3 : 1) : 0, (const uint8_t*)w_tiled, next_prof(e), (bf16*)swiglu_out, cg,
-                NT <= 64 ? (swiglu_out ? e->tc_prefetch_gu : e->tc_prefetch) : 0, ep);
+                ep);
 }
 
 // 3x3 convolution (pad 1) as an implicit GEMM on the tcgen05 path: act bf16 NHWC [B][H][W][Cin], Wc bf16
@@ -566,7 +558,6 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
   else if (k == "use_tiled") e->use_tiled = (int)value;
-  else if (k == "rn_threads") e->rn_threads = (int)value;
   else if (k == "norm_tma") e->norm_tma = (int)value;
   else if (k == "prefill_attn_tc") e->prefill_attn_tc = (int)value;
   else if (k == "sig_attn_tc") e->sig_attn_tc = (int)value;
@@ -576,13 +567,6 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "use_tc2") e->use_tc2 = (int)value;
   else if (k == "tc2_stages") e->tc2_stages = std::max(2, std::min(4, (int)value));
   else if (k == "sig_fuse") e->sig_fuse = (int)value;
-  else if (k == "tc_prefetch") e->tc_prefetch = (int)value;
-  else if (k == "tc_prefetch_gu") e->tc_prefetch_gu = (int)value;
-  else if (k == "norm_smem_kb") e->norm_smem_kb = (int)value;
-  else if (k == "norm_smem_mask") e->norm_smem_mask = (int)value;
-  else if (k == "kvpf_den") e->kvpf_den = std::max(1, (int)value);
-  else if (k == "kvpf1") e->kvpf1 = (int)value;
-  else if (k == "kvpf2") e->kvpf2 = (int)value;
   else if (k == "fuse_conv_epilogue") e->fuse_conv_epilogue = (int)value;
   else if (k == "tc_wide_stages") e->tc_wide_stages = std::max(2, (int)value);
   else if (k == "use_implicit_conv") e->use_implicit_conv = (int)value;
@@ -628,11 +612,8 @@ extern "C" int pg_engine_get_counter(const pg_engine* e, const char* key, int64_
   } while (0)
 
 static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t sstride, const float* w, void* xn,
-                        float* y, int rows, int in_stride, int in_off, int flags, cudaStream_t st,
-                        const KvPrefetch* pfp = nullptr, size_t smem = 0) {
+                        float* y, int rows, int in_stride, int in_off, int flags, cudaStream_t st) {
   const int D = e->d.D;
-  KvPrefetch pf = {};
-  if (pfp) pf = *pfp;
   // decode steps: slabs + residual row through TMA bulk copies into shared memory (bit-identical, see lm_kernels.cuh)
   const size_t tma_smem = (size_t)(S + 1) * D * 4 + 128;
   const int tma_threads = std::min(RN_THREADS, std::max(128, (D / 4 + 31) / 32 * 32));   // one element quad per thread
@@ -641,19 +622,19 @@ static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t
       (((uintptr_t)part | (uintptr_t)x) & 15) == 0) {
     DISPATCH_T(e,
                launch(e, resid_rmsnorm_tma_kernel<bf16>, dim3(rows), dim3(tma_threads), tma_smem, st, x, part, S, sstride, w, (bf16*)xn, y, D,
-                      e->d.rms_eps, flags, e->step_ctr, next_prof(e), pf),
+                      e->d.rms_eps, flags, e->step_ctr, next_prof(e)),
                launch(e, resid_rmsnorm_tma_kernel<float>, dim3(rows), dim3(tma_threads), tma_smem, st, x, part, S, sstride, w, (float*)xn, y, D,
-                      e->d.rms_eps, flags, e->step_ctr, next_prof(e), pf));
+                      e->d.rms_eps, flags, e->step_ctr, next_prof(e)));
     return 0;
   }
   // few rows (decode): 1024 threads so one row's split-K loads are all in flight; many rows (prefill): 256+
-  int threads = rows <= 256 ? (e->rn_threads > 0 ? e->rn_threads : RN_THREADS) : 256;
+  int threads = rows <= 256 ? RN_THREADS : 256;
   while (threads * RN_MAX_PER_THREAD < D) threads *= 2;
   DISPATCH_T(e,
-             launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(threads), smem, st, x, part, S, sstride, w, (bf16*)xn, y, D,
-                    e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e), pf),
-             launch(e, resid_rmsnorm_kernel<float>, dim3(rows), dim3(threads), smem, st, x, part, S, sstride, w, (float*)xn, y,
-                    D, e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e), pf));
+             launch(e, resid_rmsnorm_kernel<bf16>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (bf16*)xn, y, D,
+                    e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e)),
+             launch(e, resid_rmsnorm_kernel<float>, dim3(rows), dim3(threads), 0, st, x, part, S, sstride, w, (float*)xn, y,
+                    D, e->d.rms_eps, in_stride, in_off, flags, e->step_ctr, next_prof(e)));
   return 0;
 }
 
@@ -972,19 +953,6 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
   const int trig = regime == 0 ? (e->bf16 ? 1 : 0) : ROPE_REL;
   const int nsp = attn_split_count(e, R, T_hint);
   int S = 1;
-  // KV tiles of attention launch (layer tl) prefetched into L2 by the norm kernels in front of it; tl == L means layer 0
-  // of the NEXT step (one more token in the cache)
-  const bool kvpf_on = e->bf16 && e->attn_impl >= 1 && R <= AT_MAX_ROWS && (e->kvpf1 > 0 || e->kvpf2 > 0);
-  auto kv_prefetch = [&](int tl, int lo, int hi) {
-    KvPrefetch pf = {};
-    if (!kvpf_on || hi <= lo) return pf;
-    const int layer = tl % d.L;
-    pf.k = (const uint8_t*)kv_ptr(e, layer, 0, R); pf.v = (const uint8_t*)kv_ptr(e, layer, 1, R);
-    pf.kv_start = kv_start; pf.step_ptr = step_ptr; pf.H = d.H; pf.Tmax = e->Tmax;
-    pf.pos = pos_base + (tl >= d.L ? 1 : 0);
-    pf.lo = lo; pf.hi = hi; pf.den = e->kvpf_den; pf.tile_bytes = 32 * HEAD_DIM * e->esz;
-    return pf;
-  };
   for (int l = 0; l < d.L; ++l) {
     LayerW w;
     TRY(layer_weights(e, l, &w));
@@ -1009,22 +977,17 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
                         e->attn_cnt, d.H, e->Tmax, pos_base, step_ptr, scale, trig));
     }
     TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &S, st));
-    const KvPrefetch pf1 = kv_prefetch(l + 1, 0, e->kvpf1);
-    TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st, &pf1,
-                     (e->norm_smem_mask & 1) ? (size_t)e->norm_smem_kb * 1024 : 0));
+    TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st));
     TRY(k_gate_up(e, w, R, st));
     TRY(run_gemm(e, e->hbuf, w.wd, R, D, F, e->part, e->part_bytes, &S, st));
     if (l + 1 < d.L) {
       LayerW wn;
       TRY(layer_weights(e, l + 1, &wn));
-      const KvPrefetch pf2 = kv_prefetch(l + 1, e->kvpf1, e->kvpf1 + e->kvpf2);
-      TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, wn.ln1, e->xn, nullptr, R, 1, 0, rflag, st, &pf2,
-                       (e->norm_smem_mask & 2) ? (size_t)e->norm_smem_kb * 1024 : 0));
+      TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, wn.ln1, e->xn, nullptr, R, 1, 0, rflag, st));
     }
   }
-  const KvPrefetch pf_last = kv_prefetch(d.L, e->kvpf1, e->kvpf1 + e->kvpf2);
   TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, normw, e->hidden_t, e->hidden_f, R, 1, 0,
-                   rflag | (inc_step ? RN_INC_STEP : 0), st, &pf_last));
+                   rflag | (inc_step ? RN_INC_STEP : 0), st));
   return 0;
 }
 

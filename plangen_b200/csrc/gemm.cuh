@@ -138,8 +138,7 @@ template <int NT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,
                float* __restrict__ C, int M, int N, int K, int kb_per_split, int num_stages, int use_pdl,
-               const uint8_t* __restrict__ w_tiled, Prof prof, bf16* __restrict__ swiglu_out, ConvGeom cg, int w_prefetch,
-               EpiFuse ep) {
+               const uint8_t* __restrict__ w_tiled, Prof prof, bf16* __restrict__ swiglu_out, ConvGeom cg, EpiFuse ep) {
   using Cfg = TcCfg<NT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -205,9 +204,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant_
     const uint64_t pol_w = policy_evict_first();     // weights are streamed once per step
     if ((use_pdl & 3) == 1) pdl_wait();
     for (int i = first; i < nkb; i += 2) {
-      // w_prefetch > 0: at most that many weight tiles are requested before the previous kernel has finished (the rest
-      // of the ring fills right after): bounds the request queue the predecessor's critical loads sit behind
-      if (w_prefetch > 0 && (use_pdl & 1) && i >= w_prefetch && i < w_prefetch + 2) pdl_wait();
       const int s = i % num_stages;
       mbar_wait(&empty_bar[s], (((uint32_t)(i / num_stages)) & 1u) ^ 1u, 1);
       if (dbg && blockIdx.x == 5 && blockIdx.z == 0 && i < 64) dbg[16384 + 64 + i] = global_timer_ns();

@@ -25,7 +25,6 @@ constexpr int TC2_NT = 256;                        // tokens per pair tile (MMA 
 constexpr int TC2_BHALF = (TC2_NT / 2) * TC_BK * 2;  // one CTA's half of the token tile: 16 KB
 constexpr int TC2_STAGE_BYTES = TC_A_BYTES + TC2_BHALF;
 constexpr uint32_t TC2_PEER_MASK = 0xFEFFFFFFu;    // clears the CTA-rank bit of a shared::cluster address: CTA 0's copy
-static constexpr int tc2_smem_bytes(int stages) { return stages * TC2_STAGE_BYTES + 1024 + 256; }
 
 PG_DEVINL void tma2_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, uint64_t policy) {
   asm volatile(

@@ -70,36 +70,6 @@ __global__ void embed_gather_kernel(const int32_t* __restrict__ ids, const float
 // x[tok] += rnd(sum_s part[s][tok]);  xn = w * (x * rsqrt(mean(x^2) + eps))   (HF modeling_llama.py:60-65)
 // One CTA per output row.  Input row index = blockIdx.x * in_stride + in_off (lets the final norm of
 // a prefill pick only the last position of every prompt row).
-// L2 prefetch of the NEXT attention launch's KV tiles, issued by a decode-step norm kernel before its dependency
-// wait.  Between the attention kernels of two layers the step is a chain of latency-bound contractions and HBM
-// idles (in-situ timeline: ~36 us of the 66 us layer); the attention kernel then has to pull its whole K/V
-// working set (131 MB per layer at configs[1]) at once.  Fetching a fraction of the tiles into L2 during the
-// idle window shortens that stream.  Tiles are taken by residue (tile index mod den in [lo, hi)) so every
-// group stream of the attention kernel sees the same mix of L2 hits and misses (its static even cut stays balanced).
-// Pure cache hint: no effect on results.
-struct KvPrefetch {
-  const uint8_t* k;          // K strip base of the target layer ([R][H][Tmax][128] elements), nullptr = off
-  const uint8_t* v;
-  const int32_t* kv_start;   // [R] first valid (left-pad) position per row
-  const int* step_ptr;
-  int H, Tmax, pos, lo, hi, den, tile_bytes;   // pos = pos_base (+ *step_ptr): tokens [start, pos) exist
-};
-PG_DEVINL void kv_prefetch_l2(const KvPrefetch& pf, int row) {
-  const int pos = pf.pos + (pf.step_ptr ? *pf.step_ptr : 0);
-  const int start = pf.kv_start[row];
-  if (pos <= start) return;
-  const int t_first = start / 32, t_last = (pos - 1) / 32;
-  for (int idx = threadIdx.x;; idx += blockDim.x) {
-    const int sel = idx & 1, h = (idx >> 1) % pf.H, tile = t_first + idx / (2 * pf.H);
-    if (tile > t_last) break;
-    const int res = tile % pf.den;
-    if (res >= pf.lo && res < pf.hi) {
-      const uint8_t* p = (sel ? pf.v : pf.k) + ((size_t)(row * pf.H + h) * pf.Tmax + (size_t)tile * 32) * (size_t)(pf.tile_bytes / 32);
-      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(pf.tile_bytes) : "memory");
-    }
-  }
-}
-
 // debug timeline (tools/norm_timeline.py): 8 %globaltimer stamps per CTA of the decode-step norm kernels of the
 // step g_norm_dbg_step, indexed by the kernel's timeline slot; nullptr in production
 __device__ unsigned long long* g_norm_dbg = nullptr;
@@ -114,13 +84,12 @@ template <typename T>
 __global__ void __launch_bounds__(RN_THREADS)
 resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int S, size_t split_stride,
                      const float* __restrict__ w, T* __restrict__ xn_out, float* __restrict__ y_out, int D,
-                     float eps, int in_stride, int in_off, int flags, int* step_ptr, Prof prof, KvPrefetch pf) {
+                     float eps, int in_stride, int in_off, int flags, int* step_ptr, Prof prof) {
   __shared__ float red[32];
   pdl_launch_dependents();
   prof_begin(prof);
   unsigned long long* nd = (prof.buf && g_norm_dbg && step_ptr && *step_ptr == g_norm_dbg_step && blockIdx.x < 64) ? g_norm_dbg : nullptr;
   norm_stamp(nd, prof.slot, 0);
-  if (pf.k != nullptr) kv_prefetch_l2(pf, blockIdx.x);
   // the norm weight is a constant: fetch it before the dependency wait instead of after the reduction
   float wv[RN_MAX_PER_THREAD];
 #pragma unroll
@@ -199,7 +168,7 @@ template <typename T>
 __global__ void __launch_bounds__(RN_THREADS)
 resid_rmsnorm_tma_kernel(float* __restrict__ x, const float* __restrict__ part, int S, size_t split_stride,
                          const float* __restrict__ w, T* __restrict__ xn_out, float* __restrict__ y_out, int D,
-                         float eps, int flags, int* step_ptr, Prof prof, KvPrefetch pf) {
+                         float eps, int flags, int* step_ptr, Prof prof) {
   extern __shared__ uint8_t rn_smem_raw[];
   __shared__ float red[32];
   __shared__ uint64_t bar;
@@ -208,7 +177,6 @@ resid_rmsnorm_tma_kernel(float* __restrict__ x, const float* __restrict__ part, 
   prof_begin(prof);
   unsigned long long* nd = (prof.buf && g_norm_dbg && step_ptr && *step_ptr == g_norm_dbg_step && blockIdx.x < 64) ? g_norm_dbg : nullptr;
   norm_stamp(nd, prof.slot, 0);
-  if (pf.k != nullptr) kv_prefetch_l2(pf, blockIdx.x);
   const int tid = threadIdx.x;
   if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
   // thread t owns the element quads 4 (t + k blockDim); the norm weight is a constant: fetched before the wait
