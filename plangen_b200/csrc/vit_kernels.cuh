@@ -118,19 +118,30 @@ vit_resid_ln_warp_kernel(float* __restrict__ x, const float* __restrict__ part, 
                          const float* __restrict__ bias, const float* __restrict__ w, const float* __restrict__ b,
                          T* __restrict__ xn_out, int C, float eps, int rows) {
   pdl_launch_dependents();
-  pdl_wait();
   const int lane = threadIdx.x & 31;
   const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  // the affine parameters are constants: fetched before the dependency wait, all loads of the row in flight together
+  float4 wv[LNW_MAXQ], bv[LNW_MAXQ];
+#pragma unroll
+  for (int q = 0; q < LNW_MAXQ; ++q) {
+    const int d = 4 * (lane + 32 * q);
+    wv[q] = bv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (d < C && xn_out != nullptr) { wv[q] = *reinterpret_cast<const float4*>(w + d); bv[q] = *reinterpret_cast<const float4*>(b + d); }
+  }
+  pdl_wait();
   if (row >= (size_t)rows) return;
   float* xr = x + row * C;
   float4 v[LNW_MAXQ];
+#pragma unroll
+  for (int q = 0; q < LNW_MAXQ; ++q) {
+    const int d = 4 * (lane + 32 * q);
+    v[q] = (d < C) ? __ldcs(reinterpret_cast<const float4*>(xr + d)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float sum = 0.f;
 #pragma unroll
   for (int q = 0; q < LNW_MAXQ; ++q) {
     const int d = 4 * (lane + 32 * q);
-    v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (d < C) {
-      v[q] = *reinterpret_cast<const float4*>(xr + d);
       if (part != nullptr) {
         float a[4];
 #pragma unroll
@@ -157,10 +168,9 @@ vit_resid_ln_warp_kernel(float* __restrict__ x, const float* __restrict__ part, 
   for (int q = 0; q < LNW_MAXQ; ++q) {
     const int d = 4 * (lane + 32 * q);
     if (d < C) {
-      const float4 wv = *reinterpret_cast<const float4*>(w + d), bv = *reinterpret_cast<const float4*>(b + d);
       T* dst = xn_out + row * C + d;
-      const float y0 = (v[q].x - mean) * rstd * wv.x + bv.x, y1 = (v[q].y - mean) * rstd * wv.y + bv.y;
-      const float y2 = (v[q].z - mean) * rstd * wv.z + bv.z, y3 = (v[q].w - mean) * rstd * wv.w + bv.w;
+      const float y0 = (v[q].x - mean) * rstd * wv[q].x + bv[q].x, y1 = (v[q].y - mean) * rstd * wv[q].y + bv[q].y;
+      const float y2 = (v[q].z - mean) * rstd * wv[q].z + bv[q].z, y3 = (v[q].w - mean) * rstd * wv[q].w + bv[q].w;
       if constexpr (sizeof(T) == 2) {
         const __nv_bfloat162 lo = __floats2bfloat162_rn(y0, y1), hi = __floats2bfloat162_rn(y2, y3);
         uint2 pk; pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
