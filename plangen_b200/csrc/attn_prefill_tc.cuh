@@ -67,6 +67,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   const int q0 = blockIdx.x * PA_BQ, h = blockIdx.y, r = blockIdx.z;
   const int HD = H * HEAD_DIM;
   pdl_launch_dependents();
+  // packed stream: a duplicate row has no tokens of its own (its K / V are copied from the row it repeats).  row_off is
+  // written before the first prefill kernel is launched, so reading it ahead of the dependency wait is safe.
+  if (row_off != nullptr && row_off[r + 1] == row_off[r]) return;
   if (tid == 0) {
     tma_prefetch_desc(&map_q); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_vt);
     mbar_init(bar_load, 1); mbar_init(bar_mma, 1);

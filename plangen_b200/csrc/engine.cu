@@ -108,6 +108,8 @@ struct pg_engine {
   size_t sig_part_bytes = 0;
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
   int use_tc2 = 1, tc2_stages = 4;                    // wide-tile contractions on CTA pairs (gemm_tc2.cuh, tcgen05 cta_group::2)
+  int prefill_dedup = 1;                              // packed prefill: rows repeating an earlier row are prefilled once (lm_kernels.cuh)
+  int32_t* dup_of = nullptr; int32_t* row_differs = nullptr;
   int prefill_pack = 1;                               // fused loops prefill the real tokens only (lm_kernels.cuh packed_row_of)
   float* xpack = nullptr; float* x_last = nullptr; int32_t* row_off = nullptr; int32_t* row_off_host = nullptr;
   int prefill_fuse = 1;                               // prefill contractions with bf16 / residual epilogues (gemm.cuh EpiFuse) instead of fp32 partials
@@ -346,6 +348,8 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->xpack = (float*)c.take(max_tok * d.D * 4);
   e->x_last = (float*)c.take(R * d.D * 4);
   e->row_off = (int32_t*)c.take((R + 1) * 4);
+  e->dup_of = (int32_t*)c.take(R * 4);
+  e->row_differs = (int32_t*)c.take(R * 4);
   e->xn = c.take(max_tok * d.D * es);
   e->qbuf = c.take(max_tok * e->HD * es);
   e->attn_out = c.take(max_tok * e->HD * es);
@@ -564,6 +568,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "gu_streamk") e->gu_streamk = (int)value;
   else if (k == "prefill_fuse") e->prefill_fuse = (int)value;
   else if (k == "prefill_pack") e->prefill_pack = (int)value;
+  else if (k == "prefill_dedup") e->prefill_dedup = (int)value;
   else if (k == "use_tc2") e->use_tc2 = (int)value;
   else if (k == "tc2_stages") e->tc2_stages = std::max(2, std::min(4, (int)value));
   else if (k == "sig_fuse") e->sig_fuse = (int)value;
@@ -817,21 +822,38 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
   int S = 1;
   // ---- packed prefill (fused loops only: the drop-in call returns every position, pads included)
   const int32_t* row_off = nullptr;
+  int packed_dups = 0;
   if (!all_positions && e->bf16 && e->use_tc && e->prefill_attn_tc && e->prefill_fuse && e->prefill_pack && D % 8 == 0 && HD % 8 == 0 &&
       F % 64 == 0) {
-    if (!e->row_off_host) CK(cudaMallocHost(&e->row_off_host, (size_t)(d.max_rows + 1) * 4));
+    if (!e->row_off_host) CK(cudaMallocHost(&e->row_off_host, (size_t)(3 * d.max_rows + 2) * 4));
+    int32_t* differs_host = e->row_off_host + d.max_rows + 1;
+    const bool dedup = e->prefill_dedup && R > 2 && D % 4 == 0;
+    if (dedup) {
+      CK(cudaMemsetAsync(e->row_differs, 0, (size_t)R * 4, st));
+      prefill_row_differs_kernel<<<dim3(P, R), 256, 0, st>>>((const float*)x, kv_start, e->row_differs, P, D);
+      CK(cudaGetLastError());
+      e->launches++;
+      CK(cudaMemcpyAsync(differs_host, e->row_differs, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaMemcpyAsync(e->row_off_host, kv_start, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    std::vector<int32_t> off((size_t)R + 1, 0);
+    std::vector<int32_t> off((size_t)R + 1, 0), dup((size_t)R, 0);
     bool ok = true;
+    int n_dup = 0;
     for (int r = 0; r < R; ++r) {
       const int len = P - e->row_off_host[r];
       if (len < 1 || len > P) ok = false;                  // an empty row: leave it to the padded path
-      off[r + 1] = off[r] + std::max(len, 0);
+      dup[r] = (dedup && r >= 2 && differs_host[r] == 0) ? dup[r - 2] : r;     // chains: all repeats point at the first copy
+      if (dup[r] != r) ++n_dup;
+      off[r + 1] = off[r] + (dup[r] == r ? std::max(len, 0) : 0);
     }
     if (ok && off[R] < R * P) {
       memcpy(e->row_off_host, off.data(), (size_t)(R + 1) * 4);
       CK(cudaMemcpyAsync(e->row_off, e->row_off_host, (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, st));
+      int32_t* dup_host = e->row_off_host + 2 * d.max_rows + 1;
+      memcpy(dup_host, dup.data(), (size_t)R * 4);
+      CK(cudaMemcpyAsync(e->dup_of, dup_host, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+      packed_dups = n_dup;
       TRY(launch(e, prefill_pack_kernel, dim3(P, R), dim3(256), 0, st, (const float*)x, e->xpack, kv_start, (const int32_t*)e->row_off, P, D));
       x = e->xpack;
       tok = off[R];
@@ -916,7 +938,10 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
   const float* last_part = fuse ? nullptr : e->part;      // fused: the last down projection is already in the stream
   if (row_off != nullptr) {
     // packed: the last real token of every row
-    TRY(launch(e, gather_last_rows_kernel, dim3(R), dim3(256), 0, st, (const float*)x, e->x_last, row_off, D));
+    if (packed_dups > 0)     // rows that repeat an earlier row: their K / V strips are copies
+      TRY(launch(e, kv_broadcast_rows_kernel, dim3(d.L * 2 * d.H, R), dim3(256), 0, st, (bf16*)e->kv, (const int32_t*)e->dup_of, kv_start, R, d.H,
+                 e->Tmax, P));
+    TRY(launch(e, gather_last_rows_kernel, dim3(R), dim3(256), 0, st, (const float*)x, e->x_last, row_off, (const int32_t*)e->dup_of, D));
     TRY(k_resid_norm(e, e->x_last, nullptr, 0, 0, normw, e->hidden_t, e->hidden_f, R, 1, 0, 0, st));
     if (hidden_out) CK(cudaMemcpyAsync(hidden_out, e->hidden_f, (size_t)R * D * 4, cudaMemcpyDeviceToDevice, st));
   } else if (all_positions) {

@@ -377,6 +377,44 @@ PG_DEVINL int packed_row_of(const int32_t* __restrict__ row_off, int R, int t) {
   }
   return lo;
 }
+// Rows that repeat an earlier row (PlanGen's unconditional rows all carry the same negative prompt, cfg/base.py:129) are
+// prefilled ONCE: row r with dup_of[r] != r contributes no tokens to the packed stream (row_off[r+1] == row_off[r]); its
+// K / V strips and its final hidden state are copied from row dup_of[r] afterwards (identical inputs through deterministic
+// kernels give identical bits, so the copy equals the recomputation).
+// differs[r] = 1 unless row r (>= 2) has the same left padding and bitwise the same embeddings as row r - 2: grid (P, R)
+__global__ void __launch_bounds__(256)
+prefill_row_differs_kernel(const float* __restrict__ x, const int32_t* __restrict__ kv_start, int32_t* __restrict__ differs, int P, int D) {
+  const int p = blockIdx.x, r = blockIdx.y;
+  if (r < 2) { if (p == 0 && threadIdx.x == 0) differs[r] = 1; return; }
+  const int start = kv_start[r];
+  if (start != kv_start[r - 2]) { if (p == 0 && threadIdx.x == 0) differs[r] = 1; return; }
+  if (p < start) return;
+  const uint4* a = reinterpret_cast<const uint4*>(x + ((size_t)r * P + p) * D);
+  const uint4* b = reinterpret_cast<const uint4*>(x + ((size_t)(r - 2) * P + p) * D);
+  bool diff = false;
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const uint4 u = a[i], v = b[i];
+    diff |= (u.x != v.x) | (u.y != v.y) | (u.z != v.z) | (u.w != v.w);
+  }
+  if (diff) differs[r] = 1;                               // benign race: every writer stores 1
+}
+// K / V strips of the prompt columns of duplicate rows: grid (L * 2 * H, R), cache [L][2][R][H][Tmax][128] bf16
+__global__ void __launch_bounds__(256)
+kv_broadcast_rows_kernel(bf16* __restrict__ kv, const int32_t* __restrict__ dup_of, const int32_t* __restrict__ kv_start, int R, int H,
+                         int Tmax, int P) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r = blockIdx.y, src = dup_of[r];
+  if (src == r) return;
+  const int lkh = blockIdx.x, h = lkh % H, lk = lkh / H;
+  const int start = kv_start[r];
+  const size_t strip = (size_t)Tmax * HEAD_DIM;
+  const uint4* s4 = reinterpret_cast<const uint4*>(kv + (((size_t)lk * R + src) * H + h) * strip + (size_t)start * HEAD_DIM);
+  uint4* d4 = reinterpret_cast<uint4*>(kv + (((size_t)lk * R + r) * H + h) * strip + (size_t)start * HEAD_DIM);
+  const int n16 = (P - start) * HEAD_DIM * 2 / 16;
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = s4[i];
+}
+
 // x [R][P][D] -> xp [sum len][D]: grid (P, R)
 __global__ void __launch_bounds__(256)
 prefill_pack_kernel(const float* __restrict__ x, float* __restrict__ xp, const int32_t* __restrict__ kv_start,
@@ -385,18 +423,19 @@ prefill_pack_kernel(const float* __restrict__ x, float* __restrict__ xp, const i
   pdl_wait();
   const int p = blockIdx.x, r = blockIdx.y;
   const int start = kv_start[r];
-  if (p < start) return;
+  if (p < start || row_off[r + 1] == row_off[r]) return;       // pad column, or a duplicate row (no tokens of its own)
   const float4* src = reinterpret_cast<const float4*>(x + ((size_t)r * P + p) * D);
   float4* dst = reinterpret_cast<float4*>(xp + (size_t)(row_off[r] + p - start) * D);
   for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = src[i];
 }
-// last real token of every row: xp[row_off[r+1] - 1] -> out[r]
+// last real token of every row (of the row it duplicates): xp[row_off[dup_of[r] + 1] - 1] -> out[r]
 __global__ void __launch_bounds__(256)
-gather_last_rows_kernel(const float* __restrict__ xp, float* __restrict__ out, const int32_t* __restrict__ row_off, int D) {
+gather_last_rows_kernel(const float* __restrict__ xp, float* __restrict__ out, const int32_t* __restrict__ row_off,
+                        const int32_t* __restrict__ dup_of, int D) {
   pdl_launch_dependents();
   pdl_wait();
   const int r = blockIdx.x;
-  const float4* src = reinterpret_cast<const float4*>(xp + (size_t)(row_off[r + 1] - 1) * D);
+  const float4* src = reinterpret_cast<const float4*>(xp + (size_t)(row_off[dup_of[r] + 1] - 1) * D);
   float4* dst = reinterpret_cast<float4*>(out + (size_t)r * D);
   for (int i = threadIdx.x; i < D / 4; i += blockDim.x) dst[i] = src[i];
 }

@@ -275,6 +275,55 @@ def test_packed_prefill_is_bit_identical_to_padded_prefill():
     assert torch.equal(got[0], got[1])
 
 
+def test_prefill_row_dedup_is_bit_identical():
+    """Rows that repeat row r - 2 (PlanGen's unconditional rows all carry the same negative prompt, cfg/base.py:129) are
+    prefilled once and their K / V strips copied (lm_kernels.cuh kv_broadcast_rows_kernel).  Mixed batch: six prompts share a
+    negative prompt, two carry their own (one of the same length), one conditional prompt repeats its neighbour; the CFG
+    logits of the following steps and the sampled tokens are bit-identical with `prefill_dedup` on and off."""
+    dims = O.SMALL
+    steps = 5
+    g = torch.Generator().manual_seed(77)
+    rnd = lambda n: torch.randint(0, dims.vocab - 2, (n,), generator=g).tolist()
+    a, shared = rnd(60), rnd(23)
+    # prompts 0 and 1 are the same text (rows 0 / 2 repeat); prompt 3 has the same length as 2 but other tokens; prompt 7
+    # shares only a suffix with prompt 6
+    cond = [a, list(a), rnd(200), rnd(200), rnd(5), rnd(131), rnd(256), None]
+    cond[7] = rnd(196) + cond[6][-60:]
+    neg = [shared, shared, shared, shared, rnd(23), shared, rnd(9), shared]
+    lens = [len(c) for c in cond]
+    ids, mask = O.t2i_infer_collate_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
+    eng = get_engine(dims, "bf16", with_vq=False, max_batch=8, max_prompt=256)
+    outs, toks = [], []
+    for dedup in (1, 0):
+        eng.set_option("prefill_dedup", dedup)
+        dbg = torch.zeros(steps, len(lens), dims.img_vocab, device="cuda")
+        eng.set_option("dbg_logits_ptr", dbg.data_ptr())
+        try:
+            emb = eng.language_model.get_input_embeddings()(ids.cuda())
+            toks.append(eng.sample_image(emb, len(lens), steps, mask.cuda(), 5.0, 1.0, generator=3).cpu())
+            torch.cuda.synchronize()
+        finally:
+            eng.set_option("dbg_logits_ptr", 0)
+            eng.set_option("prefill_dedup", 1)
+        outs.append(dbg.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(toks[0], toks[1])
+    assert float(outs[0].abs().max()) > 0
+    # identical adjacent-pair rows in a text prefill (rows r and r - 2 the same prompt)
+    sd = O.init_state_dict(dims, seed=0, with_vq=False, with_lm_head=True)
+    from plangen_b200.engine import FastJanus
+    from tests.gpu_util import product_dims
+    te = FastJanus(sd, product_dims(dims), mode="bf16", max_batch=6, max_prompt=256, max_steps=32, with_vq=False)
+    tid, tmask = O.pad_input_ids([cond[0], cond[2], cond[0], cond[2][:150], cond[0], cond[4]], dims.pad_id)
+    got = []
+    for dedup in (1, 0):
+        te.set_option("prefill_dedup", dedup)
+        emb = te.language_model.get_input_embeddings()(tid.cuda())
+        got.append(te.language_model.generate(inputs_embeds=emb, attention_mask=tmask.cuda(), pad_token_id=7, eos_token_id=7,
+                                              max_new_tokens=8).cpu())
+    assert torch.equal(got[0], got[1])
+    assert torch.equal(got[0][0], got[0][2]) and torch.equal(got[0][0], got[0][4])
+
+
 @pytest.mark.parametrize("B", [5, 16, 32])
 def test_bf16_streamk_gate_up_matches_reference(B):
     """Stream-K gate|up + SwiGLU (gemm_sk.cuh; the default for Janus-Pro-7B, forced here): token tiles of 16 / 32 / 64
