@@ -112,12 +112,16 @@ struct AttnCut {
 // padding is not a multiple of 32), the last one ends at the newest cached token.  The untouched token slots of the
 // stage keep whatever an earlier tile left there (the kernel zero-fills its ring once at entry, so that is always a
 // finite value); the consumer masks them.  Saves ~31 of the tokens read per (row, head): 8 of 146 MB per launch at configs[1].
+// Shared prompts: when row r's prompt K / V are a copy of row src_row[r]'s (prefill de-duplication: PlanGen's unconditional
+// rows all carry the same negative prompt) the prompt columns (< alias_P) are read from the SOURCE row's strips, so all
+// copies ask for the same addresses and all but the first are served by L2 (kept there: pol_shared) instead of HBM.
 template <int SPG>
 PG_DEVINL void attn_produce_group(int gb, int ge, const int* row_units, int R, int H, int Tmax, int pos,
                                   const int32_t* __restrict__ kv_start, const bf16* __restrict__ kcache,
                                   const bf16* __restrict__ vcache, uint8_t* ring, int stage_stride_bytes,
                                   const int* stage_of, uint64_t* full_bar, uint64_t* empty_bar, int& kload,
-                                  uint64_t pol, int r_hint = 0) {
+                                  uint64_t pol, int r_hint = 0, const int32_t* __restrict__ src_row = nullptr, int alias_P = 0,
+                                  uint64_t pol_shared = 0) {
   int r = r_hint;
   while (r + 1 < R && row_units[r + 1] * H <= gb) ++r;
   int ur = row_units[r + 1] - row_units[r];
@@ -135,8 +139,22 @@ PG_DEVINL void attn_produce_group(int gb, int ge, const int* row_units, int R, i
       mbar_expect_tx(&full_bar[s], 2 * bytes);
       const size_t off = (((size_t)r * H + h) * Tmax + t0k + a) * HEAD_DIM;
       uint8_t* dst = ring + (size_t)s * stage_stride_bytes + (size_t)a * (HEAD_DIM * 2);
-      bulk_load(dst, kcache + off, bytes, &full_bar[s], pol);
-      bulk_load(dst + AT_TILE_BYTES, vcache + off, bytes, &full_bar[s], pol);
+      const int rs = (src_row != nullptr && t0k + a < alias_P) ? src_row[r] : r;
+      if (rs != r) {
+        // tokens [t0k + a, min(t0k + b, alias_P)) from the source row, the rest (generated tokens) from the row itself
+        const int nb = min(b, alias_P - t0k) - a;
+        const uint32_t sb = (uint32_t)nb * (HEAD_DIM * 2);
+        const size_t soff = (((size_t)rs * H + h) * Tmax + t0k + a) * HEAD_DIM;
+        bulk_load(dst, kcache + soff, sb, &full_bar[s], pol_shared);
+        bulk_load(dst + AT_TILE_BYTES, vcache + soff, sb, &full_bar[s], pol_shared);
+        if (sb < bytes) {
+          bulk_load(dst + sb, kcache + off + (size_t)nb * HEAD_DIM, bytes - sb, &full_bar[s], pol);
+          bulk_load(dst + AT_TILE_BYTES + sb, vcache + off + (size_t)nb * HEAD_DIM, bytes - sb, &full_bar[s], pol);
+        }
+      } else {
+        bulk_load(dst, kcache + off, bytes, &full_bar[s], pol);
+        bulk_load(dst + AT_TILE_BYTES, vcache + off, bytes, &full_bar[s], pol);
+      }
       ++kload;
     }
     // advance (r, h, k) to the next unit without divisions

@@ -353,7 +353,7 @@ attn_decode_v5_kernel(const float* __restrict__ part, int S, size_t split_stride
                       const int32_t* __restrict__ kv_start, bf16* __restrict__ out, float* __restrict__ ws_ll_f,
                       int R, int H, int Tmax, int pos_base,
                       const int* __restrict__ step_ptr, float scale, int bf16_trig, int early_trigger, Prof prof,
-                      unsigned long long* dbg) {
+                      unsigned long long* dbg, const int32_t* __restrict__ src_row, int alias_P) {
   extern __shared__ uint8_t smem_raw[];
   unsigned long long* ws_ll = reinterpret_cast<unsigned long long*>(ws_ll_f);   // zero-initialised {flag, value} words
   uint8_t* ring = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
@@ -399,7 +399,8 @@ attn_decode_v5_kernel(const float* __restrict__ part, int S, size_t split_stride
     if (lane == 0) {
       int kload = 0;
       attn_produce_group<A5_SPG>(gb, ge, row_units, R, H, Tmax, pos, row_start, kcache, vcache, ring, 2 * AT_TILE_BYTES,
-                                 stage_tab + g * A5_SPG, full_bar, empty_bar, kload, policy_evict_first(), r0);
+                                 stage_tab + g * A5_SPG, full_bar, empty_bar, kload, policy_evict_first(), r0, src_row, alias_P,
+                                 policy_evict_last());
       at_stamp(dbg, g, 7);
     }
     pdl_wait();

@@ -108,6 +108,7 @@ struct pg_engine {
   size_t sig_part_bytes = 0;
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
   int use_tc2 = 1, tc2_stages = 4;                    // wide-tile contractions on CTA pairs (gemm_tc2.cuh, tcgen05 cta_group::2)
+  int attn_alias = 1;                                 // decode attention reads a duplicate row's prompt K / V from its source row (attn_tma.cuh)
   int prefill_dedup = 1;                              // packed prefill: rows repeating an earlier row are prefilled once (lm_kernels.cuh)
   int32_t* dup_of = nullptr; int32_t* row_differs = nullptr;
   int prefill_pack = 1;                               // fused loops prefill the real tokens only (lm_kernels.cuh packed_row_of)
@@ -569,6 +570,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "prefill_fuse") e->prefill_fuse = (int)value;
   else if (k == "prefill_pack") e->prefill_pack = (int)value;
   else if (k == "prefill_dedup") e->prefill_dedup = (int)value;
+  else if (k == "attn_alias") e->attn_alias = (int)value;
   else if (k == "use_tc2") e->use_tc2 = (int)value;
   else if (k == "tc2_stages") e->tc2_stages = std::max(2, std::min(4, (int)value));
   else if (k == "sig_fuse") e->sig_fuse = (int)value;
@@ -860,6 +862,11 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
       row_off = e->row_off;
     }
   }
+  if (row_off == nullptr) {     // no packed prefill, no de-duplication: every row owns its prompt K / V (decode attention's src_row)
+    iota_i32_kernel<<<(R + 255) / 256, 256, 0, st>>>(e->dup_of, R);
+    CK(cudaGetLastError());
+    e->launches++;
+  }
   // fused epilogues (bf16 regime on tcgen05): QKV and gate|up leave the contraction as bf16 rows, O and down add straight
   // into the fp32 residual stream - no fp32 partial round trip (same values: the row kernels rounded the partials first)
   const bool fuse = e->bf16 && e->use_tc && e->prefill_fuse && D % 8 == 0 && HD % 8 == 0 && F % 64 == 0 &&
@@ -967,7 +974,7 @@ static int attn_split_count(pg_engine* e, int R, int T) {
 // positions); regime 1: text decode inside generate() (fp32 embed_tokens rows => fp32 residual stream, fp32 trig,
 // mask-aware positions) - the rounding points HF's autocast produces for each input dtype
 static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_base, const int* step_ptr,
-                         bool first_norm_done, bool inc_step, int T_hint, cudaStream_t st, int regime = 0) {
+                         bool first_norm_done, bool inc_step, int T_hint, cudaStream_t st, int regime = 0, int alias_P = 0) {
   const pg_dims& d = e->d;
   NEED(cosT, float, "rope_cos");
   NEED(sinT, float, "rope_sin");
@@ -989,7 +996,8 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
       if (!e->attn_attr) e->use_pdl = 0;
       int rc = launch(e, attn_decode_v5_kernel, dim3(ctas), dim3(AT_THREADS), A5_SMEM, st, e->part, S, (size_t)R * 3 * HD, cosT, sinT,
                       (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), kv_start, (bf16*)e->attn_out, e->attn_ll,
-                      R, d.H, e->Tmax, pos_base, step_ptr, scale, trig, e->attn_trigger, next_prof(e), (unsigned long long*)nullptr);
+                      R, d.H, e->Tmax, pos_base, step_ptr, scale, trig, e->attn_trigger, next_prof(e), (unsigned long long*)nullptr,
+                      (const int32_t*)((alias_P > 0 && e->attn_alias) ? e->dup_of : nullptr), alias_P);
       e->use_pdl = saved;
       TRY(rc);
     } else {
@@ -1140,7 +1148,7 @@ static int one_step(pg_engine* e, const int32_t* kv_start, int R, int P, int n_s
                with_lm ? e->xn : nullptr, st));
   if (with_lm)
     TRY(decode_layers(e, kv_start, R, host ? P + step_host : P, host ? nullptr : e->step_ctr, true, !host,
-                      P + n_steps / 2, st));
+                      P + n_steps / 2, st, 0, P));
   return 0;
 }
 
@@ -1867,7 +1875,7 @@ extern "C" int pg_test_attn_decode(pg_engine* e, const int32_t* kv_start, int R,
   int rc = launch(e, attn_decode_v5_kernel, dim3(ctas), dim3(AT_THREADS), A5_SMEM, st, (const float*)e->part, 1, (size_t)R * 3 * HD,
                   cosT, sinT, (bf16*)kv_ptr(e, layer, 0, R), (bf16*)kv_ptr(e, layer, 1, R), kv_start, (bf16*)e->attn_out,
                   e->attn_ll, R, e->d.H, e->Tmax, pos, (const int*)nullptr, 1.0f / sqrtf((float)HEAD_DIM), 1,
-                  (int)e->attn_test_flags, next_prof(e), (unsigned long long*)e->attn_dbg_ptr);
+                  (int)e->attn_test_flags, next_prof(e), (unsigned long long*)e->attn_dbg_ptr, (const int32_t*)nullptr, 0);
   e->use_pdl = saved;
   return rc;
 }

@@ -398,6 +398,10 @@ prefill_row_differs_kernel(const float* __restrict__ x, const int32_t* __restric
   }
   if (diff) differs[r] = 1;                               // benign race: every writer stores 1
 }
+__global__ void iota_i32_kernel(int32_t* __restrict__ p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
+}
 // K / V strips of the prompt columns of duplicate rows: grid (L * 2 * H, R), cache [L][2][R][H][Tmax][128] bf16
 __global__ void __launch_bounds__(256)
 kv_broadcast_rows_kernel(bf16* __restrict__ kv, const int32_t* __restrict__ dup_of, const int32_t* __restrict__ kv_start, int R, int H,

@@ -294,8 +294,9 @@ def test_prefill_row_dedup_is_bit_identical():
     ids, mask = O.t2i_infer_collate_batch(cond, neg, dims.pad_id, dims.n_img_tokens)
     eng = get_engine(dims, "bf16", with_vq=False, max_batch=8, max_prompt=256)
     outs, toks = [], []
-    for dedup in (1, 0):
+    for dedup, alias in ((1, 1), (0, 1), (1, 0)):
         eng.set_option("prefill_dedup", dedup)
+        eng.set_option("attn_alias", alias)           # decode attention reads a duplicate row's prompt K / V from its source row
         dbg = torch.zeros(steps, len(lens), dims.img_vocab, device="cuda")
         eng.set_option("dbg_logits_ptr", dbg.data_ptr())
         try:
@@ -305,8 +306,10 @@ def test_prefill_row_dedup_is_bit_identical():
         finally:
             eng.set_option("dbg_logits_ptr", 0)
             eng.set_option("prefill_dedup", 1)
+            eng.set_option("attn_alias", 1)
         outs.append(dbg.cpu())
     assert torch.equal(outs[0], outs[1]) and torch.equal(toks[0], toks[1])
+    assert torch.equal(outs[0], outs[2]) and torch.equal(toks[0], toks[2])
     assert float(outs[0].abs().max()) > 0
     # identical adjacent-pair rows in a text prefill (rows r and r - 2 the same prompt)
     sd = O.init_state_dict(dims, seed=0, with_vq=False, with_lm_head=True)
