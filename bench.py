@@ -274,6 +274,7 @@ def kernel_roofline(eng, kv_start, lens, P: int, peaks: dict, iters: int = 6):
     st = torch.cuda.current_stream(eng.device)
     sp = C.c_void_p(st.cuda_stream)
     _lib.check(eng._lib.pg_debug_zero_part(eng._h, R * 3 * d.H * d.head_dim * 4, sp))
+    eng.set_option("attn_test_alias_p", P)                 # as in the real step: repeated prompt rows read their source row's strips
 
     def one_pass():
         for l in range(d.L):
@@ -289,6 +290,7 @@ def kernel_roofline(eng, kv_start, lens, P: int, peaks: dict, iters: int = 6):
     e1.record(st)
     torch.cuda.synchronize()
     per_launch_s = e0.elapsed_time(e1) / 1e3 / (iters * d.L)
+    eng.set_option("attn_test_alias_p", 0)
     kv_tok = 2 * d.H * d.head_dim * 2                      # K and V bytes per cached token per row per layer (bf16)
     alg_bytes = sum((ln + d.n_img_tokens // 2) * kv_tok for ln in lens) + R * kv_tok
     achieved = alg_bytes / per_launch_s / 1e9
@@ -299,8 +301,9 @@ def kernel_roofline(eng, kv_start, lens, P: int, peaks: dict, iters: int = 6):
     return {"bound": "hbm", "kernel": "attn_decode_v5_kernel (KV-cache decode attention, paired CFG batch, 1 launch/layer)",
             "achieved": achieved, "peak": peak, "peak_source": which, "unit": "GB/s", "frac": achieved / peak,
             "traffic": _ncu_traffic_bytes(), "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-            "at step ~290 of the same workload (profiles/r02_attn_decode.full.txt); algorithmic K+V bytes there ~129 MB (the first / "
-            "last tile of a row copy only their valid tokens since round 2: 1.03x, was 1.14x)",
+            "at step ~290 of the same workload (profiles/r02_attn_decode.full.txt); algorithmic K+V bytes there ~129 MB.  Below 1x: the "
+            "16 unconditional rows repeat one negative prompt and read its K/V from the first copy's strips, served by L2 "
+            "(1.03x with that switched off, 1.14x in round 1 before the first / last tile of a row were trimmed to their valid tokens)",
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": per_launch_s * 1e6, "position": pos}
 
 

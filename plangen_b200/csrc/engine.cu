@@ -108,6 +108,7 @@ struct pg_engine {
   size_t sig_part_bytes = 0;
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
   int use_tc2 = 1, tc2_stages = 4;                    // wide-tile contractions on CTA pairs (gemm_tc2.cuh, tcgen05 cta_group::2)
+  int attn_test_alias_p = 0;                          // pg_test_attn_decode: prompt length of the batch whose dup_of is current
   int attn_alias = 1;                                 // decode attention reads a duplicate row's prompt K / V from its source row (attn_tma.cuh)
   int prefill_dedup = 1;                              // packed prefill: rows repeating an earlier row are prefilled once (lm_kernels.cuh)
   int32_t* dup_of = nullptr; int32_t* row_differs = nullptr;
@@ -571,6 +572,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "prefill_pack") e->prefill_pack = (int)value;
   else if (k == "prefill_dedup") e->prefill_dedup = (int)value;
   else if (k == "attn_alias") e->attn_alias = (int)value;
+  else if (k == "attn_test_alias_p") e->attn_test_alias_p = (int)value;
   else if (k == "use_tc2") e->use_tc2 = (int)value;
   else if (k == "tc2_stages") e->tc2_stages = std::max(2, std::min(4, (int)value));
   else if (k == "sig_fuse") e->sig_fuse = (int)value;
@@ -1875,7 +1877,8 @@ extern "C" int pg_test_attn_decode(pg_engine* e, const int32_t* kv_start, int R,
   int rc = launch(e, attn_decode_v5_kernel, dim3(ctas), dim3(AT_THREADS), A5_SMEM, st, (const float*)e->part, 1, (size_t)R * 3 * HD,
                   cosT, sinT, (bf16*)kv_ptr(e, layer, 0, R), (bf16*)kv_ptr(e, layer, 1, R), kv_start, (bf16*)e->attn_out,
                   e->attn_ll, R, e->d.H, e->Tmax, pos, (const int*)nullptr, 1.0f / sqrtf((float)HEAD_DIM), 1,
-                  (int)e->attn_test_flags, next_prof(e), (unsigned long long*)e->attn_dbg_ptr, (const int32_t*)nullptr, 0);
+                  (int)e->attn_test_flags, next_prof(e), (unsigned long long*)e->attn_dbg_ptr,
+                  (const int32_t*)((e->attn_test_alias_p > 0 && e->attn_alias) ? e->dup_of : nullptr), e->attn_test_alias_p);
   e->use_pdl = saved;
   return rc;
 }

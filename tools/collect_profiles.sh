@@ -10,7 +10,7 @@ R=${1:-r02}
 mkdir -p gpurun_out
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${R}_bench.json 2> gpurun_out/${R}_bench.err
 tail -c 400 gpurun_out/${R}_bench.err
-KREG='^(gemm_tc|gemm_swiglu_sk|gemm_simt|attn_|resid_rmsnorm|swiglu|bias_act|cfg_sample|qkv_rope|embed_gather|prefill_pack|gather_last)'
+KREG='^(gemm_tc|gemm_swiglu_sk|gemm_simt|attn_|resid_rmsnorm|swiglu|bias_act|cfg_sample|qkv_rope|embed_gather|prefill_|gather_last|kv_broadcast)'
 PG_STEPS=300 PG_GRAPH=0 timeout 400 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
   -k regex:"$KREG" -s 43300 -c 180 --csv --log-file gpurun_out/${R}_launches_decode_step.csv python tools/profile_step.py > gpurun_out/p_a.log 2>&1
 PG_STEPS=300 PG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"attn_decode_v5" -s 7000 -c 1 \
@@ -18,16 +18,20 @@ PG_STEPS=300 PG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import
 PG_STEPS=300 PG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel" -s 28900 -c 4 \
   -o gpurun_out/${R}_gemm_tc python tools/profile_step.py > gpurun_out/p_c.log 2>&1
 PG_STEPS=2 PG_GRAPH=0 PG_VQ=1 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none \
-  -k regex:"^(gemm_tc|gemm_simt|im2col|v_transpose|gn_|conv_epilogue|softmax_rows|vq_codebook|attn_prefill|qkv_rope|resid_rmsnorm|swiglu|prefill_pack|gather_last)" -c 2000 \
+  -k regex:"^(gemm_tc|gemm_simt|im2col|v_transpose|gn_|conv_epilogue|softmax_rows|vq_codebook|attn_prefill|qkv_rope|resid_rmsnorm|swiglu|prefill_|gather_last|kv_broadcast)" -c 2000 \
   --csv --log-file gpurun_out/${R}_launches_prefill_vq.csv python tools/profile_step.py > gpurun_out/p_d.log 2>&1
-PG_STEPS=2 PG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc_kernel" -s 1 -c 4 \
+PG_STEPS=2 PG_GRAPH=0 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"gemm_tc2_kernel" -s 1 -c 4 \
   -o gpurun_out/${R}_gemm_prefill python tools/profile_step.py > gpurun_out/p_e.log 2>&1
 PG_B=32 PG_ITERS=1 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"^(gemm_tc|vit_|bias_act|to_f32)" -c 900 \
   --csv --log-file gpurun_out/${R}_launches_siglip.csv python tools/siglip_time.py > gpurun_out/p_f.log 2>&1
 PG_B=32 PG_ITERS=1 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"vit_attn_tc|gemm_tc_kernel" -s 40 -c 6 \
   -o gpurun_out/${R}_siglip python tools/siglip_time.py > gpurun_out/p_g.log 2>&1
 timeout 300 python tools/siglip_time.py > gpurun_out/${R}_siglip_time.json 2>/dev/null
-ls -la gpurun_out | tail -14
+# post-process on the box (gpurun copies back at most 64 MiB: the .ncu-rep files stay behind)
+for k in decode_step prefill_vq siglip; do python tools/summarize_launches.py gpurun_out/${R}_launches_$k.csv > gpurun_out/${R}_launches_$k.txt; done
+for k in attn_decode gemm_tc gemm_prefill siglip; do python tools/extract_ncu.py gpurun_out/${R}_$k.ncu-rep > gpurun_out/${R}_$k.full.txt; done
+rm -f gpurun_out/*.ncu-rep
+ls -la gpurun_out | tail -24
 # afterwards, where ncu is installed:
 #   python tools/summarize_launches.py gpurun_out/${R}_launches_decode_step.csv > profiles/${R}_launches_decode_step.txt   (same for prefill_vq, siglip)
 #   python tools/extract_ncu.py gpurun_out/${R}_attn_decode.ncu-rep > profiles/${R}_attn_decode.full.txt   (same for gemm_tc, gemm_prefill, siglip)
