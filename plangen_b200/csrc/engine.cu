@@ -108,6 +108,8 @@ struct pg_engine {
   size_t sig_part_bytes = 0;
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
   int use_tc2 = 1, tc2_stages = 4;                    // wide-tile contractions on CTA pairs (gemm_tc2.cuh, tcgen05 cta_group::2)
+  int stage_cap_once = 0, down_stages = 4;            // ring cap of the next launch_tc; decode down projection (see decode_layers)
+  int tc_stages_n = 0;                                // tc_stages applies to contractions with this N only (0 = all)
   int attn_test_alias_p = 0;                          // pg_test_attn_decode: prompt length of the batch whose dup_of is current
   int attn_alias = 1;                                 // decode attention reads a duplicate row's prompt K / V from its source row (attn_tma.cuh)
   int prefill_dedup = 1;                              // packed prefill: rows repeating an earlier row are prefilled once (lm_kernels.cuh)
@@ -201,7 +203,9 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   // shapes want the deepest ring (1.64 ms/step at 8-10 stages, 1.76 at 4)
   int stages = NT >= 192 ? e->tc_wide_stages : (200 * 1024) / Cfg::STAGE_BYTES;
   // options: cap the ring depth of the split-K contractions / of the (unsplit, long-stream) gate|up contraction
-  if (e->tc_stages > 0 && !swiglu_out) stages = std::min(stages, e->tc_stages);
+  if (e->tc_stages > 0 && !swiglu_out && (e->tc_stages_n == 0 || e->tc_stages_n == N)) stages = std::min(stages, e->tc_stages);
+  if (e->stage_cap_once > 0) stages = std::min(stages, e->stage_cap_once);
+  e->stage_cap_once = 0;
   if (e->tc_stages_gu > 0 && swiglu_out) stages = std::min(stages, e->tc_stages_gu);
   stages = std::max(2, std::min(stages, 12));
   stages = std::min(stages, std::max(2, kb_per_split));
@@ -560,6 +564,8 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "use_graph") e->use_graph = (int)value;
   else if (k == "tc_stages") e->tc_stages = (int)value;
   else if (k == "tc_stages_gu") e->tc_stages_gu = (int)value;
+  else if (k == "tc_stages_n") e->tc_stages_n = (int)value;
+  else if (k == "down_stages") e->down_stages = (int)value;
   else if (k == "vq_chunk") e->vq_chunk = (int)value;
   else if (k == "attn_splits") e->attn_splits = (int)value;
   else if (k == "attn_impl") e->attn_impl = (int)value;
@@ -1014,7 +1020,14 @@ static int decode_layers(pg_engine* e, const int32_t* kv_start, int R, int pos_b
     TRY(run_gemm(e, e->attn_out, w.wo, R, D, HD, e->part, e->part_bytes, &S, st));
     TRY(k_resid_norm(e, e->x_dec, e->part, S, (size_t)R * D, w.ln2, e->xn, nullptr, R, 1, 0, rflag, st));
     TRY(k_gate_up(e, w, R, st));
+    // gate|up runs one CTA per weight tile; when that leaves SMs free (Janus-1.3B: 88 tiles on 148 SMs) the early-launched
+    // CTAs of the down projection start on them and have their weight share in flight before gate|up ends.  With an 80 KB
+    // ring (4 stages) instead of 200 KB TWO of them fit on a free SM: 120 of the 144 CTAs prefetch early instead of 60
+    // (measured at R = 32: 1.469 -> 1.453 ms per step; 6 or 8 stages are slower than either).  Only there: with 16 or fewer
+    // rows (1.212 -> 1.241 ms at R = 16) and with 64 (1.651 -> 1.673) the deep ring wins, and without free SMs (stream-K) too.
+    if (e->bf16 && e->use_tc && e->down_stages > 0 && 2 * F / TC_BM < e->num_sms && R > 16 && R <= 32) e->stage_cap_once = e->down_stages;
     TRY(run_gemm(e, e->hbuf, w.wd, R, D, F, e->part, e->part_bytes, &S, st));
+    e->stage_cap_once = 0;
     if (l + 1 < d.L) {
       LayerW wn;
       TRY(layer_weights(e, l + 1, &wn));
