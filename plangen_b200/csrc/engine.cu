@@ -109,6 +109,7 @@ struct pg_engine {
   int32_t *sig_rank_dst = nullptr, *sig_inv_src = nullptr, *sig_counts = nullptr;
   int use_tc2 = 1, tc2_stages = 4;                    // wide-tile contractions on CTA pairs (gemm_tc2.cuh, tcgen05 cta_group::2)
   int stage_cap_once = 0, down_stages = 4;            // ring cap of the next launch_tc; decode down projection (see decode_layers)
+  int tc_stages_k = 0;
   int tc_stages_n = 0;                                // tc_stages applies to contractions with this N only (0 = all)
   int attn_test_alias_p = 0;                          // pg_test_attn_decode: prompt length of the batch whose dup_of is current
   int attn_alias = 1;                                 // decode attention reads a duplicate row's prompt K / V from its source row (attn_tma.cuh)
@@ -203,7 +204,7 @@ static int launch_tc(pg_engine* e, const CUtensorMap& mw, const CUtensorMap& mx,
   // shapes want the deepest ring (1.64 ms/step at 8-10 stages, 1.76 at 4)
   int stages = NT >= 192 ? e->tc_wide_stages : (200 * 1024) / Cfg::STAGE_BYTES;
   // options: cap the ring depth of the split-K contractions / of the (unsplit, long-stream) gate|up contraction
-  if (e->tc_stages > 0 && !swiglu_out && (e->tc_stages_n == 0 || e->tc_stages_n == N)) stages = std::min(stages, e->tc_stages);
+  if (e->tc_stages > 0 && !swiglu_out && (e->tc_stages_n == 0 || e->tc_stages_n == N) && (e->tc_stages_k == 0 || e->tc_stages_k == K)) stages = std::min(stages, e->tc_stages);
   if (e->stage_cap_once > 0) stages = std::min(stages, e->stage_cap_once);
   e->stage_cap_once = 0;
   if (e->tc_stages_gu > 0 && swiglu_out) stages = std::min(stages, e->tc_stages_gu);
@@ -565,6 +566,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "tc_stages") e->tc_stages = (int)value;
   else if (k == "tc_stages_gu") e->tc_stages_gu = (int)value;
   else if (k == "tc_stages_n") e->tc_stages_n = (int)value;
+  else if (k == "tc_stages_k") e->tc_stages_k = (int)value;
   else if (k == "down_stages") e->down_stages = (int)value;
   else if (k == "vq_chunk") e->vq_chunk = (int)value;
   else if (k == "attn_splits") e->attn_splits = (int)value;
