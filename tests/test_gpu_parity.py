@@ -160,6 +160,14 @@ def test_vq_bf16_matches_autocast_reference(dims):
     a, b = out.cpu().numpy(), want.cpu().numpy()
     assert_close(a, b, 2e-2, 5e-2, "vq bf16")
     assert np.abs(a - b).mean() < 1e-2 * np.abs(b).max()
+    # the convolution epilogue fused into the contraction (bias + skip + bf16 store) rounds at the same points as the
+    # separate epilogue kernel it replaced: identical images with the switch off
+    eng.set_option("fuse_conv_epilogue", 0)
+    try:
+        out2 = eng.gen_vision_model.decode_code(codes.cuda(), shape=[3, dims.code_dim, dims.grid, dims.grid]).float()
+    finally:
+        eng.set_option("fuse_conv_epilogue", 1)
+    assert torch.equal(out, out2)
 
 
 def test_t2i_end_to_end_small():
