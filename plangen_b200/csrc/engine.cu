@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -115,6 +116,7 @@ struct pg_engine {
   int attn_alias = 1;                                 // decode attention reads a duplicate row's prompt K / V from its source row (attn_tma.cuh)
   int prefill_dedup = 1;                              // packed prefill: rows repeating an earlier row are prefilled once (lm_kernels.cuh)
   int32_t* dup_of = nullptr; int32_t* row_differs = nullptr;
+  unsigned long long* row_hash = nullptr; unsigned long long* row_hash_host = nullptr;   // content hash per prompt row (device / pinned)
   int prefill_pack = 1;                               // fused loops prefill the real tokens only (lm_kernels.cuh packed_row_of)
   float* xpack = nullptr; float* x_last = nullptr; int32_t* row_off = nullptr; int32_t* row_off_host = nullptr;
   int prefill_fuse = 1;                               // prefill contractions with bf16 / residual epilogues (gemm.cuh EpiFuse) instead of fp32 partials
@@ -357,6 +359,7 @@ static void layout_workspace(pg_engine* e, Carve& c) {
   e->row_off = (int32_t*)c.take((R + 1) * 4);
   e->dup_of = (int32_t*)c.take(R * 4);
   e->row_differs = (int32_t*)c.take(R * 4);
+  e->row_hash = (unsigned long long*)c.take(R * 8);
   e->xn = c.take(max_tok * d.D * es);
   e->qbuf = c.take(max_tok * e->HD * es);
   e->attn_out = c.take(max_tok * e->HD * es);
@@ -517,6 +520,7 @@ extern "C" int pg_engine_destroy(pg_engine* e) {
   drop_graphs(e);
   if (e->poll_host) cudaFreeHost(e->poll_host);
   if (e->row_off_host) cudaFreeHost(e->row_off_host);
+  if (e->row_hash_host) cudaFreeHost(e->row_hash_host);
   if (e->tiled_buf) cudaFree(e->tiled_buf);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -838,31 +842,52 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
   if (!all_positions && e->bf16 && e->use_tc && e->prefill_attn_tc && e->prefill_fuse && e->prefill_pack && D % 8 == 0 && HD % 8 == 0 &&
       F % 64 == 0) {
     if (!e->row_off_host) CK(cudaMallocHost(&e->row_off_host, (size_t)(3 * d.max_rows + 2) * 4));
+    if (!e->row_hash_host) CK(cudaMallocHost(&e->row_hash_host, (size_t)d.max_rows * 8));
     int32_t* differs_host = e->row_off_host + d.max_rows + 1;
-    const bool dedup = e->prefill_dedup && R > 2 && D % 4 == 0;
+    int32_t* dup_host = e->row_off_host + 2 * d.max_rows + 1;
+    const bool dedup = e->prefill_dedup && R > 1 && D % 4 == 0;
     if (dedup) {
-      CK(cudaMemsetAsync(e->row_differs, 0, (size_t)R * 4, st));
-      prefill_row_differs_kernel<<<dim3(P, R), 256, 0, st>>>((const float*)x, kv_start, e->row_differs, P, D);
+      CK(cudaMemsetAsync(e->row_hash, 0, (size_t)R * 8, st));
+      prefill_row_hash_kernel<<<dim3(P, R), 256, 0, st>>>((const float*)x, kv_start, e->row_hash, P, D);
       CK(cudaGetLastError());
       e->launches++;
-      CK(cudaMemcpyAsync(differs_host, e->row_differs, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(e->row_hash_host, e->row_hash, (size_t)R * 8, cudaMemcpyDeviceToHost, st));
     }
     CK(cudaMemcpyAsync(e->row_off_host, kv_start, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    std::vector<int32_t> off((size_t)R + 1, 0), dup((size_t)R, 0);
+    std::vector<int32_t> off((size_t)R + 1, 0), dup((size_t)R, 0), start((size_t)R, 0);
+    for (int r = 0; r < R; ++r) { start[r] = e->row_off_host[r]; dup[r] = r; }
+    if (dedup) {
+      // proposal: the first row with the same left padding and content hash; verified word for word on the device
+      std::map<std::pair<int32_t, unsigned long long>, int> first;
+      int proposals = 0;
+      for (int r = 0; r < R; ++r) {
+        auto ins = first.emplace(std::make_pair(start[r], e->row_hash_host[r]), r);
+        if (!ins.second) { dup[r] = ins.first->second; ++proposals; }
+      }
+      if (proposals > 0) {
+        memcpy(dup_host, dup.data(), (size_t)R * 4);
+        CK(cudaMemcpyAsync(e->dup_of, dup_host, (size_t)R * 4, cudaMemcpyHostToDevice, st));
+        CK(cudaMemsetAsync(e->row_differs, 0, (size_t)R * 4, st));
+        prefill_row_verify_kernel<<<dim3(P, R), 256, 0, st>>>((const float*)x, kv_start, (const int32_t*)e->dup_of, e->row_differs, P, D);
+        CK(cudaGetLastError());
+        e->launches++;
+        CK(cudaMemcpyAsync(differs_host, e->row_differs, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int r = 0; r < R; ++r) if (dup[r] != r && differs_host[r] != 0) dup[r] = r;
+      }
+    }
     bool ok = true;
     int n_dup = 0;
     for (int r = 0; r < R; ++r) {
-      const int len = P - e->row_off_host[r];
+      const int len = P - start[r];
       if (len < 1 || len > P) ok = false;                  // an empty row: leave it to the padded path
-      dup[r] = (dedup && r >= 2 && differs_host[r] == 0) ? dup[r - 2] : r;     // chains: all repeats point at the first copy
       if (dup[r] != r) ++n_dup;
       off[r + 1] = off[r] + (dup[r] == r ? std::max(len, 0) : 0);
     }
     if (ok && off[R] < R * P) {
       memcpy(e->row_off_host, off.data(), (size_t)(R + 1) * 4);
       CK(cudaMemcpyAsync(e->row_off, e->row_off_host, (size_t)(R + 1) * 4, cudaMemcpyHostToDevice, st));
-      int32_t* dup_host = e->row_off_host + 2 * d.max_rows + 1;
       memcpy(dup_host, dup.data(), (size_t)R * 4);
       CK(cudaMemcpyAsync(e->dup_of, dup_host, (size_t)R * 4, cudaMemcpyHostToDevice, st));
       packed_dups = n_dup;

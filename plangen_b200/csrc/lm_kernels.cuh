@@ -377,20 +377,49 @@ PG_DEVINL int packed_row_of(const int32_t* __restrict__ row_off, int R, int t) {
   }
   return lo;
 }
-// Rows that repeat an earlier row (PlanGen's unconditional rows all carry the same negative prompt, cfg/base.py:129) are
+// Rows that repeat an EARLIER row (PlanGen's unconditional rows all carry the same negative prompt, cfg/base.py:129) are
 // prefilled ONCE: row r with dup_of[r] != r contributes no tokens to the packed stream (row_off[r+1] == row_off[r]); its
 // K / V strips and its final hidden state are copied from row dup_of[r] afterwards (identical inputs through deterministic
 // kernels give identical bits, so the copy equals the recomputation).
-// differs[r] = 1 unless row r (>= 2) has the same left padding and bitwise the same embeddings as row r - 2: grid (P, R)
+// Finding the repeats takes two passes.  (1) a 64-bit content hash per row (sum over the real columns of a mixed
+// (word, position) pair: order-independent, so blocks just atomicAdd their share); the host groups rows by (left padding,
+// hash) and proposes the FIRST row of each group as the source of the others.  (2) every proposal is verified word for word
+// (a hash collision only costs the row its shortcut).  Repeats may sit anywhere in the batch: the unconditional rows of one
+// negative prompt (distance 2), the copies of `parallel_size` > 1 (distance 2 * bs), repeated captions.
+PG_DEVINL unsigned long long mix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// grid (P, R)
 __global__ void __launch_bounds__(256)
-prefill_row_differs_kernel(const float* __restrict__ x, const int32_t* __restrict__ kv_start, int32_t* __restrict__ differs, int P, int D) {
+prefill_row_hash_kernel(const float* __restrict__ x, const int32_t* __restrict__ kv_start, unsigned long long* __restrict__ hash, int P, int D) {
   const int p = blockIdx.x, r = blockIdx.y;
-  if (r < 2) { if (p == 0 && threadIdx.x == 0) differs[r] = 1; return; }
-  const int start = kv_start[r];
-  if (start != kv_start[r - 2]) { if (p == 0 && threadIdx.x == 0) differs[r] = 1; return; }
-  if (p < start) return;
+  if (p < kv_start[r]) return;
+  const uint32_t* a = reinterpret_cast<const uint32_t*>(x + ((size_t)r * P + p) * D);
+  unsigned long long h = 0;
+  for (int i = threadIdx.x; i < D; i += blockDim.x)
+    h += mix64(((unsigned long long)a[i] << 32) | (unsigned long long)(uint32_t)(p * D + i));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  __shared__ unsigned long long wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = h;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w];
+    atomicAdd(hash + r, t);
+  }
+}
+// differs[r] = 1 when row r is not bitwise the row cand[r] over the real columns (same left padding by construction): grid (P, R)
+__global__ void __launch_bounds__(256)
+prefill_row_verify_kernel(const float* __restrict__ x, const int32_t* __restrict__ kv_start, const int32_t* __restrict__ cand,
+                          int32_t* __restrict__ differs, int P, int D) {
+  const int p = blockIdx.x, r = blockIdx.y, c = cand[r];
+  if (c == r || p < kv_start[r]) return;
   const uint4* a = reinterpret_cast<const uint4*>(x + ((size_t)r * P + p) * D);
-  const uint4* b = reinterpret_cast<const uint4*>(x + ((size_t)(r - 2) * P + p) * D);
+  const uint4* b = reinterpret_cast<const uint4*>(x + ((size_t)c * P + p) * D);
   bool diff = false;
   for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
     const uint4 u = a[i], v = b[i];

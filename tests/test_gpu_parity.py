@@ -284,10 +284,11 @@ def test_packed_prefill_is_bit_identical_to_padded_prefill():
 
 
 def test_prefill_row_dedup_is_bit_identical():
-    """Rows that repeat row r - 2 (PlanGen's unconditional rows all carry the same negative prompt, cfg/base.py:129) are
-    prefilled once and their K / V strips copied (lm_kernels.cuh kv_broadcast_rows_kernel).  Mixed batch: six prompts share a
-    negative prompt, two carry their own (one of the same length), one conditional prompt repeats its neighbour; the CFG
-    logits of the following steps and the sampled tokens are bit-identical with `prefill_dedup` on and off."""
+    """Rows that repeat an earlier row (PlanGen's unconditional rows all carry the same negative prompt, cfg/base.py:129;
+    `parallel_size` > 1 repeats whole batches) are prefilled once and their K / V strips copied (lm_kernels.cuh
+    kv_broadcast_rows_kernel).  Mixed batch: six prompts share a negative prompt (rows 1, 3, 5, 7, 11, 15), two carry their
+    own (one of the same length), one conditional prompt appears three times (rows 0, 2, 10); the CFG logits of the following
+    steps and the sampled tokens are bit-identical with `prefill_dedup` / `attn_alias` on and off."""
     dims = O.SMALL
     steps = 5
     g = torch.Generator().manual_seed(77)
@@ -295,7 +296,7 @@ def test_prefill_row_dedup_is_bit_identical():
     a, shared = rnd(60), rnd(23)
     # prompts 0 and 1 are the same text (rows 0 / 2 repeat); prompt 3 has the same length as 2 but other tokens; prompt 7
     # shares only a suffix with prompt 6
-    cond = [a, list(a), rnd(200), rnd(200), rnd(5), rnd(131), rnd(256), None]
+    cond = [a, list(a), rnd(200), rnd(200), rnd(5), list(a), rnd(256), None]
     cond[7] = rnd(196) + cond[6][-60:]
     neg = [shared, shared, shared, shared, rnd(23), shared, rnd(9), shared]
     lens = [len(c) for c in cond]
@@ -333,6 +334,20 @@ def test_prefill_row_dedup_is_bit_identical():
                                               max_new_tokens=8).cpu())
     assert torch.equal(got[0], got[1])
     assert torch.equal(got[0][0], got[0][2]) and torch.equal(got[0][0], got[0][4])
+    # parallel_size = 2 (plangen_base.py:547-549: the whole (2B, P) block repeated): every row of the second copy repeats a
+    # row 2B earlier; same images with the shortcut on and off, and the two copies differ (independent sampling)
+    ve = get_engine(dims, "bf16", with_vq=True, max_batch=8, max_prompt=256)
+    ids4, mask4 = O.t2i_infer_collate_batch(cond[2:5], neg[2:5], dims.pad_id, dims.n_img_tokens)
+    imgs = []
+    for dedup in (1, 0):
+        ve.set_option("prefill_dedup", dedup)
+        try:
+            dec, _ = ve.t2i(tokens=ids4.cuda(), mask=mask4.cuda(), parallel_size=2, image_token_num_per_image=dims.n_img_tokens)
+        finally:
+            ve.set_option("prefill_dedup", 1)
+        imgs.append(dec.float().cpu())
+    assert imgs[0].shape[0] == 6 and torch.equal(imgs[0], imgs[1])
+    assert not torch.equal(imgs[0][:3], imgs[0][3:])
 
 
 @pytest.mark.parametrize("B", [5, 16, 32])
