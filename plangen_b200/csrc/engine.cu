@@ -273,7 +273,8 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
     const int NT = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : M <= 128 ? 128 : 256;
     const int tiles = ((N + TC_BM - 1) / TC_BM) * ((M + NT - 1) / NT);
     const int num_kb = (K + TC_BK - 1) / TC_BK;
-    int want = force_splits > 0 ? force_splits : (e->gemm_splits > 0 ? e->gemm_splits : 0);
+    const bool opt_splits = e->gemm_splits > 0 && (e->tc_stages_n == 0 || e->tc_stages_n == N) && (e->tc_stages_k == 0 || e->tc_stages_k == K);
+    int want = force_splits > 0 ? force_splits : (opt_splits ? e->gemm_splits : 0);
     if (want == 0) {
       // split-K count: every CTA pays a fixed fill / drain cost (~3 us, about 9 k-blocks of streaming) on top of its
       // k-blocks, CTAs run one per SM in waves.  Minimise waves x (9 + k-blocks per split); e.g. the 7B QKV projection
