@@ -98,21 +98,44 @@ cfg_sample_embed_cluster_kernel(const float* __restrict__ part, int S, size_t sp
   __shared__ SampleXchg xc;          // read by the other CTAs of the cluster
   pdl_launch_dependents();
   SAMPLE_STAMP(0);
-  pdl_wait();
-  SAMPLE_STAMP(1);
   const int tid = threadIdx.x;
   const uint32_t rank = cluster_ctarank();
   const int b = blockIdx.x / SAMPLE_CLUSTER;
   const int chunk = (V + SAMPLE_CLUSTER - 1) / SAMPLE_CLUSTER;
   const int v_lo = (int)rank * chunk, v_hi = min(V, v_lo + chunk);
+  // The step counter is only written by the last kernel of a decode step; graph replays are fully ordered, and with plain
+  // launches the host passes the step explicitly (step_ptr == nullptr), so reading it before the PDL wait is safe.
   const int step = step_base + (step_ptr ? *step_ptr : 0);
   const uint64_t offset = offset_base + offset_per_step * (uint64_t)(step - step_base);
+  // The exponential variates of torch.multinomial depend on (seed, offset, element index) only - not on the logits: they
+  // are drawn while the head contraction is still streaming its weights (this kernel is launched ahead of its dependency).
+  constexpr int QPRE = 8;
+  float qpre[QPRE];
+  const bool pre = !greedy && (v_hi - v_lo) <= QPRE * SAMPLE_CL_THREADS;
+  if (pre) {
+#pragma unroll
+    for (int j = 0; j < QPRE; ++j) {
+      const int v = v_lo + tid + j * SAMPLE_CL_THREADS;
+      qpre[j] = v < v_hi ? torch_exponential_at((uint64_t)b * V + v, philox_stride, seed, offset) : 1.f;
+    }
+  }
+  float bias_r[QPRE];
+  const bool bias_pre = bias != nullptr && (v_hi - v_lo) <= QPRE * SAMPLE_CL_THREADS;     // the bias is a weight: before the wait too
+  if (bias_pre) {
+#pragma unroll
+    for (int j = 0; j < QPRE; ++j) {
+      const int v = v_lo + tid + j * SAMPLE_CL_THREADS;
+      bias_r[j] = v < v_hi ? bias[v] : 0.f;
+    }
+  }
+  pdl_wait();
+  SAMPLE_STAMP(1);
   const size_t rc = (size_t)(2 * b) * V, ru = (size_t)(2 * b + 1) * V;
   float mx = -INFINITY;
-  for (int v0 = v_lo + tid; v0 < v_hi; v0 += 4 * SAMPLE_CL_THREADS) {
-    float cs[4], us[4];
+  for (int v0 = v_lo + tid, it = 0; v0 < v_hi; v0 += QPRE * SAMPLE_CL_THREADS, ++it) {
+    float cs[QPRE], us[QPRE];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < QPRE; ++j) {         // all of a thread's loads in flight at once
       const int v = v0 + j * SAMPLE_CL_THREADS;
       cs[j] = us[j] = 0.f;
       if (v < v_hi) {
@@ -121,11 +144,11 @@ cfg_sample_embed_cluster_kernel(const float* __restrict__ part, int S, size_t sp
       }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < QPRE; ++j) {
       const int v = v0 + j * SAMPLE_CL_THREADS;
       if (v < v_hi) {
         float c = cs[j], u = us[j];
-        if (bias) { const float bb = bias[v]; c += bb; u += bb; }
+        if (bias) { const float bb = (bias_pre && it == 0) ? bias_r[j] : bias[v]; c += bb; u += bb; }
         c = Act<T>::rnd(c); u = Act<T>::rnd(u);
         float t = Act<T>::rnd(__fsub_rn(c, u));           // plangen_base.py:587-588, one rounded op each
         t = Act<T>::rnd(__fmul_rn(cfg_weight, t));
@@ -215,14 +238,25 @@ cfg_sample_embed_cluster_kernel(const float* __restrict__ part, int S, size_t sp
   // argmax over p/q (first index wins ties, like torch.argmax)
   float bv = -INFINITY;
   int bi = 0x7fffffff;
-  for (int v = v_lo + tid; v < v_hi; v += SAMPLE_CL_THREADS) {
-    const float p = __fdiv_rn(sh[v - v_lo], sum);
-    float score = p;
-    if (!greedy) {
-      const float q = torch_exponential_at((uint64_t)b * V + v, philox_stride, seed, offset);
-      score = __fdiv_rn(p, q);
+  if (pre) {
+#pragma unroll
+    for (int j = 0; j < QPRE; ++j) {
+      const int v = v_lo + tid + j * SAMPLE_CL_THREADS;
+      if (v < v_hi) {
+        const float score = __fdiv_rn(__fdiv_rn(sh[v - v_lo], sum), qpre[j]);
+        if (score > bv || (score == bv && v < bi)) { bv = score; bi = v; }
+      }
     }
-    if (score > bv || (score == bv && v < bi)) { bv = score; bi = v; }
+  } else {
+    for (int v = v_lo + tid; v < v_hi; v += SAMPLE_CL_THREADS) {
+      const float p = __fdiv_rn(sh[v - v_lo], sum);
+      float score = p;
+      if (!greedy) {
+        const float q = torch_exponential_at((uint64_t)b * V + v, philox_stride, seed, offset);
+        score = __fdiv_rn(p, q);
+      }
+      if (score > bv || (score == bv && v < bi)) { bv = score; bi = v; }
+    }
   }
   SAMPLE_STAMP(4);
 #pragma unroll
