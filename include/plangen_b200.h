@@ -167,6 +167,12 @@ int pg_debug_copy(pg_engine* e, const char* name, void* dst_dev, size_t nbytes, 
 int pg_test_attn_decode(pg_engine* e, const int32_t* kv_start, int R, int pos, int layer, void* stream);
 int pg_debug_zero_part(pg_engine* e, size_t nbytes, void* stream);
 
+/* Host-only helper of the prefill (no device work, callable without a GPU): proposes, for every prompt row, the FIRST
+ * row of the batch with the same left padding `start[r]` and the same 64-bit content hash (itself when there is none).
+ * The prefill verifies every proposal word for word on the device before using it (t2i's shared negative prompt,
+ * cfg/base.py:129; the `parallel_size` copies of plangen_base.py:547-549).  Returns the number of proposals. */
+int pg_host_group_rows(const int32_t* start, const uint64_t* hash, int R, int32_t* source_row);
+
 /* Plain GEMM exposed for unit tests:  C[m,n] = sum_k X[m,k] * W[n,k]
  * impl 0 = SIMT (fp32 or bf16 inputs), 1 = tcgen05 (bf16 inputs).  C fp32 [splits][M][N]. */
 int pg_test_gemm(pg_engine* e, int impl, int is_bf16, const void* X, const void* W, int M, int N,

@@ -815,6 +815,18 @@ static int k_gate_up(pg_engine* e, const LayerW& w, int tok, cudaStream_t st) {
   return 0;
 }
 
+extern "C" int pg_host_group_rows(const int32_t* start, const uint64_t* hash, int R, int32_t* source_row) {
+  if (!start || !hash || !source_row || R < 0) return -1;
+  std::map<std::pair<int32_t, uint64_t>, int> first;
+  int proposals = 0;
+  for (int r = 0; r < R; ++r) {
+    auto ins = first.emplace(std::make_pair(start[r], hash[r]), r);
+    source_row[r] = ins.first->second;
+    if (!ins.second) ++proposals;
+  }
+  return proposals;
+}
+
 // a3: prompt prefill.  x fp32 [R*P, D] in place.
 static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, int P, float* hidden_out, int all_positions,
                         bool rope_rel, void* stream);
@@ -860,12 +872,7 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
     for (int r = 0; r < R; ++r) { start[r] = e->row_off_host[r]; dup[r] = r; }
     if (dedup) {
       // proposal: the first row with the same left padding and content hash; verified word for word on the device
-      std::map<std::pair<int32_t, unsigned long long>, int> first;
-      int proposals = 0;
-      for (int r = 0; r < R; ++r) {
-        auto ins = first.emplace(std::make_pair(start[r], e->row_hash_host[r]), r);
-        if (!ins.second) { dup[r] = ins.first->second; ++proposals; }
-      }
+      const int proposals = pg_host_group_rows(start.data(), (const uint64_t*)e->row_hash_host, R, dup.data());
       if (proposals > 0) {
         memcpy(dup_host, dup.data(), (size_t)R * 4);
         CK(cudaMemcpyAsync(e->dup_of, dup_host, (size_t)R * 4, cudaMemcpyHostToDevice, st));

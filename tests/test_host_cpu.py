@@ -27,6 +27,27 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert cdll.pg_abi_version() == int(m.group(1))
 
 
+def test_prefill_row_grouping_host_logic():
+    """pg_host_group_rows (host half of the prefill's repeated-row shortcut): the first row with the same left padding and
+    content hash is proposed as the source; equal hashes with different padding, or equal padding with different hashes, are
+    not grouped; the first member of a group points at itself."""
+    import numpy as np
+    from plangen_b200 import _lib
+    lib = _lib.load()
+    start = np.array([5, 40, 5, 40, 7, 40, 5, 41], dtype=np.int32)
+    h = np.array([11, 99, 11, 99, 11, 98, 12, 99], dtype=np.uint64)
+    out = np.full(8, -1, dtype=np.int32)
+    n = lib.pg_host_group_rows(start.ctypes.data, h.ctypes.data, 8, out.ctypes.data)
+    assert n == 2 and out.tolist() == [0, 1, 0, 1, 4, 5, 6, 7]
+    # parallel_size = 2 layout (rows repeat 2B later) and the shared negative prompt (odd rows)
+    start = np.array([0, 9, 3, 9, 0, 9, 3, 9], dtype=np.int32)
+    h = np.array([1, 7, 2, 7, 1, 7, 2, 7], dtype=np.uint64)
+    n = lib.pg_host_group_rows(start.ctypes.data, h.ctypes.data, 8, out.ctypes.data)
+    assert n == 5 and out.tolist() == [0, 1, 2, 1, 0, 1, 2, 1]
+    assert lib.pg_host_group_rows(start.ctypes.data, h.ctypes.data, 0, out.ctypes.data) == 0
+    assert lib.pg_host_group_rows(None, h.ctypes.data, 4, out.ctypes.data) < 0
+
+
 def test_engine_fails_loudly_without_gpu():
     if torch.cuda.is_available():
         pytest.skip("GPU present")
