@@ -51,7 +51,8 @@ v_transpose_kernel(const bf16* __restrict__ vcache, bf16* __restrict__ vT, int P
 __global__ void __launch_bounds__(128, 1)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_vt, const int32_t* __restrict__ kv_start,
-                       bf16* __restrict__ out, int P, int H, int Tmax, float scale, const int32_t* __restrict__ row_off) {
+                       bf16* __restrict__ out, int P, int H, int Tmax, float scale, const int32_t* __restrict__ row_off,
+                       int v_direct) {
   extern __shared__ uint8_t pa_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)pa_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;                      // 2 tiles: dims 0-63 | 64-127 of the 128 queries
@@ -114,9 +115,14 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
         const int krow = (r * H + h) * Tmax + key0;
         tma_load_2d(sK, &map_k, bar_load, 0, krow, pol);
         tma_load_2d(sK + PA_TILE, &map_k, bar_load, 64, krow, pol);
-        const int vrow = (r * H + h) * HEAD_DIM;
-        tma_load_2d(sV, &map_vt, bar_load, key0, vrow, pol);
-        tma_load_2d(sV + PA_TILE, &map_vt, bar_load, key0 + 64, vrow, pol);
+        if (v_direct) {          // V rows of the cache, [128 keys][64 dims] per tile: dims 0-63 | 64-127 (MN-major B operand)
+          tma_load_2d(sV, &map_vt, bar_load, 0, krow, pol);
+          tma_load_2d(sV + PA_TILE, &map_vt, bar_load, 64, krow, pol);
+        } else {                 // key-contiguous copy, [128 dims][64 keys] per tile: keys 0-63 | 64-127
+          const int vrow = (r * H + h) * HEAD_DIM;
+          tma_load_2d(sV, &map_vt, bar_load, key0, vrow, pol);
+          tma_load_2d(sV + PA_TILE, &map_vt, bar_load, key0 + 64, vrow, pol);
+        }
         mbar_wait(bar_load, (uint32_t)(it & 1), 50);
         tc_fence_after();
         // S = Q K^T : 8 K-steps of 16 dims over the two dim tiles
@@ -188,8 +194,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
           const uint64_t da = umma_desc_k_sw128(smem_u32(sP + (kk >> 2) * PA_TILE)) + (uint64_t)(2 * (kk & 3));
-          const uint64_t db = umma_desc_k_sw128(smem_u32(sV + (kk >> 2) * PA_TILE)) + (uint64_t)(2 * (kk & 3));
-          umma_bf16(tmem_base + 128u, da, db, idesc, kk != 0);
+          // MN-major V: 16 keys = 2048 bytes down each [keys][64 dims] tile, the second 64 dims one tile further
+          const uint64_t db = v_direct ? umma_desc_mn_sw128(smem_u32(sV) + (uint32_t)kk * 2048u, (uint32_t)PA_TILE)
+                                       : umma_desc_k_sw128(smem_u32(sV + (kk >> 2) * PA_TILE)) + (uint64_t)(2 * (kk & 3));
+          umma_bf16(tmem_base + 128u, da, db, v_direct ? umma_idesc_bf16_bmn(PA_BQ, HEAD_DIM) : idesc, kk != 0);
         }
         umma_commit(bar_mma);
       }

@@ -276,10 +276,24 @@ PG_DEVINL uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// MN-major operand tile, SWIZZLE_128B: rows are K indices, 128 bytes (64 bf16 along M / N) each, eight rows per 1024-byte
+// swizzle atom - exactly what a TMA box of [k rows][64 elements] leaves in shared memory.  Stride byte offset = the next
+// eight K rows (1024 B), leading byte offset = the next 64 elements along M / N (a second box).  One K = 16 step is 2048 B.
+PG_DEVINL uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
 // Instruction descriptor, kind::f16: D fp32 (1<<4), A bf16 (1<<7), B bf16 (1<<10),
 // A and B K-major (bits 15,16 = 0), N>>3 at bit 17, M>>4 at bit 24.
 __host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
+// the same with B MN-major (bit 16): B is read as [k][n] rows, n contiguous
+__host__ __device__ inline uint32_t umma_idesc_bf16_bmn(int M, int N) { return umma_idesc_bf16(M, N) | (1u << 16); }
 
 }  // namespace pg

@@ -122,6 +122,8 @@ struct pg_engine {
   int prefill_fuse = 1;                               // prefill contractions with bf16 / residual epilogues (gemm.cuh EpiFuse) instead of fp32 partials
   int gu_streamk = 1;                                 // decode gate|up + SwiGLU as a stream-K launch over all SMs (gemm_sk.cuh)
   int* sk_counters = nullptr;
+  int prefill_v_direct = 1;                           // prefill attention reads V from the cache rows (MN-major operand), no transposed copy
+  int sig_v_direct = 1;                               // ViT attention reads V in place (MN-major operand) instead of a transposed copy
   int sig_attn_tc = 1;                                // tcgen05 attention (bf16, head_dim 64); 0 = CUDA-core kernel
   int sig_fuse = 1;                                   // bias / GELU / residual in the contraction epilogues (gemm.cuh EpiFuse)
   size_t part_bytes = 0;
@@ -549,6 +551,9 @@ extern "C" int pg_engine_bind_buffers(pg_engine* e, void* kv, size_t kv_bytes, v
   if (ws_bytes < need_ws) return fail("workspace too small: %zu < %zu", ws_bytes, need_ws);
   if (((uintptr_t)kv & 255) || ((uintptr_t)ws & 255)) return fail("buffers must be 256-byte aligned");
   e->kv = kv; e->kv_bytes = kv_bytes; e->ws = ws; e->ws_bytes = ws_bytes;
+  // TMA tiles of the attention kernels read cache slots past the newest token (and pad slots): they are masked, but a masked
+  // probability of 0 times a NaN bit pattern is NaN, so the cache must hold finite values from the start
+  CK(cudaMemset(kv, 0, kv_bytes));
   Carve c;
   c.base = (uint8_t*)align_up((uintptr_t)ws, 1024);
   layout_workspace(e, c);
@@ -580,6 +585,8 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "norm_tma") e->norm_tma = (int)value;
   else if (k == "prefill_attn_tc") e->prefill_attn_tc = (int)value;
   else if (k == "sig_attn_tc") e->sig_attn_tc = (int)value;
+  else if (k == "sig_v_direct") e->sig_v_direct = (int)value;
+  else if (k == "prefill_v_direct") e->prefill_v_direct = (int)value;
   else if (k == "gu_streamk") e->gu_streamk = (int)value;
   else if (k == "prefill_fuse") e->prefill_fuse = (int)value;
   else if (k == "prefill_pack") e->prefill_pack = (int)value;
@@ -936,16 +943,21 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
                       rope_rel ? kv_start : (const int32_t*)nullptr));
     }
     if (e->bf16 && e->use_tc && e->prefill_attn_tc) {
-      // tensor-core path: key-contiguous V copy, then one CTA per (row, head, 128-query tile)
+      // tensor-core path: one CTA per (row, head, 128-query tile); V is read from the cache rows as an MN-major operand
+      // (prefill_v_direct = 0: from a key-contiguous copy made first)
       const int Ppad = (int)align_up((size_t)P, 64);
-      TRY(launch(e, v_transpose_kernel, dim3(Ppad / 64, d.H, R), dim3(256), 0, st, (const bf16*)kv_ptr(e, l, 1, R), (bf16*)e->vT, P, Ppad,
-                 d.H, e->Tmax));
       CUtensorMap mq, mk, mv;
       TRY(make_map_2d(e, &mq, e->qbuf, (uint64_t)tok, (uint64_t)HD, PA_BQ));
       TRY(make_map_2d(e, &mk, kv_ptr(e, l, 0, R), (uint64_t)R * d.H * e->Tmax, (uint64_t)HEAD_DIM, PA_BK));
-      TRY(make_map_2d(e, &mv, e->vT, (uint64_t)R * d.H * HEAD_DIM, (uint64_t)Ppad, HEAD_DIM));
+      if (e->prefill_v_direct) {
+        TRY(make_map_2d(e, &mv, kv_ptr(e, l, 1, R), (uint64_t)R * d.H * e->Tmax, (uint64_t)HEAD_DIM, PA_BK));
+      } else {
+        TRY(launch(e, v_transpose_kernel, dim3(Ppad / 64, d.H, R), dim3(256), 0, st, (const bf16*)kv_ptr(e, l, 1, R), (bf16*)e->vT, P, Ppad,
+                   d.H, e->Tmax));
+        TRY(make_map_2d(e, &mv, e->vT, (uint64_t)R * d.H * HEAD_DIM, (uint64_t)Ppad, HEAD_DIM));
+      }
       TRY(launch(e, attn_prefill_tc_kernel, dim3((P + PA_BQ - 1) / PA_BQ, d.H, R), dim3(128), PA_SMEM, st, mq, mk, mv, kv_start,
-                 (bf16*)e->attn_out, P, d.H, e->Tmax, scale, row_off));
+                 (bf16*)e->attn_out, P, d.H, e->Tmax, scale, row_off, e->prefill_v_direct));
     } else
     DISPATCH_T(e,
                launch(e, attn_prefill_kernel<bf16>, dim3((P + 63) / 64, d.H, R), dim3(256), ATTN_PREFILL_SMEM, st,
@@ -1460,13 +1472,17 @@ static int sig_tower(pg_engine* e, const float* pixel, int n, void* feat, cudaSt
     TRY(linear_out(e->sig_xn, wqkv, bqkv, e->sig_qkv, 3 * W, W, 0));
     if (tc_attn) {
       const int NPpad = (int)align_up((size_t)NP, 8);
-      TRY(launch(e, vit_v_transpose_kernel, dim3((NPpad + 63) / 64, heads, n), dim3(256), 0, st, (const bf16*)e->sig_qkv, (bf16*)e->sig_vT, NP, NPpad, W, heads, hd));
       CUtensorMap mq, mk, mv;
       TRY(make_map_2d(e, &mq, e->sig_qkv, (uint64_t)M, (uint64_t)3 * W, VT_BQ));
       TRY(make_map_2d(e, &mk, e->sig_qkv, (uint64_t)M, (uint64_t)3 * W, VT_BK));
-      TRY(make_map_2d(e, &mv, e->sig_vT, (uint64_t)n * heads * hd, (uint64_t)NPpad, 64));
+      if (e->sig_v_direct) {
+        mv = mk;            // V rows are read in place as an MN-major operand: no key-contiguous copy
+      } else {
+        TRY(launch(e, vit_v_transpose_kernel, dim3((NPpad + 63) / 64, heads, n), dim3(256), 0, st, (const bf16*)e->sig_qkv, (bf16*)e->sig_vT, NP, NPpad, W, heads, hd));
+        TRY(make_map_2d(e, &mv, e->sig_vT, (uint64_t)n * heads * hd, (uint64_t)NPpad, 64));
+      }
       TRY(launch(e, vit_attn_tc_kernel, dim3((NP + VT_BQ - 1) / VT_BQ, heads, n), dim3(128), VT_SMEM, st, mq, mk, mv, (bf16*)e->sig_attn, NP, W,
-                 heads, 1.0f / sqrtf((float)hd)));
+                 heads, 1.0f / sqrtf((float)hd), e->sig_v_direct));
     } else {
       DISPATCH_T(e,
                  launch(e, vit_attn_kernel<bf16>, dim3((NP + 3) / 4, heads, n), dim3(128), 0, st, (const bf16*)e->sig_qkv, (bf16*)e->sig_attn, NP, W, heads, hd, 1.0f / sqrtf((float)hd)),

@@ -296,7 +296,8 @@ constexpr int VT_SMEM = VT_QTILE + VT_KP_BYTES + (VT_BK / 64) * VT_VTILE + 1024 
 
 __global__ void __launch_bounds__(128, 2)
 vit_attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_constant__ CUtensorMap map_k,
-                   const __grid_constant__ CUtensorMap map_vt, bf16* __restrict__ out, int NP, int W, int heads, float scale) {
+                   const __grid_constant__ CUtensorMap map_vt, bf16* __restrict__ out, int NP, int W, int heads, float scale,
+                   int v_direct) {
   extern __shared__ uint8_t vt_smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)vt_smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -332,7 +333,9 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
   const float sl2 = scale * 1.4426950408889634f;     // scores in log2 units
   const uint32_t t_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
   const uint32_t idesc_s = umma_idesc_bf16(VT_BQ, VT_BK);
-  const uint32_t idesc_o = umma_idesc_bf16(VT_BQ, VT_HD);
+  // v_direct: V is taken straight from the qkv rows ([key][64 dims], one TMA box) as an MN-major B operand; otherwise
+  // from the key-contiguous copy vit_v_transpose_kernel made (K-major)
+  const uint32_t idesc_o = v_direct ? umma_idesc_bf16_bmn(VT_BQ, VT_HD) : umma_idesc_bf16(VT_BQ, VT_HD);
   const int nkb = (NP + VT_BK - 1) / VT_BK;
   for (int kb = 0; kb < nkb; ++kb) {
     const int key0 = kb * VT_BK;
@@ -341,9 +344,13 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
       mbar_expect_tx(bar_load, (kb == 0 ? VT_QTILE : 0) + VT_KTILE + (VT_BK / 64) * VT_VTILE);
       if (kb == 0) tma_load_2d(sQ, &map_qk, bar_load, h * VT_HD, img * NP + q0, pol);
       tma_load_2d(sK, &map_k, bar_load, W + h * VT_HD, img * NP + key0, pol);
+      if (v_direct) {
+        tma_load_2d(sV, &map_k, bar_load, 2 * W + h * VT_HD, img * NP + key0, pol);
+      } else {
 #pragma unroll
-      for (int t = 0; t < VT_BK / 64; ++t)
-        tma_load_2d(sV + t * VT_VTILE, &map_vt, bar_load, key0 + 64 * t, (img * heads + h) * VT_HD, pol);
+        for (int t = 0; t < VT_BK / 64; ++t)
+          tma_load_2d(sV + t * VT_VTILE, &map_vt, bar_load, key0 + 64 * t, (img * heads + h) * VT_HD, pol);
+      }
       mbar_wait(bar_load, (uint32_t)(kb & 1), 60);
       tc_fence_after();
 #pragma unroll
@@ -403,7 +410,9 @@ vit_attn_tc_kernel(const __grid_constant__ CUtensorMap map_qk, const __grid_cons
 #pragma unroll
       for (int kk = 0; kk < VT_BK / 16; ++kk)
         umma_bf16(tmem_base + (uint32_t)VT_BK, umma_desc_k_sw128(smem_u32(sP + (kk >> 2) * VT_PTILE)) + (uint64_t)(2 * (kk & 3)),
-                  umma_desc_k_sw128(smem_u32(sV + (kk >> 2) * VT_VTILE)) + (uint64_t)(2 * (kk & 3)), idesc_o, kk != 0);
+                  v_direct ? umma_desc_mn_sw128(smem_u32(sV) + (uint32_t)kk * 2048u, 1024u)
+                           : umma_desc_k_sw128(smem_u32(sV + (kk >> 2) * VT_VTILE)) + (uint64_t)(2 * (kk & 3)),
+                  idesc_o, kk != 0);
       umma_commit(bar_mma);
     }
     mbar_wait(bar_mma, 1u, 62);
