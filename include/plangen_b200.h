@@ -50,7 +50,8 @@ int pg_abi_version(void);
 int pg_engine_create(const pg_dims* dims, int device, pg_engine** out);
 int pg_engine_destroy(pg_engine* e);
 
-/* Bytes of KV cache / scratch workspace the caller must allocate and bind. */
+/* Bytes of KV cache / scratch workspace the caller must allocate and bind.  pg_engine_bind_buffers zero-fills the KV
+ * cache once (the attention kernels' TMA tiles read masked slots past the newest token: they must hold finite values). */
 int pg_engine_query_bytes(const pg_engine* e, size_t* kv_bytes, size_t* ws_bytes);
 int pg_engine_bind_buffers(pg_engine* e, void* kv, size_t kv_bytes, void* ws, size_t ws_bytes);
 
