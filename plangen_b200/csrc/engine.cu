@@ -122,6 +122,7 @@ struct pg_engine {
   int prefill_fuse = 1;                               // prefill contractions with bf16 / residual epilogues (gemm.cuh EpiFuse) instead of fp32 partials
   int gu_streamk = 1;                                 // decode gate|up + SwiGLU as a stream-K launch over all SMs (gemm_sk.cuh)
   int* sk_counters = nullptr;
+  int norm_warp = 1;                                  // prefill RMSNorm: one warp per row (lm_kernels.cuh rmsnorm_rows_warp_kernel)
   int prefill_v_direct = 1;                           // prefill attention reads V from the cache rows (MN-major operand), no transposed copy
   int sig_v_direct = 1;                               // ViT attention reads V in place (MN-major operand) instead of a transposed copy
   int sig_attn_tc = 1;                                // tcgen05 attention (bf16, head_dim 64); 0 = CUDA-core kernel
@@ -587,6 +588,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "sig_attn_tc") e->sig_attn_tc = (int)value;
   else if (k == "sig_v_direct") e->sig_v_direct = (int)value;
   else if (k == "prefill_v_direct") e->prefill_v_direct = (int)value;
+  else if (k == "norm_warp") e->norm_warp = (int)value;
   else if (k == "gu_streamk") e->gu_streamk = (int)value;
   else if (k == "prefill_fuse") e->prefill_fuse = (int)value;
   else if (k == "prefill_pack") e->prefill_pack = (int)value;
@@ -655,6 +657,14 @@ static int k_resid_norm(pg_engine* e, float* x, const float* part, int S, size_t
                launch(e, resid_rmsnorm_tma_kernel<float>, dim3(rows), dim3(tma_threads), tma_smem, st, x, part, S, sstride, w, (float*)xn, y, D,
                       e->d.rms_eps, flags, e->step_ctr, next_prof(e)));
     return 0;
+  }
+  // prefill with fused epilogues: plain RMSNorm of thousands of rows to bf16 - one warp per row (lm_kernels.cuh)
+  if (e->bf16 && e->norm_warp && part == nullptr && y == nullptr && xn != nullptr && in_stride == 1 && in_off == 0 && flags == 0 &&
+      rows > 256 && D % 128 == 0 && (((uintptr_t)x | (uintptr_t)xn | (uintptr_t)w) & 15) == 0) {
+    const dim3 grid((rows + 7) / 8);
+    if (D == 2048) return launch(e, rmsnorm_rows_warp_kernel<16>, grid, dim3(256), 0, st, (const float*)x, w, (bf16*)xn, rows, D, e->d.rms_eps);
+    if (D == 4096) return launch(e, rmsnorm_rows_warp_kernel<32>, grid, dim3(256), 0, st, (const float*)x, w, (bf16*)xn, rows, D, e->d.rms_eps);
+    return launch(e, rmsnorm_rows_warp_kernel<0>, grid, dim3(256), 0, st, (const float*)x, w, (bf16*)xn, rows, D, e->d.rms_eps);
   }
   // few rows (decode): 1024 threads so one row's split-K loads are all in flight; many rows (prefill): 256+
   int threads = rows <= 256 ? RN_THREADS : 256;

@@ -153,6 +153,53 @@ resid_rmsnorm_kernel(float* __restrict__ x, const float* __restrict__ part, int 
   prof_end(prof);
 }
 
+// Prefill variant (fused epilogues: the residual is already in x, bf16 output only, thousands of rows): ONE WARP PER ROW,
+// the row in registers as float4 (NV per lane; NV = 0: two passes over the row, the second from L1 / L2), no shared
+// memory, no block barrier.  The one-CTA-per-row kernel above moved 76 MB in 44.7 us (1.7 TB/s) at configs[1]'s prefill.
+// Same expression per element (w * (x * r), r from the row's sum of squares); the sum is taken lane-sequentially and then
+// over the lanes, so r can differ from the block-tree version in the last bit.
+template <int NV>
+__global__ void __launch_bounds__(256)
+rmsnorm_rows_warp_kernel(const float* __restrict__ x, const float* __restrict__ w, bf16* __restrict__ xn, int rows, int D, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
+  const float4* w4 = reinterpret_cast<const float4*>(w);
+  uint2* out = reinterpret_cast<uint2*>(xn + (size_t)row * D);
+  const int n4 = D / 128;                         // float4 per lane
+  float ss = 0.f;
+  float4 v[NV > 0 ? NV : 1];
+  if (NV > 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = xr[lane + 32 * k];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) ss += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+  } else {
+    for (int k = 0; k < n4; ++k) {
+      const float4 t = xr[lane + 32 * k];
+      ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float r = rsqrtf(ss / (float)D + eps);
+  auto emit = [&](int k, const float4& t) {
+    const float4 ww = w4[lane + 32 * k];
+    const __nv_bfloat162 a = __floats2bfloat162_rn(ww.x * (t.x * r), ww.y * (t.y * r));
+    const __nv_bfloat162 b = __floats2bfloat162_rn(ww.z * (t.z * r), ww.w * (t.w * r));
+    out[lane + 32 * k] = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+  };
+  if (NV > 0) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) emit(k, v[k]);
+  } else {
+    for (int k = 0; k < n4; ++k) emit(k, xr[lane + 32 * k]);
+  }
+}
+
 // Decode-step variant: the S split-K slabs of the row and the residual row are brought into shared memory by
 // S + 1 TMA bulk copies issued by one thread, instead of 18-34 scalar loads per thread.  In-kernel stamps
 // (tools/norm_timeline.py) showed the scalar version spending 3.3-3.7 us in its single round of L2 loads whether
