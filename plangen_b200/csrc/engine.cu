@@ -122,6 +122,7 @@ struct pg_engine {
   int prefill_fuse = 1;                               // prefill contractions with bf16 / residual epilogues (gemm.cuh EpiFuse) instead of fp32 partials
   int gu_streamk = 1;                                 // decode gate|up + SwiGLU as a stream-K launch over all SMs (gemm_sk.cuh)
   int* sk_counters = nullptr;
+  int prefill_swiglu_fuse = 1;                        // prefill gate|up: SwiGLU in the CTA-pair contraction's epilogue
   int norm_warp = 1;                                  // prefill RMSNorm: one warp per row (lm_kernels.cuh rmsnorm_rows_warp_kernel)
   int prefill_v_direct = 1;                           // prefill attention reads V from the cache rows (MN-major operand), no transposed copy
   int sig_v_direct = 1;                               // ViT attention reads V in place (MN-major operand) instead of a transposed copy
@@ -316,6 +317,7 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
       *splits_out = 1;
       return 0;
     }
+    if (epi && epi->gelu == 2) return fail("internal: the SwiGLU epilogue exists in the CTA-pair contraction only (M=%d N=%d)", M, N);
     TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
     switch (NT) {
       case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st, nullptr, 0, epi)); break;
@@ -589,6 +591,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "sig_v_direct") e->sig_v_direct = (int)value;
   else if (k == "prefill_v_direct") e->prefill_v_direct = (int)value;
   else if (k == "norm_warp") e->norm_warp = (int)value;
+  else if (k == "prefill_swiglu_fuse") e->prefill_swiglu_fuse = (int)value;
   else if (k == "gu_streamk") e->gu_streamk = (int)value;
   else if (k == "prefill_fuse") e->prefill_fuse = (int)value;
   else if (k == "prefill_pack") e->prefill_pack = (int)value;
@@ -983,10 +986,16 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
       if (fused_swiglu_ok(e, tok)) {
         TRY(k_gate_up(e, w, tok, st));
       } else {
+        if (e->prefill_swiglu_fuse && e->use_tc2 && tok > 128 && (2 * F) % TC_BM == 0) {
+          // SwiGLU in the CTA-pair contraction's epilogue (gemm_tc2.cuh, EpiFuse::gelu == 2): h leaves the kernel directly
+          EpiFuse eg = {nullptr, (bf16*)e->hbuf, nullptr, 2};
+          TRY(run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &eg));
+        } else {
         EpiFuse eg = {nullptr, stage16, nullptr, 0};
         TRY(run_gemm(e, e->xn, w.wgu, tok, 2 * F, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &eg));
         const size_t total8 = (size_t)tok * F / 8;
         TRY(launch(e, swiglu_bf16_kernel, dim3(elementwise_blocks(e, total8)), dim3(256), 0, st, (const bf16*)stage16, (bf16*)e->hbuf, F, total8));
+        }
       }
       TRY(run_gemm(e, e->hbuf, w.wd, tok, D, F, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &er));
       if (l + 1 < d.L) {

@@ -182,7 +182,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               float x = bf16_round(__uint_as_float(v[h2][q]) + bias_n);
-              if (ep.gelu) x = x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
+              if (ep.gelu == 1) x = x * 0.5f * (1.0f + erf_fast(x * 0.70710678118654752440f));
               const unsigned short hb = __bfloat16_as_ushort(__float2bfloat16_rn(x));
               asm volatile("st.shared.u16 [%0], %1;" ::"r"(stg + (uint32_t)((c0 + h2 * 16 + q) * 256 + nl * 2)), "h"(hb) : "memory");
             }
@@ -191,6 +191,34 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[set]);   // TMEM set drained: the issuer may start tile j + 2 into it
         asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (ep.gelu == 2) {
+          // SwiGLU (prefill gate|up): the tile's 128 weight rows are gate(f0 .. f0+63) | up(f0 .. f0+63) (rows interleaved in
+          // blocks of 64, weights.py), so a staged token row holds g in bytes 0-127 and u in bytes 128-255:
+          // h = rnd(rnd(silu(g)) * u), 64 values = 128 bytes per token into out [M][N / 2]  (swiglu_bf16_kernel's arithmetic)
+          const int c8 = tE & 7, rr0 = tE >> 3, F = N >> 1, f0 = (n0 / TC_BM) * 64;
+          if (n0 < N) {
+#pragma unroll 2
+            for (int r = rr0; r < TC2_NT; r += 32) {
+              const size_t m = (size_t)m0 + r;
+              if (m < (size_t)M) {
+                uint32_t gw[4], uw[4], ow[4];
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(gw[0]), "=r"(gw[1]), "=r"(gw[2]), "=r"(gw[3])
+                             : "r"(stg + (uint32_t)(r * 256 + c8 * 16)));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(uw[0]), "=r"(uw[1]), "=r"(uw[2]), "=r"(uw[3])
+                             : "r"(stg + (uint32_t)(r * 256 + 128 + c8 * 16)));
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float g0 = bf16lo(gw[u]), g1 = bf16hi(gw[u]), u0 = bf16lo(uw[u]), u1 = bf16hi(uw[u]);
+                  const float h0 = bf16_round(g0 / (1.0f + expf(-g0))) * u0, h1 = bf16_round(g1 / (1.0f + expf(-g1))) * u1;
+                  const __nv_bfloat162 o = __floats2bfloat162_rn(h0, h1);
+                  ow[u] = *reinterpret_cast<const uint32_t*>(&o);
+                }
+                *reinterpret_cast<uint4*>(ep.out + m * F + f0 + c8 * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+              }
+            }
+          }
+          continue;
+        }
         const int ch = tE & 15, r0 = tE >> 4;
         if (n0 + ch * 8 < N) {
 #pragma unroll 4
