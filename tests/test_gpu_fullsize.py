@@ -194,6 +194,17 @@ def test_fullsize_loop_properties():
     finally:
         eng.set_option("use_graph", 1)
     assert torch.equal(a, c), "graph replay and plain launches disagree"
+    # scheduling switches that move no arithmetic: the shared-prompt shortcuts (prefill once, K / V read from one copy) and
+    # the down projection's ring depth - the same 96 tokens of all 16 images
+    for opts in ({"prefill_dedup": 0}, {"attn_alias": 0}, {"down_stages": 0}):
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        try:
+            e2 = eng.sample_image(emb, B, 96, mask, 5.0, 1.0, generator=0).cpu()
+        finally:
+            for k in opts:
+                eng.set_option(k, {"prefill_dedup": 1, "attn_alias": 1, "down_stages": 4}[k])
+        assert torch.equal(a[:, :96], e2), opts
     # a different seed gives a different sample; teacher forcing reproduces the labels exactly
     s2 = eng.sample_image(emb, B, 32, mask, 5.0, 1.0, generator=1).cpu()
     assert not torch.equal(a[:, :32], s2)
