@@ -122,6 +122,8 @@ struct pg_engine {
   int prefill_fuse = 1;                               // prefill contractions with bf16 / residual epilogues (gemm.cuh EpiFuse) instead of fp32 partials
   int gu_streamk = 1;                                 // decode gate|up + SwiGLU as a stream-K launch over all SMs (gemm_sk.cuh)
   int* sk_counters = nullptr;
+  int prefill_qkv_fuse = 1;                           // prefill QKV: RoPE + q / cache stores in the CTA-pair contraction's epilogue
+  QkvEpi qkv_epi_next = {};                           // consumed (and cleared) by the next CTA-pair launch
   int prefill_swiglu_fuse = 1;                        // prefill gate|up: SwiGLU in the CTA-pair contraction's epilogue
   int norm_warp = 1;                                  // prefill RMSNorm: one warp per row (lm_kernels.cuh rmsnorm_rows_warp_kernel)
   int prefill_v_direct = 1;                           // prefill attention reads V from the cache rows (MN-major operand), no transposed copy
@@ -312,12 +314,15 @@ static int run_gemm(pg_engine* e, const void* X, const void* W, int M, int N, in
       if (epi) ep2 = *epi;
       const int n_tiles = (((N + TC_BM - 1) / TC_BM + 1) / 2) * ((M + TC2_NT - 1) / TC2_NT);
       const int pairs = std::max(1, std::min(n_tiles, e->num_sms / 2));       // persistent: one CTA per SM
+      const QkvEpi qe = e->qkv_epi_next;
+      e->qkv_epi_next = QkvEpi{};
+      if (ep2.gelu == 3 && (qe.q_out == nullptr || N != 3 * qe.H * HEAD_DIM)) return fail("internal: QKV epilogue without its destinations");
       TRY(launch(e, gemm_tc2_kernel, dim3(2 * pairs, 1, 1), dim3(TC2_THREADS), (size_t)tc2p_smem_bytes(e->tc2_stages), st, mw, mx, C, M,
-                 N, K, e->tc2_stages, e->use_pdl, next_prof(e), ep2));
+                 N, K, e->tc2_stages, e->use_pdl, next_prof(e), ep2, qe));
       *splits_out = 1;
       return 0;
     }
-    if (epi && epi->gelu == 2) return fail("internal: the SwiGLU epilogue exists in the CTA-pair contraction only (M=%d N=%d)", M, N);
+    if (epi && epi->gelu >= 2) return fail("internal: the SwiGLU / QKV epilogues exist in the CTA-pair contraction only (M=%d N=%d)", M, N);
     TRY(make_map_2d(e, &mx, X, (uint64_t)M, (uint64_t)K, (uint32_t)NT));
     switch (NT) {
       case 16: TRY(launch_tc<16>(e, mw, mx, C, M, N, K, splits, kb_per_split, w_const, w_tiled, swiglu_out, st, nullptr, 0, epi)); break;
@@ -592,6 +597,7 @@ extern "C" int pg_engine_set_option(pg_engine* e, const char* key, int64_t value
   else if (k == "prefill_v_direct") e->prefill_v_direct = (int)value;
   else if (k == "norm_warp") e->norm_warp = (int)value;
   else if (k == "prefill_swiglu_fuse") e->prefill_swiglu_fuse = (int)value;
+  else if (k == "prefill_qkv_fuse") e->prefill_qkv_fuse = (int)value;
   else if (k == "gu_streamk") e->gu_streamk = (int)value;
   else if (k == "prefill_fuse") e->prefill_fuse = (int)value;
   else if (k == "prefill_pack") e->prefill_pack = (int)value;
@@ -939,7 +945,14 @@ static int prefill_impl(pg_engine* e, float* x, const int32_t* kv_start, int R, 
     LayerW w;
     TRY(layer_weights(e, l, &w));
     if (l == 0) TRY(k_resid_norm(e, x, nullptr, 0, 0, w.ln1, e->xn, nullptr, tok, 1, 0, 0, st));
-    if (fuse) {
+    if (fuse && e->prefill_qkv_fuse && e->use_tc2 && tok > 128) {
+      // RoPE + q / K / V stores in the contraction's epilogue (gemm.cuh QkvEpi)
+      EpiFuse ep = {nullptr, (bf16*)e->qbuf, nullptr, 3};
+      e->qkv_epi_next = QkvEpi{cosT, sinT, (bf16*)e->qbuf, (bf16*)kv_ptr(e, l, 0, R), (bf16*)kv_ptr(e, l, 1, R), row_off, kv_start,
+                               rope_rel ? kv_start : (const int32_t*)nullptr, R, P, d.H, e->Tmax};
+      TRY(run_gemm(e, e->xn, w.wqkv, tok, 3 * HD, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &ep));
+      e->qkv_epi_next = QkvEpi{};
+    } else if (fuse) {
       EpiFuse ep = {nullptr, stage16, nullptr, 0};
       TRY(run_gemm(e, e->xn, w.wqkv, tok, 3 * HD, D, e->part, e->part_bytes, &S, st, -1, 0, true, nullptr, nullptr, &ep));
       TRY(launch(e, qkv_rope_store_bf16_kernel, dim3(tok), dim3(256), 0, st, (const bf16*)stage16, cosT, sinT, (bf16*)e->qbuf,

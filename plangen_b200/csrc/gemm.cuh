@@ -134,6 +134,18 @@ struct EpiFuse {
   const bf16* add16;   // [M][N] bf16 added after the first rounding (out mode), or nullptr
 };
 
+// Prefill QKV projection finished inside the CTA-pair contraction (gemm_tc2.cuh, EpiFuse::gelu == 3): a staged tile is one
+// (q | k | v, head) x 256 tokens, so the row-store pass rotates q / k (RoPE pairs d, d + 64 are in the same staged row) and
+// scatters q to [tok][H*128], k / v to the cache strips - what qkv_rope_store_bf16_kernel did from a bf16 round trip.
+struct QkvEpi {
+  const float* cosT; const float* sinT;      // [position][64] fp32
+  bf16* q_out; bf16* kcache; bf16* vcache;   // q [tok][H*128]; caches [R][H][Tmax][128] of this layer
+  const int32_t* row_off;                    // packed stream offsets (nullptr: padded [R][P] block)
+  const int32_t* kv_start;
+  const int32_t* rope_start;                 // RoPE position = column - rope_start[row] (text prefill), nullptr: the column
+  int R, P, H, Tmax;
+};
+
 template <int NT>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x,

@@ -18,6 +18,7 @@
 //                        they arrive (remotely, for the peer) on the leader's accumulator-empty barrier.
 #pragma once
 #include "gemm.cuh"
+#include "lm_kernels.cuh"
 
 namespace pg {
 
@@ -71,7 +72,7 @@ constexpr int TC2_EPI = 256;                       // epilogue threads: two warp
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_x, float* __restrict__ C, int M, int N,
-                int K, int num_stages, int use_pdl, Prof prof, EpiFuse ep) {
+                int K, int num_stages, int use_pdl, Prof prof, EpiFuse ep, QkvEpi qe) {
   extern __shared__ uint8_t smem_raw2[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw2 + 1023) & ~(uintptr_t)1023);
   uint8_t* stg_buf = smem + num_stages * TC2_STAGE_BYTES;
@@ -191,6 +192,54 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive_leader(&acc_empty[set]);   // TMEM set drained: the issuer may start tile j + 2 into it
         asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (ep.gelu == 3) {
+          // prefill QKV (QkvEpi, gemm.cuh): this tile is head h of q (which = 0), k (1) or v (2) for 256 tokens
+          const int c8 = tE & 7, rr0 = tE >> 3, tile = n0 / TC_BM, which = tile / qe.H, h = tile % qe.H;
+          if (n0 < N) {
+#pragma unroll 1
+            for (int r = rr0; r < TC2_NT; r += 32) {
+              const int m = m0 + r;
+              if (m >= M) continue;
+              int rw, p;
+              if (qe.row_off != nullptr) {
+                rw = packed_row_of(qe.row_off, qe.R, m);
+                p = qe.kv_start[rw] + (m - qe.row_off[rw]);
+              } else {
+                rw = m / qe.P; p = m % qe.P;
+              }
+              uint32_t lo[4], hi[4];
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo[0]), "=r"(lo[1]), "=r"(lo[2]), "=r"(lo[3])
+                           : "r"(stg + (uint32_t)(r * 256 + c8 * 16)));
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(hi[0]), "=r"(hi[1]), "=r"(hi[2]), "=r"(hi[3])
+                           : "r"(stg + (uint32_t)(r * 256 + 128 + c8 * 16)));
+              const size_t cidx = (((size_t)rw * qe.H + h) * qe.Tmax + p) * HEAD_DIM + c8 * 8;
+              if (which == 2) {
+                *reinterpret_cast<uint4*>(qe.vcache + cidx) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint4*>(qe.vcache + cidx + 64) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              } else {
+                const int pr = qe.rope_start ? max(p - qe.rope_start[rw], 0) : p;
+                const float4* c4 = reinterpret_cast<const float4*>(qe.cosT + (size_t)pr * 64 + c8 * 8);
+                const float4* s4 = reinterpret_cast<const float4*>(qe.sinT + (size_t)pr * 64 + c8 * 8);
+                const float4 ca = c4[0], cb = c4[1], sa = s4[0], sb = s4[1];
+                const float cs[8] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w};
+                const float sn[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+                uint32_t oa[4], ob[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float a0, b0, a1, b1;
+                  rope_pair<bf16>(bf16lo(lo[u]), bf16lo(hi[u]), cs[2 * u], sn[2 * u], false, a0, b0);
+                  rope_pair<bf16>(bf16hi(lo[u]), bf16hi(hi[u]), cs[2 * u + 1], sn[2 * u + 1], false, a1, b1);
+                  const __nv_bfloat162 xa = __floats2bfloat162_rn(a0, a1), xb = __floats2bfloat162_rn(b0, b1);
+                  oa[u] = *reinterpret_cast<const uint32_t*>(&xa); ob[u] = *reinterpret_cast<const uint32_t*>(&xb);
+                }
+                bf16* dst = which == 0 ? qe.q_out + (size_t)m * (qe.H * HEAD_DIM) + h * HEAD_DIM + c8 * 8 : qe.kcache + cidx;
+                *reinterpret_cast<uint4*>(dst) = make_uint4(oa[0], oa[1], oa[2], oa[3]);
+                *reinterpret_cast<uint4*>(dst + 64) = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+              }
+            }
+          }
+          continue;
+        }
         if (ep.gelu == 2) {
           // SwiGLU (prefill gate|up): the tile's 128 weight rows are gate(f0 .. f0+63) | up(f0 .. f0+63) (rows interleaved in
           // blocks of 64, weights.py), so a staged token row holds g in bytes 0-127 and u in bytes 128-255:

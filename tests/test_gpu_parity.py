@@ -257,10 +257,12 @@ def test_packed_prefill_is_bit_identical_to_padded_prefill():
     outs, toks = [], []
     # third pass: V from the key-contiguous copy instead of the cache rows read in place (MN-major operand, the default);
     # fourth: SwiGLU as its own kernel instead of in the gate|up contraction's epilogue
-    for pack, v_direct, swiglu_fuse in ((1, 1, 1), (0, 1, 1), (1, 0, 1), (1, 1, 0)):
+    # fifth: RoPE + q / cache stores as their own kernel instead of in the QKV contraction's epilogue (also with the padded block)
+    for pack, v_direct, swiglu_fuse, qkv_fuse in ((1, 1, 1, 1), (0, 1, 1, 1), (1, 0, 1, 1), (1, 1, 0, 1), (1, 1, 1, 0), (0, 1, 1, 0)):
         eng.set_option("prefill_pack", pack)
         eng.set_option("prefill_v_direct", v_direct)
         eng.set_option("prefill_swiglu_fuse", swiglu_fuse)
+        eng.set_option("prefill_qkv_fuse", qkv_fuse)
         dbg = torch.zeros(steps, len(lens), dims.img_vocab, device="cuda")
         eng.set_option("dbg_logits_ptr", dbg.data_ptr())
         try:
@@ -272,8 +274,9 @@ def test_packed_prefill_is_bit_identical_to_padded_prefill():
             eng.set_option("prefill_pack", 1)
             eng.set_option("prefill_v_direct", 1)
             eng.set_option("prefill_swiglu_fuse", 1)
+            eng.set_option("prefill_qkv_fuse", 1)
         outs.append(dbg.cpu())
-    for k in (1, 2, 3):
+    for k in (1, 2, 3, 4, 5):
         assert torch.equal(outs[0], outs[k]) and torch.equal(toks[0], toks[k]), k
     # and for the text prefill of language_model.generate (mask-aware RoPE positions)
     sd = O.init_state_dict(dims, seed=0, with_vq=False, with_lm_head=True)
@@ -282,12 +285,14 @@ def test_packed_prefill_is_bit_identical_to_padded_prefill():
     te = FastJanus(sd, product_dims(dims), mode="bf16", max_batch=4, max_prompt=256, max_steps=32, with_vq=False)
     tid, tmask = O.pad_input_ids([c[:n] for c, n in zip(cond, (200, 1, 64, 130, 9, 255, 256, 3))], dims.pad_id)
     got = []
-    for pack in (1, 0):
+    for pack, qkv_fuse in ((1, 1), (0, 1), (1, 0)):
         te.set_option("prefill_pack", pack)
+        te.set_option("prefill_qkv_fuse", qkv_fuse)
         emb = te.language_model.get_input_embeddings()(tid.cuda())
         got.append(te.language_model.generate(inputs_embeds=emb, attention_mask=tmask.cuda(), pad_token_id=7, eos_token_id=7,
                                               max_new_tokens=8).cpu())
-    assert torch.equal(got[0], got[1])
+    te.set_option("prefill_qkv_fuse", 1)
+    assert torch.equal(got[0], got[1]) and torch.equal(got[0], got[2])
 
 
 def test_prefill_row_dedup_is_bit_identical():
