@@ -21,7 +21,7 @@ namespace pg {
 constexpr int PA_BQ = 128;                     // queries per CTA (MMA M)
 constexpr int PA_BK = 128;                     // keys per block (MMA N of the first product, K of the second)
 constexpr int PA_TILE = 128 * 64 * 2;          // one [128 rows][64 bf16] swizzled tile = 16 KB
-constexpr int PA_SMEM = 8 * PA_TILE + 1024 + 64;   // Q, K, V^T, P: two tiles each
+constexpr int PA_SMEM = 6 * PA_TILE + 1024 + 64;   // Q, K (later P), V: two tiles each; 97 KB -> two CTAs per SM
 
 // V [r][h][key][128] (cache layout) -> vT [r][h][128][Ppad] (keys contiguous) for keys < P
 __global__ void __launch_bounds__(256)
@@ -48,7 +48,7 @@ v_transpose_kernel(const bf16* __restrict__ vcache, bf16* __restrict__ vT, int P
   }
 }
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_vt, const int32_t* __restrict__ kv_start,
                        bf16* __restrict__ out, int P, int H, int Tmax, float scale, const int32_t* __restrict__ row_off,
@@ -58,8 +58,10 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   uint8_t* sQ = smem;                      // 2 tiles: dims 0-63 | 64-127 of the 128 queries
   uint8_t* sK = smem + 2 * PA_TILE;        // 2 tiles: dims 0-63 | 64-127 of the 128 keys
   uint8_t* sV = smem + 4 * PA_TILE;        // 2 tiles: keys 0-63 | 64-127 of the 128 dims (V^T)
-  uint8_t* sP = smem + 6 * PA_TILE;        // 2 tiles: keys 0-63 | 64-127 of the 128 queries (probabilities)
-  uint64_t* bars = (uint64_t*)(smem + 8 * PA_TILE);
+  uint8_t* sP = sK;                        // probabilities (2 tiles: keys 0-63 | 64-127 of the 128 queries) overwrite the K tiles:
+                                           // every thread has waited for S = Q K^T before it writes P, and the next K load is
+                                           // issued only after O_b = P V has completed
+  uint64_t* bars = (uint64_t*)(smem + 6 * PA_TILE);
   uint64_t* bar_load = bars;
   uint64_t* bar_mma = bars + 1;
   uint32_t* tmem_slot = (uint32_t*)(bars + 2);
